@@ -1,0 +1,139 @@
+/*
+ * linna_b200 C ABI -- B200 (sm_100a) implementation of LINNA's emulator-likelihood hot path.
+ *
+ * Plain C: pointers, sizes, an opaque handle.  No torch / CUDA types in the signatures
+ * (`stream` is a cudaStream_t passed as void*; NULL = the legacy default stream).
+ * Every entry point returns 0 on success and a negative LINNA_E* code on failure;
+ * linna_last_error() gives the message.  There is no CPU fallback: creating a model
+ * without a CUDA device fails with LINNA_ENODEV.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * reference checkout, chto/linna).  INTEGRATION.md shows the reference-side ctypes
+ * binding.
+ */
+#ifndef LINNA_B200_H
+#define LINNA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LINNA_ABI_VERSION 1
+
+enum {
+    LINNA_OK = 0,
+    LINNA_EINVAL = -1,  /* bad argument / unsupported shape */
+    LINNA_ENODEV = -2,  /* no CUDA device / wrong architecture */
+    LINNA_ECUDA = -3,   /* CUDA runtime error (message in linna_last_error) */
+    LINNA_ENOMEM = -4,
+    LINNA_ESTATE = -5   /* call order: e.g. lnP before linna_model_set_likelihood */
+};
+
+/* ---- network description: mirrors linna/nn.py ----------------------------------------- */
+enum { LINNA_OP_LINEAR = 0, LINNA_OP_RES = 1 };
+enum { LINNA_ACT_NONE = 0, LINNA_ACT_RELU = 1 };
+
+/* One layer.  All weight pointers are HOST float32 in torch nn.Linear layout [out][in].
+ *   LINEAR:  y = act(W x + b)                                     (linna/nn.py:121,125-130)
+ *   RES:     h = relu(W x + b);  y = relu(alpha*(W2 h + b2) + Ws x)   (linna/nn.py:45-56)
+ *            Ws == NULL means the identity skip (in_dim == out_dim, linna/nn.py:28-29). */
+typedef struct {
+    int32_t kind;
+    int32_t in_dim, mid_dim, out_dim;
+    int32_t act;
+    float alpha;
+    const float *w, *b;   /* LINEAR: [out][in],[out]   RES layer1: [mid][in],[mid] */
+    const float *w2, *b2; /* RES layer2: [out][mid],[out] */
+    const float *ws;      /* RES skip_layer.weight [out][in] or NULL */
+} linna_op_desc_t;
+
+/* Emulator = op list + the diagonal input/output transforms that Predictor.predict applies
+ * (linna/predictor_gpu.py:461-504):
+ *   X_transform_class  (linna/util.py:483-497): xhat = (theta' - x_mean)/x_std, theta'_i = log10(theta_i)
+ *                                               for flagged i
+ *   Y_transform_class  (linna/util.py:532-542): y = yhat*y_std + y_mean  (exp(.) if ypositive)
+ *   Y_invtransform_data(linna/util.py:457-458): m = y*sigma
+ * extra_linear_*: ChtoModelv2_linear's "+ 1e-3*linearlayer(xhat)" (linna/nn.py:193), or NULL. */
+typedef struct {
+    int32_t n_in, n_out, n_ops;
+    const linna_op_desc_t *ops;
+    const float *x_mean, *x_std;     /* [n_in]  */
+    const uint8_t *log10_flag;       /* [n_in] or NULL */
+    const float *y_mean, *y_std;     /* [n_out] */
+    int32_t ypositive;
+    const float *sigma;              /* [n_out] or NULL (=1) */
+    const float *extra_linear_w, *extra_linear_b; /* [n_out][n_in], [n_out] or NULL */
+    float extra_linear_scale;
+} linna_model_desc_t;
+
+/* Likelihood constants of Log_prob (linna/util.py:957-1021):
+ *   priors: Transform.__call__ (linna/util.py:323-347): theta_i = u_i*arg2+arg1 (gauss, kind 0) or
+ *           Phi(u_i)*(arg2-arg1)+arg1 (flat, kind 1); lnprior = -1/2 sum u^2 (linna/util.py:1160-1165)
+ *   data, quadratic form: gaussianlogliklihood (linna/util.py:953-955): -1/2 d C^-1 d^T, d = m - data.
+ *     quad_kind LINNA_QUAD_CHOL : `quad` is L, lower-triangular row-major with C^-1 = L L^T
+ *                                (chi^2 = |L^T d|^2, the north-star form);
+ *     quad_kind LINNA_QUAD_DENSE: `quad` is the dense (symmetrised) C^-1 itself, as the reference uses.
+ *   temperature: lnL/T (linna/util.py:1013, linna/main.py:153). */
+enum { LINNA_PRIOR_GAUSS = 0, LINNA_PRIOR_FLAT = 1 };
+enum { LINNA_QUAD_CHOL = 0, LINNA_QUAD_DENSE = 1 };
+typedef struct {
+    const int32_t *prior_kind;       /* [n_in] */
+    const float *prior_arg1, *prior_arg2;
+    const float *data;               /* [n_out] */
+    const float *quad;               /* [n_out][n_out] */
+    int32_t quad_kind;
+    float temperature;
+} linna_like_desc_t;
+
+typedef struct linna_model linna_model_t;
+
+int linna_abi_version(void);
+const char *linna_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t linna_launch_count(void);
+
+/* Packs the weights (forward and transposed layouts, zero-padded rows) and constants into one
+ * device blob on `device`.  Replaces retrieve_model()'s host-side model build (linna/util.py:611-639). */
+int linna_model_create(const linna_model_desc_t *desc, int device, linna_model_t **out);
+void linna_model_destroy(linna_model_t *m);
+int linna_model_set_likelihood(linna_model_t *m, const linna_like_desc_t *like);
+/* Re-upload weights after a training update; `ops` must have the shapes given at create time. */
+int linna_model_set_weights(linna_model_t *m, const linna_op_desc_t *ops, int32_t n_ops,
+                            const float *extra_linear_w, const float *extra_linear_b);
+
+/* What linna_predict writes, row-major [n][n_out]. */
+enum { LINNA_OUT_YHAT = 0,  /* network output, normalised space (model(X_transform(X)))            */
+       LINNA_OUT_Y = 1,     /* Predictor.predict: y_transform applied   (predictor_gpu.py:500)      */
+       LINNA_OUT_M = 2 };   /* y_invtransform_data(predict(.)): data-space model vector (util.py:1012) */
+
+/* Batched Predictor.predict (linna/predictor_gpu.py:461-504).  theta, out: DEVICE pointers. */
+int linna_predict(linna_model_t *m, const float *theta, int64_t n, float *out, int32_t out_kind, void *stream);
+
+/* Batched Log_prob.__call__ (linna/util.py:990-1021): u [n][n_in] latent positions -> lnP [n].
+ * NaN results are returned as -inf (linna/util.py:1015-1016).  DEVICE pointers. */
+int linna_lnp(linna_model_t *m, const float *u, int64_t n, float *lnp, void *stream);
+
+/* lnP and d lnP/du in one launch; replaces Log_prob(nograd=False) + torch.autograd.grad
+ * (linna/HMCSampler.py:29-48, linna/util.py:1023-1035 Dlnp).  grad: [n][n_in].  DEVICE pointers. */
+int linna_lnp_grad(linna_model_t *m, const float *u, int64_t n, float *lnp, float *grad, void *stream);
+
+/* Host-buffer forms of the three calls above: the arrays are HOST memory (any pageable or pinned
+ * buffer); the library stages them through pinned memory, runs the kernel and copies the result
+ * back before returning.  These are what a per-call numpy caller (emcee/zeus with vectorize=True)
+ * binds, and what bench.py's `e2e` leg times. */
+int linna_predict_host(linna_model_t *m, const float *theta, int64_t n, float *out, int32_t out_kind);
+int linna_lnp_host(linna_model_t *m, const float *u, int64_t n, float *lnp);
+int linna_lnp_grad_host(linna_model_t *m, const float *u, int64_t n, float *lnp, float *grad);
+
+/* Introspection used by bench.py / tests. */
+int linna_model_info(const linna_model_t *m, int32_t *n_in, int32_t *n_out, int64_t *n_params, int32_t *num_sms);
+/* Force the row-tile height (8, 16 or 32; 0 = automatic) -- test hook for the tiling variants. */
+int linna_model_set_tile_rows(linna_model_t *m, int32_t rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LINNA_B200_H */

@@ -1,0 +1,679 @@
+// C-ABI of linna_b200 (see include/linna_b200.h): model packing, step-program construction and
+// kernel dispatch.  Host code only; the kernels live in fused_ffma.cu (and later tc_*.cu).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/linna_b200.h"
+#include "linna_device.cuh"
+
+namespace linna {
+cudaError_t launch_fused_ffma(const KernelArgs &args, int rg, int grid, cudaStream_t stream);
+int fused_ffma_max_ctas_per_sm(int rg);
+}  // namespace linna
+
+using namespace linna;
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(x)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (x);                                                                         \
+        if (e_ != cudaSuccess) return fail(LINNA_ECUDA, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), \
+                                           __FILE__, __LINE__);                                       \
+    } while (0)
+
+static inline int pad4(int n) { return (n + 3) & ~3; }
+
+struct OpHost {
+    int kind, in, mid, out, act;
+    float alpha;
+    std::vector<float> w, b, w2, b2, ws;
+    bool has_ws;
+};
+
+enum ProgKind { PROG_PREDICT = 0, PROG_LNP = 1, PROG_GRAD = 2, PROG_COUNT = 3 };
+
+struct linna_model {
+    int device = 0, num_sms = 0;
+    int n_in = 0, n_out = 0, ypositive = 0;
+    int64_t n_params = 0;
+    std::vector<OpHost> ops;
+    std::vector<float> x_mean, x_std, y_mean, y_std, sigma;
+    std::vector<uint8_t> log10_flag;
+    bool has_log10 = false, has_extra = false;
+    std::vector<float> extra_w, extra_b;
+    float extra_scale = 0.f;
+    // likelihood
+    bool has_like = false;
+    std::vector<int32_t> prior_kind;
+    std::vector<float> prior_scale, prior_shift, data, quad;
+    int quad_kind = LINNA_QUAD_CHOL;
+    float temperature = 1.f;
+    // device state
+    float *blob = nullptr;
+    size_t blob_floats = 0;
+    Program *prog_dev = nullptr;  // [PROG_COUNT]
+    Program prog_host[PROG_COUNT];
+    bool prog_valid[PROG_COUNT] = {false, false, false};
+    Consts consts;
+    float *arena = nullptr;
+    uint8_t *masks = nullptr;
+    size_t arena_bytes = 0, masks_bytes = 0;
+    int occ[3] = {0, 0, 0};  // CTAs/SM for RG = 1, 2, 4
+    int force_rows = 0;
+    // the scratch arena is shared by every launch on this model: launches on different streams are
+    // chained through this event so that they never overlap
+    cudaEvent_t last_done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool have_last = false;
+    // host-buffer API staging
+    cudaStream_t hstream = nullptr;
+    float *d_in = nullptr, *d_out = nullptr, *d_lnp = nullptr, *d_grad = nullptr;
+    size_t d_in_cap = 0, d_out_cap = 0, d_lnp_cap = 0, d_grad_cap = 0;
+};
+
+// ----------------------------------------------------------------------------------------------
+// blob builder: one host mirror, sub-allocations aligned to 64 floats (256 B)
+struct Builder {
+    std::vector<float> h;
+    size_t alloc(size_t n)
+    {
+        size_t o = (h.size() + 63) / 64 * 64;
+        h.resize(o + n, 0.f);
+        return o;
+    }
+    size_t put(const std::vector<float> &v)
+    {
+        size_t o = alloc(v.size());
+        std::copy(v.begin(), v.end(), h.begin() + o);
+        return o;
+    }
+    // W is [out][in] (torch layout).  forward operand: Wt[k=in][n=out], ld = pad4(out)
+    size_t put_fwd(const std::vector<float> &W, int out, int in, float scale = 1.f)
+    {
+        int ld = pad4(out);
+        size_t o = alloc((size_t)in * ld);
+        for (int n = 0; n < out; ++n)
+            for (int k = 0; k < in; ++k) h[o + (size_t)k * ld + n] = scale * W[(size_t)n * in + k];
+        return o;
+    }
+    // backward operand: Wb[k=out][n=in] = W itself with rows padded to pad4(in)
+    size_t put_bwd(const std::vector<float> &W, int out, int in, float scale = 1.f)
+    {
+        int ld = pad4(in);
+        size_t o = alloc((size_t)out * ld);
+        for (int n = 0; n < out; ++n)
+            for (int k = 0; k < in; ++k) h[o + (size_t)n * ld + k] = scale * W[(size_t)n * in + k];
+        return o;
+    }
+};
+
+struct OpOffsets {
+    size_t w_f, w_b, b, w2_f, w2_b, b2, ws_f, ws_b;
+    int mask_y, mask_h;  // mask arena offsets (features), -1 if none
+};
+
+static void free_device(linna_model *m)
+{
+    cudaSetDevice(m->device);
+    if (m->blob) cudaFree(m->blob);
+    if (m->prog_dev) cudaFree(m->prog_dev);
+    if (m->arena) cudaFree(m->arena);
+    if (m->masks) cudaFree(m->masks);
+    m->blob = nullptr, m->prog_dev = nullptr, m->arena = nullptr, m->masks = nullptr;
+}
+
+// (Re)build the device blob and the three step programs from the host copies.
+static int rebuild(linna_model *m)
+{
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaDeviceSynchronize());  // no launch may still be reading the blob we are about to replace
+    const int n_in = m->n_in, n_out = m->n_out;
+    Builder B;
+    std::vector<OpOffsets> off(m->ops.size());
+    int maxW = std::max(n_in, n_out), maxMid = 4, mask_total = 0;
+    for (size_t i = 0; i < m->ops.size(); ++i) {
+        OpHost &op = m->ops[i];
+        OpOffsets &o = off[i];
+        maxW = std::max(maxW, std::max(op.in, op.out));
+        o.mask_y = o.mask_h = -1;
+        if (op.kind == LINNA_OP_LINEAR) {
+            o.w_f = B.put_fwd(op.w, op.out, op.in);
+            o.w_b = B.put_bwd(op.w, op.out, op.in);
+            o.b = B.put(op.b);
+            if (op.act == LINNA_ACT_RELU) { o.mask_y = mask_total; mask_total += op.out; }
+        } else {
+            maxMid = std::max(maxMid, op.mid);
+            o.w_f = B.put_fwd(op.w, op.mid, op.in);
+            o.w_b = B.put_bwd(op.w, op.mid, op.in);
+            o.b = B.put(op.b);
+            o.w2_f = B.put_fwd(op.w2, op.out, op.mid);
+            o.w2_b = B.put_bwd(op.w2, op.out, op.mid);
+            o.b2 = B.put(op.b2);
+            if (op.has_ws) {
+                o.ws_f = B.put_fwd(op.ws, op.out, op.in);
+                o.ws_b = B.put_bwd(op.ws, op.out, op.in);
+            }
+            o.mask_h = mask_total; mask_total += op.mid;
+            o.mask_y = mask_total; mask_total += op.out;
+        }
+    }
+    size_t o_xmean = B.put(m->x_mean), o_xstd = B.put(m->x_std), o_ymean = B.put(m->y_mean), o_ystd = B.put(m->y_std);
+    size_t o_sigma = B.put(m->sigma);
+    size_t o_log10 = 0;
+    if (m->has_log10) {
+        o_log10 = B.alloc((n_in + 3) / 4);
+        memcpy(&B.h[o_log10], m->log10_flag.data(), n_in);
+    }
+    size_t o_extra_f = 0, o_extra_b = 0, o_lastbias = 0;
+    if (m->has_extra) {
+        // yhat += s*(Wl xhat + bl): fold s into the packed operand and s*bl into the last bias
+        o_extra_f = B.put_fwd(m->extra_w, n_out, n_in, m->extra_scale);
+        o_extra_b = B.put_bwd(m->extra_w, n_out, n_in, m->extra_scale);
+        OpHost &last = m->ops.back();
+        std::vector<float> bb = last.b;
+        for (int j = 0; j < n_out; ++j) bb[j] += m->extra_scale * m->extra_b[j];
+        o_lastbias = B.put(bb);
+    }
+    size_t o_pk = 0, o_ps = 0, o_psh = 0, o_data = 0, o_quadF = 0, o_quadB = 0, o_cs = 0;
+    if (m->has_like) {
+        o_pk = B.alloc(n_in);
+        memcpy(&B.h[o_pk], m->prior_kind.data(), sizeof(int32_t) * n_in);
+        o_ps = B.put(m->prior_scale);
+        o_psh = B.put(m->prior_shift);
+        o_data = B.put(m->data);
+        // chi^2 operand in [k][n] form: r_n = sum_k Q[k][n] d_k.  CHOL: Q = L (r = L^T d); DENSE: Q = C^-1.
+        o_quadF = B.put_bwd(m->quad, n_out, n_out);   // Q itself, rows padded
+        // backward operand: g_k = sum_n Qb[n][k] r_n with Qb = L^T stored row-major => put_fwd(L)
+        o_quadB = (m->quad_kind == LINNA_QUAD_CHOL) ? B.put_fwd(m->quad, n_out, n_out) : o_quadF;
+        std::vector<float> cs(n_out);
+        for (int j = 0; j < n_out; ++j) cs[j] = -(m->sigma[j] * m->y_std[j]) / m->temperature;
+        o_cs = B.put(cs);
+    }
+
+    // ---- upload
+    if (m->blob && m->blob_floats < B.h.size()) { cudaFree(m->blob); m->blob = nullptr; }
+    if (!m->blob) {
+        m->blob_floats = B.h.size() + 1024;
+        CUDA_TRY(cudaMalloc(&m->blob, m->blob_floats * sizeof(float)));
+    }
+    CUDA_TRY(cudaMemcpy(m->blob, B.h.data(), B.h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    auto P = [&](size_t o) { return (const float *)(m->blob + o); };
+
+    Consts &c = m->consts;
+    memset(&c, 0, sizeof c);
+    c.x_mean = P(o_xmean), c.x_std = P(o_xstd), c.y_mean = P(o_ymean), c.y_std = P(o_ystd), c.sigma = P(o_sigma);
+    c.log10_flag = m->has_log10 ? (const uint8_t *)P(o_log10) : nullptr;
+    c.n_in = n_in, c.n_out = n_out, c.ypositive = m->ypositive, c.quad_kind = m->quad_kind;
+    c.inv_T = 1.0f / m->temperature;
+    if (m->has_like) {
+        c.prior_kind = (const int32_t *)P(o_pk);
+        c.prior_scale = P(o_ps), c.prior_shift = P(o_psh), c.data = P(o_data);
+    }
+
+    // ---- arena layout (features): X | A | B | H | Y | GX
+    const int bufX = 0, bufA = n_in, bufB = bufA + maxW, bufH = bufB + maxW, bufY = bufH + maxMid,
+              bufGX = bufY + n_out, arena_features = bufGX + n_in;
+
+    for (int pk = 0; pk < PROG_COUNT; ++pk) {
+        m->prog_valid[pk] = false;
+        if (pk != PROG_PREDICT && !m->has_like) continue;
+        const bool grad = pk == PROG_GRAD;
+        Program &pg = m->prog_host[pk];
+        memset(&pg, 0, sizeof pg);
+        pg.arena_features = arena_features;
+        pg.mask_features = grad ? mask_total : 0;
+        pg.in_buf = bufX;
+        int ns = 0;
+        auto new_step = [&]() -> Step & {
+            Step &s = pg.steps[ns++];
+            memset(&s, 0, sizeof s);
+            s.src1 = s.src2 = s.dst = -1;
+            s.scale = 1.f;
+            s.mask_off = 0;
+            return s;
+        };
+        if ((int)m->ops.size() * 2 + 2 * (int)m->ops.size() + 6 > kMaxSteps)
+            return fail(LINNA_EINVAL, "too many layers (%zu)", m->ops.size());
+        int cur = bufX;
+        auto other = [&](int b) { return b == bufA ? bufB : bufA; };
+        // ------------------------------ forward
+        for (size_t i = 0; i < m->ops.size(); ++i) {
+            const OpHost &op = m->ops[i];
+            const OpOffsets &o = off[i];
+            const bool last = i + 1 == m->ops.size();
+            if (op.kind == LINNA_OP_LINEAR) {
+                Step &s = new_step();
+                s.src1 = cur, s.K1 = op.in, s.wt1 = P(o.w_f), s.ldw1 = pad4(op.out), s.N = op.out;
+                s.bias = P(o.b);
+                if (op.act == LINNA_ACT_RELU) {
+                    s.flags |= F_RELU;
+                    if (grad) s.flags |= F_SAVE_MASK, s.mask_off = o.mask_y;
+                }
+                s.epi = last ? EPI_HEAD : EPI_ACT;
+                s.dst = other(cur);
+                if (last && m->has_extra) {
+                    s.src2 = bufX, s.K2 = n_in, s.wt2 = P(o_extra_f), s.ldw2 = pad4(n_out), s.bias = P(o_lastbias);
+                }
+                cur = s.dst;
+            } else {
+                if (last && m->has_extra) return fail(LINNA_EINVAL, "extra linear branch needs a LINEAR last op");
+                Step &h = new_step();
+                h.src1 = cur, h.K1 = op.in, h.wt1 = P(o.w_f), h.ldw1 = pad4(op.mid), h.N = op.mid, h.bias = P(o.b);
+                h.flags = F_RELU | (grad ? F_SAVE_MASK : 0), h.mask_off = o.mask_h, h.epi = EPI_ACT, h.dst = bufH;
+                Step &y = new_step();
+                y.src1 = bufH, y.K1 = op.mid, y.wt1 = P(o.w2_f), y.ldw1 = pad4(op.out), y.N = op.out;
+                y.bias = P(o.b2), y.scale = op.alpha;
+                y.src2 = cur;
+                if (op.has_ws) y.K2 = op.in, y.wt2 = P(o.ws_f), y.ldw2 = pad4(op.out);
+                else y.flags |= F_ADD_SRC2;
+                y.flags |= F_RELU | (grad ? F_SAVE_MASK : 0), y.mask_off = o.mask_y;
+                y.epi = last ? EPI_HEAD : EPI_ACT;
+                y.dst = other(cur);
+                cur = y.dst;
+            }
+            if (last) {
+                Step &s = pg.steps[ns - 1];
+                if (pk == PROG_PREDICT) s.flags |= F_OUT_VEC;
+                if (grad && m->ypositive) s.flags |= F_SAVE_Y, s.ybuf = bufY;
+            }
+        }
+        if (pk != PROG_PREDICT) {
+            const int dbuf = cur;
+            Step &q = new_step();
+            q.src1 = dbuf, q.K1 = n_out, q.wt1 = P(o_quadF), q.ldw1 = pad4(n_out), q.N = n_out, q.epi = EPI_CHI2;
+            q.dst = other(dbuf);
+            const bool chol = m->quad_kind == LINNA_QUAD_CHOL;
+            if (grad && chol) q.flags |= F_STORE_DST;
+            if (grad) {
+                // g_yhat = -(1/T) * Q_b r  (.) sigma*y_std (.* y if ypositive)
+                Step &g0 = new_step();
+                g0.src1 = chol ? q.dst : dbuf;
+                g0.K1 = n_out, g0.wt1 = P(o_quadB), g0.ldw1 = pad4(n_out), g0.N = n_out, g0.epi = EPI_BWD;
+                g0.colscale = P(o_cs);
+                if (m->ypositive) g0.flags |= F_MUL_YSAVE, g0.ybuf = bufY;
+                const OpHost &lastop = m->ops.back();
+                const bool last_relu = lastop.kind == LINNA_OP_RES || lastop.act == LINNA_ACT_RELU;
+                if (last_relu) g0.flags |= F_APPLY_MASK, g0.mask_off = off.back().mask_y;
+                g0.dst = chol ? dbuf : other(dbuf);
+                cur = g0.dst;
+                if (m->has_extra) {
+                    Step &gx = new_step();
+                    gx.src1 = cur, gx.K1 = n_out, gx.wt1 = P(o_extra_b), gx.ldw1 = pad4(n_in), gx.N = n_in;
+                    gx.epi = EPI_BWD, gx.dst = bufGX;
+                }
+                for (int i = (int)m->ops.size() - 1; i >= 0; --i) {
+                    const OpHost &op = m->ops[i];
+                    const OpOffsets &o = off[i];
+                    // mask of the producer of this op's input
+                    int pmask = -1;
+                    if (i > 0) {
+                        const OpHost &pv = m->ops[i - 1];
+                        if (pv.kind == LINNA_OP_RES || pv.act == LINNA_ACT_RELU) pmask = off[i - 1].mask_y;
+                    }
+                    if (op.kind == LINNA_OP_LINEAR) {
+                        Step &s = new_step();
+                        s.src1 = cur, s.K1 = op.out, s.wt1 = P(o.w_b), s.ldw1 = pad4(op.in), s.N = op.in;
+                        s.epi = i == 0 ? EPI_GRAD : EPI_BWD;
+                        if (pmask >= 0) s.flags |= F_APPLY_MASK, s.mask_off = pmask;
+                        if (i == 0 && m->has_extra) s.flags |= F_ADD_SRC2, s.src2 = bufGX;
+                        s.dst = other(cur);
+                        cur = s.dst;
+                    } else {
+                        if (i == 0 && m->has_extra) return fail(LINNA_EINVAL, "extra linear branch needs a LINEAR first op");
+                        Step &h = new_step();
+                        h.src1 = cur, h.K1 = op.out, h.wt1 = P(o.w2_b), h.ldw1 = pad4(op.mid), h.N = op.mid;
+                        h.scale = op.alpha, h.epi = EPI_BWD, h.flags = F_APPLY_MASK, h.mask_off = o.mask_h, h.dst = bufH;
+                        Step &x = new_step();
+                        if (op.has_ws) {
+                            x.src1 = cur, x.K1 = op.out, x.wt1 = P(o.ws_b), x.ldw1 = pad4(op.in);
+                            x.src2 = bufH, x.K2 = op.mid, x.wt2 = P(o.w_b), x.ldw2 = pad4(op.in);
+                        } else {
+                            x.src1 = bufH, x.K1 = op.mid, x.wt1 = P(o.w_b), x.ldw1 = pad4(op.in);
+                            x.src2 = cur, x.flags |= F_ADD_SRC2;
+                        }
+                        x.N = op.in;
+                        x.epi = i == 0 ? EPI_GRAD : EPI_BWD;
+                        if (pmask >= 0) x.flags |= F_APPLY_MASK, x.mask_off = pmask;
+                        x.dst = other(cur);
+                        cur = x.dst;
+                    }
+                }
+            }
+        }
+        pg.n_steps = ns;
+        m->prog_valid[pk] = true;
+    }
+    if (!m->prog_dev) CUDA_TRY(cudaMalloc(&m->prog_dev, sizeof(Program) * PROG_COUNT));
+    CUDA_TRY(cudaMemcpy(m->prog_dev, m->prog_host, sizeof(Program) * PROG_COUNT, cudaMemcpyHostToDevice));
+
+    // ---- scratch arenas sized for the largest grid
+    for (int i = 0; i < 3; ++i)
+        if (!m->occ[i]) m->occ[i] = fused_ffma_max_ctas_per_sm(1 << i);
+    int max_ctas = m->num_sms * std::max(m->occ[0], std::max(m->occ[1], m->occ[2]));
+    size_t need_arena = (size_t)max_ctas * arena_features * 32 * sizeof(float);
+    size_t need_masks = (size_t)max_ctas * std::max(mask_total, 1) * 4;
+    if (need_arena > m->arena_bytes) {
+        if (m->arena) cudaFree(m->arena);
+        m->arena = nullptr;
+        CUDA_TRY(cudaMalloc(&m->arena, need_arena));
+        m->arena_bytes = need_arena;
+    }
+    if (need_masks > m->masks_bytes) {
+        if (m->masks) cudaFree(m->masks);
+        m->masks = nullptr;
+        CUDA_TRY(cudaMalloc(&m->masks, need_masks));
+        m->masks_bytes = need_masks;
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    return LINNA_OK;
+}
+
+static int copy_ops(linna_model *m, const linna_op_desc_t *ops, int n_ops, bool check_shapes)
+{
+    if (check_shapes && (int)m->ops.size() != n_ops) return fail(LINNA_EINVAL, "op count changed");
+    std::vector<OpHost> v(n_ops);
+    int64_t np = 0;
+    int width = m->n_in;
+    for (int i = 0; i < n_ops; ++i) {
+        const linna_op_desc_t &d = ops[i];
+        OpHost &o = v[i];
+        o.kind = d.kind, o.in = d.in_dim, o.mid = d.mid_dim, o.out = d.out_dim, o.act = d.act, o.alpha = d.alpha;
+        if (d.in_dim != width) return fail(LINNA_EINVAL, "op %d: in_dim %d does not chain (expected %d)", i, d.in_dim, width);
+        if (d.in_dim <= 0 || d.out_dim <= 0) return fail(LINNA_EINVAL, "op %d: bad dims", i);
+        if (!d.w || !d.b) return fail(LINNA_EINVAL, "op %d: null weights", i);
+        if (d.kind == LINNA_OP_LINEAR) {
+            o.w.assign(d.w, d.w + (size_t)d.out_dim * d.in_dim);
+            o.b.assign(d.b, d.b + d.out_dim);
+            np += (int64_t)d.out_dim * d.in_dim + d.out_dim;
+        } else if (d.kind == LINNA_OP_RES) {
+            if (d.mid_dim <= 0 || !d.w2 || !d.b2) return fail(LINNA_EINVAL, "op %d: bad res block", i);
+            if (!d.ws && d.in_dim != d.out_dim) return fail(LINNA_EINVAL, "op %d: identity skip needs in == out", i);
+            o.w.assign(d.w, d.w + (size_t)d.mid_dim * d.in_dim);
+            o.b.assign(d.b, d.b + d.mid_dim);
+            o.w2.assign(d.w2, d.w2 + (size_t)d.out_dim * d.mid_dim);
+            o.b2.assign(d.b2, d.b2 + d.out_dim);
+            o.has_ws = d.ws != nullptr;
+            if (o.has_ws) o.ws.assign(d.ws, d.ws + (size_t)d.out_dim * d.in_dim);
+            np += (int64_t)d.mid_dim * d.in_dim + d.mid_dim + (int64_t)d.out_dim * d.mid_dim + d.out_dim +
+                  (o.has_ws ? (int64_t)d.out_dim * d.in_dim : 0);
+        } else
+            return fail(LINNA_EINVAL, "op %d: unknown kind %d", i, d.kind);
+        if (check_shapes) {
+            const OpHost &p = m->ops[i];
+            if (p.kind != o.kind || p.in != o.in || p.mid != o.mid || p.out != o.out)
+                return fail(LINNA_EINVAL, "op %d: shape changed", i);
+        }
+        width = d.out_dim;
+    }
+    if (width != m->n_out) return fail(LINNA_EINVAL, "last op out_dim %d != n_out %d", width, m->n_out);
+    m->ops.swap(v);
+    m->n_params = np;
+    return LINNA_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+extern "C" {
+
+int linna_abi_version(void) { return LINNA_ABI_VERSION; }
+const char *linna_last_error(void) { return g_err.c_str(); }
+int64_t linna_launch_count(void) { return g_launches.load(); }
+
+int linna_model_create(const linna_model_desc_t *d, int device, linna_model_t **out)
+{
+    if (!d || !out) return fail(LINNA_EINVAL, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(LINNA_ENODEV, "no CUDA device: linna_b200 has no CPU path");
+    if (device < 0 || device >= ndev) return fail(LINNA_ENODEV, "device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(LINNA_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    if (d->n_in <= 0 || d->n_out <= 0 || d->n_ops <= 0 || !d->ops) return fail(LINNA_EINVAL, "bad model dims");
+    if (!d->x_mean || !d->x_std || !d->y_mean || !d->y_std) return fail(LINNA_EINVAL, "null transform arrays");
+    linna_model *m = new linna_model();
+    m->device = device, m->num_sms = prop.multiProcessorCount;
+    m->n_in = d->n_in, m->n_out = d->n_out, m->ypositive = d->ypositive ? 1 : 0;
+    int rc = copy_ops(m, d->ops, d->n_ops, false);
+    if (rc) { delete m; return rc; }
+    m->x_mean.assign(d->x_mean, d->x_mean + d->n_in);
+    m->x_std.assign(d->x_std, d->x_std + d->n_in);
+    m->y_mean.assign(d->y_mean, d->y_mean + d->n_out);
+    m->y_std.assign(d->y_std, d->y_std + d->n_out);
+    if (d->sigma) m->sigma.assign(d->sigma, d->sigma + d->n_out);
+    else m->sigma.assign(d->n_out, 1.f);
+    m->log10_flag.assign(d->n_in, 0);
+    if (d->log10_flag)
+        for (int i = 0; i < d->n_in; ++i) { m->log10_flag[i] = d->log10_flag[i] ? 1 : 0; m->has_log10 |= d->log10_flag[i] != 0; }
+    if (d->extra_linear_w) {
+        if (!d->extra_linear_b) { delete m; return fail(LINNA_EINVAL, "extra_linear_b is null"); }
+        m->has_extra = true;
+        m->extra_w.assign(d->extra_linear_w, d->extra_linear_w + (size_t)d->n_out * d->n_in);
+        m->extra_b.assign(d->extra_linear_b, d->extra_linear_b + d->n_out);
+        m->extra_scale = d->extra_linear_scale;
+        m->n_params += (int64_t)d->n_out * d->n_in + d->n_out;
+    }
+    cudaSetDevice(device);
+    rc = rebuild(m);
+    if (rc) { free_device(m); delete m; return rc; }
+    if (cudaStreamCreateWithFlags(&m->hstream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->last_done, cudaEventDisableTiming) != cudaSuccess) {
+        free_device(m); delete m;
+        return fail(LINNA_ECUDA, "cudaStreamCreate/cudaEventCreate failed");
+    }
+    *out = m;
+    return LINNA_OK;
+}
+
+void linna_model_destroy(linna_model_t *m)
+{
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    if (m->hstream) cudaStreamDestroy(m->hstream);
+    if (m->last_done) cudaEventDestroy(m->last_done);
+    if (m->d_in) cudaFree(m->d_in);
+    if (m->d_out) cudaFree(m->d_out);
+    if (m->d_lnp) cudaFree(m->d_lnp);
+    if (m->d_grad) cudaFree(m->d_grad);
+    free_device(m);
+    delete m;
+}
+
+int linna_model_set_likelihood(linna_model_t *m, const linna_like_desc_t *l)
+{
+    if (!m || !l) return fail(LINNA_EINVAL, "null argument");
+    if (!l->prior_kind || !l->prior_arg1 || !l->prior_arg2 || !l->data || !l->quad)
+        return fail(LINNA_EINVAL, "null likelihood arrays");
+    if (!(l->temperature > 0)) return fail(LINNA_EINVAL, "temperature must be > 0");
+    if (l->quad_kind != LINNA_QUAD_CHOL && l->quad_kind != LINNA_QUAD_DENSE) return fail(LINNA_EINVAL, "bad quad_kind");
+    m->prior_kind.assign(l->prior_kind, l->prior_kind + m->n_in);
+    m->prior_scale.resize(m->n_in), m->prior_shift.resize(m->n_in);
+    for (int i = 0; i < m->n_in; ++i) {
+        if (l->prior_kind[i] == LINNA_PRIOR_GAUSS) m->prior_scale[i] = l->prior_arg2[i];
+        else if (l->prior_kind[i] == LINNA_PRIOR_FLAT) m->prior_scale[i] = l->prior_arg2[i] - l->prior_arg1[i];
+        else return fail(LINNA_EINVAL, "prior %d: unknown dist %d", i, l->prior_kind[i]);  // main.py:128-129
+        m->prior_shift[i] = l->prior_arg1[i];
+    }
+    m->data.assign(l->data, l->data + m->n_out);
+    m->quad.assign(l->quad, l->quad + (size_t)m->n_out * m->n_out);
+    m->quad_kind = l->quad_kind;
+    if (l->quad_kind == LINNA_QUAD_DENSE) {  // x^T A x == x^T sym(A) x; the gradient then is -sym(A) d / T
+        const int n = m->n_out;
+        for (int i = 0; i < n; ++i)
+            for (int j = i + 1; j < n; ++j) {
+                float s = 0.5f * (m->quad[(size_t)i * n + j] + m->quad[(size_t)j * n + i]);
+                m->quad[(size_t)i * n + j] = m->quad[(size_t)j * n + i] = s;
+            }
+    }
+    m->temperature = l->temperature;
+    m->has_like = true;
+    return rebuild(m);
+}
+
+int linna_model_set_weights(linna_model_t *m, const linna_op_desc_t *ops, int32_t n_ops, const float *ew, const float *eb)
+{
+    if (!m || !ops) return fail(LINNA_EINVAL, "null argument");
+    int rc = copy_ops(m, ops, n_ops, true);
+    if (rc) return rc;
+    if (m->has_extra) {
+        if (!ew || !eb) return fail(LINNA_EINVAL, "extra linear weights required");
+        m->extra_w.assign(ew, ew + (size_t)m->n_out * m->n_in);
+        m->extra_b.assign(eb, eb + m->n_out);
+        m->n_params += (int64_t)m->n_out * m->n_in + m->n_out;
+    }
+    return rebuild(m);
+}
+
+int linna_model_info(const linna_model_t *m, int32_t *n_in, int32_t *n_out, int64_t *n_params, int32_t *num_sms)
+{
+    if (!m) return fail(LINNA_EINVAL, "null model");
+    if (n_in) *n_in = m->n_in;
+    if (n_out) *n_out = m->n_out;
+    if (n_params) *n_params = m->n_params;
+    if (num_sms) *num_sms = m->num_sms;
+    return LINNA_OK;
+}
+
+int linna_model_set_tile_rows(linna_model_t *m, int32_t rows)
+{
+    if (!m || (rows != 0 && rows != 8 && rows != 16 && rows != 32)) return fail(LINNA_EINVAL, "rows must be 0, 8, 16 or 32");
+    m->force_rows = rows;
+    return LINNA_OK;
+}
+
+static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_vec, int out_kind, float *lnp, float *grad,
+               int input_theta, cudaStream_t stream)
+{
+    if (!m) return fail(LINNA_EINVAL, "null model");
+    if (n < 0) return fail(LINNA_EINVAL, "negative n");
+    if (n == 0) return LINNA_OK;
+    if (!in) return fail(LINNA_EINVAL, "null input");
+    if (!m->prog_valid[pk]) return fail(LINNA_ESTATE, "likelihood constants not set (linna_model_set_likelihood)");
+    CUDA_TRY(cudaSetDevice(m->device));
+    int rows = m->force_rows;
+    if (!rows) {
+        if ((n + 31) / 32 >= m->num_sms) rows = 32;
+        else if ((n + 15) / 16 >= m->num_sms) rows = 16;
+        else rows = 8;
+    }
+    const int rg = rows / 8;
+    const int occ = m->occ[rg == 4 ? 2 : rg == 2 ? 1 : 0];
+    const int64_t tiles = (n + rows - 1) / rows;
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)m->num_sms * occ);
+    KernelArgs a;
+    memset(&a, 0, sizeof a);
+    a.prog = m->prog_dev + pk;
+    a.c = m->consts;
+    a.in = in, a.out_vec = out_vec, a.lnp = lnp, a.grad = grad;
+    a.arena = m->arena, a.masks = m->masks;
+    a.n = n, a.input_theta = input_theta, a.out_kind = out_kind;
+    if (m->have_last && m->last_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, m->last_done, 0));
+    CUDA_TRY(launch_fused_ffma(a, rg, grid, stream));
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaEventRecord(m->last_done, stream));
+    m->last_stream = stream, m->have_last = true;
+    return LINNA_OK;
+}
+
+int linna_predict(linna_model_t *m, const float *theta, int64_t n, float *out, int32_t out_kind, void *stream)
+{
+    if (out_kind < LINNA_OUT_YHAT || out_kind > LINNA_OUT_M) return fail(LINNA_EINVAL, "bad out_kind");
+    if (n > 0 && !out) return fail(LINNA_EINVAL, "null output");
+    return run(m, PROG_PREDICT, theta, n, out, out_kind, nullptr, nullptr, 1, (cudaStream_t)stream);
+}
+
+int linna_lnp(linna_model_t *m, const float *u, int64_t n, float *lnp, void *stream)
+{
+    if (n > 0 && !lnp) return fail(LINNA_EINVAL, "null output");
+    return run(m, PROG_LNP, u, n, nullptr, 0, lnp, nullptr, 0, (cudaStream_t)stream);
+}
+
+int linna_lnp_grad(linna_model_t *m, const float *u, int64_t n, float *lnp, float *grad, void *stream)
+{
+    if (n > 0 && (!lnp || !grad)) return fail(LINNA_EINVAL, "null output");
+    return run(m, PROG_GRAD, u, n, nullptr, 0, lnp, grad, 0, (cudaStream_t)stream);
+}
+
+static int ensure(float **p, size_t *cap, size_t need)
+{
+    if (*cap >= need) return LINNA_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr, *cap = 0;
+    size_t want = need + need / 4;
+    if (cudaMalloc(p, want * sizeof(float)) != cudaSuccess) return fail(LINNA_ENOMEM, "cudaMalloc of %zu floats failed", want);
+    *cap = want;
+    return LINNA_OK;
+}
+
+int linna_predict_host(linna_model_t *m, const float *theta, int64_t n, float *out, int32_t out_kind)
+{
+    if (!m) return fail(LINNA_EINVAL, "null model");
+    if (n <= 0) return n == 0 ? LINNA_OK : fail(LINNA_EINVAL, "negative n");
+    if (!theta || !out) return fail(LINNA_EINVAL, "null buffer");
+    CUDA_TRY(cudaSetDevice(m->device));
+    int rc;
+    if ((rc = ensure(&m->d_in, &m->d_in_cap, (size_t)n * m->n_in))) return rc;
+    if ((rc = ensure(&m->d_out, &m->d_out_cap, (size_t)n * m->n_out))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(m->d_in, theta, (size_t)n * m->n_in * sizeof(float), cudaMemcpyHostToDevice, m->hstream));
+    if ((rc = linna_predict(m, m->d_in, n, m->d_out, out_kind, m->hstream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, m->d_out, (size_t)n * m->n_out * sizeof(float), cudaMemcpyDeviceToHost, m->hstream));
+    CUDA_TRY(cudaStreamSynchronize(m->hstream));
+    return LINNA_OK;
+}
+
+int linna_lnp_host(linna_model_t *m, const float *u, int64_t n, float *lnp)
+{
+    if (!m) return fail(LINNA_EINVAL, "null model");
+    if (n <= 0) return n == 0 ? LINNA_OK : fail(LINNA_EINVAL, "negative n");
+    if (!u || !lnp) return fail(LINNA_EINVAL, "null buffer");
+    CUDA_TRY(cudaSetDevice(m->device));
+    int rc;
+    if ((rc = ensure(&m->d_in, &m->d_in_cap, (size_t)n * m->n_in))) return rc;
+    if ((rc = ensure(&m->d_lnp, &m->d_lnp_cap, (size_t)n))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(m->d_in, u, (size_t)n * m->n_in * sizeof(float), cudaMemcpyHostToDevice, m->hstream));
+    if ((rc = linna_lnp(m, m->d_in, n, m->d_lnp, m->hstream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(lnp, m->d_lnp, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, m->hstream));
+    CUDA_TRY(cudaStreamSynchronize(m->hstream));
+    return LINNA_OK;
+}
+
+int linna_lnp_grad_host(linna_model_t *m, const float *u, int64_t n, float *lnp, float *grad)
+{
+    if (!m) return fail(LINNA_EINVAL, "null model");
+    if (n <= 0) return n == 0 ? LINNA_OK : fail(LINNA_EINVAL, "negative n");
+    if (!u || !lnp || !grad) return fail(LINNA_EINVAL, "null buffer");
+    CUDA_TRY(cudaSetDevice(m->device));
+    int rc;
+    if ((rc = ensure(&m->d_in, &m->d_in_cap, (size_t)n * m->n_in))) return rc;
+    if ((rc = ensure(&m->d_lnp, &m->d_lnp_cap, (size_t)n))) return rc;
+    if ((rc = ensure(&m->d_grad, &m->d_grad_cap, (size_t)n * m->n_in))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(m->d_in, u, (size_t)n * m->n_in * sizeof(float), cudaMemcpyHostToDevice, m->hstream));
+    if ((rc = linna_lnp_grad(m, m->d_in, n, m->d_lnp, m->d_grad, m->hstream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(lnp, m->d_lnp, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, m->hstream));
+    CUDA_TRY(cudaMemcpyAsync(grad, m->d_grad, (size_t)n * m->n_in * sizeof(float), cudaMemcpyDeviceToHost, m->hstream));
+    CUDA_TRY(cudaStreamSynchronize(m->hstream));
+    return LINNA_OK;
+}
+
+}  // extern "C"

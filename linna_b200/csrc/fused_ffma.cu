@@ -1,0 +1,451 @@
+// Fused FP32 (FFMA) emulator-likelihood kernel for sm_100a.
+//
+// One persistent CTA owns a tile of BM = 8*RG walkers and runs the whole step program on it:
+//   prologue : latent u -> prior CDF map -> log10 -> input normalisation          (a2, a3 of SURVEY 8a)
+//   steps    : every layer / res-block of the MLP as a register-tiled GEMM         (a5)
+//              head epilogue = inverse output transform + residual d = m - data    (a6, a7)
+//              chi^2 step    = Cholesky-factor product r = L^T d, shuffle-reduced  (a8)
+//              backward steps reuse the relu masks saved by the forward            (a11)
+//   finish   : lnP = -chi^2/(2T) - |u|^2/2, NaN -> -inf                            (a1, a9, a10)
+//
+// GEMM mapping (per step, per 8*CG-column chunk):  256 threads = RG row-groups x KS k-slices x CG
+// column-groups; every thread owns an 8x8 register tile (rows rg*8.., columns {4cg..4cg+3} and
+// {4CG+4cg..}), so the inner loop is 4 LDS.128 per 64 FFMA for every layer width: narrow layers
+// trade column groups for k-slices (split-K inside the CTA, reduced through shared memory).
+// Weights ([k][n] packed) and activations ([feature][row] in the per-CTA L2-resident arena) are
+// streamed through a 3-stage cp.async ring.
+#include "linna_device.cuh"
+#include "../../include/linna_b200.h"
+
+namespace linna {
+
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc, bool valid)
+{
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+struct Geo {  // thread geometry of one GEMM step
+    int cg_log2, CG, KS, ks_log2, NCH;
+    int cg, ks, rg;
+};
+
+template <int RG>
+__device__ __forceinline__ Geo make_geo(int N, int tid)
+{
+    Geo g;
+    constexpr int CGMAX_LOG2 = (RG == 4) ? 6 : (RG == 2) ? 7 : 8;  // 256/RG column groups at most
+    int need = (N + 7) >> 3;                                       // column groups needed
+    int l = 3;                                                     // at least 8 column groups (64 columns)
+    while ((1 << l) < need && l < CGMAX_LOG2) ++l;
+    g.cg_log2 = l;
+    g.CG = 1 << l;
+    g.ks_log2 = CGMAX_LOG2 - l;
+    g.KS = 1 << g.ks_log2;
+    g.NCH = 8 << l;
+    g.cg = tid & (g.CG - 1);
+    int t = tid >> l;
+    g.ks = t & (g.KS - 1);
+    g.rg = t >> g.ks_log2;
+    return g;
+}
+
+// acc += A[K][BM]^T-tile @ Wt[K][ldw] columns [n0, n0+NCH)
+template <int RG>
+__device__ __forceinline__ void gemm_phase(float (&acc)[8][8], float *smem, const float *__restrict__ A,
+                                           const float *__restrict__ Wt, int K, int ldw, int n0, const Geo &g,
+                                           int tid)
+{
+    constexpr int BM = 8 * RG, BK = 2 * RG;
+    constexpr int BK_LOG2 = (RG == 4) ? 3 : (RG == 2) ? 2 : 1;
+    constexpr int R4_LOG2 = BK_LOG2;  // BM/4 = 2*RG = BK
+    const int kslice = (((K + g.KS - 1) >> g.ks_log2) + BK - 1) / BK * BK;
+    const int nt = kslice / BK;
+    const int nA4 = g.KS * BK * (BM / 4);
+
+    auto load_tile = [&](int kt, int stage) {
+        float *sW = smem + stage * kStageFloats;
+        float *sA = sW + kStageWFloats;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int f = tid + i * kThreads;
+            int c4 = f & (2 * g.CG - 1);
+            int t = f >> (g.cg_log2 + 1);
+            int kk = t & (BK - 1);
+            int ksl = t >> BK_LOG2;
+            int k = ksl * kslice + kt * BK + kk;
+            int col = n0 + 4 * c4;
+            bool v = (k < K) && (col < ldw);
+            const float *src = v ? Wt + (size_t)k * ldw + col : Wt;
+            cp_async16(sW + ((ksl * BK + kk) * g.NCH + 4 * c4), src, v);
+        }
+        for (int f = tid; f < nA4; f += kThreads) {
+            int r4 = f & (BM / 4 - 1);
+            int t = f >> R4_LOG2;
+            int kk = t & (BK - 1);
+            int ksl = t >> BK_LOG2;
+            int k = ksl * kslice + kt * BK + kk;
+            bool v = k < K;
+            const float *src = v ? A + (size_t)k * BM + 4 * r4 : A;
+            cp_async16(sA + ((ksl * BK + kk) * BM + 4 * r4), src, v);
+        }
+    };
+
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s) {
+        if (s < nt) load_tile(s, s);
+        cp_async_commit();
+    }
+    const int offW = (g.ks * BK) * g.NCH + 4 * g.cg;
+    const int offA = kStageWFloats + (g.ks * BK) * BM + g.rg * 8;
+    const int hi = 4 * g.CG;
+    for (int kt = 0; kt < nt; ++kt) {
+        cp_async_wait<kStages - 2>();
+        __syncthreads();
+        {
+            int nx = kt + kStages - 1;
+            if (nx < nt) load_tile(nx, nx % kStages);
+            cp_async_commit();
+        }
+        const float *sW = smem + (kt % kStages) * kStageFloats + offW;
+        const float *sA = smem + (kt % kStages) * kStageFloats + offA;
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float4 a0 = *reinterpret_cast<const float4 *>(sA + kk * BM);
+            float4 a1 = *reinterpret_cast<const float4 *>(sA + kk * BM + 4);
+            float4 b0 = *reinterpret_cast<const float4 *>(sW + kk * g.NCH);
+            float4 b1 = *reinterpret_cast<const float4 *>(sW + kk * g.NCH + hi);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+}
+
+// Sum the KS partial tiles of one (rg, cg) into the ks == 0 thread.
+__device__ __forceinline__ void reduce_ks(float (&acc)[8][8], float *smem, const Geo &g, int tid)
+{
+    if (g.KS == 1) return;
+    float4 *red = reinterpret_cast<float4 *>(smem);  // [16][256] float4 = 64 KB <= ring size
+    if (g.ks != 0) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            red[q * kThreads + tid] = make_float4(acc[q >> 1][(q & 1) * 4 + 0], acc[q >> 1][(q & 1) * 4 + 1],
+                                                  acc[q >> 1][(q & 1) * 4 + 2], acc[q >> 1][(q & 1) * 4 + 3]);
+    }
+    __syncthreads();
+    if (g.ks == 0) {
+        for (int s = 1; s < g.KS; ++s) {
+            int other = tid + s * g.CG;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                float4 v = red[q * kThreads + other];
+                acc[q >> 1][(q & 1) * 4 + 0] += v.x;
+                acc[q >> 1][(q & 1) * 4 + 1] += v.y;
+                acc[q >> 1][(q & 1) * 4 + 2] += v.z;
+                acc[q >> 1][(q & 1) * 4 + 3] += v.w;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void store8(float *p, const float (&v)[8])
+{
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4 *>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void load8_cg(const float *p, float (&v)[8])
+{
+    float4 a = __ldcg(reinterpret_cast<const float4 *>(p));
+    float4 b = __ldcg(reinterpret_cast<const float4 *>(p + 4));
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+
+// Prior CDF map of one latent coordinate (Transform.__call__, linna/util.py:339-343).
+__device__ __forceinline__ float prior_map(float u, int kind, float scale, float shift)
+{
+    float t = u;
+    if (kind == LINNA_PRIOR_FLAT) t = 0.5f * (1.0f + erff(u / 1.41421356237309515f));  // gauss2unif, util.py:300
+    return t * scale + shift;
+}
+
+template <int RG>
+__global__ void __launch_bounds__(kThreads, 2) fused_ffma_kernel(const KernelArgs args)
+{
+    constexpr int BM = 8 * RG;
+    extern __shared__ float4 smem4[];
+    float *smem = reinterpret_cast<float *>(smem4);
+    double *chi_part = reinterpret_cast<double *>(smem + kStages * kStageFloats);  // [RG*nsub<=8][8]
+    double *chi_acc = chi_part + 64;                                               // [BM]
+    float *lnprior = reinterpret_cast<float *>(chi_acc + 32);                      // [BM]
+
+    __shared__ Step s_steps[kMaxSteps];  // the step program, staged once per CTA (broadcast LDS afterwards)
+
+    const int tid = threadIdx.x;
+    const Program *__restrict__ prog = args.prog;
+    const Consts &c = args.c;
+    float *arena = args.arena + (size_t)blockIdx.x * prog->arena_features * BM;
+    uint8_t *masks = args.masks + (size_t)blockIdx.x * prog->mask_features * RG;
+    const int n_in = c.n_in, n_out = c.n_out;
+    const int64_t ntiles = (args.n + BM - 1) / BM;
+    const int n_steps = prog->n_steps;
+    {
+        const int nwords = n_steps * (int)(sizeof(Step) / 4);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(prog->steps);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_steps);
+        for (int i = tid; i < nwords; i += kThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * BM;
+        const int nrows = (int)((args.n - row0) < BM ? (args.n - row0) : BM);
+
+        // ---------------- prologue: u -> theta -> xhat (feature-major) ----------------
+        {
+            float *xb = arena + (size_t)prog->in_buf * BM;
+            const float *in = args.in + row0 * n_in;
+            for (int e = tid; e < BM * n_in; e += kThreads) {
+                int r = e / n_in, i = e - r * n_in;
+                float th = 0.f;
+                if (r < nrows) {
+                    float u = in[e];
+                    th = args.input_theta ? u : prior_map(u, c.prior_kind[i], c.prior_scale[i], c.prior_shift[i]);
+                    if (c.log10_flag && c.log10_flag[i]) th = log10f(th);            // util.py:491-496
+                    th = (th - c.x_mean[i]) / c.x_std[i];                             // util.py:497
+                }
+                xb[(size_t)i * BM + r] = th;
+            }
+            if (tid < BM) {
+                float s = 0.f;
+                if (tid < nrows && !args.input_theta)
+                    for (int i = 0; i < n_in; ++i) { float u = in[tid * n_in + i]; s = fmaf(u, u, s); }
+                lnprior[tid] = -0.5f * s;                                             // util.py:1165
+                chi_acc[tid] = 0.0;
+            }
+        }
+        __syncthreads();
+
+        // ---------------- the step program ----------------
+        for (int si = 0; si < n_steps; ++si) {
+            const Step &st = s_steps[si];
+            const int N = st.N;
+            const Geo g = make_geo<RG>(N, tid);
+            const int row_base = g.rg * 8;
+            for (int n0 = 0; n0 < N; n0 += g.NCH) {
+                float acc[8][8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+                if (st.K1 > 0)
+                    gemm_phase<RG>(acc, smem, arena + (size_t)st.src1 * BM, st.wt1, st.K1, st.ldw1, n0, g, tid);
+                if (st.scale != 1.0f) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[i][j] *= st.scale;
+                }
+                if (st.K2 > 0)
+                    gemm_phase<RG>(acc, smem, arena + (size_t)st.src2 * BM, st.wt2, st.K2, st.ldw2, n0, g, tid);
+                reduce_ks(acc, smem, g, tid);
+
+                double part[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) part[i] = 0.0;
+
+                if (g.ks == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int cidx = n0 + ((j < 4) ? (4 * g.cg + j) : (4 * g.CG + 4 * g.cg + (j - 4)));
+                        if (cidx >= N) continue;
+                        float v[8];
+                        const float b = st.bias ? st.scale * __ldg(st.bias + cidx) : 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = acc[i][j] + b;
+                        if (st.flags & F_ADD_SRC2) {
+                            float s2[8];
+                            load8_cg(arena + (size_t)(st.src2 + cidx) * BM + row_base, s2);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] += s2[i];
+                        }
+                        if (st.epi == EPI_ACT || st.epi == EPI_HEAD) {
+                            if (st.flags & F_RELU) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                            }
+                            if (st.flags & F_SAVE_MASK) {
+                                unsigned m = 0;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) m |= (v[i] > 0.f ? 1u : 0u) << i;
+                                masks[(size_t)(st.mask_off + cidx) * RG + g.rg] = (uint8_t)m;
+                            }
+                        }
+                        if (st.epi == EPI_ACT) {
+                            store8(arena + (size_t)(st.dst + cidx) * BM + row_base, v);
+                        } else if (st.epi == EPI_HEAD) {
+                            const float ys = __ldg(c.y_std + cidx), ym = __ldg(c.y_mean + cidx);
+                            const float sg = c.sigma ? __ldg(c.sigma + cidx) : 1.f;
+                            const float dt = c.data ? __ldg(c.data + cidx) : 0.f;
+                            float y[8], d[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float yy = fmaf(v[i], ys, ym);                        // util.py:542
+                                if (c.ypositive) yy = expf(yy);                      // util.py:540
+                                y[i] = yy;
+                                d[i] = yy * sg - dt;                                  // util.py:458, :954
+                            }
+                            store8(arena + (size_t)(st.dst + cidx) * BM + row_base, d);
+                            if (st.flags & F_SAVE_Y) store8(arena + (size_t)(st.ybuf + cidx) * BM + row_base, y);
+                            if (st.flags & F_OUT_VEC) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    int r = row_base + i;
+                                    if (r < nrows) {
+                                        float o = args.out_kind == LINNA_OUT_YHAT ? v[i]
+                                                  : args.out_kind == LINNA_OUT_Y  ? y[i]
+                                                                                  : y[i] * sg;
+                                        args.out_vec[(row0 + r) * n_out + cidx] = o;
+                                    }
+                                }
+                            }
+                        } else if (st.epi == EPI_CHI2) {
+                            if (c.quad_kind == LINNA_QUAD_CHOL) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) part[i] += (double)(v[i] * v[i]);
+                            } else {
+                                float d[8];
+                                load8_cg(arena + (size_t)(st.src1 + cidx) * BM + row_base, d);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) part[i] += (double)(v[i] * d[i]);
+                            }
+                            if (st.flags & F_STORE_DST) store8(arena + (size_t)(st.dst + cidx) * BM + row_base, v);
+                        } else if (st.epi == EPI_BWD) {
+                            if (st.colscale) {
+                                const float cs = __ldg(st.colscale + cidx);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] *= cs;
+                            }
+                            if (st.flags & F_MUL_YSAVE) {
+                                float y[8];
+                                load8_cg(arena + (size_t)(st.ybuf + cidx) * BM + row_base, y);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] *= y[i];
+                            }
+                            if (st.flags & F_APPLY_MASK) {
+                                const unsigned m = __ldcg(masks + (size_t)(st.mask_off + cidx) * RG + g.rg);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = ((m >> i) & 1u) ? v[i] : 0.f;
+                            }
+                            store8(arena + (size_t)(st.dst + cidx) * BM + row_base, v);
+                        } else if (st.epi == EPI_GRAD) {
+                            // chain through xhat = (theta' - mean)/std, theta' = log10(theta), theta = prior(u)
+                            const int kind = c.prior_kind[cidx];
+                            const float ps = c.prior_scale[cidx], psh = c.prior_shift[cidx];
+                            const float inv_std = 1.0f / c.x_std[cidx];
+                            const bool lg = c.log10_flag && c.log10_flag[cidx];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                int r = row_base + i;
+                                if (r < nrows) {
+                                    float u = args.in[(row0 + r) * n_in + cidx];
+                                    float gx = v[i] * inv_std;
+                                    if (lg) gx /= (prior_map(u, kind, ps, psh) * 2.30258509299404568f);
+                                    float jac = ps;
+                                    if (kind == LINNA_PRIOR_FLAT) jac *= 0.398942280401432678f * expf(-0.5f * u * u);
+                                    args.grad[(row0 + r) * n_in + cidx] = gx * jac - u;
+                                }
+                            }
+                        }
+                    }
+                }
+
+                if (st.epi == EPI_CHI2) {
+                    // shuffle-reduce the row partials over the column groups of one (rg, ks) lane group
+                    const int width = g.CG < 32 ? g.CG : 32;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        double p = part[i];
+                        for (int o = width >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+                        part[i] = p;
+                    }
+                    const int nsub = g.CG >> 5 ? g.CG >> 5 : 1;
+                    if (g.ks == 0 && (g.cg & (width - 1)) == 0) {
+                        const int sub = g.cg >> 5;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) chi_part[(g.rg * nsub + sub) * 8 + i] = part[i];
+                    }
+                    __syncthreads();
+                    if (tid < BM) {
+                        double s = chi_acc[tid];
+                        for (int sub = 0; sub < nsub; ++sub) s += chi_part[((tid >> 3) * nsub + sub) * 8 + (tid & 7)];
+                        chi_acc[tid] = s;
+                    }
+                }
+                __syncthreads();  // dst visible to the next step; ring + chi_part reusable
+            }
+            if (st.epi == EPI_CHI2 && tid < nrows && args.lnp) {
+                float l = (float)(-0.5 * chi_acc[tid]) * c.inv_T + lnprior[tid];       // util.py:1013
+                if (l != l) l = -INFINITY;                                            // util.py:1015-1016
+                args.lnp[row0 + tid] = l;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static size_t fused_smem_bytes() { return (size_t)kStages * kStageFloats * sizeof(float) + 64 * 8 + 32 * 8 + 32 * 4; }
+
+cudaError_t launch_fused_ffma(const KernelArgs &args, int rg, int grid, cudaStream_t stream)
+{
+    static bool attr_set[3] = {false, false, false};
+    const size_t smem = fused_smem_bytes();
+    cudaError_t e = cudaSuccess;
+#define LINNA_LAUNCH(RGV, IDX)                                                                                  \
+    {                                                                                                           \
+        if (!attr_set[IDX]) {                                                                                   \
+            e = cudaFuncSetAttribute(fused_ffma_kernel<RGV>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                     (int)smem);                                                                \
+            if (e != cudaSuccess) return e;                                                                     \
+            attr_set[IDX] = true;                                                                               \
+        }                                                                                                       \
+        fused_ffma_kernel<RGV><<<grid, kThreads, smem, stream>>>(args);                                         \
+    }
+    if (rg == 4) LINNA_LAUNCH(4, 0)
+    else if (rg == 2) LINNA_LAUNCH(2, 1)
+    else LINNA_LAUNCH(1, 2)
+#undef LINNA_LAUNCH
+    return cudaGetLastError();
+}
+
+int fused_ffma_max_ctas_per_sm(int rg)
+{
+    int nb = 0;
+    const size_t smem = fused_smem_bytes();
+    if (rg == 4) {
+        cudaFuncSetAttribute(fused_ffma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fused_ffma_kernel<4>, kThreads, smem);
+    } else if (rg == 2) {
+        cudaFuncSetAttribute(fused_ffma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fused_ffma_kernel<2>, kThreads, smem);
+    } else {
+        cudaFuncSetAttribute(fused_ffma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fused_ffma_kernel<1>, kThreads, smem);
+    }
+    return nb > 0 ? nb : 1;
+}
+
+}  // namespace linna

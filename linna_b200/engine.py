@@ -1,0 +1,317 @@
+"""ctypes binding of the linna_b200 C ABI (``include/linna_b200.h``) and the ``Engine``
+object the LINNA-facing classes (``Predictor``, ``Log_prob``, ``HMCSampler``) sit on.
+
+PyTorch is used for device memory and streams only; every number on the hot path is
+produced by the hand-written sm_100a kernels in ``csrc/``.  There is no CPU path: if
+the shared library is missing or no B200 is visible, construction raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import arch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "liblinna_b200.so")
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_i32_p = ctypes.POINTER(ctypes.c_int32)
+c_u8_p = ctypes.POINTER(ctypes.c_uint8)
+
+LINNA_OUT_YHAT, LINNA_OUT_Y, LINNA_OUT_M = 0, 1, 2
+LINNA_QUAD_CHOL, LINNA_QUAD_DENSE = 0, 1
+_PRIOR = {"gauss": 0, "flat": 1}
+
+
+class OpDesc(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("in_dim", ctypes.c_int32), ("mid_dim", ctypes.c_int32),
+                ("out_dim", ctypes.c_int32), ("act", ctypes.c_int32), ("alpha", ctypes.c_float),
+                ("w", c_float_p), ("b", c_float_p), ("w2", c_float_p), ("b2", c_float_p), ("ws", c_float_p)]
+
+
+class ModelDesc(ctypes.Structure):
+    _fields_ = [("n_in", ctypes.c_int32), ("n_out", ctypes.c_int32), ("n_ops", ctypes.c_int32),
+                ("ops", ctypes.POINTER(OpDesc)),
+                ("x_mean", c_float_p), ("x_std", c_float_p), ("log10_flag", c_u8_p),
+                ("y_mean", c_float_p), ("y_std", c_float_p), ("ypositive", ctypes.c_int32),
+                ("sigma", c_float_p), ("extra_linear_w", c_float_p), ("extra_linear_b", c_float_p),
+                ("extra_linear_scale", ctypes.c_float)]
+
+
+class LikeDesc(ctypes.Structure):
+    _fields_ = [("prior_kind", c_i32_p), ("prior_arg1", c_float_p), ("prior_arg2", c_float_p),
+                ("data", c_float_p), ("quad", c_float_p), ("quad_kind", ctypes.c_int32),
+                ("temperature", ctypes.c_float)]
+
+
+class LinnaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """Load ``liblinna_b200.so`` (built in-tree by ``__graft_entry__.build()``).  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LinnaError("linna_b200: %s not found -- run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                         "there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    lib.linna_abi_version.restype = ctypes.c_int
+    lib.linna_last_error.restype = ctypes.c_char_p
+    lib.linna_launch_count.restype = ctypes.c_int64
+    lib.linna_model_create.argtypes = [ctypes.POINTER(ModelDesc), ctypes.c_int, ctypes.POINTER(vp)]
+    lib.linna_model_destroy.argtypes = [vp]
+    lib.linna_model_destroy.restype = None
+    lib.linna_model_set_likelihood.argtypes = [vp, ctypes.POINTER(LikeDesc)]
+    lib.linna_model_set_weights.argtypes = [vp, ctypes.POINTER(OpDesc), i32, c_float_p, c_float_p]
+    lib.linna_predict.argtypes = [vp, vp, i64, vp, i32, vp]
+    lib.linna_lnp.argtypes = [vp, vp, i64, vp, vp]
+    lib.linna_lnp_grad.argtypes = [vp, vp, i64, vp, vp, vp]
+    lib.linna_predict_host.argtypes = [vp, vp, i64, vp, i32]
+    lib.linna_lnp_host.argtypes = [vp, vp, i64, vp]
+    lib.linna_lnp_grad_host.argtypes = [vp, vp, i64, vp, vp]
+    lib.linna_model_info.argtypes = [vp, c_i32_p, c_i32_p, ctypes.POINTER(i64), c_i32_p]
+    lib.linna_model_set_tile_rows.argtypes = [vp, i32]
+    if lib.linna_abi_version() != 1:
+        raise LinnaError("linna_b200: ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def launch_count():
+    return int(load_library().linna_launch_count())
+
+
+def _f32(a):
+    if hasattr(a, "detach"):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def _fp(a):
+    return a.ctypes.data_as(c_float_p) if a is not None else None
+
+
+def build_op_descs(kind, n_in, n_out, state_dict):
+    """(ctypes OpDesc array, keep-alive list, extra-linear (w, b) or None) from a reference-layout
+    ``state_dict`` (keys of SURVEY 8b)."""
+    ops = arch.chto_ops(kind, n_in, n_out)
+    arr = (OpDesc * len(ops))()
+    keep = []
+
+    def g(key):
+        a = _f32(state_dict[key])
+        keep.append(a)
+        return a
+
+    for i, op in enumerate(ops):
+        d = arr[i]
+        nm = op["name"]
+        d.in_dim, d.out_dim = op["in"], op["out"]
+        if op["kind"] == "linear":
+            d.kind, d.mid_dim, d.alpha = 0, 0, 1.0
+            d.act = 1 if op["act"] == "relu" else 0
+            w, b = g(nm + ".weight"), g(nm + ".bias")
+            assert w.shape == (op["out"], op["in"]) and b.shape == (op["out"],), nm
+            d.w, d.b = _fp(w), _fp(b)
+        else:
+            d.kind, d.mid_dim, d.alpha, d.act = 1, op["mid"], op["alpha"], 1
+            w, b = g(nm + ".layer1.weight"), g(nm + ".layer1.bias")
+            w2, b2 = g(nm + ".layer2.weight"), g(nm + ".layer2.bias")
+            assert w.shape == (op["mid"], op["in"]) and w2.shape == (op["out"], op["mid"]), nm
+            d.w, d.b, d.w2, d.b2 = _fp(w), _fp(b), _fp(w2), _fp(b2)
+            if op["in"] != op["out"]:
+                ws = g(nm + ".skip_layer.weight")
+                assert ws.shape == (op["out"], op["in"]), nm
+                d.ws = _fp(ws)
+    extra = None
+    if kind == "ChtoModelv2_linear":
+        extra = (g("linearlayer.weight"), g("linearlayer.bias"))
+    return arr, keep, extra
+
+
+def cholesky_of_inverse(inv_cov):
+    """L (lower, float64) with inv_cov = L L^T, or None when the matrix is not positive definite."""
+    a = np.asarray(inv_cov, np.float64)
+    a = 0.5 * (a + a.T)
+    try:
+        return np.linalg.cholesky(a)
+    except np.linalg.LinAlgError:
+        return None
+
+
+class Engine:
+    """One packed emulator (+ optionally its likelihood constants) on one GPU."""
+
+    def __init__(self, kind, n_in, n_out, state_dict, X_mean, X_std, y_mean, y_std, dolog10index=None,
+                 ypositive=False, sigma=None, device=0):
+        self.lib = load_library()
+        self.kind, self.n_in, self.n_out = str(kind), int(n_in), int(n_out)
+        self.device = int(device)
+        self.handle = ctypes.c_void_p()
+        self._has_like = False
+        arr, keep, extra = build_op_descs(self.kind, self.n_in, self.n_out, state_dict)
+        d = ModelDesc()
+        d.n_in, d.n_out, d.n_ops, d.ops = self.n_in, self.n_out, len(arr), arr
+        xm, xs, ym, ys = _f32(X_mean), _f32(X_std), _f32(y_mean), _f32(y_std)
+        assert xm.shape == (n_in,) and xs.shape == (n_in,) and ym.shape == (n_out,) and ys.shape == (n_out,)
+        d.x_mean, d.x_std, d.y_mean, d.y_std = _fp(xm), _fp(xs), _fp(ym), _fp(ys)
+        flags = np.zeros(n_in, np.uint8)
+        if dolog10index is not None:
+            flags[list(dolog10index)] = 1
+        d.log10_flag = flags.ctypes.data_as(c_u8_p)
+        d.ypositive = int(bool(ypositive))
+        sg = _f32(sigma) if sigma is not None else None
+        d.sigma = _fp(sg)
+        if extra is not None:
+            d.extra_linear_w, d.extra_linear_b, d.extra_linear_scale = _fp(extra[0]), _fp(extra[1]), 1e-3
+        rc = self.lib.linna_model_create(ctypes.byref(d), self.device, ctypes.byref(self.handle))
+        self._check(rc)
+        del keep
+
+    # -- plumbing ------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise LinnaError("linna_b200 error %d: %s" % (rc, self.lib.linna_last_error().decode()))
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.linna_model_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_tile_rows(self, rows):
+        self._check(self.lib.linna_model_set_tile_rows(self.handle, int(rows)))
+
+    def set_weights(self, state_dict):
+        arr, keep, extra = build_op_descs(self.kind, self.n_in, self.n_out, state_dict)
+        ew, eb = (_fp(extra[0]), _fp(extra[1])) if extra is not None else (None, None)
+        self._check(self.lib.linna_model_set_weights(self.handle, arr, len(arr), ew, eb))
+
+    def set_likelihood(self, priors, data, inv_cov, temperature=1.0, quad="chol"):
+        """priors: list of {'dist','arg1','arg2'} (README.rst:73-80); inv_cov: float64 C^-1 as
+        ``np.linalg.inv(cov)`` (linna/main.py:120).  quad='chol' factors it in float64 (chi^2 =
+        |L^T d|^2); quad='dense' uses the f32 matrix itself like the reference (util.py:953-955)."""
+        n_in, n_out = self.n_in, self.n_out
+        if len(priors) != n_in:
+            raise ValueError("need %d priors, got %d" % (n_in, len(priors)))
+        kinds = []
+        for p in priors:
+            if p["dist"] not in _PRIOR:
+                print("not implement dist : {0}".format(p["dist"]), flush=True)   # linna/main.py:128-129
+                assert 0
+            kinds.append(_PRIOR[p["dist"]])
+        pk = np.asarray(kinds, np.int32)
+        a1 = _f32([p["arg1"] for p in priors])
+        a2 = _f32([p["arg2"] for p in priors])
+        dat = _f32(data)
+        inv_cov = np.asarray(inv_cov)
+        assert dat.shape == (n_out,) and inv_cov.shape == (n_out, n_out)
+        kind = LINNA_QUAD_DENSE
+        q = None
+        if quad == "chol":
+            L = cholesky_of_inverse(inv_cov)
+            if L is not None:
+                q, kind = _f32(L), LINNA_QUAD_CHOL
+        if q is None:
+            q = _f32(inv_cov)
+        ld = LikeDesc()
+        ld.prior_kind = pk.ctypes.data_as(c_i32_p)
+        ld.prior_arg1, ld.prior_arg2, ld.data, ld.quad = _fp(a1), _fp(a2), _fp(dat), _fp(q)
+        ld.quad_kind, ld.temperature = kind, float(temperature)
+        self._check(self.lib.linna_model_set_likelihood(self.handle, ctypes.byref(ld)))
+        self._has_like = True
+        self.quad_kind = "chol" if kind == LINNA_QUAD_CHOL else "dense"
+        self.temperature = float(temperature)
+
+    # -- tensor helpers ------------------------------------------------------------------
+    @staticmethod
+    def _stream():
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _prep_dev(self, x, width):
+        import torch
+        if x.device.type != "cuda" or x.device.index != self.device:
+            raise LinnaError("tensor must live on cuda:%d" % self.device)
+        x = x.detach()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.to(torch.float32).contiguous()
+        if x.dim() != 2 or x.shape[1] != width:
+            raise ValueError("expected shape [n, %d], got %s" % (width, tuple(x.shape)))
+        return x
+
+    # -- the three calls ------------------------------------------------------------------
+    def predict(self, theta, out_kind=LINNA_OUT_Y):
+        """Batched Predictor.predict.  torch CUDA tensor in -> torch CUDA tensor out;
+        numpy in -> numpy out through the host-buffer entry point."""
+        import torch
+        if isinstance(theta, np.ndarray):
+            th = np.ascontiguousarray(theta, np.float32).reshape(-1, self.n_in)
+            out = np.empty((th.shape[0], self.n_out), np.float32)
+            self._check(self.lib.linna_predict_host(self.handle, th.ctypes.data, th.shape[0], out.ctypes.data, out_kind))
+            return out
+        th = self._prep_dev(theta, self.n_in)
+        out = torch.empty((th.shape[0], self.n_out), dtype=torch.float32, device=th.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.linna_predict(self.handle, th.data_ptr(), th.shape[0], out.data_ptr(), out_kind,
+                                               self._stream()))
+        return out
+
+    def lnp(self, u):
+        import torch
+        if isinstance(u, np.ndarray):
+            uu = np.ascontiguousarray(u, np.float32).reshape(-1, self.n_in)
+            out = np.empty(uu.shape[0], np.float32)
+            self._check(self.lib.linna_lnp_host(self.handle, uu.ctypes.data, uu.shape[0], out.ctypes.data))
+            return out
+        uu = self._prep_dev(u, self.n_in)
+        out = torch.empty(uu.shape[0], dtype=torch.float32, device=uu.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.linna_lnp(self.handle, uu.data_ptr(), uu.shape[0], out.data_ptr(), self._stream()))
+        return out
+
+    def lnp_grad(self, u):
+        import torch
+        if isinstance(u, np.ndarray):
+            uu = np.ascontiguousarray(u, np.float32).reshape(-1, self.n_in)
+            out = np.empty(uu.shape[0], np.float32)
+            g = np.empty_like(uu)
+            self._check(self.lib.linna_lnp_grad_host(self.handle, uu.ctypes.data, uu.shape[0], out.ctypes.data,
+                                                     g.ctypes.data))
+            return out, g
+        uu = self._prep_dev(u, self.n_in)
+        out = torch.empty(uu.shape[0], dtype=torch.float32, device=uu.device)
+        g = torch.empty_like(uu)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.linna_lnp_grad(self.handle, uu.data_ptr(), uu.shape[0], out.data_ptr(), g.data_ptr(),
+                                                self._stream()))
+        return out, g
+
+    def info(self):
+        n_in, n_out, sms = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        npar = ctypes.c_int64()
+        self._check(self.lib.linna_model_info(self.handle, ctypes.byref(n_in), ctypes.byref(n_out),
+                                              ctypes.byref(npar), ctypes.byref(sms)))
+        return dict(n_in=n_in.value, n_out=n_out.value, n_params=npar.value, num_sms=sms.value)
+
+
+def engine_from_problem(p, device=0, quad="chol", with_likelihood=True):
+    """Engine for a ``linna_b200.synthetic.Problem`` (tests, bench)."""
+    e = Engine(p.kind, p.n_in, p.n_out, p.state_dict, p.X_mean, p.X_std, p.y_mean, p.y_std,
+               dolog10index=p.dolog10index, ypositive=p.ypositive, sigma=np.asarray(p.sigma, np.float32),
+               device=device)
+    if with_likelihood and p.data is not None:
+        e.set_likelihood(p.priors, np.asarray(p.data, np.float32), p.inv_cov, p.temperature, quad=quad)
+    return e
