@@ -257,9 +257,10 @@ def main():
     # ---- roofline of the dominant (only) kernel: useful flops / measured kernel time
     peaks = load_peaks()
     flops_eval = arch.flops_lnl_grad(p.kind, p.n_in, p.n_out) if args.mode == "grad" else arch.flops_lnl(p.kind, p.n_in, p.n_out)
-    launches_per_rank = max(launches, 1)
-    per_launch_s = (ms * 1e-3) / launches_per_rank
-    achieved = flops_eval * n / per_launch_s / 1e12
+    # one step = one wave-planned pass (1-3 launches of the same kernel template: 32-row waves, then the
+    # 16/8-row remainder); the roofline is taken over the whole pass, i.e. all launches of the step.
+    per_step_s = (ms * 1e-3) / args.steps
+    achieved = flops_eval * n / per_step_s / 1e12
     sms = eng.info()["num_sms"]
     sm_mhz = clocks["sm_mhz"] or 0.0
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",

@@ -571,26 +571,39 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
     if (!in) return fail(LINNA_EINVAL, "null input");
     if (!m->prog_valid[pk]) return fail(LINNA_ESTATE, "likelihood constants not set (linna_model_set_likelihood)");
     CUDA_TRY(cudaSetDevice(m->device));
-    int rows = m->force_rows;
-    if (!rows) {
-        if ((n + 31) / 32 >= m->num_sms) rows = 32;
-        else if ((n + 15) / 16 >= m->num_sms) rows = 16;
-        else rows = 8;
-    }
-    const int rg = rows / 8;
-    const int occ = m->occ[rg == 4 ? 2 : rg == 2 ? 1 : 0];
-    const int64_t tiles = (n + rows - 1) / rows;
-    const int grid = (int)std::min<int64_t>(tiles, (int64_t)m->num_sms * occ);
-    KernelArgs a;
-    memset(&a, 0, sizeof a);
-    a.prog = m->prog_dev + pk;
-    a.c = m->consts;
-    a.in = in, a.out_vec = out_vec, a.lnp = lnp, a.grad = grad;
-    a.arena = m->arena, a.masks = m->masks;
-    a.n = n, a.input_theta = input_theta, a.out_kind = out_kind;
     if (m->have_last && m->last_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, m->last_done, 0));
-    CUDA_TRY(launch_fused_ffma(a, rg, grid, stream));
-    g_launches.fetch_add(1);
+    // Launch plan: full waves of 32-row tiles, then the remainder in 16- and 8-row tiles, so that the
+    // last wave costs a fraction of a full one instead of leaving most SMs idle for a whole tile time.
+    int64_t done = 0;
+    while (done < n) {
+        const int64_t left = n - done;
+        int rows = m->force_rows;
+        int64_t take = left;
+        if (!rows) {
+            const int64_t g32 = (int64_t)m->num_sms * m->occ[2] * 32, g16 = (int64_t)m->num_sms * m->occ[1] * 16;
+            if (left >= g32) rows = 32, take = left / g32 * g32;
+            else if (left >= g16) rows = 16, take = left / g16 * g16;
+            else if (left > (int64_t)m->num_sms * 16) rows = 16;
+            else rows = 8;
+        }
+        const int rg = rows / 8;
+        const int occ = m->occ[rg == 4 ? 2 : rg == 2 ? 1 : 0];
+        const int64_t tiles = (take + rows - 1) / rows;
+        const int grid = (int)std::min<int64_t>(tiles, (int64_t)m->num_sms * occ);
+        KernelArgs a;
+        memset(&a, 0, sizeof a);
+        a.prog = m->prog_dev + pk;
+        a.c = m->consts;
+        a.in = in + done * m->n_in;
+        a.out_vec = out_vec ? out_vec + done * m->n_out : nullptr;
+        a.lnp = lnp ? lnp + done : nullptr;
+        a.grad = grad ? grad + done * m->n_in : nullptr;
+        a.arena = m->arena, a.masks = m->masks;
+        a.n = take, a.input_theta = input_theta, a.out_kind = out_kind;
+        CUDA_TRY(launch_fused_ffma(a, rg, grid, stream));
+        g_launches.fetch_add(1);
+        done += take;
+    }
     CUDA_TRY(cudaEventRecord(m->last_done, stream));
     m->last_stream = stream, m->have_last = true;
     return LINNA_OK;

@@ -38,16 +38,23 @@ struct Geo {  // thread geometry of one GEMM step
 };
 
 template <int RG>
+struct Cfg {
+    static constexpr int BM = 8 * RG, BK = 2 * RG;
+    static constexpr int BK_LOG2 = (RG == 4) ? 3 : (RG == 2) ? 2 : 1;
+    static constexpr int CGMAX_LOG2 = (RG == 4) ? 6 : (RG == 2) ? 7 : 8;  // 256/RG column groups at most
+    static constexpr int CGMIN_LOG2 = CGMAX_LOG2 - 3;                     // at most 8 k-slices
+};
+
+template <int RG>
 __device__ __forceinline__ Geo make_geo(int N, int tid)
 {
     Geo g;
-    constexpr int CGMAX_LOG2 = (RG == 4) ? 6 : (RG == 2) ? 7 : 8;  // 256/RG column groups at most
-    int need = (N + 7) >> 3;                                       // column groups needed
-    int l = 3;                                                     // at least 8 column groups (64 columns)
-    while ((1 << l) < need && l < CGMAX_LOG2) ++l;
+    int need = (N + 7) >> 3;  // column groups needed
+    int l = Cfg<RG>::CGMIN_LOG2;
+    while ((1 << l) < need && l < Cfg<RG>::CGMAX_LOG2) ++l;
     g.cg_log2 = l;
     g.CG = 1 << l;
-    g.ks_log2 = CGMAX_LOG2 - l;
+    g.ks_log2 = Cfg<RG>::CGMAX_LOG2 - l;
     g.KS = 1 << g.ks_log2;
     g.NCH = 8 << l;
     g.cg = tid & (g.CG - 1);
@@ -57,44 +64,64 @@ __device__ __forceinline__ Geo make_geo(int N, int tid)
     return g;
 }
 
-// acc += A[K][BM]^T-tile @ Wt[K][ldw] columns [n0, n0+NCH)
-template <int RG>
+// acc += A[K][BM]^T-tile @ Wt[K][ldw] columns [n0, n0+NCH).  The column-group count is a template
+// parameter so that every shared-memory stride in the inner loop is an immediate.
+template <int RG, int CGL>
 __device__ __forceinline__ void gemm_phase(float (&acc)[8][8], float *smem, const float *__restrict__ A,
-                                           const float *__restrict__ Wt, int K, int ldw, int n0, const Geo &g,
-                                           int tid)
+                                           const float *__restrict__ Wt, int K, int ldw, int n0, int tid)
 {
-    constexpr int BM = 8 * RG, BK = 2 * RG;
-    constexpr int BK_LOG2 = (RG == 4) ? 3 : (RG == 2) ? 2 : 1;
-    constexpr int R4_LOG2 = BK_LOG2;  // BM/4 = 2*RG = BK
-    const int kslice = (((K + g.KS - 1) >> g.ks_log2) + BK - 1) / BK * BK;
+    constexpr int BM = Cfg<RG>::BM, BK = Cfg<RG>::BK, BKL = Cfg<RG>::BK_LOG2;
+    constexpr int CG = 1 << CGL, KSL = Cfg<RG>::CGMAX_LOG2 - CGL, KS = 1 << KSL, NCH = 8 * CG;
+    constexpr int R4L = BKL;              // log2(BM/4) == log2(BK)
+    constexpr int NA4 = KS * BK * (BM / 4);  // float4 copies of the activation slab
+    const int kslice = (((K + KS - 1) >> KSL) + BK - 1) / BK * BK;
     const int nt = kslice / BK;
-    const int nA4 = g.KS * BK * (BM / 4);
+
+    // ---- per-thread copy descriptors, computed once
+    const float *wp[4];
+    int wk[4], wdst[4];
+    bool wcol[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int f = tid + i * kThreads;
+        const int c4 = f & (2 * CG - 1);
+        const int t = f >> (CGL + 1);  // row of the [KS*BK][NCH] slab
+        const int krow = (t >> BKL) * kslice + (t & (BK - 1));
+        const int col = n0 + 4 * c4;
+        wk[i] = krow;
+        wcol[i] = col < ldw;
+        wp[i] = Wt + (size_t)krow * ldw + (wcol[i] ? col : 0);
+        wdst[i] = t * NCH + 4 * c4;
+    }
+    const float *ap[2];
+    int ak[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int f = tid + i * kThreads;
+        const int t = f >> R4L;
+        const int krow = (t >> BKL) * kslice + (t & (BK - 1));
+        ak[i] = krow;
+        ap[i] = A + (size_t)krow * BM + 4 * (f & (BM / 4 - 1));
+    }
+    const size_t wstep = (size_t)BK * ldw;
 
     auto load_tile = [&](int kt, int stage) {
         float *sW = smem + stage * kStageFloats;
         float *sA = sW + kStageWFloats;
+        const int k0 = kt * BK;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            int f = tid + i * kThreads;
-            int c4 = f & (2 * g.CG - 1);
-            int t = f >> (g.cg_log2 + 1);
-            int kk = t & (BK - 1);
-            int ksl = t >> BK_LOG2;
-            int k = ksl * kslice + kt * BK + kk;
-            int col = n0 + 4 * c4;
-            bool v = (k < K) && (col < ldw);
-            const float *src = v ? Wt + (size_t)k * ldw + col : Wt;
-            cp_async16(sW + ((ksl * BK + kk) * g.NCH + 4 * c4), src, v);
+            const bool v = wcol[i] && (wk[i] + k0 < K);
+            cp_async16(sW + wdst[i], v ? wp[i] : Wt, v);
+            wp[i] += wstep;
         }
-        for (int f = tid; f < nA4; f += kThreads) {
-            int r4 = f & (BM / 4 - 1);
-            int t = f >> R4_LOG2;
-            int kk = t & (BK - 1);
-            int ksl = t >> BK_LOG2;
-            int k = ksl * kslice + kt * BK + kk;
-            bool v = k < K;
-            const float *src = v ? A + (size_t)k * BM + 4 * r4 : A;
-            cp_async16(sA + ((ksl * BK + kk) * BM + 4 * r4), src, v);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (i * kThreads < NA4 && (NA4 >= (i + 1) * kThreads || tid < NA4 - i * kThreads)) {
+                const bool v = ak[i] + k0 < K;
+                cp_async16(sA + 4 * (tid + i * kThreads), v ? ap[i] : A, v);
+                ap[i] += BK * BM;
+            }
         }
     };
 
@@ -103,25 +130,28 @@ __device__ __forceinline__ void gemm_phase(float (&acc)[8][8], float *smem, cons
         if (s < nt) load_tile(s, s);
         cp_async_commit();
     }
-    const int offW = (g.ks * BK) * g.NCH + 4 * g.cg;
-    const int offA = kStageWFloats + (g.ks * BK) * BM + g.rg * 8;
-    const int hi = 4 * g.CG;
+    const int cg = tid & (CG - 1), ks = (tid >> CGL) & (KS - 1), rg = tid >> (CGL + KSL);
+    const int offW = (ks * BK) * NCH + 4 * cg;
+    const int offA = kStageWFloats + (ks * BK) * BM + rg * 8;
+    int stage = 0;
     for (int kt = 0; kt < nt; ++kt) {
         cp_async_wait<kStages - 2>();
         __syncthreads();
         {
-            int nx = kt + kStages - 1;
-            if (nx < nt) load_tile(nx, nx % kStages);
+            const int nx = kt + kStages - 1;
+            int st2 = stage + kStages - 1;
+            if (st2 >= kStages) st2 -= kStages;
+            if (nx < nt) load_tile(nx, st2);
             cp_async_commit();
         }
-        const float *sW = smem + (kt % kStages) * kStageFloats + offW;
-        const float *sA = smem + (kt % kStages) * kStageFloats + offA;
+        const float *sW = smem + stage * kStageFloats + offW;
+        const float *sA = smem + stage * kStageFloats + offA;
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
-            float4 a0 = *reinterpret_cast<const float4 *>(sA + kk * BM);
-            float4 a1 = *reinterpret_cast<const float4 *>(sA + kk * BM + 4);
-            float4 b0 = *reinterpret_cast<const float4 *>(sW + kk * g.NCH);
-            float4 b1 = *reinterpret_cast<const float4 *>(sW + kk * g.NCH + hi);
+            const float4 a0 = *reinterpret_cast<const float4 *>(sA + kk * BM);
+            const float4 a1 = *reinterpret_cast<const float4 *>(sA + kk * BM + 4);
+            const float4 b0 = *reinterpret_cast<const float4 *>(sW + kk * NCH);
+            const float4 b1 = *reinterpret_cast<const float4 *>(sW + kk * NCH + 4 * CG);
             const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -129,9 +159,23 @@ __device__ __forceinline__ void gemm_phase(float (&acc)[8][8], float *smem, cons
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
+        if (++stage == kStages) stage = 0;
     }
     cp_async_wait<0>();
     __syncthreads();
+}
+
+template <int RG>
+__device__ __forceinline__ void gemm_dispatch(float (&acc)[8][8], float *smem, const float *A, const float *Wt, int K,
+                                              int ldw, int n0, int cg_log2, int tid)
+{
+    constexpr int L0 = Cfg<RG>::CGMIN_LOG2;
+    switch (cg_log2 - L0) {
+    case 0: gemm_phase<RG, L0 + 0>(acc, smem, A, Wt, K, ldw, n0, tid); break;
+    case 1: gemm_phase<RG, L0 + 1>(acc, smem, A, Wt, K, ldw, n0, tid); break;
+    case 2: gemm_phase<RG, L0 + 2>(acc, smem, A, Wt, K, ldw, n0, tid); break;
+    default: gemm_phase<RG, L0 + 3>(acc, smem, A, Wt, K, ldw, n0, tid); break;
+    }
 }
 
 // Sum the KS partial tiles of one (rg, cg) into the ks == 0 thread.
@@ -252,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ffma_kernel(const KernelArg
 #pragma unroll
                     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
                 if (st.K1 > 0)
-                    gemm_phase<RG>(acc, smem, arena + (size_t)st.src1 * BM, st.wt1, st.K1, st.ldw1, n0, g, tid);
+                    gemm_dispatch<RG>(acc, smem, arena + (size_t)st.src1 * BM, st.wt1, st.K1, st.ldw1, n0, g.cg_log2, tid);
                 if (st.scale != 1.0f) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
@@ -260,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ffma_kernel(const KernelArg
                         for (int j = 0; j < 8; ++j) acc[i][j] *= st.scale;
                 }
                 if (st.K2 > 0)
-                    gemm_phase<RG>(acc, smem, arena + (size_t)st.src2 * BM, st.wt2, st.K2, st.ldw2, n0, g, tid);
+                    gemm_dispatch<RG>(acc, smem, arena + (size_t)st.src2 * BM, st.wt2, st.K2, st.ldw2, n0, g.cg_log2, tid);
                 reduce_ks(acc, smem, g, tid);
 
                 double part[8];
