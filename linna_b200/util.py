@@ -1,0 +1,559 @@
+"""Host-side mirror of ``linna/util.py`` for the emulator-likelihood path: same class and
+function names, argument meaning, pickled attribute names and error behaviour, so that the
+reference's pickles (``X_transform.pkl`` ...), call sites (``ml_sampler_core``) and user code keep
+working -- with the arithmetic moved into the fused sm_100a kernels (``engine.Engine``).
+
+What is different by design:
+  * ``Log_prob.__call__`` is batch-capable: ``x`` may be one walker ``[n_in]`` (reference shape,
+    returns a 0-dim tensor) or a whole ensemble ``[N, n_in]`` (returns ``[N]``) -- one kernel launch
+    either way instead of one Python call per walker (reference: linna/util.py:990-1021).
+  * the emulator is evaluated on the GPU even when ``Predictor`` was built with ``device='cpu'``
+    (the reference reloads every model on the CPU, linna/util.py:637); ``device`` only decides
+    where returned tensors live.
+  * reference defects Q2/Q3/Q11 are fixed rather than reproduced.
+"""
+import io
+import os
+import pickle
+from copy import deepcopy
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, Dataset
+
+from . import predictor_gpu
+from .nn import ChtoModelsimple, ChtoModelv2, ChtoModelv2_linear, ResBlock_batchnorm  # noqa: F401
+
+_SQRT2 = float(np.sqrt(2.0))
+
+
+# ------------------------------------------------------------------------------------------
+# prior maps (linna/util.py:291-381)
+def gauss2unif(x):
+    """Phi(x): unit Gaussian -> uniform on [0,1]  (linna/util.py:291-300)."""
+    return 0.5 * (1 + torch.erf(x / np.sqrt(2)))
+
+
+def invgauss2unif(x):
+    """Inverse of ``gauss2unif`` (linna/util.py:302-311)."""
+    return np.sqrt(2) * torch.erfinv(2 * x - 1)
+
+
+def _as_f32_tensor(x):
+    return torch.from_numpy(np.asarray(x).astype(np.float32)).to("cpu").clone().requires_grad_()
+
+
+class _PriorMap:
+    """Shared body of Transform / invTransform: column-wise map, same I/O conventions
+    (linna/util.py:323-347, :359-381)."""
+
+    def __init__(self, priors):
+        self.priors = priors
+
+    def _col(self, col, p):
+        raise NotImplementedError
+
+    def __call__(self, x, returnnumpy=True, inputnumpy=True):
+        if inputnumpy:
+            x = _as_f32_tensor(x)
+        if len(x.shape) < 2:
+            x = x.reshape(-1, len(x))
+        cols = [self._col(x[:, i], p) for i, p in enumerate(self.priors)]
+        out = torch.stack(cols).T.squeeze()
+        return out.detach().cpu().numpy() if returnnumpy else out
+
+
+class Transform(_PriorMap):
+    """latent u (unit Gaussian for every parameter) -> physical theta."""
+
+    def _col(self, col, p):
+        if p["dist"] == "gauss":
+            return col * p["arg2"] + p["arg1"]
+        return gauss2unif(col) * (p["arg2"] - p["arg1"]) + p["arg1"]
+
+
+class invTransform(_PriorMap):
+    """physical theta -> latent u."""
+
+    def _col(self, col, p):
+        if p["dist"] == "gauss":
+            return (col - p["arg1"]) / p["arg2"]
+        return invgauss2unif((col - p["arg1"]) / (p["arg2"] - p["arg1"]))
+
+
+class ArrayDataset(Dataset):
+    """float32 (X, y) rows for torch DataLoader (linna/util.py:383-400)."""
+
+    def __init__(self, X, y):
+        self.X = X.astype(np.float32)
+        self.y = y.astype(np.float32)
+
+    def __len__(self):
+        return self.X.shape[0]
+
+    def __getitem__(self, i):
+        return self.X[i, :], self.y[i, :]
+
+
+# ------------------------------------------------------------------------------------------
+# diagonal input / output transforms (linna/util.py:402-596).  Attribute names are the pickle
+# format and must not change.
+class _Picklable:
+    def pickle(self, path):
+        with open(path, "wb") as f:
+            new = deepcopy(self)
+            new.dev = "cpu"
+            pickle.dump(new, f, pickle.HIGHEST_PROTOCOL)
+
+
+def _scale_cov(cov, scale):
+    """D^-1 C D^-1 in float64 with D = diag(scale)."""
+    d = torch.diag(1 / scale.type(torch.float64))
+    return d.inner(cov).inner(d)
+
+
+class Y_transform_data(_Picklable):
+    """y -> y / sigma  (linna/util.py:402-447)."""
+
+    def __init__(self, sigma, device):
+        self.device = device
+        self.sigma = torch.from_numpy(sigma.astype(np.float32)).to(device).clone().requires_grad_()
+
+    def __call__(self, y):
+        return y / self.sigma[None, :].to(y.device)
+
+    def transform_cov(self, cov):
+        return _scale_cov(cov, self.sigma.detach().to(cov.device))
+
+
+class Y_invtransform_data(_Picklable):
+    """y -> y * sigma  (linna/util.py:449-464)."""
+
+    def __init__(self, sigma, device):
+        self.sigma = torch.from_numpy(sigma.astype(np.float32)).to(device).clone().requires_grad_()
+        self.device = device
+
+    def __call__(self, y):
+        return y * self.sigma[None, :].to(y.device)
+
+
+class X_transform_class(_Picklable):
+    """x -> (x - mean)/std, with log10 on ``dolog10index`` first (linna/util.py:466-510)."""
+
+    def __init__(self, X_mean, X_std, device, dolog10index=None):
+        self.X_mean = X_mean
+        self.X_std = X_std
+        self.dev = device
+        self.dolog10index = dolog10index
+
+    def __call__(self, X):
+        X1 = X.clone()
+        if self.dolog10index is not None:
+            for ind in self.dolog10index:
+                if X1.dim() > 1:
+                    X1[:, ind] = torch.log10(X[:, ind])
+                else:
+                    X1[ind] = torch.log10(X1[ind])
+        return (X1 - self.X_mean[None, :].to(X.device)) / self.X_std[None, :].to(X.device)
+
+
+class Y_transform_class(_Picklable):
+    """yhat -> yhat*std + mean, exp(.) if ``ypositive`` (linna/util.py:512-554)."""
+
+    def __init__(self, y_mean, y_std, dev, ypositive=False):
+        self.y_mean = y_mean
+        self.y_std = y_std
+        self.dev = dev
+        self.ypositive = ypositive
+
+    def __call__(self, y):
+        out = y * self.y_std[None, :].to(y.device) + self.y_mean[None, :].to(y.device)
+        return torch.exp(out) if self.ypositive else out
+
+
+class Y_invtransform_class(_Picklable):
+    """y -> (y - mean)/std, log first if ``ypositive`` (linna/util.py:556-596)."""
+
+    def __init__(self, y_mean, y_std, data_tensor, dev, ypositive=False):
+        self.y_mean = y_mean
+        self.y_std = y_std
+        self.dev = dev
+        self.ypositive = ypositive
+        self.data_tensor = data_tensor
+
+    def __call__(self, y):
+        if self.ypositive:
+            y = torch.log(y)
+        return (y - self.y_mean[None, :].to(y.device)) / self.y_std[None, :].to(y.device)
+
+    def transform_cov(self, cov):
+        std = self.y_std.detach().to(cov.device)
+        if not self.ypositive:
+            return _scale_cov(cov, std)
+        rel = _scale_cov(cov, self.data_tensor.detach().to(cov.device))   # log-normal moment matching
+        rel[rel <= -1] = 1e-10 - 1
+        return _scale_cov(torch.log(1 + rel), std)
+
+
+class _FunctionWrapper(object):
+    """Binds extra args to the user's ``theory(x, outdirs)`` (linna/util.py:598-609)."""
+
+    def __init__(self, f, args, kwargs):
+        self.f = f
+        self.args = [] if args is None else args
+        self.kwargs = {} if kwargs is None else kwargs
+
+    def __call__(self, x):
+        return self.f(x, *self.args, **self.kwargs)
+
+
+class CPU_Unpickler(pickle.Unpickler):
+    """Loads pickles holding CUDA torch storages on any host (linna/util.py:51-55)."""
+
+    def find_class(self, module, name):
+        if module == "torch.storage" and name == "_load_from_bytes":
+            return lambda b: torch.load(io.BytesIO(b), map_location="cpu", weights_only=False)
+        return super().find_class(module, name)
+
+
+def _unpickle(path):
+    with open(path, "rb") as f:
+        return CPU_Unpickler(f).load()
+
+
+# ------------------------------------------------------------------------------------------
+# model retrieval (linna/util.py:611-734)
+def retrieve_model(outdir, inshape, outshape, nnmodel_in=ChtoModelv2):
+    """(Predictor, Y_invtransform_data) from ``<outdir>/{X_transform,y_transform,y_invtransform_data}.pkl``
+    and ``best.pth.tar`` (linna/util.py:611-639)."""
+    y_invtransform_data = _unpickle(os.path.join(outdir, "y_invtransform_data.pkl"))
+    X_transform = _unpickle(os.path.join(outdir, "X_transform.pkl"))
+    X_transform.dev = "cpu"
+    y_transform = _unpickle(os.path.join(outdir, "y_transform.pkl"))
+    y_transform.dev = "cpu"
+    nnmodel = nnmodel_in(inshape, outshape, None)
+    model = predictor_gpu.Predictor(inshape, outshape, X_transform=X_transform, y_transform=y_transform,
+                                    device="cpu", outdir=outdir, model=nnmodel)
+    model.load_checkpoint()
+    return model, y_invtransform_data
+
+
+def retrieve_model_wrapper_in(outdir, nnmodel_in=ChtoModelv2, no_grad=True):
+    """theta -> data-space model vector, as a callable (linna/util.py:715-734)."""
+    nshapein = np.loadtxt(os.path.join(outdir, "train_samples_x.txt")).shape[1]
+    nshapeout = np.load(os.path.join(outdir, "train_samples_y.npy")).shape[1]
+    model, y_invtransform_data = retrieve_model(outdir, nshapein, nshapeout, nnmodel_in=nnmodel_in)
+    model.set_output_scale(y_invtransform_data.sigma)
+    return lambda x: model.predict_data_vector(x, no_grad=no_grad)
+
+
+# ------------------------------------------------------------------------------------------
+# likelihood (linna/util.py:953-1051, :1160-1165)
+def gaussianlogliklihood(m, data, invcov):
+    """-1/2 (m-d) C^-1 (m-d)^T for one model vector ``m`` [1, n_out] (linna/util.py:953-955).
+    ``Log_prob`` recognises this function and evaluates it inside the fused kernel instead; the
+    body is only reached when user code calls it directly."""
+    d = m - data
+    return (d @ invcov @ d.T * (-0.5))[0][0]
+
+
+def lnprior(x):
+    """-1/2 |u|^2: every prior is a unit Gaussian in latent space (linna/util.py:1160-1165)."""
+    return -0.5 * torch.sum(x.square())
+
+
+class _LnPFunction(torch.autograd.Function):
+    """lnP with the kernel-computed gradient attached, so that ``torch.autograd.grad(lnP, x)``
+    (linna/HMCSampler.py:32) works on the result."""
+
+    @staticmethod
+    def forward(ctx, x, owner):
+        eng = owner.engine()
+        x2 = x.detach().reshape(-1, eng.n_in)
+        dev = torch.device("cuda", eng.device)
+        lnp, grad = eng.lnp_grad(x2.to(dev, torch.float32))
+        ctx.save_for_backward(grad.to(x.device).reshape(x.shape))
+        ctx.batched = x.dim() > 1
+        lnp = lnp.to(x.device)
+        return lnp if ctx.batched else lnp.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (g.unsqueeze(-1) * grad if ctx.batched else g * grad), None
+
+
+class Log_prob:
+    """lnP(u) = lnL(m(theta(u)))/T + lnprior(u) [+ externalloglike(theta)]  (linna/util.py:957-1021).
+
+    Same constructor and call signature as the reference.  With the default Gaussian likelihood the
+    whole chain -- prior map, emulator, inverse transform, chi^2, prior -- is one kernel launch for
+    the full ensemble.  A user ``loglikelihoodfunc`` / ``externalloglike`` still works: the kernel
+    then returns the model vectors and the callable runs on the host per walker, as in the
+    reference.
+    """
+
+    def __init__(self, data_new, invcov_new, model, y_invtransform_data, transform, temperature,
+                 loglikelihoodfunc=None, nograd=False, externalloglike=None):
+        tt = lambda a: a if torch.is_tensor(a) else _as_f32_tensor(a)
+        self.data_new = tt(data_new)
+        self.invcov_new = tt(invcov_new)
+        self.model = model
+        self.y_invtransform_data = y_invtransform_data
+        self.transform = transform
+        self.T = temperature
+        self.no_grad = nograd
+        self.loglikelihoodfunc = gaussianlogliklihood if loglikelihoodfunc is None else loglikelihoodfunc
+        self.noduplicate = True
+        self.externalloglike = externalloglike
+        self._engine = None
+        self._engine_key = None
+
+    # -- engine management ----------------------------------------------------------------
+    @property
+    def fused(self):
+        return self.loglikelihoodfunc is gaussianlogliklihood
+
+    def engine(self):
+        """The packed model + likelihood constants on the current CUDA device (built lazily, rebuilt
+        if the emulator weights or the temperature changed)."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("Log_prob: no CUDA device -- linna_b200 has no CPU fallback")
+        dev = torch.cuda.current_device()
+        key = (dev, self.model.param_key(), float(self.T))
+        if self._engine is None or self._engine_key != key:
+            eng = self.model.make_engine(dev, sigma=self.y_invtransform_data.sigma)
+            inv = self.invcov_new.detach().cpu().numpy().astype(np.float64)
+            eng.set_likelihood(self.transform.priors, self.data_new.detach().cpu().numpy(), inv, float(self.T))
+            if self._engine is not None:
+                self._engine.close()
+            self._engine, self._engine_key = eng, key
+        return self._engine
+
+    def __getstate__(self):   # instances are pickled to pool workers in the reference (util.py:149-152)
+        d = self.__dict__.copy()
+        d["_engine"], d["_engine_key"] = None, None
+        return d
+
+    # -- evaluation -----------------------------------------------------------------------
+    def value_and_grad(self, x):
+        """(lnP [N], d lnP/du [N, n_in]) for torch CUDA ``x`` [N, n_in]; the batched form of
+        ``Dlnp`` / autograd (linna/util.py:1023-1035, linna/HMCSampler.py:29-48)."""
+        if not self.fused or self.externalloglike is not None:
+            raise NotImplementedError("gradients need the built-in Gaussian likelihood")
+        return self.engine().lnp_grad(x)
+
+    def _host_terms(self, u_np):
+        """Per-walker host callables of the reference (linna/util.py:1005-1013), vectorised over rows."""
+        theta = np.atleast_2d(Transform(self.transform.priors)(u_np, returnnumpy=True, inputnumpy=True))
+        out = np.zeros(theta.shape[0], np.float32)
+        if not self.fused:
+            eng = self.engine()
+            from . import engine as _e
+            m = eng.predict(np.ascontiguousarray(theta, np.float32), _e.LINNA_OUT_M)
+            for i in range(theta.shape[0]):
+                lnl = self.loglikelihoodfunc(torch.from_numpy(m[i:i + 1]), self.data_new.detach(), self.invcov_new.detach())
+                out[i] = float(lnl) / self.T - 0.5 * float(np.sum(np.square(u_np.reshape(theta.shape[0], -1)[i].astype(np.float32))))
+        if self.externalloglike is not None:
+            for i in range(theta.shape[0]):
+                out[i] += np.float32(self.externalloglike(theta[i]))
+        return out
+
+    def __call__(self, x, returntorch=True, inputnumpy=True):
+        was_tensor = torch.is_tensor(x)
+        one = (x.dim() if was_tensor else np.ndim(x)) == 1
+        eng = self.engine()
+        if was_tensor and x.requires_grad and not self.no_grad and self.fused and self.externalloglike is None:
+            like = _LnPFunction.apply(x, self)
+        else:
+            if was_tensor and x.is_cuda:
+                u_dev = x.detach().reshape(-1, eng.n_in)
+                u_np = None
+            else:
+                u_np = (x.detach().cpu().numpy() if was_tensor else np.asarray(x)).astype(np.float32).reshape(-1, eng.n_in)
+                u_dev = None
+            if self.fused:
+                like = eng.lnp(u_dev) if u_dev is not None else torch.from_numpy(eng.lnp(u_np))
+                if self.externalloglike is not None:
+                    extra = self._host_terms(u_np if u_np is not None else u_dev.cpu().numpy())
+                    like = like + torch.from_numpy(extra).to(like.device)
+            else:
+                like = torch.from_numpy(self._host_terms(u_np if u_np is not None else u_dev.cpu().numpy()))
+            like = torch.where(torch.isnan(like), torch.full_like(like, -torch.inf), like)   # util.py:1015-1016
+            if one:
+                like = like.reshape(())
+        if returntorch:
+            return like
+        return like.detach().cpu().numpy()
+
+
+class Dlnp:
+    """d lnP/du (linna/util.py:1023-1035; the reference constructor is broken)."""
+
+    def __init__(self, data_new, invcov_new, model, y_invtransform_data, transform, temperature):
+        self.log_prob = Log_prob(data_new, invcov_new, model, y_invtransform_data, transform, temperature,
+                                 gaussianlogliklihood)
+
+    def __call__(self, x, lnP=None, returntorch=None, inputnumpy=None):
+        u = (x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)).astype(np.float32)
+        _, g = self.log_prob.engine().lnp_grad(u.reshape(-1, u.shape[-1]))
+        return g.reshape(u.shape)
+
+
+class Ddlnp:
+    """Hessian of lnP by central differences of the kernel gradient: 2*n_in batched gradient rows
+    in ONE launch (reference: n_in extra autograd passes, linna/util.py:1037-1051).  Used once for
+    the HMC mass matrix (linna/sampler.py:430-433)."""
+
+    def __init__(self, data_new, invcov_new, model, y_invtransform_data, transform, temperature, eps=1e-3):
+        self.log_prob = Log_prob(data_new, invcov_new, model, y_invtransform_data, transform, temperature,
+                                 gaussianlogliklihood)
+        self.eps = eps
+
+    def __call__(self, x):
+        u = np.asarray(x, np.float64).reshape(-1)
+        n = u.size
+        pts = np.repeat(u[None, :], 2 * n, axis=0)
+        pts[np.arange(n), np.arange(n)] += self.eps
+        pts[n + np.arange(n), np.arange(n)] -= self.eps
+        _, g = self.log_prob.engine().lnp_grad(pts.astype(np.float32))
+        hess = (g[:n].astype(np.float64) - g[n:].astype(np.float64)) / (2 * self.eps)
+        return 0.5 * (hess + hess.T)
+
+
+class LogPrior:
+    """Physical-space prior used by the importance re-weighting (linna/util.py:1129-1157)."""
+
+    def __init__(self, prior):
+        self.prior = prior
+
+    def __call__(self, xlist):
+        logp = 0
+        for item, x in zip(self.prior, xlist):
+            if item["dist"] == "flat" and (x < item["arg1"] or x > item["arg2"]):
+                return -np.inf
+            if item["dist"] == "gauss":
+                logp += -0.5 * (x - item["arg1"]) ** 2 / item["arg2"] ** 2
+        return logp
+
+
+def logp_theory_data(samples, theory, data, invcov, logprior):
+    """Exact-theory log posterior for importance weights (linna/util.py:1506-1517)."""
+    out = []
+    for t, s in zip(theory, samples):
+        d = t[:len(data)] - data
+        out.append(-0.5 * d.dot(invcov.dot(d)) + logprior(s))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# training loss (linna/util.py:1055-1127).  The fused training kernels compute the same quantities
+# on the device; these classes carry the constants (and the pickle-compatible names).
+class Auxilleryfunc:
+    def __init__(self, data_in, cov_tensor, inv_cov_tensor, y_transform_data, y_inv_transform, device):
+        self.inv_cov_tensor = inv_cov_tensor
+        self.transformed_cov = y_inv_transform.transform_cov(y_transform_data.transform_cov(cov_tensor))
+        self.inv_transformed_cov = torch.inverse(self.transformed_cov).type(torch.float32).detach()
+        self.y_transform_data = y_transform_data
+        self.y_inv_transform = y_inv_transform
+        self.device = device
+        self.data = data_in
+        self.data_in = torch.nan_to_num(self.y_inv_transform(self.y_transform_data(self.data)).to(self.device),
+                                        nan=1e-30).detach()
+
+    def constants(self):
+        """(data_hat [n_out] f32, C_hat^-1 [n_out, n_out] f32, sigma f32, y_mean, y_std, ypositive) for
+        the training kernels."""
+        yt = self.y_inv_transform
+        return (self.data_in.detach().cpu().numpy().astype(np.float32),
+                self.inv_transformed_cov.detach().cpu().numpy().astype(np.float32),
+                self.y_transform_data.sigma.detach().cpu().numpy().astype(np.float32),
+                yt.y_mean.detach().cpu().numpy().astype(np.float32),
+                yt.y_std.detach().cpu().numpy().astype(np.float32), bool(yt.ypositive))
+
+    def __call__(self, y_pred, y_target):
+        from .train import loss_terms
+        return loss_terms(self, y_pred, y_target)
+
+
+class Loss_fn:
+    """mean over the batch of chi2(target, pred)/max(chi2(target, data), n_out/2) in normalised
+    space (linna/util.py:1090-1116)."""
+
+    def __init__(self, data_in, cov_tensor, inv_cov_tensor, y_transform_data, y_inv_transform, device):
+        self.auxileryfunction = Auxilleryfunc(data_in, cov_tensor, inv_cov_tensor, y_transform_data,
+                                              y_inv_transform, device)
+
+    def __call__(self, y_pred, y_target):
+        loss, _, _ = self.auxileryfunction(y_pred, y_target)
+        return torch.mean(loss)
+
+
+class Val_metric_fn:
+    """[median loss, max |chi2_nn,d/chi2_M,d - 1|, median of same] (linna/util.py:1118-1127)."""
+
+    def __init__(self, data_in, cov_tensor, inv_cov_tensor, y_transform_data, y_inv_transform, device):
+        self.auxileryfunction = Auxilleryfunc(data_in, cov_tensor, inv_cov_tensor, y_transform_data,
+                                              y_inv_transform, device)
+
+    def __call__(self, y_pred, y_target):
+        loss, chisqMd, chisqnnd = self.auxileryfunction(y_pred, y_target)
+        fracerr = torch.abs(chisqnnd / chisqMd - 1)
+        return torch.tensor([torch.median(loss), torch.max(fracerr), torch.median(fracerr)])
+
+
+def median_absolute_deviation(y, median, dim):
+    return torch.abs(y - median).median(axis=dim).values
+
+
+# ------------------------------------------------------------------------------------------
+# pools (linna/util.py:258-289).  The MPI farm (chtoPool) is replaced by the batched kernel; a
+# plain multiprocessing pool is kept for the user's `theory` callback.
+class chtoMultiprocessPool:
+    def __init__(self, nprocess):
+        from multiprocessing import Pool
+        self.pool = Pool(processes=nprocess)
+        self.noduplicate = False
+
+    def map(self, worker, tasks, callback=None):
+        return self.pool.map(worker, tasks)
+
+    def noduplicate_close(self):
+        self.noduplicate = False
+
+    def close(self):
+        self.pool.close()
+
+    def is_master(self):
+        return True
+
+
+class NN_samplerv1:
+    """Per-iteration bookkeeping object of the reference (linna/util.py:736-951); instances are stored
+    in ``model_args.pkl``.  The sampling/training-set methods live in ``linna_b200.orchestrate``."""
+
+    def __init__(self, outdir, prior_range):
+        self.outdir = outdir
+        self.prior_range = prior_range
+        self.seed = 123456
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        from . import orchestrate
+        fn = getattr(orchestrate, "nnsampler_" + name, None)
+        if fn is None:
+            raise AttributeError(name)
+        return lambda *a, **k: fn(self, *a, **k)
+
+
+for _c in (Transform, invTransform, ArrayDataset, Y_transform_data, Y_invtransform_data, X_transform_class,
+           Y_transform_class, Y_invtransform_class, _FunctionWrapper, CPU_Unpickler, Log_prob, Dlnp, Ddlnp, LogPrior,
+           Auxilleryfunc, Loss_fn, Val_metric_fn, chtoMultiprocessPool, NN_samplerv1):
+    _c.__module__ = "linna.util"
+for _f in (gauss2unif, invgauss2unif, gaussianlogliklihood, lnprior, retrieve_model, retrieve_model_wrapper_in,
+           logp_theory_data, median_absolute_deviation):
+    _f.__module__ = "linna.util"
+del _c, _f
+
+from .trainer import train_nn, train_NN  # noqa: E402,F401  (pickled by path linna.util.train_NN, main.py:189-198)

@@ -1,0 +1,164 @@
+"""GPU tests of the reference-facing Python API (Predictor / Log_prob / retrieve_model /
+HMCSampler) on the reference's own fixture files and goldens."""
+import os
+import pickle
+import shutil
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from tests.helpers import GOLDEN, lnp_tol, load_golden, rel_inf
+
+pytestmark = pytest.mark.gpu
+FIX = os.path.join(GOLDEN, "ref_fixture_iter_0")
+
+
+@pytest.fixture()
+def fixture_dir(tmp_path):
+    d = tmp_path / "iter_0"
+    shutil.copytree(FIX, d)
+    return str(d)
+
+
+def _log_prob(fixture_dir, T=1.0, nograd=True, **kw):
+    import linna.util as U
+    pred, yinv = U.retrieve_model(fixture_dir, 2, 2)
+    with open(os.path.join(fixture_dir, "model_args.pkl"), "rb") as f:
+        args = pickle.load(f)
+    inv_cov, data = args[2], args[6]
+    priors = [dict(param="x%d" % i, dist="flat", arg1=-2.0, arg2=2.0) for i in range(2)]
+    lp = U.Log_prob(np.asarray(data), np.asarray(inv_cov), pred, yinv, U.Transform(priors), T,
+                    U.gaussianlogliklihood, nograd=nograd, **kw)
+    return lp, pred, yinv, priors
+
+
+def test_retrieve_model_and_predict(fixture_dir):
+    g = load_golden("fixture")
+    import linna.util as U
+    pred, yinv = U.retrieve_model(fixture_dir, 2, 2)
+    th = torch.from_numpy(g["theta"])
+    y = pred.predict(th)
+    assert y.shape == (6, 2) and not y.is_cuda
+    assert rel_inf(y.numpy(), g["y"]) < 1e-5
+    y1 = pred.predict(th[0])
+    assert y1.shape == (2,) and np.allclose(y1.numpy(), g["y_1d"], atol=1e-6)      # 1-D in => 1-D out
+    m = yinv(pred.predict(th.cuda()).cpu()).detach().numpy()
+    assert rel_inf(m, g["m"]) < 1e-5
+    f = U.retrieve_model_wrapper_in(fixture_dir)
+    assert rel_inf(f(th).numpy(), g["m"]) < 1e-5
+
+
+def test_log_prob_per_walker_and_batched(fixture_dir):
+    g = load_golden("fixture")
+    lp, *_ = _log_prob(fixture_dir)
+    # reference call shape: one walker, numpy float64 in, 0-dim tensor out (emcee float()s it)
+    v = lp(g["u"][0].astype(np.float64))
+    assert torch.is_tensor(v) and v.dim() == 0 and abs(float(v) - g["lnp"][0]) < 1e-5
+    assert abs(float(lp(g["u"][0], returntorch=False)) - g["lnp"][0]) < 1e-5
+    # batched extension
+    vb = lp(g["u"])
+    assert vb.shape == (16,)
+    assert np.all(np.abs(vb.numpy() - g["lnp"]) <= lnp_tol(g["lnp"]))
+    lp4, *_ = _log_prob(fixture_dir, T=4.0)
+    assert np.all(np.abs(lp4(g["u"]).numpy() - g["lnp_T4"]) <= lnp_tol(g["lnp_T4"]))
+    # pickles (pool workers) and rebuilds lazily
+    lp2 = pickle.loads(pickle.dumps(lp))
+    assert abs(float(lp2(g["u"][3])) - g["lnp"][3]) < 1e-5
+
+
+def test_log_prob_autograd_and_dlnp(fixture_dir):
+    g = load_golden("fixture")
+    import linna.util as U
+    lp, pred, yinv, priors = _log_prob(fixture_dir, nograd=False)
+    x = torch.from_numpy(g["u"][0].copy()).requires_grad_()
+    v = lp(x, inputnumpy=False)
+    (gr,) = torch.autograd.grad(v, x)
+    np.testing.assert_allclose(gr.numpy(), g["grad"][0], atol=3e-6)
+    np.testing.assert_allclose(gr.numpy(), [-0.53383291, 0.99314642], atol=3e-6)
+    xb = torch.from_numpy(g["u"].copy()).cuda().requires_grad_()
+    vb = lp(xb, inputnumpy=False)
+    (gb,) = torch.autograd.grad(vb.sum(), xb)
+    assert rel_inf(gb.cpu().numpy(), g["grad"]) < 2e-5
+    with open(os.path.join(fixture_dir, "model_args.pkl"), "rb") as f:
+        args = pickle.load(f)
+    d = U.Dlnp(np.asarray(args[6]), np.asarray(args[2]), pred, yinv, U.Transform(priors), 1.0)
+    np.testing.assert_allclose(d(g["u"][0]), g["grad"][0], atol=3e-6)
+    H = U.Ddlnp(np.asarray(args[6]), np.asarray(args[2]), pred, yinv, U.Transform(priors), 1.0)(g["u"][0])
+    assert H.shape == (2, 2) and np.allclose(H, H.T)
+    # against central differences of the float64 oracle gradient
+    from linna_b200 import arch
+    from oracle.oracle import Oracle
+    from tests.helpers import fixture_problem
+    o = Oracle(fixture_problem(g), arch)
+    u0, eps = g["u"][0].astype(np.float64), 1e-4
+    pts = np.stack([u0 + eps * np.eye(2)[i] for i in range(2)] + [u0 - eps * np.eye(2)[i] for i in range(2)])
+    gg = o.lnp(pts, np.float64, grad=True)["grad"]
+    Href = (gg[:2] - gg[2:]) / (2 * eps)
+    assert np.max(np.abs(H - 0.5 * (Href + Href.T))) < 2e-2 * np.max(np.abs(Href)), (H, Href)
+
+
+def test_custom_likelihood_and_external_term(fixture_dir):
+    g = load_golden("fixture")
+    import linna.util as U
+    def mylike(m, data, invcov):
+        d = m - data
+        return (d @ invcov @ d.T * (-0.5))[0][0]
+    lp, *_ = _log_prob(fixture_dir)
+    lp.loglikelihoodfunc = mylike                      # user-supplied callable => host path on kernel-made m
+    assert not lp.fused
+    v = lp(g["u"][:5])
+    assert np.all(np.abs(v.numpy() - g["lnp"][:5]) <= 2e-5)
+    lpe, *_ = _log_prob(fixture_dir, externalloglike=lambda th: -0.2 * (th[0] - 0.3) ** 2)
+    th = U.Transform(lpe.transform.priors)(g["u"][:5])
+    want = g["lnp"][:5] - 0.2 * (th[:, 0] - 0.3) ** 2
+    assert np.all(np.abs(lpe(g["u"][:5]).numpy() - want) <= 2e-5)
+
+
+def test_hmc_sampler_reproduces_reference_chain(fixture_dir):
+    """linna/HMCSampler.py on the fixture, same torch/numpy seeds as tests/golden/make_golden.py."""
+    g = load_golden("fixture")
+    import linna.util as U
+    from linna.HMCSampler import HMCSampler
+    lp, pred, yinv, priors = _log_prob(fixture_dir, nograd=False)
+    tr = U.Transform(priors)
+    torch.manual_seed(11)
+    np.random.seed(11)
+    samp = HMCSampler(lp, torch.tensor([0.1, -0.2]), torch.ones(2),
+                      transform=lambda x: tr(x, returnnumpy=False, inputnumpy=False))
+    chain = samp.sample(25, 5, 0.1)
+    acc = np.array([c["accepted"] for c in chain])
+    assert np.array_equal(acc, g["hmc_acc"])
+    np.testing.assert_allclose(np.array([c["x"] for c in chain]), g["hmc_x"], atol=2e-4)
+    np.testing.assert_allclose(np.array([float(c["lnP"]) for c in chain]), g["hmc_lnp"], atol=2e-4)
+    np.testing.assert_allclose(np.array([float(c["accpet_ratio"]) for c in chain]), g["hmc_ratio"], atol=2e-4)
+
+
+def test_batched_device_hmc_moments(fixture_dir):
+    """Many chains on the device: posterior moments agree with a long single-chain reference-style run
+    and with direct quadrature of the oracle posterior."""
+    import linna.util as U
+    from linna.HMCSampler import HMCSampler
+    from linna_b200 import arch
+    from oracle.oracle import Oracle
+    from tests.helpers import fixture_problem
+    lp, pred, yinv, priors = _log_prob(fixture_dir, nograd=False)
+    C = 4096
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x0 = 0.1 * torch.randn(C, 2, device="cuda", generator=gen)
+    samp = HMCSampler(lp, x0, torch.ones(2), device="cuda")
+    xs, ls, accfrac = samp.sample_chains(60, 5, 0.15, generator=gen)
+    assert 0.5 < accfrac <= 1.0
+    flat = xs[20:].reshape(-1, 2).cpu().numpy().astype(np.float64)
+    # quadrature of exp(lnP) on a grid with the oracle
+    o = Oracle(fixture_problem(load_golden("fixture")), arch)
+    ax = np.linspace(-4, 4, 161)
+    U1, U2 = np.meshgrid(ax, ax, indexing="ij")
+    grid = np.stack([U1.ravel(), U2.ravel()], 1)
+    w = np.exp(o.lnp(grid, np.float64)["lnp"])
+    w /= w.sum()
+    mean = (grid * w[:, None]).sum(0)
+    std = np.sqrt(((grid - mean) ** 2 * w[:, None]).sum(0))
+    assert np.all(np.abs(flat.mean(0) - mean) < 0.03), (flat.mean(0), mean)
+    assert np.all(np.abs(flat.std(0) / std - 1) < 0.05), (flat.std(0), std)
