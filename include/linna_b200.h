@@ -133,6 +133,47 @@ int linna_model_info(const linna_model_t *m, int32_t *n_in, int32_t *n_out, int6
 /* Force the row-tile height (8, 16 or 32; 0 = automatic) -- test hook for the tiling variants. */
 int linna_model_set_tile_rows(linna_model_t *m, int32_t rows);
 
+/* ---- emulator training: Predictor.train inner loop (linna/predictor_gpu.py:268-288) ------------------
+ * One optimiser step = fused forward + loss + backward-data pass over the batch, then ONE weight-
+ * gradient launch for all layers with the AdamW update fused into its epilogue (or, for data-parallel
+ * training, gradients written to `grads` for an NCCL all-reduce followed by linna_train_adamw).
+ *   loss: Auxilleryfunc / Loss_fn (linna/util.py:1070-1116) in normalised space:
+ *         mean_b chi2(target_b, pred_b) / max(chi2(target_b, data), n_out/2)
+ *   data_hat, icov_hat: Auxilleryfunc.__init__ constants (linna/util.py:1060-1069), computed by the
+ *         caller in float64 and cast.
+ * Parameters, AdamW moments and gradients are flat DEVICE float32 vectors in the reference's
+ * state_dict() order, owned by the caller. */
+typedef struct {
+    const float *data_hat;  /* [n_out] */
+    const float *icov_hat;  /* [n_out][n_out] */
+    int32_t max_batch;      /* largest batch linna_train_step will see */
+} linna_train_desc_t;
+
+int linna_train_setup(linna_model_t *m, const linna_train_desc_t *desc);
+int64_t linna_train_num_params(const linna_model_t *m);
+
+/* Per-row quadratic forms of the loss for rows (X physical parameters, Y physical targets), any n:
+ * kind 0: chi2(target, pred)   1: chi2(target, data) (NOT clamped)   2: chi2(pred, data)
+ * (chisqMnn, chisqMd, chisqnnd of linna/util.py:1077-1085; Val_metric_fn, :1124-1127). */
+int linna_train_chisq(linna_model_t *m, const float *X, const float *Y, int64_t n, int32_t kind, float *chi2,
+                      void *stream);
+
+/* One optimiser step.  cmd[b] = max(chi2(target_b, data), n_out/2) (targets only, precomputed with
+ * linna_train_chisq kind 1).  step counts from 1.  fuse_adam != 0: update params/adam_m/adam_v and the
+ * packed weights in place; fuse_adam == 0: write the flat gradient to `grads` only.
+ * loss_rows [B] and loss_mean [1] are DEVICE outputs (no host synchronisation). */
+int linna_train_step(linna_model_t *m, const float *X, const float *Y, const float *cmd, int64_t B, float *params,
+                     float *adam_m, float *adam_v, float *grads, int64_t step, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int32_t fuse_adam, float *loss_rows, float *loss_mean,
+                     void *stream);
+/* torch.optim.AdamW update from an (all-reduced) flat gradient; refreshes the packed weights. */
+int linna_train_adamw(linna_model_t *m, float *params, float *adam_m, float *adam_v, const float *grads, int64_t step,
+                      float lr, float beta1, float beta2, float eps, float weight_decay, void *stream);
+/* Overwrite the packed weights from a flat DEVICE parameter vector (after load_state_dict / re-init). */
+int linna_train_load_params(linna_model_t *m, const float *params, void *stream);
+/* Adopt a flat HOST parameter vector as the model's weights (end of training). */
+int linna_train_commit(linna_model_t *m, const float *params_host);
+
 #ifdef __cplusplus
 }
 #endif

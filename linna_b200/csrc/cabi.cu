@@ -15,6 +15,13 @@
 namespace linna {
 cudaError_t launch_fused_ffma(const KernelArgs &args, int rg, int grid, cudaStream_t stream);
 int fused_ffma_max_ctas_per_sm(int rg);
+cudaError_t launch_wgrad(const WgradLayer *layers, const WgradTile *tiles, int n_tiles, const float *rm_base, int B,
+                         const AdamArgs &ad, cudaStream_t stream);
+cudaError_t launch_adamw(const AdamArgs &ad, int n_params, int num_sms, cudaStream_t stream);
+cudaError_t launch_mean(const float *x, int n, float *out, cudaStream_t stream);
+cudaError_t launch_fill_col(float *base, int ld, int col, int rows, float value, cudaStream_t stream);
+cudaError_t launch_scatter_params(const float *params, float *blob, const int32_t *map_fwd, const int32_t *map_bwd,
+                                  int n_params, cudaStream_t stream);
 }  // namespace linna
 
 using namespace linna;
@@ -48,7 +55,7 @@ struct OpHost {
     bool has_ws;
 };
 
-enum ProgKind { PROG_PREDICT = 0, PROG_LNP = 1, PROG_GRAD = 2, PROG_COUNT = 3 };
+enum ProgKind { PROG_PREDICT = 0, PROG_LNP = 1, PROG_GRAD = 2, PROG_LOSS = 3, PROG_TRAIN = 4, PROG_COUNT = 5 };
 
 struct linna_model {
     int device = 0, num_sms = 0;
@@ -66,12 +73,22 @@ struct linna_model {
     std::vector<float> prior_scale, prior_shift, data, quad;
     int quad_kind = LINNA_QUAD_CHOL;
     float temperature = 1.f;
+    // training (linna_train_setup)
+    bool has_train = false;
+    std::vector<float> data_hat, icov_hat;
+    int max_batch = 0;
+    float *rm = nullptr;        // row-major activation / gradient store
+    size_t rm_floats = 0;
+    WgradLayer *wg_layers_dev = nullptr;
+    WgradTile *wg_tiles_dev = nullptr;
+    int n_wg_tiles = 0;
+    int32_t *map_fwd_dev = nullptr, *map_bwd_dev = nullptr;
     // device state
     float *blob = nullptr;
     size_t blob_floats = 0;
     Program *prog_dev = nullptr;  // [PROG_COUNT]
     Program prog_host[PROG_COUNT];
-    bool prog_valid[PROG_COUNT] = {false, false, false};
+    bool prog_valid[PROG_COUNT] = {false, false, false, false, false};
     Consts consts;
     float *arena = nullptr;
     uint8_t *masks = nullptr;
@@ -137,7 +154,13 @@ static void free_device(linna_model *m)
     if (m->prog_dev) cudaFree(m->prog_dev);
     if (m->arena) cudaFree(m->arena);
     if (m->masks) cudaFree(m->masks);
-    m->blob = nullptr, m->prog_dev = nullptr, m->arena = nullptr, m->masks = nullptr;
+    if (m->rm) cudaFree(m->rm);
+    if (m->wg_layers_dev) cudaFree(m->wg_layers_dev);
+    if (m->wg_tiles_dev) cudaFree(m->wg_tiles_dev);
+    if (m->map_fwd_dev) cudaFree(m->map_fwd_dev);
+    if (m->map_bwd_dev) cudaFree(m->map_bwd_dev);
+    m->blob = nullptr, m->prog_dev = nullptr, m->arena = nullptr, m->masks = nullptr, m->rm = nullptr;
+    m->wg_layers_dev = nullptr, m->wg_tiles_dev = nullptr, m->map_fwd_dev = nullptr, m->map_bwd_dev = nullptr;
 }
 
 // (Re)build the device blob and the three step programs from the host copies.
@@ -208,6 +231,74 @@ static int rebuild(linna_model *m)
         o_cs = B.put(cs);
     }
 
+    size_t o_dhat = 0, o_icov = 0;
+    if (m->has_train) {
+        o_dhat = B.put(m->data_hat);
+        o_icov = B.put_bwd(m->icov_hat, n_out, n_out);
+    }
+
+    // ---- flat parameter vector (reference state_dict order) and its maps into the packed copies
+    struct FlatOff { int w = -1, b = -1, w2 = -1, b2 = -1, ws = -1; };
+    std::vector<FlatOff> fo(m->ops.size());
+    int64_t nflat = 0;
+    for (size_t i = 0; i < m->ops.size(); ++i) {
+        const OpHost &op = m->ops[i];
+        if (op.kind == LINNA_OP_LINEAR) {
+            fo[i].w = (int)nflat, nflat += (int64_t)op.out * op.in;
+            fo[i].b = (int)nflat, nflat += op.out;
+        } else {
+            fo[i].w = (int)nflat, nflat += (int64_t)op.mid * op.in;
+            fo[i].b = (int)nflat, nflat += op.mid;
+            fo[i].w2 = (int)nflat, nflat += (int64_t)op.out * op.mid;
+            fo[i].b2 = (int)nflat, nflat += op.out;
+            if (op.has_ws) fo[i].ws = (int)nflat, nflat += (int64_t)op.out * op.in;
+        }
+    }
+    std::vector<int32_t> map_fwd, map_bwd;
+    if (m->has_train) {
+        map_fwd.assign(nflat, -1), map_bwd.assign(nflat, -1);
+        auto map_w = [&](int f0, size_t of, size_t ob, int N, int K) {
+            for (int n = 0; n < N; ++n)
+                for (int k = 0; k < K; ++k) {
+                    map_fwd[f0 + (size_t)n * K + k] = (int32_t)(of + (size_t)k * pad4(N) + n);
+                    map_bwd[f0 + (size_t)n * K + k] = (int32_t)(ob + (size_t)n * pad4(K) + k);
+                }
+        };
+        auto map_b = [&](int f0, size_t ob, int N) { for (int n = 0; n < N; ++n) map_fwd[f0 + n] = (int32_t)(ob + n); };
+        for (size_t i = 0; i < m->ops.size(); ++i) {
+            const OpHost &op = m->ops[i];
+            const OpOffsets &o = off[i];
+            if (op.kind == LINNA_OP_LINEAR) {
+                map_w(fo[i].w, o.w_f, o.w_b, op.out, op.in), map_b(fo[i].b, o.b, op.out);
+            } else {
+                map_w(fo[i].w, o.w_f, o.w_b, op.mid, op.in), map_b(fo[i].b, o.b, op.mid);
+                map_w(fo[i].w2, o.w2_f, o.w2_b, op.out, op.mid), map_b(fo[i].b2, o.b2, op.out);
+                if (op.has_ws) map_w(fo[i].ws, o.ws_f, o.ws_b, op.out, op.in);
+            }
+        }
+    }
+    // ---- row-major store layout for the weight-gradient kernel
+    struct RM { int off = -1, ld = 0; };
+    std::vector<RM> rm_act(m->ops.size()), rm_hid(m->ops.size()), rm_gz(m->ops.size()), rm_gzh(m->ops.size());
+    size_t rm_total = 0;
+    if (m->has_train) {
+        auto rm_alloc = [&](int width) {
+            RM r;
+            r.ld = pad4(width);
+            r.off = (int)rm_total;
+            rm_total += ((size_t)m->max_batch * r.ld + 63) / 64 * 64;
+            return r;
+        };
+        for (size_t i = 0; i < m->ops.size(); ++i) {
+            const OpHost &op = m->ops[i];
+            rm_act[i] = rm_alloc(op.in + 1);
+            rm_gz[i] = rm_alloc(op.out);
+            if (op.kind == LINNA_OP_RES) rm_hid[i] = rm_alloc(op.mid + 1), rm_gzh[i] = rm_alloc(op.mid);
+        }
+    }
+    int mask_loss = mask_total;
+    if (m->has_train) mask_total += n_out;
+
     // ---- upload
     if (m->blob && m->blob_floats < B.h.size()) { cudaFree(m->blob); m->blob = nullptr; }
     if (!m->blob) {
@@ -227,6 +318,7 @@ static int rebuild(linna_model *m)
         c.prior_kind = (const int32_t *)P(o_pk);
         c.prior_scale = P(o_ps), c.prior_shift = P(o_psh), c.data = P(o_data);
     }
+    if (m->has_train) c.data_hat = P(o_dhat);
 
     // ---- arena layout (features): X | A | B | H | Y | GX
     const int bufX = 0, bufA = n_in, bufB = bufA + maxW, bufH = bufB + maxW, bufY = bufH + maxMid,
@@ -234,13 +326,17 @@ static int rebuild(linna_model *m)
 
     for (int pk = 0; pk < PROG_COUNT; ++pk) {
         m->prog_valid[pk] = false;
-        if (pk != PROG_PREDICT && !m->has_like) continue;
-        const bool grad = pk == PROG_GRAD;
+        if ((pk == PROG_LNP || pk == PROG_GRAD) && !m->has_like) continue;
+        if ((pk == PROG_LOSS || pk == PROG_TRAIN) && !m->has_train) continue;
+        const bool train = pk == PROG_TRAIN, lossprog = pk == PROG_LOSS || pk == PROG_TRAIN;
+        const bool grad = pk == PROG_GRAD || train;   // forward saves relu masks
         Program &pg = m->prog_host[pk];
         memset(&pg, 0, sizeof pg);
         pg.arena_features = arena_features;
         pg.mask_features = grad ? mask_total : 0;
         pg.in_buf = bufX;
+        pg.in_rm_off = train ? rm_act[0].off : -1;
+        pg.in_rm_ld = train ? rm_act[0].ld : 0;
         int ns = 0;
         auto new_step = [&]() -> Step & {
             Step &s = pg.steps[ns++];
@@ -248,6 +344,7 @@ static int rebuild(linna_model *m)
             s.src1 = s.src2 = s.dst = -1;
             s.scale = 1.f;
             s.mask_off = 0;
+            s.rm_off = -1;
             return s;
         };
         if ((int)m->ops.size() * 2 + 2 * (int)m->ops.size() + 6 > kMaxSteps)
@@ -267,8 +364,10 @@ static int rebuild(linna_model *m)
                     s.flags |= F_RELU;
                     if (grad) s.flags |= F_SAVE_MASK, s.mask_off = o.mask_y;
                 }
-                s.epi = last ? EPI_HEAD : EPI_ACT;
+                s.epi = last ? (lossprog ? EPI_LOSSHEAD : EPI_HEAD) : EPI_ACT;
                 s.dst = other(cur);
+                if (train && !last) s.rm_off = rm_act[i + 1].off, s.rm_ld = rm_act[i + 1].ld;
+                if (last && lossprog && train) s.flags |= F_SAVE_MASK, s.mask_off = mask_loss;
                 if (last && m->has_extra) {
                     s.src2 = bufX, s.K2 = n_in, s.wt2 = P(o_extra_f), s.ldw2 = pad4(n_out), s.bias = P(o_lastbias);
                 }
@@ -278,6 +377,7 @@ static int rebuild(linna_model *m)
                 Step &h = new_step();
                 h.src1 = cur, h.K1 = op.in, h.wt1 = P(o.w_f), h.ldw1 = pad4(op.mid), h.N = op.mid, h.bias = P(o.b);
                 h.flags = F_RELU | (grad ? F_SAVE_MASK : 0), h.mask_off = o.mask_h, h.epi = EPI_ACT, h.dst = bufH;
+                if (train) h.rm_off = rm_hid[i].off, h.rm_ld = rm_hid[i].ld;
                 Step &y = new_step();
                 y.src1 = bufH, y.K1 = op.mid, y.wt1 = P(o.w2_f), y.ldw1 = pad4(op.out), y.N = op.out;
                 y.bias = P(o.b2), y.scale = op.alpha;
@@ -285,24 +385,75 @@ static int rebuild(linna_model *m)
                 if (op.has_ws) y.K2 = op.in, y.wt2 = P(o.ws_f), y.ldw2 = pad4(op.out);
                 else y.flags |= F_ADD_SRC2;
                 y.flags |= F_RELU | (grad ? F_SAVE_MASK : 0), y.mask_off = o.mask_y;
+                if (last && lossprog) return fail(LINNA_EINVAL, "training needs a LINEAR last layer without activation");
                 y.epi = last ? EPI_HEAD : EPI_ACT;
                 y.dst = other(cur);
+                if (train && !last) y.rm_off = rm_act[i + 1].off, y.rm_ld = rm_act[i + 1].ld;
                 cur = y.dst;
             }
             if (last) {
                 Step &s = pg.steps[ns - 1];
                 if (pk == PROG_PREDICT) s.flags |= F_OUT_VEC;
-                if (grad && m->ypositive) s.flags |= F_SAVE_Y, s.ybuf = bufY;
+                if (pk == PROG_GRAD && m->ypositive) s.flags |= F_SAVE_Y, s.ybuf = bufY;
             }
         }
-        if (pk != PROG_PREDICT) {
+        if (lossprog) {
+            // q = delta @ Chat^-1 ; chi2 = q . delta ; (training) g_yhat = -2 q mask / (cmd B)
+            const int dbuf = cur;
+            Step &q = new_step();
+            q.src1 = dbuf, q.K1 = n_out, q.wt1 = P(o_icov), q.ldw1 = pad4(n_out), q.N = n_out, q.epi = EPI_LOSSQ;
+            q.dst = other(dbuf);
+            if (train) {
+                q.flags |= F_LOSS_GRAD, q.mask_off = mask_loss;
+                q.rm_off = rm_gz.back().off, q.rm_ld = rm_gz.back().ld;
+                cur = q.dst;
+                for (int i = (int)m->ops.size() - 1; i >= 0; --i) {
+                    const OpHost &op = m->ops[i];
+                    const OpOffsets &o = off[i];
+                    int pmask = -1;
+                    if (i > 0) {
+                        const OpHost &pv = m->ops[i - 1];
+                        if (pv.kind == LINNA_OP_RES || pv.act == LINNA_ACT_RELU) pmask = off[i - 1].mask_y;
+                    }
+                    if (op.kind == LINNA_OP_LINEAR) {
+                        if (i == 0) break;   // d loss / d xhat is not needed for training
+                        Step &s2 = new_step();
+                        s2.src1 = cur, s2.K1 = op.out, s2.wt1 = P(o.w_b), s2.ldw1 = pad4(op.in), s2.N = op.in;
+                        s2.epi = EPI_BWD;
+                        if (pmask >= 0) s2.flags |= F_APPLY_MASK, s2.mask_off = pmask;
+                        s2.rm_off = rm_gz[i - 1].off, s2.rm_ld = rm_gz[i - 1].ld;
+                        s2.dst = other(cur);
+                        cur = s2.dst;
+                    } else {
+                        Step &h = new_step();
+                        h.src1 = cur, h.K1 = op.out, h.wt1 = P(o.w2_b), h.ldw1 = pad4(op.mid), h.N = op.mid;
+                        h.scale = op.alpha, h.epi = EPI_BWD, h.flags = F_APPLY_MASK, h.mask_off = o.mask_h, h.dst = bufH;
+                        h.rm_off = rm_gzh[i].off, h.rm_ld = rm_gzh[i].ld;
+                        if (i == 0) break;
+                        Step &x = new_step();
+                        if (op.has_ws) {
+                            x.src1 = cur, x.K1 = op.out, x.wt1 = P(o.ws_b), x.ldw1 = pad4(op.in);
+                            x.src2 = bufH, x.K2 = op.mid, x.wt2 = P(o.w_b), x.ldw2 = pad4(op.in);
+                        } else {
+                            x.src1 = bufH, x.K1 = op.mid, x.wt1 = P(o.w_b), x.ldw1 = pad4(op.in);
+                            x.src2 = cur, x.flags |= F_ADD_SRC2;
+                        }
+                        x.N = op.in, x.epi = EPI_BWD;
+                        if (pmask >= 0) x.flags |= F_APPLY_MASK, x.mask_off = pmask;
+                        x.rm_off = rm_gz[i - 1].off, x.rm_ld = rm_gz[i - 1].ld;
+                        x.dst = other(cur);
+                        cur = x.dst;
+                    }
+                }
+            }
+        } else if (pk != PROG_PREDICT) {
             const int dbuf = cur;
             Step &q = new_step();
             q.src1 = dbuf, q.K1 = n_out, q.wt1 = P(o_quadF), q.ldw1 = pad4(n_out), q.N = n_out, q.epi = EPI_CHI2;
             q.dst = other(dbuf);
             const bool chol = m->quad_kind == LINNA_QUAD_CHOL;
-            if (grad && chol) q.flags |= F_STORE_DST;
-            if (grad) {
+            if (pk == PROG_GRAD && chol) q.flags |= F_STORE_DST;
+            if (pk == PROG_GRAD) {
                 // g_yhat = -(1/T) * Q_b r  (.) sigma*y_std (.* y if ypositive)
                 Step &g0 = new_step();
                 g0.src1 = chol ? q.dst : dbuf;
@@ -381,6 +532,60 @@ static int rebuild(linna_model *m)
         m->masks = nullptr;
         CUDA_TRY(cudaMalloc(&m->masks, need_masks));
         m->masks_bytes = need_masks;
+    }
+    if (m->has_train) {
+        // weight-gradient layer table and tile list (one launch covers every linear map)
+        std::vector<WgradLayer> layers;
+        auto add_layer = [&](const RM &gz, const RM &x, int N, int K, int wf, int bf, float gs) {
+            WgradLayer L;
+            memset(&L, 0, sizeof L);
+            L.gz_off = gz.off, L.gz_ld = gz.ld, L.x_off = x.off, L.x_ld = x.ld, L.N = N, L.K = K;
+            L.w_flat = wf, L.b_flat = bf, L.gscale = gs;
+            layers.push_back(L);
+        };
+        for (size_t i = 0; i < m->ops.size(); ++i) {
+            const OpHost &op = m->ops[i];
+            if (op.kind == LINNA_OP_LINEAR) {
+                add_layer(rm_gz[i], rm_act[i], op.out, op.in, fo[i].w, fo[i].b, 1.f);
+            } else {
+                add_layer(rm_gzh[i], rm_act[i], op.mid, op.in, fo[i].w, fo[i].b, 1.f);
+                add_layer(rm_gz[i], rm_hid[i], op.out, op.mid, fo[i].w2, fo[i].b2, op.alpha);
+                if (op.has_ws) add_layer(rm_gz[i], rm_act[i], op.out, op.in, fo[i].ws, -1, 1.f);
+            }
+        }
+        std::vector<WgradTile> tiles;
+        for (size_t l = 0; l < layers.size(); ++l) {
+            const int kmax = layers[l].K + (layers[l].b_flat >= 0 ? 1 : 0);
+            for (int n0 = 0; n0 < layers[l].N; n0 += 64)
+                for (int k0 = 0; k0 < kmax; k0 += 64) tiles.push_back(WgradTile{(int32_t)l, n0, k0, 0});
+        }
+        if (m->wg_layers_dev) cudaFree(m->wg_layers_dev);
+        if (m->wg_tiles_dev) cudaFree(m->wg_tiles_dev);
+        if (m->map_fwd_dev) cudaFree(m->map_fwd_dev);
+        if (m->map_bwd_dev) cudaFree(m->map_bwd_dev);
+        m->wg_layers_dev = nullptr, m->wg_tiles_dev = nullptr, m->map_fwd_dev = nullptr, m->map_bwd_dev = nullptr;
+        CUDA_TRY(cudaMalloc(&m->wg_layers_dev, layers.size() * sizeof(WgradLayer)));
+        CUDA_TRY(cudaMalloc(&m->wg_tiles_dev, tiles.size() * sizeof(WgradTile)));
+        CUDA_TRY(cudaMalloc(&m->map_fwd_dev, nflat * sizeof(int32_t)));
+        CUDA_TRY(cudaMalloc(&m->map_bwd_dev, nflat * sizeof(int32_t)));
+        CUDA_TRY(cudaMemcpy(m->wg_layers_dev, layers.data(), layers.size() * sizeof(WgradLayer), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(m->wg_tiles_dev, tiles.data(), tiles.size() * sizeof(WgradTile), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(m->map_fwd_dev, map_fwd.data(), nflat * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(m->map_bwd_dev, map_bwd.data(), nflat * sizeof(int32_t), cudaMemcpyHostToDevice));
+        m->n_wg_tiles = (int)tiles.size();
+        if (rm_total > m->rm_floats) {
+            if (m->rm) cudaFree(m->rm);
+            m->rm = nullptr;
+            CUDA_TRY(cudaMalloc(&m->rm, rm_total * sizeof(float)));
+            m->rm_floats = rm_total;
+        }
+        CUDA_TRY(cudaMemset(m->rm, 0, m->rm_floats * sizeof(float)));
+        for (size_t i = 0; i < m->ops.size(); ++i) {   // the bias column of every layer input is 1
+            const OpHost &op = m->ops[i];
+            CUDA_TRY(launch_fill_col(m->rm + rm_act[i].off, rm_act[i].ld, op.in, m->max_batch, 1.f, 0));
+            if (op.kind == LINNA_OP_RES)
+                CUDA_TRY(launch_fill_col(m->rm + rm_hid[i].off, rm_hid[i].ld, op.mid, m->max_batch, 1.f, 0));
+        }
     }
     CUDA_TRY(cudaDeviceSynchronize());
     return LINNA_OK;
@@ -563,7 +768,7 @@ int linna_model_set_tile_rows(linna_model_t *m, int32_t rows)
 }
 
 static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_vec, int out_kind, float *lnp, float *grad,
-               int input_theta, cudaStream_t stream)
+               int input_theta, cudaStream_t stream, const KernelArgs *proto = nullptr)
 {
     if (!m) return fail(LINNA_EINVAL, "null model");
     if (n < 0) return fail(LINNA_EINVAL, "negative n");
@@ -600,6 +805,12 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
         a.grad = grad ? grad + done * m->n_in : nullptr;
         a.arena = m->arena, a.masks = m->masks;
         a.n = take, a.input_theta = input_theta, a.out_kind = out_kind;
+        if (proto) {
+            a.target = proto->target ? proto->target + done * m->n_out : nullptr;
+            a.cmd = proto->cmd ? proto->cmd + done : nullptr;
+            a.rm_base = proto->rm_base, a.rm_row0 = done;
+            a.loss_inv_B = proto->loss_inv_B, a.delta_kind = proto->delta_kind;
+        }
         CUDA_TRY(launch_fused_ffma(a, rg, grid, stream));
         g_launches.fetch_add(1);
         done += take;
@@ -687,6 +898,126 @@ int linna_lnp_grad_host(linna_model_t *m, const float *u, int64_t n, float *lnp,
     CUDA_TRY(cudaMemcpyAsync(grad, m->d_grad, (size_t)n * m->n_in * sizeof(float), cudaMemcpyDeviceToHost, m->hstream));
     CUDA_TRY(cudaStreamSynchronize(m->hstream));
     return LINNA_OK;
+}
+
+// ------------------------------------------------------------------------------------------ training
+int linna_train_setup(linna_model_t *m, const linna_train_desc_t *d)
+{
+    if (!m || !d || !d->data_hat || !d->icov_hat) return fail(LINNA_EINVAL, "null argument");
+    if (d->max_batch <= 0) return fail(LINNA_EINVAL, "max_batch must be > 0");
+    if (m->has_extra) return fail(LINNA_EINVAL, "training the ChtoModelv2_linear variant is not supported");
+    const OpHost &last = m->ops.back();
+    if (last.kind != LINNA_OP_LINEAR || last.act != LINNA_ACT_NONE)
+        return fail(LINNA_EINVAL, "training needs a LINEAR last layer without activation");
+    const int n = m->n_out;
+    m->data_hat.assign(d->data_hat, d->data_hat + n);
+    m->icov_hat.assign(d->icov_hat, d->icov_hat + (size_t)n * n);
+    for (int i = 0; i < n; ++i)   // x^T A x == x^T sym(A) x and the gradient is then 2 sym(A) x
+        for (int j = i + 1; j < n; ++j) {
+            float v = 0.5f * (m->icov_hat[(size_t)i * n + j] + m->icov_hat[(size_t)j * n + i]);
+            m->icov_hat[(size_t)i * n + j] = m->icov_hat[(size_t)j * n + i] = v;
+        }
+    m->max_batch = d->max_batch;
+    m->has_train = true;
+    return rebuild(m);
+}
+
+int64_t linna_train_num_params(const linna_model_t *m) { return m ? m->n_params : -1; }
+
+int linna_train_chisq(linna_model_t *m, const float *X, const float *Y, int64_t n, int32_t kind, float *chi2, void *stream)
+{
+    if (!m || !m->has_train) return fail(LINNA_ESTATE, "linna_train_setup has not been called");
+    if (kind < 0 || kind > 2) return fail(LINNA_EINVAL, "bad kind");
+    if (n > 0 && (!Y || !chi2)) return fail(LINNA_EINVAL, "null buffer");
+    KernelArgs p;
+    memset(&p, 0, sizeof p);
+    p.target = Y, p.delta_kind = kind, p.loss_inv_B = 1.f;
+    return run(m, PROG_LOSS, X, n, nullptr, 0, chi2, nullptr, 1, (cudaStream_t)stream, &p);
+}
+
+static AdamArgs adam_args(linna_model *m, float *params, float *am, float *av, float *grads, int64_t step, float lr,
+                          float b1, float b2, float eps, float wd, int fuse)
+{
+    AdamArgs a;
+    memset(&a, 0, sizeof a);
+    a.params = params, a.m = am, a.v = av, a.grads = grads, a.blob = m->blob;
+    a.map_fwd = m->map_fwd_dev, a.map_bwd = m->map_bwd_dev;
+    a.lr = lr, a.beta1 = b1, a.beta2 = b2, a.eps = eps, a.wd = wd;
+    a.bc1 = (float)(1.0 - std::pow((double)b1, (double)step));
+    a.bc2_sqrt = (float)std::sqrt(1.0 - std::pow((double)b2, (double)step));
+    a.fuse = fuse;
+    return a;
+}
+
+int linna_train_step(linna_model_t *m, const float *X, const float *Y, const float *cmd, int64_t B, float *params,
+                     float *adam_m, float *adam_v, float *grads, int64_t step, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int32_t fuse_adam, float *loss_rows, float *loss_mean, void *stream)
+{
+    if (!m || !m->has_train) return fail(LINNA_ESTATE, "linna_train_setup has not been called");
+    if (B <= 0 || B > m->max_batch) return fail(LINNA_EINVAL, "batch %lld outside (0, max_batch=%d]", (long long)B, m->max_batch);
+    if (!X || !Y || !cmd || !loss_rows) return fail(LINNA_EINVAL, "null buffer");
+    if (fuse_adam ? (!params || !adam_m || !adam_v) : !grads) return fail(LINNA_EINVAL, "null optimiser buffer");
+    if (step < 1) return fail(LINNA_EINVAL, "step counts from 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    KernelArgs p;
+    memset(&p, 0, sizeof p);
+    p.target = Y, p.cmd = cmd, p.rm_base = m->rm, p.loss_inv_B = 1.0f / (float)B, p.delta_kind = 0;
+    int rc = run(m, PROG_TRAIN, X, B, nullptr, 0, loss_rows, nullptr, 1, st, &p);
+    if (rc) return rc;
+    AdamArgs a = adam_args(m, params, adam_m, adam_v, grads, step, lr, beta1, beta2, eps, weight_decay, fuse_adam ? 1 : 0);
+    CUDA_TRY(launch_wgrad(m->wg_layers_dev, m->wg_tiles_dev, m->n_wg_tiles, m->rm, (int)B, a, st));
+    g_launches.fetch_add(1);
+    if (loss_mean) {
+        CUDA_TRY(launch_mean(loss_rows, (int)B, loss_mean, st));
+        g_launches.fetch_add(1);
+    }
+    CUDA_TRY(cudaEventRecord(m->last_done, st));
+    return LINNA_OK;
+}
+
+int linna_train_adamw(linna_model_t *m, float *params, float *adam_m, float *adam_v, const float *grads, int64_t step,
+                      float lr, float beta1, float beta2, float eps, float weight_decay, void *stream)
+{
+    if (!m || !m->has_train) return fail(LINNA_ESTATE, "linna_train_setup has not been called");
+    if (!params || !adam_m || !adam_v || !grads) return fail(LINNA_EINVAL, "null buffer");
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->have_last && m->last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, m->last_done, 0));
+    AdamArgs a = adam_args(m, params, adam_m, adam_v, const_cast<float *>(grads), step, lr, beta1, beta2, eps, weight_decay, 1);
+    CUDA_TRY(launch_adamw(a, (int)m->n_params, m->num_sms, st));
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaEventRecord(m->last_done, st));
+    m->last_stream = st, m->have_last = true;
+    return LINNA_OK;
+}
+
+int linna_train_load_params(linna_model_t *m, const float *params, void *stream)
+{
+    if (!m || !m->has_train) return fail(LINNA_ESTATE, "linna_train_setup has not been called");
+    if (!params) return fail(LINNA_EINVAL, "null buffer");
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->have_last && m->last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, m->last_done, 0));
+    CUDA_TRY(launch_scatter_params(params, m->blob, m->map_fwd_dev, m->map_bwd_dev, (int)m->n_params, st));
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaEventRecord(m->last_done, st));
+    m->last_stream = st, m->have_last = true;
+    return LINNA_OK;
+}
+
+int linna_train_commit(linna_model_t *m, const float *ph)
+{
+    if (!m || !ph) return fail(LINNA_EINVAL, "null argument");
+    size_t o = 0;
+    auto take = [&](std::vector<float> &v) { std::copy(ph + o, ph + o + v.size(), v.begin()); o += v.size(); };
+    for (OpHost &op : m->ops) {
+        take(op.w), take(op.b);
+        if (op.kind == LINNA_OP_RES) {
+            take(op.w2), take(op.b2);
+            if (op.has_ws) take(op.ws);
+        }
+    }
+    return rebuild(m);
 }
 
 }  // extern "C"

@@ -218,6 +218,16 @@ __device__ __forceinline__ void load8_cg(const float *p, float (&v)[8])
     v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
 }
 
+// Row-major copy of an epilogue column (training: operands of the weight-gradient GEMM).
+__device__ __forceinline__ void store_rm(float *rm_base, const Step &st, int64_t row0, int row_base, int nrows, int cidx,
+                                         const float (&v)[8])
+{
+    float *p = rm_base + (size_t)st.rm_off + (size_t)(row0 + row_base) * st.rm_ld + cidx;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (row_base + i < nrows) p[(size_t)i * st.rm_ld] = v[i];
+}
+
 // Prior CDF map of one latent coordinate (Transform.__call__, linna/util.py:339-343).
 __device__ __forceinline__ float prior_map(float u, int kind, float scale, float shift)
 {
@@ -272,6 +282,8 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ffma_kernel(const KernelArg
                     th = (th - c.x_mean[i]) / c.x_std[i];                             // util.py:497
                 }
                 xb[(size_t)i * BM + r] = th;
+                if (args.rm_base && prog->in_rm_off >= 0 && r < nrows)
+                    args.rm_base[(size_t)prog->in_rm_off + (size_t)(row0 + args.rm_row0 + r) * prog->in_rm_ld + i] = th;
             }
             if (tid < BM) {
                 float s = 0.f;
@@ -340,6 +352,48 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ffma_kernel(const KernelArg
                         }
                         if (st.epi == EPI_ACT) {
                             store8(arena + (size_t)(st.dst + cidx) * BM + row_base, v);
+                            if (st.rm_off >= 0) store_rm(args.rm_base, st, row0 + args.rm_row0, row_base, nrows, cidx, v);
+                        } else if (st.epi == EPI_LOSSHEAD) {
+                            const float ys = __ldg(c.y_std + cidx), ym = __ldg(c.y_mean + cidx);
+                            const float sg = c.sigma ? __ldg(c.sigma + cidx) : 1.f;
+                            const float dh = __ldg(c.data_hat + cidx);
+                            float dl[8];
+                            unsigned mb = 0;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int r = row_base + i;
+                                float dv = 0.f;
+                                if (r < nrows) {
+                                    const float Y = __ldg(args.target + (row0 + r) * n_out + cidx);
+                                    float t = Y / sg;                                              // util.py:432
+                                    if (c.ypositive) t = logf(t);                                  // util.py:567-568
+                                    t = (t - ym) / ys;                                             // util.py:570
+                                    const bool ok = !(Y == 1e-30f || Y == 1e10f || dh == 1e-30f);   // util.py:1072
+                                    dv = args.delta_kind == 0 ? t - v[i] : args.delta_kind == 1 ? t - dh : v[i] - dh;
+                                    if (!ok) dv = 0.f;
+                                    mb |= (ok ? 1u : 0u) << i;
+                                }
+                                dl[i] = dv;
+                            }
+                            store8(arena + (size_t)(st.dst + cidx) * BM + row_base, dl);
+                            if (st.flags & F_SAVE_MASK) masks[(size_t)(st.mask_off + cidx) * RG + g.rg] = (uint8_t)mb;
+                        } else if (st.epi == EPI_LOSSQ) {
+                            float d[8];
+                            load8_cg(arena + (size_t)(st.src1 + cidx) * BM + row_base, d);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) part[i] += (double)(v[i] * d[i]);
+                            if (st.flags & F_LOSS_GRAD) {
+                                const unsigned m = __ldcg(masks + (size_t)(st.mask_off + cidx) * RG + g.rg);
+                                float gq[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const int r = row_base + i;
+                                    const float rs = r < nrows ? -2.0f * args.loss_inv_B / __ldg(args.cmd + row0 + r) : 0.f;
+                                    gq[i] = ((m >> i) & 1u) ? v[i] * rs : 0.f;
+                                }
+                                store8(arena + (size_t)(st.dst + cidx) * BM + row_base, gq);
+                                if (st.rm_off >= 0) store_rm(args.rm_base, st, row0 + args.rm_row0, row_base, nrows, cidx, gq);
+                            }
                         } else if (st.epi == EPI_HEAD) {
                             const float ys = __ldg(c.y_std + cidx), ym = __ldg(c.y_mean + cidx);
                             const float sg = c.sigma ? __ldg(c.sigma + cidx) : 1.f;
@@ -395,6 +449,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ffma_kernel(const KernelArg
                                 for (int i = 0; i < 8; ++i) v[i] = ((m >> i) & 1u) ? v[i] : 0.f;
                             }
                             store8(arena + (size_t)(st.dst + cidx) * BM + row_base, v);
+                            if (st.rm_off >= 0) store_rm(args.rm_base, st, row0 + args.rm_row0, row_base, nrows, cidx, v);
                         } else if (st.epi == EPI_GRAD) {
                             // chain through xhat = (theta' - mean)/std, theta' = log10(theta), theta = prior(u)
                             const int kind = c.prior_kind[cidx];
@@ -417,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ffma_kernel(const KernelArg
                     }
                 }
 
-                if (st.epi == EPI_CHI2) {
+                if (st.epi == EPI_CHI2 || st.epi == EPI_LOSSQ) {
                     // shuffle-reduce the row partials over the column groups of one (rg, ks) lane group
                     const int width = g.CG < 32 ? g.CG : 32;
 #pragma unroll
@@ -440,6 +495,10 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ffma_kernel(const KernelArg
                     }
                 }
                 __syncthreads();  // dst visible to the next step; ring + chi_part reusable
+            }
+            if (st.epi == EPI_LOSSQ && tid < nrows && args.lnp) {
+                const double chi = chi_acc[tid];
+                args.lnp[row0 + tid] = args.cmd ? (float)chi / __ldg(args.cmd + row0 + tid) : (float)chi;   // util.py:1087
             }
             if (st.epi == EPI_CHI2 && tid < nrows && args.lnp) {
                 float l = (float)(-0.5 * chi_acc[tid]) * c.inv_T + lnprior[tid];       // util.py:1013

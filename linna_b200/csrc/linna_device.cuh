@@ -24,7 +24,10 @@ enum Epilogue : int32_t {
     EPI_HEAD = 1,  // EPI_ACT then y = v*y_std+y_mean (exp), m = y*sigma, d = m - data -> dst; optional output
     EPI_CHI2 = 2,  // r = v ; chi2_row += r*r (CHOL) or r*d (DENSE) ; optionally r -> dst
     EPI_BWD = 3,   // v*colscale (*ysave) (*mask) -> dst
-    EPI_GRAD = 4   // v = d lnL/d xhat -> prologue Jacobian -> d lnP/du -> global grad
+    EPI_GRAD = 4,  // v = d lnL/d xhat -> prologue Jacobian -> d lnP/du -> global grad
+    // training loss, normalised space (Auxilleryfunc, linna/util.py:1070-1088)
+    EPI_LOSSHEAD = 5,  // v = yhat ; delta = (that - yhat | yhat - dhat | that - dhat) * mask -> dst, mask bits saved
+    EPI_LOSSQ = 6      // q = v = delta @ Chat^-1 ; chi2_row += q*delta ; optionally g_yhat = -2 q mask /(cmd B) -> dst
 };
 
 enum StepFlags : int32_t {
@@ -35,7 +38,8 @@ enum StepFlags : int32_t {
     F_STORE_DST = 16,   // CHI2: keep r in dst for the backward pass
     F_MUL_YSAVE = 32,   // BWD: multiply by saved y (ypositive: d exp)
     F_SAVE_Y = 64,      // HEAD: save y into ybuf (ypositive + backward)
-    F_OUT_VEC = 128     // HEAD: write the selected vector (yhat / y / m) to the global output
+    F_OUT_VEC = 128,    // HEAD: write the selected vector (yhat / y / m) to the global output
+    F_LOSS_GRAD = 256   // LOSSQ: also emit d loss / d yhat (training); otherwise chi^2 only
 };
 
 struct Step {
@@ -49,6 +53,8 @@ struct Step {
     int32_t mask_off;         // mask arena offset in features
     int32_t ybuf;             // arena offset of the saved y (F_SAVE_Y / F_MUL_YSAVE)
     float scale;
+    int32_t rm_off;           // >= 0: also store the output row-major at rm_base[rm_off + row*rm_ld + c] (training)
+    int32_t rm_ld;
     int32_t pad_;
 };
 
@@ -57,6 +63,9 @@ struct Program {
     int32_t arena_features;  // per-CTA scratch, in features (x BM floats)
     int32_t mask_features;   // per-CTA mask scratch, in features (x RG bytes)
     int32_t in_buf;          // arena offset where the prologue writes xhat
+    int32_t in_rm_off;       // >= 0: row-major copy of xhat for the weight-gradient kernel
+    int32_t in_rm_ld;
+    int32_t pad_[2];
     Step steps[kMaxSteps];
 };
 
@@ -67,6 +76,7 @@ struct Consts {
     const float *prior_scale, *prior_shift;  // theta = t*scale + shift, t = u (gauss) or Phi(u) (flat)
     const int32_t *prior_kind;
     const float *data;
+    const float *data_hat;  // normalised data vector (training loss)
     int32_t n_in, n_out, ypositive, quad_kind;
     float inv_T;
 };
@@ -83,6 +93,35 @@ struct KernelArgs {
     int64_t n;
     int32_t input_theta;  // 1: `in` holds physical parameters (Predictor.predict)
     int32_t out_kind;     // LINNA_OUT_*
+    // training / loss programs
+    const float *target;  // [n][n_out] targets in physical units
+    const float *cmd;     // [n] chi2(target, data) per row (clamped), or nullptr => raw chi^2 out
+    float *rm_base;       // row-major activation / gradient store for the weight-gradient kernel
+    float loss_inv_B;     // 1 / (rows in the optimiser batch)
+    int64_t rm_row0;      // row index of this launch's first row inside the row-major store
+    int32_t delta_kind;   // 0: target - pred (chi2_M,nn)  1: target - data (chi2_M,d)  2: pred - data (chi2_nn,d)
+};
+
+// ---- weight-gradient / AdamW kernels --------------------------------------------------------
+struct WgradLayer {
+    int32_t gz_off, gz_ld;  // row-major d loss/d z   [B][gz_ld]  (offset into rm_base)
+    int32_t x_off, x_ld;    // row-major layer input  [B][x_ld], column K preset to 1 (bias)
+    int32_t N, K;           // out, in
+    int32_t w_flat, b_flat; // offsets into the flat parameter vector (b_flat < 0: no bias)
+    float gscale;           // alpha of the res-block second layer, else 1
+    int32_t pad_[3];
+};
+struct WgradTile {
+    int32_t layer, n0, k0, pad_;
+};
+struct AdamArgs {
+    float *params, *m, *v;   // flat, reference state_dict order
+    float *grads;            // flat gradient (written when !fuse, read by the stand-alone AdamW)
+    float *blob;             // packed operands to refresh
+    const int32_t *map_fwd;  // flat index -> blob float offset of the forward-layout copy
+    const int32_t *map_bwd;  // flat index -> blob float offset of the backward-layout copy (-1: none)
+    float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt;
+    int32_t fuse;
 };
 
 }  // namespace linna

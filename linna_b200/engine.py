@@ -45,6 +45,10 @@ class LikeDesc(ctypes.Structure):
                 ("temperature", ctypes.c_float)]
 
 
+class TrainDesc(ctypes.Structure):
+    _fields_ = [("data_hat", c_float_p), ("icov_hat", c_float_p), ("max_batch", ctypes.c_int32)]
+
+
 class LinnaError(RuntimeError):
     pass
 
@@ -78,6 +82,15 @@ def load_library():
     lib.linna_lnp_grad_host.argtypes = [vp, vp, i64, vp, vp]
     lib.linna_model_info.argtypes = [vp, c_i32_p, c_i32_p, ctypes.POINTER(i64), c_i32_p]
     lib.linna_model_set_tile_rows.argtypes = [vp, i32]
+    f32 = ctypes.c_float
+    lib.linna_train_setup.argtypes = [vp, ctypes.POINTER(TrainDesc)]
+    lib.linna_train_num_params.argtypes = [vp]
+    lib.linna_train_num_params.restype = ctypes.c_int64
+    lib.linna_train_chisq.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+    lib.linna_train_step.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, vp, vp]
+    lib.linna_train_adamw.argtypes = [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp]
+    lib.linna_train_load_params.argtypes = [vp, vp, vp]
+    lib.linna_train_commit.argtypes = [vp, vp]
     if lib.linna_abi_version() != 1:
         raise LinnaError("linna_b200: ABI version mismatch")
     _lib = lib
@@ -298,6 +311,60 @@ class Engine:
             self._check(self.lib.linna_lnp_grad(self.handle, uu.data_ptr(), uu.shape[0], out.data_ptr(), g.data_ptr(),
                                                 self._stream()))
         return out, g
+
+    # -- training ---------------------------------------------------------------------------
+    def train_setup(self, data_hat, icov_hat, max_batch):
+        """Constants of the training loss (Auxilleryfunc.__init__, linna/util.py:1060-1069)."""
+        dh, ic = _f32(data_hat), _f32(icov_hat)
+        assert dh.shape == (self.n_out,) and ic.shape == (self.n_out, self.n_out)
+        d = TrainDesc()
+        d.data_hat, d.icov_hat, d.max_batch = _fp(dh), _fp(ic), int(max_batch)
+        self._check(self.lib.linna_train_setup(self.handle, ctypes.byref(d)))
+        self.n_params = int(self.lib.linna_train_num_params(self.handle))
+
+    def train_chisq(self, X, Y, kind):
+        """Per-row chi^2 of the loss (kind 0: target/pred, 1: target/data, 2: pred/data); CUDA tensors."""
+        import torch
+        X, Y = self._prep_dev(X, self.n_in), self._prep_dev(Y, self.n_out)
+        out = torch.empty(X.shape[0], dtype=torch.float32, device=X.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.linna_train_chisq(self.handle, X.data_ptr(), Y.data_ptr(), X.shape[0], int(kind),
+                                                   out.data_ptr(), self._stream()))
+        return out
+
+    def train_step(self, X, Y, cmd, params, adam_m, adam_v, grads, step, lr, betas=(0.9, 0.999), eps=1e-8,
+                   weight_decay=1e-4, fuse_adam=True, loss_rows=None, loss_mean=None):
+        import torch
+        X, Y = self._prep_dev(X, self.n_in), self._prep_dev(Y, self.n_out)
+        B = X.shape[0]
+        if loss_rows is None:
+            loss_rows = torch.empty(B, dtype=torch.float32, device=X.device)
+        if loss_mean is None:
+            loss_mean = torch.empty(1, dtype=torch.float32, device=X.device)
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.linna_train_step(self.handle, X.data_ptr(), Y.data_ptr(), cmd.data_ptr(), B, ptr(params),
+                                                  ptr(adam_m), ptr(adam_v), ptr(grads), int(step), float(lr),
+                                                  float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                                  int(bool(fuse_adam)), loss_rows.data_ptr(), loss_mean.data_ptr(),
+                                                  self._stream()))
+        return loss_mean, loss_rows
+
+    def train_adamw(self, params, adam_m, adam_v, grads, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4):
+        import torch
+        with torch.cuda.device(self.device):
+            self._check(self.lib.linna_train_adamw(self.handle, params.data_ptr(), adam_m.data_ptr(), adam_v.data_ptr(),
+                                                   grads.data_ptr(), int(step), float(lr), float(betas[0]),
+                                                   float(betas[1]), float(eps), float(weight_decay), self._stream()))
+
+    def train_load_params(self, params):
+        import torch
+        with torch.cuda.device(self.device):
+            self._check(self.lib.linna_train_load_params(self.handle, params.data_ptr(), self._stream()))
+
+    def train_commit(self, params_host):
+        p = _f32(params_host)
+        self._check(self.lib.linna_train_commit(self.handle, p.ctypes.data))
 
     def info(self):
         n_in, n_out, sms = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
