@@ -1,0 +1,156 @@
+"""Device-side training state for one emulator: the flat parameter / AdamW-moment vectors and the
+fused optimiser step (``csrc/fused_ffma.cu`` PROG_TRAIN + ``csrc/train_kernels.cu``).
+
+Replaces the body of the reference's training inner loop -- ``zero_grad``, forward, ``loss_fn``,
+``backward``, ``AdamW.step`` and the per-step ``loss.item()`` sync
+(``linna/predictor_gpu.py:273-288``) -- by 3 kernel launches with no host synchronisation.
+Data-parallel training adds one NCCL all-reduce of the flat gradient between the weight-gradient
+launch and the stand-alone AdamW kernel.
+"""
+import numpy as np
+import torch
+
+from . import arch
+from . import engine as _engine
+
+
+def flatten_module(model):
+    """Parameters of a linna.nn model as one flat float32 vector in state_dict order."""
+    sd = model.state_dict()
+    keys = [k for k, _ in arch.state_dict_shapes(model.KIND, model.in_size, model.out_size)]
+    return torch.cat([sd[k].detach().reshape(-1).to(torch.float32).cpu() for k in keys])
+
+
+def unflatten_into_module(model, flat):
+    """Write a flat parameter vector back into the module's tensors (in place)."""
+    flat = flat.detach().cpu()
+    sd = model.state_dict()
+    o = 0
+    with torch.no_grad():
+        for k, shp in arch.state_dict_shapes(model.KIND, model.in_size, model.out_size):
+            n = int(np.prod(shp))
+            sd[k].copy_(flat[o:o + n].reshape(shp).to(sd[k].device))
+            o += n
+
+
+class FusedTrainer:
+    """Owns the packed emulator on one GPU plus flat (params, exp_avg, exp_avg_sq, grad) vectors."""
+
+    def __init__(self, model, X_transform, y_transform, aux, max_batch, device_index=None, lr=1e-3,
+                 weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, process_group=None, world_size=1):
+        from .predictor_gpu import _transform_constants
+        if not torch.cuda.is_available():
+            raise RuntimeError("FusedTrainer: no CUDA device -- linna_b200 has no CPU fallback")
+        self.model = model
+        self.dev = torch.cuda.current_device() if device_index is None else int(device_index)
+        self.device = torch.device("cuda", self.dev)
+        data_hat, icov_hat, sigma, y_mean, y_std, ypos = aux.constants()
+        xm, xs, log10, _, _, _ = _transform_constants(X_transform, None, model.in_size, model.out_size)
+        sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+        self.engine = _engine.Engine(model.KIND, model.in_size, model.out_size, sd, xm, xs, y_mean, y_std,
+                                     dolog10index=log10, ypositive=ypos, sigma=sigma, device=self.dev)
+        self.engine.train_setup(data_hat, icov_hat, int(max_batch))
+        self.n_out = model.out_size
+        self.p = flatten_module(model).to(self.device)
+        assert self.p.numel() == self.engine.n_params
+        self.m = torch.zeros_like(self.p)
+        self.v = torch.zeros_like(self.p)
+        self.g = torch.zeros_like(self.p)
+        self.t = 0
+        self.lr, self.weight_decay, self.betas, self.eps = float(lr), float(weight_decay), betas, float(eps)
+        self.pg, self.world = process_group, int(world_size)
+        self._loss_mean = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    # -- data ------------------------------------------------------------------------------
+    def chisq_md(self, X, Y):
+        """max(chi2(target, data), n_out/2) per row -- depends on the targets only, so it is computed
+        once per data set instead of once per step (linna/util.py:1080-1086)."""
+        return torch.clamp(self.engine.train_chisq(X, Y, 1), min=0.5 * self.n_out)
+
+    # -- one optimiser step ----------------------------------------------------------------
+    def step(self, X, Y, cmd, loss_out=None):
+        """X [B, n_in] physical parameters, Y [B, n_out] physical targets, cmd [B]; all CUDA.
+        Returns the mean loss as a 1-element device tensor (no sync)."""
+        self.t += 1
+        out = self._loss_mean if loss_out is None else loss_out
+        if self.world > 1:
+            import torch.distributed as dist
+            self.engine.train_step(X, Y, cmd, None, None, None, self.g, self.t, self.lr, self.betas, self.eps,
+                                   self.weight_decay, fuse_adam=False, loss_mean=out)
+            dist.all_reduce(self.g, op=dist.ReduceOp.AVG, group=self.pg)      # NCCL over NVLink
+            self.engine.train_adamw(self.p, self.m, self.v, self.g, self.t, self.lr, self.betas, self.eps,
+                                    self.weight_decay)
+        else:
+            self.engine.train_step(X, Y, cmd, self.p, self.m, self.v, None, self.t, self.lr, self.betas, self.eps,
+                                   self.weight_decay, fuse_adam=True, loss_mean=out)
+        return out
+
+    # -- validation metric (Val_metric_fn, linna/util.py:1118-1127) ------------------------
+    def val_metric(self, X, Y, cmd):
+        mnn = self.engine.train_chisq(X, Y, 0)
+        nnd = self.engine.train_chisq(X, Y, 2)
+        loss = mnn / cmd
+        frac = torch.abs(nnd / cmd - 1)
+        return torch.stack([torch.median(loss), torch.max(frac), torch.median(frac)])
+
+    # -- state exchange with the torch module / optimizer ----------------------------------
+    def reset_optimizer(self):
+        self.m.zero_(), self.v.zero_()
+        self.t = 0
+
+    def load_from_module(self):
+        """Adopt the module's current parameters (after init_weight / load_checkpoint)."""
+        self.p.copy_(flatten_module(self.model).to(self.device))
+        self.engine.train_load_params(self.p)
+
+    def sync_to_module(self):
+        unflatten_into_module(self.model, self.p)
+
+    def optim_state_dict(self):
+        """An ``AdamW.state_dict()``-shaped dict (what the reference stores as 'optim_dict')."""
+        params = list(self.model.parameters())
+        state, o = {}, 0
+        m, v = self.m.detach().cpu(), self.v.detach().cpu()
+        for i, prm in enumerate(params):
+            n = prm.numel()
+            state[i] = {"step": torch.tensor(float(self.t)), "exp_avg": m[o:o + n].reshape(prm.shape).clone(),
+                        "exp_avg_sq": v[o:o + n].reshape(prm.shape).clone()}
+            o += n
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                 "differentiable": False, "fused": None, "decoupled_weight_decay": True,
+                 "params": list(range(len(params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optim_state_dict(self, od):
+        params = list(self.model.parameters())
+        st = od.get("state", {})
+        if len(st) != len(params):
+            self.reset_optimizer()
+            return
+        m = torch.cat([st[i]["exp_avg"].reshape(-1).float().cpu() for i in range(len(params))])
+        v = torch.cat([st[i]["exp_avg_sq"].reshape(-1).float().cpu() for i in range(len(params))])
+        self.m.copy_(m.to(self.device)), self.v.copy_(v.to(self.device))
+        self.t = int(float(st[0]["step"]))
+
+    def commit(self):
+        """End of training: parameters back into the module and into the engine's host copies."""
+        self.sync_to_module()
+        self.engine.train_commit(self.p.detach().cpu().numpy())
+
+
+def loss_terms(aux, y_pred, y_target):
+    raise NotImplementedError(
+        "Auxilleryfunc/Loss_fn on free-standing tensors is not part of the fused path: the loss is evaluated "
+        "inside the training kernels (Predictor.train, train.FusedTrainer.step / val_metric)")
+
+
+def emulator_forward_autograd(model, x):
+    raise NotImplementedError(
+        "autograd through model(x) is not wired up: gradients of lnP come from Log_prob (fused kernel) and "
+        "training gradients from train.FusedTrainer")
+
+
+def predict_with_grad(pred, X):
+    raise NotImplementedError("Predictor.predict(no_grad=False) on a tensor that requires grad: use Log_prob(..., "
+                              "nograd=False) / Log_prob.value_and_grad for d lnP/du")

@@ -465,11 +465,11 @@ class Auxilleryfunc:
         """(data_hat [n_out] f32, C_hat^-1 [n_out, n_out] f32, sigma f32, y_mean, y_std, ypositive) for
         the training kernels."""
         yt = self.y_inv_transform
-        return (self.data_in.detach().cpu().numpy().astype(np.float32),
+        return (self.data_in.detach().cpu().numpy().astype(np.float32).reshape(-1),
                 self.inv_transformed_cov.detach().cpu().numpy().astype(np.float32),
-                self.y_transform_data.sigma.detach().cpu().numpy().astype(np.float32),
-                yt.y_mean.detach().cpu().numpy().astype(np.float32),
-                yt.y_std.detach().cpu().numpy().astype(np.float32), bool(yt.ypositive))
+                self.y_transform_data.sigma.detach().cpu().numpy().astype(np.float32).reshape(-1),
+                yt.y_mean.detach().cpu().numpy().astype(np.float32).reshape(-1),
+                yt.y_std.detach().cpu().numpy().astype(np.float32).reshape(-1), bool(yt.ypositive))
 
     def __call__(self, y_pred, y_target):
         from .train import loss_terms

@@ -107,3 +107,23 @@ def test_early_stopping_codes():
     es2 = EarlyStopping(patience=3)
     es2.step(1.0, 1.0)
     assert [es2.step(2.0, 1.0) for _ in range(3)][-1] == 2
+
+
+def test_loss_constants_match_oracle_setup():
+    """Auxilleryfunc.__init__ (host, float64) against the oracle's restatement, incl. ypositive."""
+    import linna.util as U
+    from linna_b200 import synthetic
+    from oracle.oracle import normalised_loss_constants
+    for ypos in (False, True):
+        p = synthetic.make_problem(4, 6, seed=4, ypositive=ypos)
+        p.data = np.abs(np.random.default_rng(1).standard_normal(6)) + 0.5
+        sig = np.asarray(p.sigma, np.float32)
+        ytd = U.Y_transform_data(sig, "cpu")
+        dt = torch.tensor(p.data.astype(np.float32))
+        yinv = U.Y_invtransform_class(torch.tensor(p.y_mean), torch.tensor(p.y_std), dt, "cpu", ypositive=ypos)
+        aux = U.Loss_fn(dt, torch.tensor(p.cov), torch.tensor(p.inv_cov), ytd, yinv, "cpu").auxileryfunction
+        dh, ic, sg, ym, ys, yp = aux.constants()
+        dn, icov = normalised_loss_constants(p.cov, sig, p.y_mean, p.y_std, p.data, ypositive=ypos)
+        assert dh.shape == (6,) and ic.shape == (6, 6) and sg.shape == (6,) and yp == ypos
+        np.testing.assert_allclose(dh, dn, rtol=1e-6)
+        np.testing.assert_allclose(ic, icov, rtol=1e-5, atol=1e-6)

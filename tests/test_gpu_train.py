@@ -93,3 +93,89 @@ def test_adamw_steps_match_reference(name, full, fused):
     p2.state_dict = {k: np.ascontiguousarray(wd[k]) for k in wd}
     e2 = engine.engine_from_problem(p2, with_likelihood=False)
     np.testing.assert_allclose(y_after, e2.predict(th, engine.LINNA_OUT_YHAT), rtol=1e-6, atol=1e-6)
+
+
+def test_train_NN_on_reference_fixture(tmp_path):
+    """The reference's own training entry point (pickled as linna.util.train_NN with model_args.pkl,
+    linna/main.py:189-198, run by linna/train_gpu.py:24-38) on its shipped 20+5-point fixture."""
+    import os
+    import pickle
+    import shutil
+    import linna.util as U
+    from tests.helpers import GOLDEN
+    d = str(tmp_path / "iter_0") + "/"
+    shutil.copytree(os.path.join(GOLDEN, "ref_fixture_iter_0"), d)
+    for f in ("best.pth.tar", "last.pth.tar", "finish.pkl"):
+        os.remove(d + f)
+    with open(d + "model_pickle.pkl", "rb") as f:
+        fn = pickle.load(f)
+    with open(d + "model_args.pkl", "rb") as f:
+        args = pickle.load(f)
+    assert fn is U.train_NN
+    args[4], args[5] = d, [d]
+    args[16] = dict(args[16], num_epochs=40)
+    fn(*args)
+    for f in ("best.pth.tar", "last.pth.tar", "X_transform.pkl", "y_transform.pkl", "y_invtransform_data.pkl",
+              "y_transform_data.pkl", "y_invtransform.pkl", "lr.npy"):
+        assert os.path.isfile(d + f), f
+    ck = torch.load(d + "best.pth.tar", weights_only=False)
+    assert set(ck) >= {"epoch", "state_dict", "optim_dict"} and len(ck["state_dict"]) == 23
+    assert set(ck["optim_dict"]) == {"state", "param_groups"} and len(ck["optim_dict"]["state"]) == 23
+    # the trained emulator reloads through the reference-shaped loader and reproduces theory(x) = x roughly
+    pred, yinv = U.retrieve_model(d, 2, 2)
+    th = torch.tensor([[0.1, 0.2], [-0.5, 0.4]])
+    m = yinv(pred.predict(th)).detach().numpy()
+    assert np.all(np.isfinite(m)) and m.shape == (2, 2)
+
+
+def test_training_converges_and_dp_path_equals_fused():
+    """A few hundred fused steps drive the loss down by orders of magnitude; the gradient-out +
+    stand-alone AdamW path (what data-parallel ranks run) follows the same trajectory."""
+    from linna_b200.train import FusedTrainer
+    import linna.nn as N
+    import linna.util as U
+    p = synthetic.make_problem(6, 8, seed=4)
+    p.data = np.zeros(8)
+    rng = np.random.default_rng(0)
+    theta = synthetic.training_set(p, 512, seed=3, spread=0.5)
+    A = rng.standard_normal((6, 8))
+    target = np.tanh(theta @ A) * p.sigma + 0.3 * p.sigma          # a smooth "theory"
+    p.data = target[0].copy()
+    sig = np.asarray(p.sigma, np.float32)
+    ytd = U.Y_transform_data(sig, "cpu")
+    ymean = torch.tensor(np.median(target / sig, axis=0).astype(np.float32))
+    ystd = torch.tensor((np.median(np.abs(target / sig - ymean.numpy()), axis=0)).astype(np.float32))
+    yinv = U.Y_invtransform_class(ymean, ystd, torch.tensor(p.data.astype(np.float32)), "cpu")
+    loss_fn = U.Loss_fn(torch.tensor(p.data.astype(np.float32)), torch.tensor(p.cov), torch.tensor(p.inv_cov), ytd, yinv, "cpu")
+    xt = U.X_transform_class(torch.tensor(theta.mean(0).astype(np.float32)), torch.tensor(theta.std(0).astype(np.float32)), "cpu")
+    yt = U.Y_transform_class(ymean, ystd, "cpu")
+    X = torch.from_numpy(theta.astype(np.float32)).cuda()
+    Y = torch.from_numpy(target.astype(np.float32)).cuda()
+    runs = []
+    for fused in (True, False):
+        torch.manual_seed(3)
+        model = N.ChtoModelv2(6, 8, None)
+        tr = FusedTrainer(model, xt, yt, loss_fn.auxileryfunction, 128, lr=2e-3)
+        cmd = tr.chisq_md(X, Y)
+        if not fused:
+            tr.world = 2          # forces the gradient-out path; all_reduce is skipped below
+            import torch.distributed as dist
+            orig = dist.all_reduce
+            dist.all_reduce = lambda *a, **k: None
+        try:
+            hist = []
+            g = torch.Generator().manual_seed(1)
+            for it in range(300):
+                idx = torch.randperm(512, generator=g)[:128].cuda()
+                hist.append(tr.step(X[idx], Y[idx], cmd[idx]).clone())
+        finally:
+            if not fused:
+                dist.all_reduce = orig
+        hist = torch.cat(hist).cpu().numpy()
+        runs.append(hist)
+        assert np.isfinite(hist).all()
+        assert hist[-20:].mean() < 0.1 * hist[:5].mean(), (hist[:5], hist[-20:])
+        vm = tr.val_metric(X, Y, cmd).cpu().numpy()
+        assert vm.shape == (3,) and vm[0] < 0.1 * hist[0]
+        tr.commit()
+    np.testing.assert_allclose(runs[0][:50], runs[1][:50], rtol=2e-3)
