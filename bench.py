@@ -296,6 +296,7 @@ def main():
     ap.add_argument("--walkers", type=int, default=0, help="override walkers per GPU")
     ap.add_argument("--ref-sample", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", default="auto", choices=["auto", "ffma", "tc"], help="kernel serving lnP")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -323,6 +324,7 @@ def main():
     m0 = eng.predict(np.asarray(p.theta0, np.float32)[None, :], engine.LINNA_OUT_M)[0]
     data = p.set_data_from_prediction(m0)
     eng.set_likelihood(p.priors, np.asarray(data, np.float32), p.inv_cov, p.temperature)
+    eng.set_path(args.path)
 
     # inputs: NBUF distinct walker sets, rotated so that consecutive steps never re-read a warm input
     nbuf = 16 if n * p.n_in * 4 * 16 <= (1 << 31) else 4

@@ -130,6 +130,10 @@ int linna_lnp_grad_host(linna_model_t *m, const float *u, int64_t n, float *lnp,
 
 /* Introspection used by bench.py / tests. */
 int linna_model_info(const linna_model_t *m, int32_t *n_in, int32_t *n_out, int64_t *n_params, int32_t *num_sms);
+/* Kernel selection for linna_lnp: 0 = automatic (tensor-core kernel for n >= tc_min_rows, FP32 FFMA kernel
+ * below), 1 = FP32 FFMA kernel only, 2 = tensor-core (tcgen05, 3xTF32) kernel only.  tc_min_rows <= 0 keeps
+ * the current threshold. */
+int linna_model_set_path(linna_model_t *m, int32_t path, int64_t tc_min_rows);
 /* Force the row-tile height (8, 16 or 32; 0 = automatic) -- test hook for the tiling variants. */
 int linna_model_set_tile_rows(linna_model_t *m, int32_t rows);
 

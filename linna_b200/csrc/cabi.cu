@@ -9,8 +9,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/linna_b200.h"
-#include "linna_device.cuh"
+#include "linna_host.hpp"
 
 namespace linna {
 cudaError_t launch_fused_ffma(const KernelArgs &args, int rg, int grid, cudaStream_t stream);
@@ -22,9 +21,10 @@ cudaError_t launch_mean(const float *x, int n, float *out, cudaStream_t stream);
 cudaError_t launch_fill_col(float *base, int ld, int col, int rows, float value, cudaStream_t stream);
 cudaError_t launch_scatter_params(const float *params, float *blob, const int32_t *map_fwd, const int32_t *map_bwd,
                                   int n_params, cudaStream_t stream);
+TcContext *tc_build(const linna_model *m, std::string &why);
+void tc_destroy(TcContext *t);
+cudaError_t tc_launch_lnp(const linna_model *m, TcContext *t, const float *u, int64_t n, float *lnp, cudaStream_t stream);
 }  // namespace linna
-
-using namespace linna;
 
 static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
@@ -45,66 +45,6 @@ static int fail(int code, const char *fmt, ...)
         if (e_ != cudaSuccess) return fail(LINNA_ECUDA, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), \
                                            __FILE__, __LINE__);                                       \
     } while (0)
-
-static inline int pad4(int n) { return (n + 3) & ~3; }
-
-struct OpHost {
-    int kind, in, mid, out, act;
-    float alpha;
-    std::vector<float> w, b, w2, b2, ws;
-    bool has_ws;
-};
-
-enum ProgKind { PROG_PREDICT = 0, PROG_LNP = 1, PROG_GRAD = 2, PROG_LOSS = 3, PROG_TRAIN = 4, PROG_COUNT = 5 };
-
-struct linna_model {
-    int device = 0, num_sms = 0;
-    int n_in = 0, n_out = 0, ypositive = 0;
-    int64_t n_params = 0;
-    std::vector<OpHost> ops;
-    std::vector<float> x_mean, x_std, y_mean, y_std, sigma;
-    std::vector<uint8_t> log10_flag;
-    bool has_log10 = false, has_extra = false;
-    std::vector<float> extra_w, extra_b;
-    float extra_scale = 0.f;
-    // likelihood
-    bool has_like = false;
-    std::vector<int32_t> prior_kind;
-    std::vector<float> prior_scale, prior_shift, data, quad;
-    int quad_kind = LINNA_QUAD_CHOL;
-    float temperature = 1.f;
-    // training (linna_train_setup)
-    bool has_train = false;
-    std::vector<float> data_hat, icov_hat;
-    int max_batch = 0;
-    float *rm = nullptr;        // row-major activation / gradient store
-    size_t rm_floats = 0;
-    WgradLayer *wg_layers_dev = nullptr;
-    WgradTile *wg_tiles_dev = nullptr;
-    int n_wg_tiles = 0;
-    int32_t *map_fwd_dev = nullptr, *map_bwd_dev = nullptr;
-    // device state
-    float *blob = nullptr;
-    size_t blob_floats = 0;
-    Program *prog_dev = nullptr;  // [PROG_COUNT]
-    Program prog_host[PROG_COUNT];
-    bool prog_valid[PROG_COUNT] = {false, false, false, false, false};
-    Consts consts;
-    float *arena = nullptr;
-    uint8_t *masks = nullptr;
-    size_t arena_bytes = 0, masks_bytes = 0;
-    int occ[3] = {0, 0, 0};  // CTAs/SM for RG = 1, 2, 4
-    int force_rows = 0;
-    // the scratch arena is shared by every launch on this model: launches on different streams are
-    // chained through this event so that they never overlap
-    cudaEvent_t last_done = nullptr;
-    cudaStream_t last_stream = nullptr;
-    bool have_last = false;
-    // host-buffer API staging
-    cudaStream_t hstream = nullptr;
-    float *d_in = nullptr, *d_out = nullptr, *d_lnp = nullptr, *d_grad = nullptr;
-    size_t d_in_cap = 0, d_out_cap = 0, d_lnp_cap = 0, d_grad_cap = 0;
-};
 
 // ----------------------------------------------------------------------------------------------
 // blob builder: one host mirror, sub-allocations aligned to 64 floats (256 B)
@@ -168,6 +108,8 @@ static int rebuild(linna_model *m)
 {
     CUDA_TRY(cudaSetDevice(m->device));
     CUDA_TRY(cudaDeviceSynchronize());  // no launch may still be reading the blob we are about to replace
+    if (m->tc) { tc_destroy(m->tc); m->tc = nullptr; }
+    m->tc_failed = false;
     const int n_in = m->n_in, n_out = m->n_out;
     Builder B;
     std::vector<OpOffsets> off(m->ops.size());
@@ -697,6 +639,7 @@ void linna_model_destroy(linna_model_t *m)
     cudaDeviceSynchronize();
     if (m->hstream) cudaStreamDestroy(m->hstream);
     if (m->last_done) cudaEventDestroy(m->last_done);
+    if (m->tc) tc_destroy(m->tc);
     if (m->d_in) cudaFree(m->d_in);
     if (m->d_out) cudaFree(m->d_out);
     if (m->d_lnp) cudaFree(m->d_lnp);
@@ -760,6 +703,14 @@ int linna_model_info(const linna_model_t *m, int32_t *n_in, int32_t *n_out, int6
     return LINNA_OK;
 }
 
+int linna_model_set_path(linna_model_t *m, int32_t path, int64_t tc_min_rows)
+{
+    if (!m || path < 0 || path > 2) return fail(LINNA_EINVAL, "path must be 0 (auto), 1 (FFMA) or 2 (tensor core)");
+    m->path = path;
+    if (tc_min_rows > 0) m->tc_min_rows = tc_min_rows;
+    return LINNA_OK;
+}
+
 int linna_model_set_tile_rows(linna_model_t *m, int32_t rows)
 {
     if (!m || (rows != 0 && rows != 8 && rows != 16 && rows != 32)) return fail(LINNA_EINVAL, "rows must be 0, 8, 16 or 32");
@@ -777,6 +728,25 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
     if (!m->prog_valid[pk]) return fail(LINNA_ESTATE, "likelihood constants not set (linna_model_set_likelihood)");
     CUDA_TRY(cudaSetDevice(m->device));
     if (m->have_last && m->last_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, m->last_done, 0));
+    // Large lnP batches go to the tensor-core (tcgen05) kernel; everything else stays on the FP32 FFMA kernel.
+    if (pk == PROG_LNP && !proto && m->path != 1 && !m->has_extra && !m->tc_failed &&
+        (m->path == 2 || n >= m->tc_min_rows)) {
+        if (!m->tc) {
+            std::string why;
+            m->tc = tc_build(m, why);
+            if (!m->tc) {
+                m->tc_failed = true;
+                if (m->path == 2) return fail(LINNA_EINVAL, "tensor-core path unavailable: %s", why.c_str());
+            }
+        }
+        if (m->tc) {
+            CUDA_TRY(tc_launch_lnp(m, m->tc, in, n, lnp, stream));
+            g_launches.fetch_add(1);
+            CUDA_TRY(cudaEventRecord(m->last_done, stream));
+            m->last_stream = stream, m->have_last = true;
+            return LINNA_OK;
+        }
+    }
     // Launch plan: full waves of 32-row tiles, then the remainder in 16- and 8-row tiles, so that the
     // last wave costs a fraction of a full one instead of leaving most SMs idle for a whole tile time.
     int64_t done = 0;
