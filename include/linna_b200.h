@@ -134,6 +134,9 @@ int linna_model_info(const linna_model_t *m, int32_t *n_in, int32_t *n_out, int6
  * below), 1 = FP32 FFMA kernel only, 2 = tensor-core (tcgen05, 3xTF32) kernel only.  tc_min_rows <= 0 keeps
  * the current threshold. */
 int linna_model_set_path(linna_model_t *m, int32_t path, int64_t tc_min_rows);
+/* lnP evaluates the last linear layer, the inverse output transform and the Cholesky product as ONE folded
+ * affine map (formed in float64 at pack time); 0 switches the folding off (unfolded reference order). */
+int linna_model_set_fold(linna_model_t *m, int32_t on);
 /* Force the row-tile height (8, 16 or 32; 0 = automatic) -- test hook for the tiling variants. */
 int linna_model_set_tile_rows(linna_model_t *m, int32_t rows);
 

@@ -172,6 +172,44 @@ static int rebuild(linna_model *m)
         for (int j = 0; j < n_out; ++j) cs[j] = -(m->sigma[j] * m->y_std[j]) / m->temperature;
         o_cs = B.put(cs);
     }
+    // Folded tail for lnP: the last linear layer, the inverse output transform, the residual and the
+    // Cholesky product are all affine in s (the last hidden activation):
+    //   r = L^T (sigma*(y_std*(W s + b) + y_mean) - data) = Af s + cf ,  chi^2 = |r|^2
+    // Af, cf are formed in float64 on the host once; the LNP/GRAD programs then run ONE n_out x K GEMM
+    // instead of two (Predictor.predict keeps the unfolded layer: it has to return m itself).
+    size_t o_foldF = 0, o_foldB = 0, o_foldc = 0, o_foldcs = 0;
+    bool fold = false;
+    {
+        const OpHost &lastop = m->ops.back();
+        fold = m->fold_enabled && m->has_like && m->quad_kind == LINNA_QUAD_CHOL && !m->ypositive && !m->has_extra &&
+               lastop.kind == LINNA_OP_LINEAR && lastop.act == LINNA_ACT_NONE && m->ops.size() >= 2;
+        if (fold) {
+            const int K = lastop.in;
+            std::vector<double> T((size_t)n_out * K), A((size_t)n_out * K, 0.0), dvec(n_out), cf(n_out, 0.0);
+            for (int j = 0; j < n_out; ++j) {
+                const double sc = (double)m->sigma[j] * (double)m->y_std[j];
+                for (int k = 0; k < K; ++k) T[(size_t)j * K + k] = sc * (double)lastop.w[(size_t)j * K + k];
+                dvec[j] = (double)m->sigma[j] * ((double)m->y_std[j] * (double)lastop.b[j] + (double)m->y_mean[j]) -
+                          (double)m->data[j];
+            }
+            for (int j = 0; j < n_out; ++j)            // A[n][:] += L[j][n] * T[j][:]  (L lower triangular)
+                for (int n = 0; n <= j; ++n) {
+                    const double l = (double)m->quad[(size_t)j * n_out + n];
+                    if (l == 0.0) continue;
+                    double *a = &A[(size_t)n * K];
+                    const double *t = &T[(size_t)j * K];
+                    for (int k = 0; k < K; ++k) a[k] += l * t[k];
+                    cf[n] += l * dvec[j];
+                }
+            std::vector<float> Af((size_t)n_out * K), cff(n_out), csf(K, -1.0f / m->temperature);
+            for (size_t i = 0; i < Af.size(); ++i) Af[i] = (float)A[i];
+            for (int n = 0; n < n_out; ++n) cff[n] = (float)cf[n];
+            o_foldF = B.put_fwd(Af, n_out, K);
+            o_foldB = B.put_bwd(Af, n_out, K);
+            o_foldc = B.put(cff);
+            o_foldcs = B.put(csf);
+        }
+    }
 
     size_t o_dhat = 0, o_icov = 0;
     if (m->has_train) {
@@ -294,10 +332,12 @@ static int rebuild(linna_model *m)
         int cur = bufX;
         auto other = [&](int b) { return b == bufA ? bufB : bufA; };
         // ------------------------------ forward
+        const bool folded = fold && (pk == PROG_LNP || pk == PROG_GRAD);
         for (size_t i = 0; i < m->ops.size(); ++i) {
             const OpHost &op = m->ops[i];
             const OpOffsets &o = off[i];
             const bool last = i + 1 == m->ops.size();
+            if (last && folded) break;   // absorbed into the chi^2 step below
             if (op.kind == LINNA_OP_LINEAR) {
                 Step &s = new_step();
                 s.src1 = cur, s.K1 = op.in, s.wt1 = P(o.w_f), s.ldw1 = pad4(op.out), s.N = op.out;
@@ -383,6 +423,58 @@ static int rebuild(linna_model *m)
                         x.N = op.in, x.epi = EPI_BWD;
                         if (pmask >= 0) x.flags |= F_APPLY_MASK, x.mask_off = pmask;
                         x.rm_off = rm_gz[i - 1].off, x.rm_ld = rm_gz[i - 1].ld;
+                        x.dst = other(cur);
+                        cur = x.dst;
+                    }
+                }
+            }
+        } else if (folded) {
+            const OpHost &lastop = m->ops.back();
+            const int K = lastop.in, sbuf = cur;
+            Step &q = new_step();
+            q.src1 = sbuf, q.K1 = K, q.wt1 = P(o_foldF), q.ldw1 = pad4(n_out), q.N = n_out, q.bias = P(o_foldc);
+            q.epi = EPI_CHI2, q.dst = other(sbuf);
+            if (pk == PROG_GRAD) {
+                q.flags |= F_STORE_DST;
+                // d lnL / d s = -(1/T) Af^T r, masked by the relu of the layer that produced s
+                const int nops = (int)m->ops.size();
+                Step &g0 = new_step();
+                g0.src1 = q.dst, g0.K1 = n_out, g0.wt1 = P(o_foldB), g0.ldw1 = pad4(K), g0.N = K, g0.epi = EPI_BWD;
+                g0.colscale = P(o_foldcs);
+                const OpHost &pv = m->ops[nops - 2];
+                if (pv.kind == LINNA_OP_RES || pv.act == LINNA_ACT_RELU) g0.flags |= F_APPLY_MASK, g0.mask_off = off[nops - 2].mask_y;
+                g0.dst = sbuf;
+                cur = g0.dst;
+                for (int i = nops - 2; i >= 0; --i) {
+                    const OpHost &op = m->ops[i];
+                    const OpOffsets &o = off[i];
+                    int pmask = -1;
+                    if (i > 0) {
+                        const OpHost &pp = m->ops[i - 1];
+                        if (pp.kind == LINNA_OP_RES || pp.act == LINNA_ACT_RELU) pmask = off[i - 1].mask_y;
+                    }
+                    if (op.kind == LINNA_OP_LINEAR) {
+                        Step &s2 = new_step();
+                        s2.src1 = cur, s2.K1 = op.out, s2.wt1 = P(o.w_b), s2.ldw1 = pad4(op.in), s2.N = op.in;
+                        s2.epi = i == 0 ? EPI_GRAD : EPI_BWD;
+                        if (pmask >= 0) s2.flags |= F_APPLY_MASK, s2.mask_off = pmask;
+                        s2.dst = other(cur);
+                        cur = s2.dst;
+                    } else {
+                        Step &h = new_step();
+                        h.src1 = cur, h.K1 = op.out, h.wt1 = P(o.w2_b), h.ldw1 = pad4(op.mid), h.N = op.mid;
+                        h.scale = op.alpha, h.epi = EPI_BWD, h.flags = F_APPLY_MASK, h.mask_off = o.mask_h, h.dst = bufH;
+                        Step &x = new_step();
+                        if (op.has_ws) {
+                            x.src1 = cur, x.K1 = op.out, x.wt1 = P(o.ws_b), x.ldw1 = pad4(op.in);
+                            x.src2 = bufH, x.K2 = op.mid, x.wt2 = P(o.w_b), x.ldw2 = pad4(op.in);
+                        } else {
+                            x.src1 = bufH, x.K1 = op.mid, x.wt1 = P(o.w_b), x.ldw1 = pad4(op.in);
+                            x.src2 = cur, x.flags |= F_ADD_SRC2;
+                        }
+                        x.N = op.in;
+                        x.epi = i == 0 ? EPI_GRAD : EPI_BWD;
+                        if (pmask >= 0) x.flags |= F_APPLY_MASK, x.mask_off = pmask;
                         x.dst = other(cur);
                         cur = x.dst;
                     }
@@ -709,6 +801,13 @@ int linna_model_set_path(linna_model_t *m, int32_t path, int64_t tc_min_rows)
     m->path = path;
     if (tc_min_rows > 0) m->tc_min_rows = tc_min_rows;
     return LINNA_OK;
+}
+
+int linna_model_set_fold(linna_model_t *m, int32_t on)
+{
+    if (!m) return fail(LINNA_EINVAL, "null model");
+    m->fold_enabled = on != 0;
+    return rebuild(m);
 }
 
 int linna_model_set_tile_rows(linna_model_t *m, int32_t rows)

@@ -62,6 +62,7 @@ struct linna_model {
     size_t arena_bytes = 0, masks_bytes = 0;
     int occ[3] = {0, 0, 0};  // CTAs/SM for RG = 1, 2, 4
     int force_rows = 0;
+    bool fold_enabled = true;     // fold last layer + inverse transform + Cholesky product for lnP
     // the scratch arena is shared by every launch on this model: launches on different streams are
     // chained through this event so that they never overlap
     cudaEvent_t last_done = nullptr;

@@ -486,6 +486,7 @@ TcContext *tc_build(const linna_model *m, std::string &why)
 {
     if (m->has_extra) { why = "extra linear branch not supported on the tensor-core path"; return nullptr; }
     if (!m->has_like) { why = "likelihood not set"; return nullptr; }
+    if (m->quad_kind != LINNA_QUAD_CHOL) { why = "tensor-core path needs the Cholesky form of the quadratic"; return nullptr; }
     EncodeTiledFn encode = nullptr;
     {
         void *fn = nullptr;

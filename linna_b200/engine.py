@@ -83,6 +83,7 @@ def load_library():
     lib.linna_model_info.argtypes = [vp, c_i32_p, c_i32_p, ctypes.POINTER(i64), c_i32_p]
     lib.linna_model_set_tile_rows.argtypes = [vp, i32]
     lib.linna_model_set_path.argtypes = [vp, i32, i64]
+    lib.linna_model_set_fold.argtypes = [vp, i32]
     f32 = ctypes.c_float
     lib.linna_train_setup.argtypes = [vp, ctypes.POINTER(TrainDesc)]
     lib.linna_train_num_params.argtypes = [vp]
@@ -212,6 +213,10 @@ class Engine:
         """'auto' | 'ffma' | 'tc' -- which kernel serves lnp()."""
         code = {"auto": 0, "ffma": 1, "tc": 2}[path]
         self._check(self.lib.linna_model_set_path(self.handle, code, int(tc_min_rows)))
+
+    def set_fold(self, on):
+        """Fold last layer + inverse transform + Cholesky product into one GEMM for lnP (default on)."""
+        self._check(self.lib.linna_model_set_fold(self.handle, int(bool(on))))
 
     def set_weights(self, state_dict):
         arr, keep, extra = build_op_descs(self.kind, self.n_in, self.n_out, state_dict)

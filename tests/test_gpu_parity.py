@@ -147,3 +147,23 @@ def test_full_size_c3_properties():
     assert rel_inf(g2.cpu().numpy()[idx], ref["grad"]) < 2e-4
     # chi^2 ~ n_out near the fiducial point: sanity on magnitudes
     assert 150 < -np.median(a) < 600
+
+
+@pytest.mark.parametrize("name", ["c1", "c3s", "c3mix", "c4s", "tiny", "simple"])
+def test_folded_tail_matches_unfolded_and_reference(name):
+    """lnP folds the last layer + inverse transform + Cholesky product into one GEMM (float64-formed
+    operand).  Both orders must satisfy the reference bar; predict() always runs unfolded."""
+    g = load_golden(name)
+    p = problem_from_golden(g)
+    e = engine.engine_from_problem(p)
+    out = {}
+    for fold in (True, False):
+        e.set_fold(fold)
+        lnp, grad = e.lnp_grad(_dev(g["u"]))
+        out[fold] = (lnp.cpu().numpy(), grad.cpu().numpy(), e.lnp(_dev(g["u"])).cpu().numpy())
+        err = np.abs(out[fold][0].astype(np.float64) - g["f64_lnp"])
+        tol = lnp_tol(g["f64_lnp"])
+        assert np.all(err <= np.maximum(tol, 2 * np.abs(g["f32_lnp"] - g["f64_lnp"]))), (fold, err.max())
+        assert np.array_equal(out[fold][0], out[fold][2])
+        assert rel_inf(out[fold][1], g["f64_grad"]) < 2e-4
+    assert np.all(np.abs(out[True][0] - out[False][0]) <= lnp_tol(out[False][0]))
