@@ -24,6 +24,9 @@ cudaError_t launch_scatter_params(const float *params, float *blob, const int32_
 TcContext *tc_build(const linna_model *m, std::string &why);
 void tc_destroy(TcContext *t);
 cudaError_t tc_launch_lnp(const linna_model *m, TcContext *t, const float *u, int64_t n, float *lnp, cudaStream_t stream);
+cudaError_t tc_launch_grad(const linna_model *m, TcContext *t, const float *u, int64_t n, float *lnp, float *grad,
+                           cudaStream_t stream);
+bool tc_has_grad(const TcContext *t);
 }  // namespace linna
 
 static thread_local std::string g_err;
@@ -185,25 +188,8 @@ static int rebuild(linna_model *m)
                lastop.kind == LINNA_OP_LINEAR && lastop.act == LINNA_ACT_NONE && m->ops.size() >= 2;
         if (fold) {
             const int K = lastop.in;
-            std::vector<double> T((size_t)n_out * K), A((size_t)n_out * K, 0.0), dvec(n_out), cf(n_out, 0.0);
-            for (int j = 0; j < n_out; ++j) {
-                const double sc = (double)m->sigma[j] * (double)m->y_std[j];
-                for (int k = 0; k < K; ++k) T[(size_t)j * K + k] = sc * (double)lastop.w[(size_t)j * K + k];
-                dvec[j] = (double)m->sigma[j] * ((double)m->y_std[j] * (double)lastop.b[j] + (double)m->y_mean[j]) -
-                          (double)m->data[j];
-            }
-            for (int j = 0; j < n_out; ++j)            // A[n][:] += L[j][n] * T[j][:]  (L lower triangular)
-                for (int n = 0; n <= j; ++n) {
-                    const double l = (double)m->quad[(size_t)j * n_out + n];
-                    if (l == 0.0) continue;
-                    double *a = &A[(size_t)n * K];
-                    const double *t = &T[(size_t)j * K];
-                    for (int k = 0; k < K; ++k) a[k] += l * t[k];
-                    cf[n] += l * dvec[j];
-                }
-            std::vector<float> Af((size_t)n_out * K), cff(n_out), csf(K, -1.0f / m->temperature);
-            for (size_t i = 0; i < Af.size(); ++i) Af[i] = (float)A[i];
-            for (int n = 0; n < n_out; ++n) cff[n] = (float)cf[n];
+            std::vector<float> Af, cff, csf(K, -1.0f / m->temperature);
+            linna_fold_tail(m, Af, cff);
             o_foldF = B.put_fwd(Af, n_out, K);
             o_foldB = B.put_bwd(Af, n_out, K);
             o_foldc = B.put(cff);
@@ -827,8 +813,9 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
     if (!m->prog_valid[pk]) return fail(LINNA_ESTATE, "likelihood constants not set (linna_model_set_likelihood)");
     CUDA_TRY(cudaSetDevice(m->device));
     if (m->have_last && m->last_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, m->last_done, 0));
-    // Large lnP batches go to the tensor-core (tcgen05) kernel; everything else stays on the FP32 FFMA kernel.
-    if (pk == PROG_LNP && !proto && m->path != 1 && !m->has_extra && !m->tc_failed &&
+    // Large lnP / lnP+gradient batches go to the tensor-core (tcgen05) kernel; everything else stays on the
+    // FP32 FFMA kernel.
+    if ((pk == PROG_LNP || pk == PROG_GRAD) && !proto && m->path != 1 && !m->has_extra && !m->tc_failed &&
         (m->path == 2 || n >= m->tc_min_rows)) {
         if (!m->tc) {
             std::string why;
@@ -838,8 +825,11 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
                 if (m->path == 2) return fail(LINNA_EINVAL, "tensor-core path unavailable: %s", why.c_str());
             }
         }
-        if (m->tc) {
-            CUDA_TRY(tc_launch_lnp(m, m->tc, in, n, lnp, stream));
+        if (m->tc && pk == PROG_GRAD && !tc_has_grad(m->tc)) {
+            if (m->path == 2) return fail(LINNA_EINVAL, "tensor-core gradient path needs the folded likelihood tail");
+        } else if (m->tc) {
+            if (pk == PROG_LNP) CUDA_TRY(tc_launch_lnp(m, m->tc, in, n, lnp, stream));
+            else CUDA_TRY(tc_launch_grad(m, m->tc, in, n, lnp, grad, stream));
             g_launches.fetch_add(1);
             CUDA_TRY(cudaEventRecord(m->last_done, stream));
             m->last_stream = stream, m->have_last = true;

@@ -79,3 +79,41 @@ struct linna_model {
     size_t d_in_cap = 0, d_out_cap = 0, d_lnp_cap = 0, d_grad_cap = 0;
 };
 
+
+// Folded tail of the likelihood: the last linear layer, the inverse output transform, the residual and
+// the Cholesky product are all affine in s (the last hidden activation):
+//   r = L^T (sigma*(y_std*(W s + b) + y_mean) - data) = Af s + cf ,  chi^2 = |r|^2
+// Af [n_out][K] and cf [n_out] are formed in float64 once (reference arithmetic: linna/nn.py:129,
+// linna/util.py:532-542, :457-458, :953-955).
+static inline bool linna_can_fold(const linna_model *m)
+{
+    if (m->ops.size() < 2) return false;
+    const OpHost &lastop = m->ops.back();
+    return m->fold_enabled && m->has_like && m->quad_kind == LINNA_QUAD_CHOL && !m->ypositive && !m->has_extra &&
+           lastop.kind == LINNA_OP_LINEAR && lastop.act == LINNA_ACT_NONE;
+}
+
+static inline void linna_fold_tail(const linna_model *m, std::vector<float> &Af, std::vector<float> &cff)
+{
+    const OpHost &lastop = m->ops.back();
+    const int K = lastop.in, n_out = m->n_out;
+    std::vector<double> T((size_t)n_out * K), A((size_t)n_out * K, 0.0), dvec(n_out), cf(n_out, 0.0);
+    for (int j = 0; j < n_out; ++j) {
+        const double sc = (double)m->sigma[j] * (double)m->y_std[j];
+        for (int k = 0; k < K; ++k) T[(size_t)j * K + k] = sc * (double)lastop.w[(size_t)j * K + k];
+        dvec[j] = (double)m->sigma[j] * ((double)m->y_std[j] * (double)lastop.b[j] + (double)m->y_mean[j]) -
+                  (double)m->data[j];
+    }
+    for (int j = 0; j < n_out; ++j)            // A[n][:] += L[j][n] * T[j][:]  (L lower triangular)
+        for (int n = 0; n <= j; ++n) {
+            const double l = (double)m->quad[(size_t)j * n_out + n];
+            if (l == 0.0) continue;
+            double *a = &A[(size_t)n * K];
+            const double *t = &T[(size_t)j * K];
+            for (int k = 0; k < K; ++k) a[k] += l * t[k];
+            cf[n] += l * dvec[j];
+        }
+    Af.resize((size_t)n_out * K), cff.resize(n_out);
+    for (size_t i = 0; i < Af.size(); ++i) Af[i] = (float)A[i];
+    for (int n = 0; n < n_out; ++n) cff[n] = (float)cf[n];
+}

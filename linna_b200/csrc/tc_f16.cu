@@ -1,0 +1,1066 @@
+// Tensor-core emulator-likelihood kernel for large walker batches (sm_100a: tcgen05 + TMEM + TMA).
+//
+// Same step program as the FFMA kernel (linna/nn.py:45-56, :110-133; linna/util.py:953-955, :990-1021), but
+// every GEMM  D[128 walkers][N] = A[128][K] . B[N][K]^T  runs on the 5th-generation tensor cores:
+//
+//   * split-fp16 product.  Every fp32 operand x is stored as two halves, hi = fp16(x), lo = fp16(x - hi)
+//     (22 significant bits; weights are pre-scaled by a power of two per step so that they sit in the
+//     middle of the fp16 range), and  D += A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  with exact fp16 x fp16
+//     products and fp32 accumulation in tensor memory.  kind::f16 runs at twice the TF32 rate and the
+//     operands are half as wide, so the three passes cost what 1.5 TF32 passes would.
+//   * two-level accumulation.  The tensor core truncates its fp32 accumulator on every tcgen05.mma
+//     (measured: a toward-zero bias of ~0.5 ulp per instruction), so every `seg_kc` k-chunks the partial
+//     tile is drained from tensor memory and added with round-to-nearest into fp32 REGISTER accumulators
+//     by the epilogue warps, while the MMA warp already fills the other TMEM buffer.
+//   * two walker tiles (X, Y: 2 x 128 rows) per CTA share every weight tile that TMA brings into
+//     shared memory: half the L2 weight traffic per walker, and twice the work per pipeline stage.
+//   * operands are K-major 64-byte-swizzled tiles filled by TMA (cp.async.bulk.tensor) from the packed
+//     hi/lo weights and from the row-major hi/lo activation arena of this CTA; layer outputs go back to the
+//     arena through a swizzled staging buffer and TMA stores.  The producer tracks, per tile, how many
+//     128-column output chunks have become visible, so the next layer starts on the first columns of an
+//     activation while the epilogue is still writing the last ones.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM allocator, warps 2 / 3 = TMA
+//     store issuers of tile X / Y (they also publish the chunks), warps 4-7 / 8-11 = epilogue of tile
+//     X / Y: every thread owns one walker (TMEM lane) and all 128 columns of a chunk, so the chi^2
+//     reduction, the relu masks of the backward pass and the final Jacobian need no cross-thread traffic
+//     at all.  setmaxnreg moves registers from the four service warps to the epilogue warps, whose 128
+//     fp32 accumulators per thread are the second accumulation level.
+//
+// Two programs: LNP (forward, chi^2) and GRAD (forward with saved relu masks, backward-data through every
+// layer with the transposed weights, prior-map Jacobian in the last epilogue).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "linna_host.hpp"
+
+namespace linna {
+
+constexpr int TF_M = 128;        // walkers per tile
+constexpr int TF_NC = 128;       // accumulator columns per chunk
+constexpr int TF_KC = 32;        // k-chunk in halves = one 64-byte swizzle row
+constexpr int TF_STAGES = 3;
+constexpr int TF_TILE_BYTES = TF_M * TF_KC * 2;                  // 8 KB operand tile
+constexpr int TF_STAGE_BYTES = 6 * TF_TILE_BYTES;                // A_x hi/lo, A_y hi/lo, B hi/lo = 48 KB
+constexpr int TF_BOX_BYTES = 128 * 64 * 2;                       // staging box: 128 rows x 64 halves = 16 KB
+constexpr int TF_STG_BYTES = 2 * TF_BOX_BYTES;                   // hi + lo per tile
+constexpr int TF_SMEM_BYTES = TF_STAGES * TF_STAGE_BYTES + 2 * TF_STG_BYTES + 1024;
+constexpr int TF_THREADS = 384;  // TMA, MMA, 2 store warps + 2 x 4 epilogue warps
+constexpr int TF_MAX_STEPS = 48;
+
+enum TfEpi : int32_t { TF_ACT = 0, TF_HEAD = 1, TF_CHI2 = 2, TF_BWD = 3, TF_GRADOUT = 4 };
+enum TfFlags : int32_t { TFF_RELU = 1, TFF_SAVE_MASK = 2, TFF_APPLY_MASK = 4, TFF_TRI = 8 };
+enum TfVariant : int32_t { TFV_ACT = 0, TFV_ACT_SAVE, TFV_CHI2, TFV_CHI2_STORE, TFV_BWD, TFV_HEAD, TFV_HEAD_EXP, TFV_GRADOUT };
+
+struct TfStep {
+    int32_t nphase;
+    int32_t src[2];       // arena column of the hi copy of this phase's A operand; lo copy at + lo_off
+    int32_t K[2];
+    int32_t mapB[2];      // tensor-map index of the hi weight operand; lo = + 1
+    int32_t src_pub[2];   // output chunks published (per tile pass) before the producer of src's first chunk
+    int32_t src_nch[2];   // number of chunks the producer of src publishes
+    int32_t N;
+    int32_t dst;          // arena column of the output (hi), -1: none
+    int32_t dst_pad;      // output width rounded up to 64 (pad columns are written as zeros)
+    int32_t epi, flags;
+    int32_t mask_word;    // first 32-bit word of this layer's relu bits inside a mask row
+    float inv_scale;      // 2^-s of the weight pre-scale (and any uniform factor folded in)
+    float clampv;         // lower clamp of the output: 0 (relu) or -inf
+    int32_t variant;      // TfVariant: which specialised chunk epilogue runs
+    const float *bias;    // [dst_pad] effective bias (zero-padded), or nullptr
+    const float *vscale;  // [dst_pad] per-column scale (HEAD), or nullptr
+    const float *sub;     // [dst_pad] data/sigma (HEAD with ypositive), or nullptr
+};
+
+struct TfProgram {
+    int32_t n_steps;
+    int32_t total_pub;     // chunks published per tile pass (prologue included)
+    int32_t in_col;        // arena column of xhat
+    int32_t lo_off;        // column offset from a hi copy to its lo copy
+    int32_t seg_kc;        // k-chunks accumulated in tensor memory between two drains
+    int32_t mask_words;    // 32-bit words per mask row
+    int32_t pad_[2];
+    TfStep steps[TF_MAX_STEPS];
+};
+
+struct TfArgs {
+    const TfProgram *prog;
+    const CUtensorMap *maps;  // [0] arena load, [1] arena store, then hi/lo per weight operand
+    Consts c;
+    const float *in;
+    float *lnp;
+    float *grad;
+    uint32_t *masks;
+    int64_t n;
+    int *err;
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ void tf_die(int *err, int code)
+{
+    if (err) atomicExch(err, code);
+    __threadfence_system();
+    __trap();
+}
+// Bounded wait: a protocol bug must trap (and report) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *err, int code)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 2000000000LL) tf_die(err, code);
+    }
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void *smem_src, const CUtensorMap *map, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile, 64-byte swizzle: rows are 64 B apart, 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t make_sdesc64(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);  // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                  // leading byte offset (unused with swizzle)
+    d |= (uint64_t)(512 >> 4) << 32;         // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+    d |= (uint64_t)4 << 61;                  // SWIZZLE_64B
+    return d;
+}
+// kind::f16 with fp16 inputs, fp32 accumulate, A and B K-major, M = 128
+__device__ __forceinline__ uint32_t make_idesc_f16(int n)
+{
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TF_M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi); two values per call (packed half2 words)
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo)
+{
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+__device__ __forceinline__ float tf_prior_map(float u, int kind, float scale, float shift)
+{
+    float t = u;
+    if (kind == LINNA_PRIOR_FLAT) t = 0.5f * (1.0f + erff(u / 1.41421356237309515f));  // gauss2unif, util.py:300
+    return t * scale + shift;
+}
+// stages (k-chunks over all phases) of output chunk n0 of a step
+__device__ __forceinline__ int tf_chunk_stages(const TfStep &st, int n0)
+{
+    int s = 0;
+    const int k0 = (st.flags & TFF_TRI) ? n0 / TF_KC : 0;
+    for (int p = 0; p < st.nphase; ++p) s += (st.K[p] + TF_KC - 1) / TF_KC - k0;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------ chunk epilogue
+struct TfEpiCtx {
+    uint8_t *my_hi, *my_lo;     // this thread's 128-byte rows of the hi / lo staging boxes
+    uint64_t *sfree, *sfull;
+    uint32_t *mask_row;
+    int *err;
+    double chi;
+    uint32_t sidx;              // staging boxes handed to the store warp so far
+    int sw;                     // 128-byte swizzle phase of this row
+};
+
+// One 128-column chunk: v = acc*scale + bias (clamped below for relu), optional exp / mask / chi^2, split into
+// fp16 hi/lo, written to the swizzled staging box that the store warp sends to the arena.  All flags are
+// compile-time so that each kind of step runs ~6 instructions per element out of a few KB of code.
+// Pad columns (>= N) come out as exact zeros: their accumulators are zero (TMA zero-fills the missing
+// weight rows) and the bias / scale vectors are zero-padded.
+template <bool BIAS, bool VSCALE, bool EXPY, bool SAVE, bool APPLY, bool CHI, bool STORE>
+__device__ __forceinline__ void tf_chunk_epilogue(const float (&racc)[128], const TfStep &st, int n0, int ch, TfEpiCtx &x)
+{
+    uint32_t mw[4] = {0u, 0u, 0u, 0u};
+    if (APPLY) {
+        if (st.flags & TFF_APPLY_MASK) {
+            const uint4 m4 = *reinterpret_cast<const uint4 *>(x.mask_row + st.mask_word + 4 * ch);
+            mw[0] = m4.x, mw[1] = m4.y, mw[2] = m4.z, mw[3] = m4.w;
+        } else {
+            mw[0] = mw[1] = mw[2] = mw[3] = 0xffffffffu;
+        }
+    }
+    const float clampv = st.clampv, inv_scale = st.inv_scale;
+    float chi_f = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int col0 = n0 + 64 * h;
+        const bool store = STORE && col0 < st.dst_pad;
+        if (!store && !(CHI && col0 < st.N)) continue;
+        if (store) mbar_wait(x.sfree, (x.sidx & 1) ^ 1, x.err, 7);   // staging box free again
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int cb = col0 + 8 * j;
+            float b[8], s[8], v[8];
+            if (BIAS) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(st.bias + cb));
+                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(st.bias + cb + 4));
+                b[0] = b0.x, b[1] = b0.y, b[2] = b0.z, b[3] = b0.w, b[4] = b1.x, b[5] = b1.y, b[6] = b1.z, b[7] = b1.w;
+            }
+            if (VSCALE) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4 *>(st.vscale + cb));
+                const float4 s1 = __ldg(reinterpret_cast<const float4 *>(st.vscale + cb + 4));
+                s[0] = s0.x, s[1] = s0.y, s[2] = s0.z, s[3] = s0.w, s[4] = s1.x, s[5] = s1.y, s[6] = s1.z, s[7] = s1.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int li = 64 * h + 8 * j + e;   // column inside the chunk
+                float y = fmaf(racc[li], VSCALE ? s[e] : inv_scale, BIAS ? b[e] : 0.f);
+                if (EXPY) y = cb + e < st.N ? expf(y) - __ldg(st.sub + cb + e) : 0.f;
+                y = fmaxf(y, clampv);
+                if (APPLY) y = ((mw[li >> 5] >> (li & 31)) & 1u) ? y : 0.f;
+                if (SAVE) mw[li >> 5] |= (y > 0.f ? 1u : 0u) << (li & 31);
+                if (CHI) chi_f = fmaf(y, y, chi_f);
+                v[e] = y;
+            }
+            if (store) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) split2(v[e], v[e + 1], hw[e >> 1], lw[e >> 1]);
+                const int o = (j ^ x.sw) << 4;
+                *reinterpret_cast<uint4 *>(x.my_hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4 *>(x.my_lo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+        }
+        if (store) {
+            fence_async_smem();
+            mbar_arrive(x.sfull);
+            ++x.sidx;
+        }
+    }
+    if (SAVE) *reinterpret_cast<uint4 *>(x.mask_row + st.mask_word + 4 * ch) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+    if (CHI) x.chi += (double)chi_f;
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[TF_STAGES], empty_bar[TF_STAGES], pfull_bar[2], pempty_bar[2];
+    __shared__ __align__(8) uint64_t sfull_bar[2], sfree_bar[2];   // staging buffer of tile X / Y: written / read out
+    __shared__ uint32_t tmem_slot;
+    __shared__ uint32_t ready_cnt[2];
+    __shared__ TfStep s_steps[TF_MAX_STEPS];
+
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *stg_all = smem + TF_STAGES * TF_STAGE_BYTES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const TfProgram *prog = args.prog;
+    const int n_steps = prog->n_steps;
+    const int lo_off = prog->lo_off;
+    const int seg_kc = prog->seg_kc;
+    const uint32_t total_pub = (uint32_t)prog->total_pub;
+    const Consts &c = args.c;
+    const CUtensorMap *maps = args.maps;
+
+    for (int i = tid; i < n_steps * (int)(sizeof(TfStep) / 4); i += TF_THREADS)
+        reinterpret_cast<uint32_t *>(s_steps)[i] = reinterpret_cast<const uint32_t *>(prog->steps)[i];
+    if (tid == 0) {
+        for (int s = 0; s < TF_STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
+        for (int b = 0; b < 2; ++b) mbar_init(&pfull_bar[b], 1), mbar_init(&pempty_bar[b], 256);
+        for (int b = 0; b < 2; ++b) mbar_init(&sfull_bar[b], 128), mbar_init(&sfree_bar[b], 1);
+        ready_cnt[0] = ready_cnt[1] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    const int64_t npairs = (args.n + 2 * TF_M - 1) / (2 * TF_M);
+    const int arena_row0 = blockIdx.x * 2 * TF_M;   // this CTA's rows of the activation arena (X then Y)
+
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(56));
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t ph = 0, seen0 = 0, seen1 = 0, pub0 = 0;
+            for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, pub0 += total_pub) {
+                for (int si = 0; si < n_steps; ++si) {
+                    const TfStep &st = s_steps[si];
+                    for (int n0 = 0; n0 < st.N; n0 += TF_NC) {
+                        const int k0 = (st.flags & TFF_TRI) ? n0 / TF_KC : 0;   // L^T: B[n][k] = 0 for k < n
+                        for (int p = 0; p < st.nphase; ++p) {
+                            const int nk = (st.K[p] + TF_KC - 1) / TF_KC;
+                            const CUtensorMap *mb = maps + st.mapB[p];
+                            for (int kc = k0; kc < nk; ++kc) {
+                                mbar_wait(&empty_bar[stage], ph ^ 1, args.err, 1);
+                                uint8_t *sb = smem + stage * TF_STAGE_BYTES;
+                                mbar_expect_tx(&full_bar[stage], TF_STAGE_BYTES);
+                                tma_load_2d(sb + 4 * TF_TILE_BYTES, mb, &full_bar[stage], kc * TF_KC, n0);
+                                tma_load_2d(sb + 5 * TF_TILE_BYTES, mb + 1, &full_bar[stage], kc * TF_KC, n0);
+                                // the activations this k-chunk reads: wait until their producer chunk is visible
+                                int chunk = (kc * TF_KC + TF_KC - 1) >> 7;
+                                if (chunk > st.src_nch[p] - 1) chunk = st.src_nch[p] - 1;
+                                const uint32_t need = pub0 + (uint32_t)st.src_pub[p] + (uint32_t)chunk + 1u;
+                                if (seen0 < need || seen1 < need) {
+                                    const long long t0 = clock64();
+                                    while ((seen0 = ld_acquire_u32(&ready_cnt[0])) < need || (seen1 = ld_acquire_u32(&ready_cnt[1])) < need) {
+                                        __nanosleep(64);
+                                        if (clock64() - t0 > 2000000000LL) tf_die(args.err, 2);
+                                    }
+                                    fence_async_all();
+                                }
+                                const int ca = st.src[p] + kc * TF_KC;
+                                tma_load_2d(sb, maps, &full_bar[stage], ca, arena_row0);
+                                tma_load_2d(sb + TF_TILE_BYTES, maps, &full_bar[stage], ca + lo_off, arena_row0);
+                                tma_load_2d(sb + 2 * TF_TILE_BYTES, maps, &full_bar[stage], ca, arena_row0 + TF_M);
+                                tma_load_2d(sb + 3 * TF_TILE_BYTES, maps, &full_bar[stage], ca + lo_off, arena_row0 + TF_M);
+                                if (++stage == TF_STAGES) stage = 0, ph ^= 1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t ph = 0, g = 0;
+            for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+                for (int si = 0; si < n_steps; ++si) {
+                    const TfStep &st = s_steps[si];
+                    for (int n0 = 0; n0 < st.N; n0 += TF_NC) {
+                        const int nvalid = st.N - n0 < TF_NC ? st.N - n0 : TF_NC;
+                        // N rounded up to the 32 columns one tcgen05.ld drains: the extra rows of B are TMA zero fill
+                        const uint32_t idesc = make_idesc_f16((nvalid + 31) & ~31);
+                        const int total = tf_chunk_stages(st, n0);
+                        const int k0 = (st.flags & TFF_TRI) ? n0 / TF_KC : 0;
+                        int in_seg = 0, done = 0;
+                        uint32_t dcol = 0;
+                        for (int p = 0; p < st.nphase; ++p) {
+                            const int nk = (st.K[p] + TF_KC - 1) / TF_KC;
+                            for (int kc = k0; kc < nk; ++kc) {
+                                if (in_seg == 0) {   // open a fresh pair of accumulator buffers (one per tile)
+                                    const int buf = g & 1;
+                                    mbar_wait(&pempty_bar[buf], ((g >> 1) & 1) ^ 1, args.err, 3);
+                                    tc_fence_after();
+                                    dcol = tmem_base + buf * TF_NC;
+                                }
+                                mbar_wait(&full_bar[stage], ph, args.err, 4);
+                                tc_fence_after();
+                                const uint32_t sb = smem_u32(smem + stage * TF_STAGE_BYTES);
+                                const uint32_t b_hi = sb + 4 * TF_TILE_BYTES, b_lo = sb + 5 * TF_TILE_BYTES;
+#pragma unroll
+                                for (int t = 0; t < 2; ++t) {
+                                    const uint32_t a_hi = sb + (2 * t) * TF_TILE_BYTES, a_lo = a_hi + TF_TILE_BYTES;
+                                    const uint32_t d = dcol + t * 2 * TF_NC;
+#pragma unroll
+                                    for (int ks = 0; ks < 2; ++ks) {
+                                        const uint32_t o = ks * 32;   // 16 halves = 32 bytes along K inside the swizzle row
+                                        umma_f16(d, make_sdesc64(a_lo + o), make_sdesc64(b_hi + o), idesc, (in_seg | ks) ? 1u : 0u);
+                                        umma_f16(d, make_sdesc64(a_hi + o), make_sdesc64(b_lo + o), idesc, 1u);
+                                        umma_f16(d, make_sdesc64(a_hi + o), make_sdesc64(b_hi + o), idesc, 1u);
+                                    }
+                                }
+                                umma_commit(&empty_bar[stage]);   // frees the smem stage when these MMAs retire
+                                if (++stage == TF_STAGES) stage = 0, ph ^= 1;
+                                ++done;
+                                if (++in_seg == seg_kc || done == total) {
+                                    umma_commit(&pfull_bar[g & 1]);   // partial tiles complete -> epilogue drains them
+                                    ++g;
+                                    in_seg = 0;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // =============================== TMA store issuers (tile X / Y) ===============================
+        if (lane == 0) {
+            const int t = warp - 2;
+            const int arow = arena_row0 + t * TF_M;
+            uint8_t *stg_hi = stg_all + t * TF_STG_BYTES, *stg_lo = stg_hi + TF_BOX_BYTES;
+            const CUtensorMap *map_st = maps + 1;
+            uint32_t sidx = 0, pub = 0;
+            auto store_box = [&](int col) {
+                mbar_wait(&sfull_bar[t], sidx & 1, args.err, 6);      // the 128 epilogue threads have written the box
+                tma_store_2d(stg_hi, map_st, col, arow);
+                tma_store_2d(stg_lo, map_st, col + lo_off, arow);
+                bulk_commit();
+                bulk_wait_read();                                      // staging read out: hand it back
+                mbar_arrive(&sfree_bar[t]);
+                ++sidx;
+            };
+            auto publish = [&]() {
+                bulk_wait_all();                                       // the stores have landed
+                fence_async_all();
+                st_release_u32(&ready_cnt[t], ++pub);
+            };
+            for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+                store_box(prog->in_col);
+                publish();
+                for (int si = 0; si < n_steps; ++si) {
+                    const TfStep &st = s_steps[si];
+                    if (st.dst < 0) continue;
+                    for (int n0 = 0; n0 < st.N; n0 += TF_NC) {
+                        store_box(st.dst + n0);
+                        if (n0 + 64 < st.dst_pad) store_box(st.dst + n0 + 64);
+                        publish();
+                    }
+                }
+            }
+        }
+    }
+    } else {
+        // =============================== epilogue warps ===============================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(216));
+        TfEpiCtx x;
+        const int t = (warp - 4) >> 2;                   // tile: 0 = X, 1 = Y
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;                   // TMEM lane == walker of the tile
+        const uint32_t tmem_tile = tmem_base + ((uint32_t)(q * 32) << 16) + t * 2 * TF_NC;
+        const int arow = arena_row0 + t * TF_M;          // first arena row of this tile
+        x.my_hi = stg_all + t * TF_STG_BYTES + row * 128, x.my_lo = x.my_hi + TF_BOX_BYTES;
+        x.sw = row & 7;
+        x.sfree = &sfree_bar[t], x.sfull = &sfull_bar[t];
+        x.sidx = 0;
+        x.mask_row = args.masks ? args.masks + (size_t)(arow + row) * prog->mask_words : nullptr;
+        x.err = args.err;
+        x.chi = 0.0;
+        const int n_in = c.n_in;
+        uint32_t g = 0;
+
+        for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+            const int64_t grow = (pair * 2 + t) * TF_M + row;
+            const bool valid = grow < args.n;
+            // ---- prologue: u -> theta -> xhat (util.py:323-347, :483-497), split, stage, TMA store
+            float lnprior = 0.f;
+            {
+                mbar_wait(x.sfree, (x.sidx & 1) ^ 1, args.err, 7);
+                const float *u = args.in + grow * n_in;
+#pragma unroll 1
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t hw[4], lw[4];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        float xv[2];
+#pragma unroll
+                        for (int z = 0; z < 2; ++z) {
+                            const int i = 8 * j + e + z;
+                            float xh = 0.f;
+                            if (i < n_in && valid) {
+                                const float uu = __ldg(u + i);
+                                lnprior = fmaf(uu, uu, lnprior);
+                                float th = tf_prior_map(uu, c.prior_kind[i], c.prior_scale[i], c.prior_shift[i]);
+                                if (c.log10_flag && c.log10_flag[i]) th = log10f(th);
+                                xh = (th - c.x_mean[i]) / c.x_std[i];
+                            }
+                            xv[z] = xh;
+                        }
+                        split2(xv[0], xv[1], hw[e >> 1], lw[e >> 1]);
+                    }
+                    const int o = (j ^ x.sw) << 4;
+                    *reinterpret_cast<uint4 *>(x.my_hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4 *>(x.my_lo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+                lnprior *= -0.5f;                                                    // util.py:1165
+                fence_async_smem();
+                mbar_arrive(x.sfull);
+                ++x.sidx;
+            }
+            x.chi = 0.0;
+            for (int si = 0; si < n_steps; ++si) {
+                const TfStep &st = s_steps[si];
+                const int nch = (st.N + TF_NC - 1) / TF_NC;
+                for (int ch = 0; ch < nch; ++ch) {
+                    const int n0 = ch * TF_NC;
+                    const int nvalid = st.N - n0 < TF_NC ? st.N - n0 : TF_NC;
+                    const int nmma = (nvalid + 31) & ~31;
+                    float racc[128];
+#pragma unroll
+                    for (int j = 0; j < 128; ++j) racc[j] = 0.f;
+                    const int nseg = (tf_chunk_stages(st, n0) + seg_kc - 1) / seg_kc;
+#pragma unroll 1
+                    for (int sg = 0; sg < nseg; ++sg) {
+                        const int buf = g & 1;
+                        mbar_wait(&pfull_bar[buf], (g >> 1) & 1, args.err, 5);
+                        tc_fence_after();
+#pragma unroll
+                        for (int cb = 0; cb < 128; cb += 32) {
+                            if (cb < nmma) {
+                                uint32_t r[32];
+                                tmem_ld32(tmem_tile + buf * TF_NC + cb, r);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) racc[cb + j] += __uint_as_float(r[j]);
+                            }
+                        }
+                        tc_fence_before();
+                        mbar_arrive(&pempty_bar[buf]);
+                        ++g;
+                    }
+                    // ---------------- chunk epilogue (one compact specialisation per kind of step)
+                    switch (st.variant) {
+                    case TFV_ACT: tf_chunk_epilogue<true, false, false, false, false, false, true>(racc, st, n0, ch, x); break;
+                    case TFV_ACT_SAVE: tf_chunk_epilogue<true, false, false, true, false, false, true>(racc, st, n0, ch, x); break;
+                    case TFV_CHI2: tf_chunk_epilogue<true, false, false, false, false, true, false>(racc, st, n0, ch, x); break;
+                    case TFV_CHI2_STORE: tf_chunk_epilogue<true, false, false, false, false, true, true>(racc, st, n0, ch, x); break;
+                    case TFV_BWD: tf_chunk_epilogue<false, false, false, false, true, false, true>(racc, st, n0, ch, x); break;
+                    case TFV_HEAD: tf_chunk_epilogue<true, true, false, false, false, false, true>(racc, st, n0, ch, x); break;
+                    case TFV_HEAD_EXP: tf_chunk_epilogue<true, true, true, false, false, false, true>(racc, st, n0, ch, x); break;
+                    default: {
+                        // TFV_GRADOUT: chain through xhat = (theta' - mean)/std, theta' = log10(theta), theta = prior(u).
+                        // The accumulators go through this thread's own staging row so that the loop stays rolled.
+                        mbar_wait(x.sfree, (x.sidx & 1) ^ 1, args.err, 7);
+                        float *scr_a = reinterpret_cast<float *>(x.my_hi), *scr_b = reinterpret_cast<float *>(x.my_lo);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            *reinterpret_cast<float4 *>(scr_a + i) = make_float4(racc[i], racc[i + 1], racc[i + 2], racc[i + 3]);
+                            *reinterpret_cast<float4 *>(scr_b + i) = make_float4(racc[32 + i], racc[33 + i], racc[34 + i], racc[35 + i]);
+                        }
+                        if (valid) {
+                            const float *u = args.in + grow * n_in;
+                            float *gout = args.grad + grow * n_in;
+#pragma unroll 1
+                            for (int i = 0; i < n_in; ++i) {
+                                const float uu = __ldg(u + i);
+                                const int kind = c.prior_kind[i];
+                                const float ps = c.prior_scale[i];
+                                float gx = (i < 32 ? scr_a[i] : scr_b[i - 32]) * st.inv_scale / c.x_std[i];
+                                if (c.log10_flag && c.log10_flag[i])
+                                    gx /= (tf_prior_map(uu, kind, ps, c.prior_shift[i]) * 2.30258509299404568f);
+                                float jac = ps;
+                                if (kind == LINNA_PRIOR_FLAT) jac *= 0.398942280401432678f * expf(-0.5f * uu * uu);
+                                gout[i] = gx * jac - uu;
+                            }
+                        }
+                    } break;
+                    }
+                }
+            }
+            if (valid && args.lnp) {
+                float l = (float)(-0.5 * x.chi) * c.inv_T + lnprior;                 // util.py:1013
+                if (l != l) l = -INFINITY;                                          // util.py:1015-1016
+                args.lnp[grow] = l;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcContext {
+    __half *wblob = nullptr;      // packed hi/lo weight operands
+    float *fblob = nullptr;       // effective biases
+    __half *arena = nullptr;
+    uint32_t *masks = nullptr;
+    CUtensorMap *maps_dev = nullptr;
+    TfProgram *prog_dev = nullptr;   // [0] LNP, [1] GRAD
+    int *err_dev = nullptr;
+    bool has_grad = false;
+    int grid = 0;
+    std::string error;
+};
+
+static inline int pad64(int n) { return (n + 63) & ~63; }
+static inline int pad8(int n) { return (n + 7) & ~7; }
+
+// k-chunks (of 32) accumulated in tensor memory between two promotions to the register accumulators
+static int tc_seg_kc()
+{
+    const char *e = getenv("LINNA_TC_SEG_KC");
+    int v = e ? atoi(e) : 2;
+    return v > 0 ? v : 2;
+}
+
+void tc_destroy(TcContext *t)
+{
+    if (!t) return;
+    if (t->wblob) cudaFree(t->wblob);
+    if (t->fblob) cudaFree(t->fblob);
+    if (t->arena) cudaFree(t->arena);
+    if (t->masks) cudaFree(t->masks);
+    if (t->maps_dev) cudaFree(t->maps_dev);
+    if (t->prog_dev) cudaFree(t->prog_dev);
+    if (t->err_dev) cudaFree(t->err_dev);
+    delete t;
+}
+
+namespace {
+struct MatSrc {
+    const float *W;   // source matrix
+    int N, K;         // operand shape: B[N][K]
+    bool transpose;   // false: W is [N][K]; true: W is [K][N]
+    float premul;
+};
+struct Packer {
+    std::vector<__half> w;       // weight blob (halves)
+    std::vector<float> f;        // float blob (biases)
+    struct Mat { size_t hi, lo; int N, K, ldk; };
+    std::vector<Mat> mats;
+    size_t walloc(size_t n) { size_t o = (w.size() + 127) / 128 * 128; w.resize(o + n, __float2half_rn(0.f)); return o; }
+    size_t fput(const std::vector<float> &v, int padded)
+    {
+        size_t o = (f.size() + 63) / 64 * 64;
+        f.resize(o + padded, 0.f);
+        std::copy(v.begin(), v.end(), f.begin() + o);
+        return o;
+    }
+    static float at(const MatSrc &s, int n, int k)
+    {
+        return s.premul * (s.transpose ? s.W[(size_t)k * s.N + n] : s.W[(size_t)n * s.K + k]);
+    }
+    // power-of-two pre-scale that puts the largest |w| of a step's operands into [256, 512)
+    static int pick_shift(const std::vector<MatSrc> &srcs)
+    {
+        float mx = 0.f;
+        for (const MatSrc &s : srcs)
+            for (int n = 0; n < s.N; ++n)
+                for (int k = 0; k < s.K; ++k) {
+                    const float a = fabsf(at(s, n, k));
+                    if (a > mx && std::isfinite(a)) mx = a;
+                }
+        if (mx <= 0.f) return 0;
+        int e;
+        frexpf(mx, &e);            // mx = f * 2^e, f in [0.5, 1)
+        int s = 9 - e;             // mx * 2^s in [256, 512)
+        return std::max(-100, std::min(100, s));
+    }
+    int put(const MatSrc &s, int shift)
+    {
+        Mat mt;
+        mt.N = s.N, mt.K = s.K, mt.ldk = pad8(s.K);
+        mt.hi = walloc((size_t)s.N * mt.ldk), mt.lo = walloc((size_t)s.N * mt.ldk);
+        const float sc = ldexpf(1.f, shift);
+        for (int n = 0; n < s.N; ++n)
+            for (int k = 0; k < s.K; ++k) {
+                const float x = at(s, n, k) * sc;
+                const __half hi = __float2half_rn(x);
+                w[mt.hi + (size_t)n * mt.ldk + k] = hi;
+                w[mt.lo + (size_t)n * mt.ldk + k] = __float2half_rn(x - __half2float(hi));
+            }
+        mats.push_back(mt);
+        return (int)mats.size() - 1;
+    }
+};
+}  // namespace
+
+// Build the tensor-core context of a model that already has likelihood constants.  Returns nullptr and
+// fills `why` when the shape is unsupported or the driver lacks the tensor-map entry point.
+TcContext *tc_build(const linna_model *m, std::string &why)
+{
+    if (m->has_extra) { why = "extra linear branch not supported on the tensor-core path"; return nullptr; }
+    if (!m->has_like) { why = "likelihood not set"; return nullptr; }
+    if (m->quad_kind != LINNA_QUAD_CHOL) { why = "tensor-core path needs the Cholesky form of the quadratic"; return nullptr; }
+    if (m->n_in > 64) { why = "tensor-core path supports at most 64 input parameters"; return nullptr; }
+    EncodeTiledFn encode = nullptr;
+    {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+            qres != cudaDriverEntryPointSuccess) {
+            why = "cuTensorMapEncodeTiled not available";
+            return nullptr;
+        }
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const int n_out = m->n_out;
+    const int nops = (int)m->ops.size();
+    const bool fold = linna_can_fold(m);
+    std::vector<float> Af, cf;
+    if (fold) linna_fold_tail(m, Af, cf);
+    for (const OpHost &op : m->ops)
+        if (op.kind != LINNA_OP_LINEAR && !op.has_ws) { why = "identity skip not supported on the tensor-core path"; return nullptr; }
+    if (m->ops.empty() || m->ops.back().kind != LINNA_OP_LINEAR || m->ops.back().act != LINNA_ACT_NONE) {
+        why = "tensor-core path needs a plain linear last layer";
+        return nullptr;
+    }
+
+    Packer P;
+    // arena slots: X = xhat, A/B = ping-pong layer outputs, H = res-block hidden
+    enum { SLOT_X = 0, SLOT_A = 1, SLOT_B = 2, SLOT_H = 3, NSLOT = 4 };
+    int slot_w[NSLOT] = {64, 64, 64, 64};
+    struct BiasRef { int prog, step, what; size_t off; };   // what: 0 bias, 1 vscale, 2 sub
+    std::vector<BiasRef> bias_refs;
+    std::vector<float> sigL;   // (diag(sigma) L) for the unfolded chi^2
+    if (!fold) {
+        sigL.resize((size_t)n_out * n_out);
+        for (int k = 0; k < n_out; ++k)
+            for (int n = 0; n < n_out; ++n) sigL[(size_t)k * n_out + n] = m->sigma[k] * m->quad[(size_t)k * n_out + n];
+    }
+
+    TfProgram pgs[2];
+    const int seg_kc = tc_seg_kc();
+    int mask_words_total = 0;
+    bool has_grad = fold;   // the backward program is built on the folded tail only
+    for (int pk = 0; pk < 2; ++pk) {
+        TfProgram &pg = pgs[pk];
+        memset(&pg, 0, sizeof pg);
+        if (pk == 1 && !has_grad) break;
+        const bool grad = pk == 1;
+        int ns = 0, pubs = 1;   // the prologue publishes chunk 0
+        int slot_pub[NSLOT] = {0, 0, 0, 0}, slot_nch[NSLOT] = {1, 1, 1, 1};
+        int mask_words = 0;
+        std::vector<int> mask_y(nops, -1), mask_h(nops, -1);
+        bool overflow = false;
+        auto new_step = [&]() -> TfStep & {
+            if (ns >= TF_MAX_STEPS) { overflow = true; ns = TF_MAX_STEPS - 1; }
+            TfStep &s = pg.steps[ns++];
+            memset(&s, 0, sizeof s);
+            s.nphase = 1, s.inv_scale = 1.f, s.dst = -1, s.mask_word = 0;
+            return s;
+        };
+        // src slots are stored in s.src[] as slot ids first and turned into columns once the widths are known
+        auto set_phase = [&](TfStep &s, int p, int slot, const MatSrc &ms, int shift) {
+            s.src[p] = slot, s.K[p] = ms.K, s.mapB[p] = 2 + 2 * P.put(ms, shift);
+            s.src_pub[p] = slot_pub[slot], s.src_nch[p] = slot_nch[slot];
+        };
+        auto set_dst = [&](TfStep &s, int slot) {
+            s.dst = slot, s.dst_pad = pad64(s.N);
+            slot_w[slot] = std::max(slot_w[slot], s.dst_pad);
+            slot_pub[slot] = pubs, slot_nch[slot] = (s.N + TF_NC - 1) / TF_NC;
+            pubs += slot_nch[slot];
+        };
+        auto set_bias = [&](const std::vector<float> &b, float scale, int N) {
+            std::vector<float> e(N, 0.f);
+            for (size_t i = 0; i < b.size() && (int)i < N; ++i) e[i] = scale * b[i];
+            bias_refs.push_back({pk, ns - 1, 0, P.fput(e, pad64(N) + 64)});
+        };
+        // HEAD: y = yhat*y_std + y_mean (exp) ; m = y*sigma ; d = m - data (util.py:532-542, :457-458), handed on
+        // as d/sigma = y - data/sigma so that it stays in the fp16 range whatever the units are.  Without exp the
+        // whole map is one per-column affine of the accumulator.
+        auto set_head = [&](const std::vector<float> &b, float scale, int N, float inv_scale) {
+            std::vector<float> vs(N), hb(N), sub(N);
+            for (int i = 0; i < N; ++i) {
+                const double dos = (double)m->data[i] / (double)m->sigma[i];
+                vs[i] = inv_scale * m->y_std[i];
+                hb[i] = (float)((double)scale * b[i] * m->y_std[i] + m->y_mean[i] - (m->ypositive ? 0.0 : dos));
+                sub[i] = (float)dos;
+            }
+            bias_refs.push_back({pk, ns - 1, 0, P.fput(hb, pad64(N) + 64)});
+            bias_refs.push_back({pk, ns - 1, 1, P.fput(vs, pad64(N) + 64)});
+            bias_refs.push_back({pk, ns - 1, 2, P.fput(sub, pad64(N) + 64)});
+        };
+        auto new_mask = [&](int N) { int o = mask_words; mask_words += 4 * ((N + TF_NC - 1) / TF_NC); return o; };
+        auto other = [&](int b) { return b == SLOT_A ? SLOT_B : SLOT_A; };
+        int cur = SLOT_X;
+        // ------------------------------ forward
+        for (int i = 0; i < nops; ++i) {
+            const OpHost &op = m->ops[i];
+            const bool last = i + 1 == nops;
+            if (last && fold) break;
+            if (op.kind == LINNA_OP_LINEAR) {
+                TfStep &s = new_step();
+                MatSrc ms{op.w.data(), op.out, op.in, false, 1.f};
+                const int sh = Packer::pick_shift({ms});
+                set_phase(s, 0, cur, ms, sh);
+                s.N = op.out, s.inv_scale = ldexpf(1.f, -sh);
+                if (op.act == LINNA_ACT_RELU) {
+                    s.flags |= TFF_RELU;
+                    if (grad) s.flags |= TFF_SAVE_MASK, s.mask_word = mask_y[i] = new_mask(op.out);
+                }
+                s.epi = last ? TF_HEAD : TF_ACT;
+                set_dst(s, other(cur));
+                if (last) set_head(op.b, 1.f, op.out, s.inv_scale);
+                else set_bias(op.b, 1.f, op.out);
+                cur = s.dst;
+            } else {
+                TfStep &hs = new_step();
+                MatSrc m1{op.w.data(), op.mid, op.in, false, 1.f};
+                const int sh1 = Packer::pick_shift({m1});
+                set_phase(hs, 0, cur, m1, sh1);
+                hs.N = op.mid, hs.inv_scale = ldexpf(1.f, -sh1), hs.flags = TFF_RELU, hs.epi = TF_ACT;
+                if (grad) hs.flags |= TFF_SAVE_MASK, hs.mask_word = mask_h[i] = new_mask(op.mid);
+                set_dst(hs, SLOT_H);
+                set_bias(op.b, 1.f, op.mid);
+                // y = relu(alpha*(W2 h + b2) + Ws x): the long skip product first, so that the MMAs do not
+                // wait for the epilogue of h
+                TfStep &ys = new_step();
+                MatSrc m3{op.ws.data(), op.out, op.in, false, 1.f};
+                MatSrc m2{op.w2.data(), op.out, op.mid, false, op.alpha};
+                const int sh = Packer::pick_shift({m2, m3});
+                ys.nphase = 2;
+                set_phase(ys, 0, cur, m3, sh);
+                set_phase(ys, 1, SLOT_H, m2, sh);
+                ys.N = op.out, ys.inv_scale = ldexpf(1.f, -sh), ys.flags = TFF_RELU, ys.epi = TF_ACT;
+                if (grad) ys.flags |= TFF_SAVE_MASK, ys.mask_word = mask_y[i] = new_mask(op.out);
+                set_dst(ys, other(cur));
+                set_bias(op.b2, op.alpha, op.out);
+                cur = ys.dst;
+            }
+        }
+        auto prev_mask = [&](int i) -> int {   // relu mask of the producer of op i's input
+            if (i <= 0) return -1;
+            const OpHost &pv = m->ops[i - 1];
+            return (pv.kind == LINNA_OP_RES || pv.act == LINNA_ACT_RELU) ? mask_y[i - 1] : -1;
+        };
+        if (fold) {
+            // r = Af s + cf ; chi^2 = |r|^2
+            const int K = m->ops.back().in, sbuf = cur;
+            TfStep &q = new_step();
+            MatSrc mq{Af.data(), n_out, K, false, 1.f};
+            const int sh = Packer::pick_shift({mq});
+            set_phase(q, 0, sbuf, mq, sh);
+            q.N = n_out, q.inv_scale = ldexpf(1.f, -sh), q.epi = TF_CHI2;
+            if (grad) set_dst(q, other(sbuf));
+            set_bias(cf, 1.f, n_out);
+            if (grad) {
+                // d lnL / d s = -(1/T) Af^T r, masked by the relu of the layer that produced s
+                TfStep &g0 = new_step();
+                MatSrc mg{Af.data(), K, n_out, true, 1.f};
+                const int shg = Packer::pick_shift({mg});
+                set_phase(g0, 0, q.dst, mg, shg);
+                g0.N = K, g0.inv_scale = ldexpf(1.f, -shg) * (-1.0f / m->temperature), g0.epi = TF_BWD;
+                const int pm = prev_mask(nops - 1);
+                if (pm >= 0) g0.flags |= TFF_APPLY_MASK, g0.mask_word = pm;
+                set_dst(g0, sbuf);
+                cur = g0.dst;
+                for (int i = nops - 2; i >= 0; --i) {
+                    const OpHost &op = m->ops[i];
+                    const int pm2 = prev_mask(i);
+                    if (op.kind == LINNA_OP_LINEAR) {
+                        TfStep &s2 = new_step();
+                        MatSrc mb{op.w.data(), op.in, op.out, true, 1.f};
+                        const int shb = Packer::pick_shift({mb});
+                        set_phase(s2, 0, cur, mb, shb);
+                        s2.N = op.in, s2.inv_scale = ldexpf(1.f, -shb), s2.epi = i == 0 ? TF_GRADOUT : TF_BWD;
+                        if (pm2 >= 0) s2.flags |= TFF_APPLY_MASK, s2.mask_word = pm2;
+                        if (i > 0) { set_dst(s2, other(cur)); cur = s2.dst; }
+                    } else {
+                        TfStep &h = new_step();
+                        MatSrc mh{op.w2.data(), op.mid, op.out, true, op.alpha};
+                        const int shh = Packer::pick_shift({mh});
+                        set_phase(h, 0, cur, mh, shh);
+                        h.N = op.mid, h.inv_scale = ldexpf(1.f, -shh), h.epi = TF_BWD, h.flags = TFF_APPLY_MASK, h.mask_word = mask_h[i];
+                        set_dst(h, SLOT_H);
+                        TfStep &x = new_step();
+                        MatSrc mxs{op.ws.data(), op.in, op.out, true, 1.f};
+                        MatSrc mxa{op.w.data(), op.in, op.mid, true, 1.f};
+                        const int shx = Packer::pick_shift({mxs, mxa});
+                        x.nphase = 2;
+                        set_phase(x, 0, cur, mxs, shx);
+                        set_phase(x, 1, SLOT_H, mxa, shx);
+                        x.N = op.in, x.inv_scale = ldexpf(1.f, -shx), x.epi = i == 0 ? TF_GRADOUT : TF_BWD;
+                        if (pm2 >= 0) x.flags |= TFF_APPLY_MASK, x.mask_word = pm2;
+                        if (i > 0) { set_dst(x, other(cur)); cur = x.dst; }
+                    }
+                }
+            }
+        } else {
+            // r = (d/sigma) . (diag(sigma) L): B[n][k] = sigma_k L[k][n], zero for k < n
+            TfStep &q = new_step();
+            MatSrc mq{sigL.data(), n_out, n_out, true, 1.f};
+            const int sh = Packer::pick_shift({mq});
+            set_phase(q, 0, cur, mq, sh);
+            q.N = n_out, q.inv_scale = ldexpf(1.f, -sh), q.epi = TF_CHI2, q.flags = TFF_TRI;
+            set_bias(std::vector<float>(), 1.f, n_out);
+        }
+        if (overflow) { why = "too many layers"; return nullptr; }
+        for (int i = 0; i < ns; ++i) {
+            TfStep &s = pg.steps[i];
+            s.clampv = (s.flags & TFF_RELU) ? 0.f : -INFINITY;
+            switch (s.epi) {
+            case TF_ACT: s.variant = (s.flags & TFF_SAVE_MASK) ? TFV_ACT_SAVE : TFV_ACT; break;
+            case TF_HEAD: s.variant = m->ypositive ? TFV_HEAD_EXP : TFV_HEAD; break;
+            case TF_CHI2: s.variant = s.dst >= 0 ? TFV_CHI2_STORE : TFV_CHI2; break;
+            case TF_BWD: s.variant = TFV_BWD; break;
+            default: s.variant = TFV_GRADOUT; break;
+            }
+        }
+        pg.n_steps = ns, pg.total_pub = pubs, pg.seg_kc = seg_kc;
+        mask_words_total = std::max(mask_words_total, (mask_words + 3) & ~3);
+    }
+    // ---- arena columns
+    int slot_col[NSLOT], ncol = 0;
+    for (int s = 0; s < NSLOT; ++s) slot_col[s] = ncol, ncol += slot_w[s];
+    const int lo_off = ncol, ld = 2 * ncol;
+    for (int pk = 0; pk < 2; ++pk) {
+        TfProgram &pg = pgs[pk];
+        pg.in_col = slot_col[SLOT_X], pg.lo_off = lo_off, pg.mask_words = std::max(mask_words_total, 4);
+        for (int i = 0; i < pg.n_steps; ++i) {
+            TfStep &s = pg.steps[i];
+            for (int p = 0; p < s.nphase; ++p) s.src[p] = slot_col[s.src[p]];
+            if (s.dst >= 0) s.dst = slot_col[s.dst];
+        }
+    }
+
+    TcContext *t = new TcContext();
+    auto bail = [&](const std::string &msg) { why = msg; tc_destroy(t); return (TcContext *)nullptr; };
+    t->grid = m->num_sms;
+    t->has_grad = has_grad;
+    if (cudaMalloc(&t->wblob, P.w.size() * sizeof(__half)) != cudaSuccess) return bail("cudaMalloc weights");
+    if (cudaMemcpy(t->wblob, P.w.data(), P.w.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) return bail("upload");
+    if (cudaMalloc(&t->fblob, std::max<size_t>(P.f.size(), 64) * sizeof(float)) != cudaSuccess) return bail("cudaMalloc biases");
+    if (!P.f.empty()) cudaMemcpy(t->fblob, P.f.data(), P.f.size() * sizeof(float), cudaMemcpyHostToDevice);
+    const size_t rows = (size_t)t->grid * 2 * TF_M;
+    if (cudaMalloc(&t->arena, rows * ld * sizeof(__half)) != cudaSuccess) return bail("cudaMalloc arena");
+    cudaMemset(t->arena, 0, rows * ld * sizeof(__half));
+    if (cudaMalloc(&t->masks, rows * (size_t)pgs[0].mask_words * sizeof(uint32_t)) != cudaSuccess) return bail("cudaMalloc masks");
+    for (auto &br : bias_refs) {
+        TfStep &s = pgs[br.prog].steps[br.step];
+        (br.what == 0 ? s.bias : br.what == 1 ? s.vscale : s.sub) = t->fblob + br.off;
+    }
+
+    // ---- tensor maps
+    std::vector<CUtensorMap> maps(2 + 2 * P.mats.size());
+    auto encode2d = [&](CUtensorMap *mp, void *base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner,
+                        uint32_t box_outer, CUtensorMapSwizzle sw) {
+        cuuint64_t dims[2] = {inner, outer};
+        cuuint64_t strides[1] = {pitch_bytes};
+        cuuint32_t box[2] = {box_inner, box_outer};
+        cuuint32_t estr[2] = {1, 1};
+        return encode(mp, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    if (encode2d(&maps[0], t->arena, (uint64_t)ld, rows, (uint64_t)ld * 2, TF_KC, TF_M, CU_TENSOR_MAP_SWIZZLE_64B) != CUDA_SUCCESS)
+        return bail("cuTensorMapEncodeTiled(arena load) failed");
+    if (encode2d(&maps[1], t->arena, (uint64_t)ld, rows, (uint64_t)ld * 2, 64, TF_M, CU_TENSOR_MAP_SWIZZLE_128B) != CUDA_SUCCESS)
+        return bail("cuTensorMapEncodeTiled(arena store) failed");
+    for (size_t i = 0; i < P.mats.size(); ++i) {
+        const Packer::Mat &mt = P.mats[i];
+        if (encode2d(&maps[2 + 2 * i], t->wblob + mt.hi, (uint64_t)mt.K, (uint64_t)mt.N, (uint64_t)mt.ldk * 2, TF_KC, TF_NC,
+                     CU_TENSOR_MAP_SWIZZLE_64B) != CUDA_SUCCESS ||
+            encode2d(&maps[3 + 2 * i], t->wblob + mt.lo, (uint64_t)mt.K, (uint64_t)mt.N, (uint64_t)mt.ldk * 2, TF_KC, TF_NC,
+                     CU_TENSOR_MAP_SWIZZLE_64B) != CUDA_SUCCESS)
+            return bail("cuTensorMapEncodeTiled(weights) failed");
+    }
+    if (cudaMalloc(&t->maps_dev, maps.size() * sizeof(CUtensorMap)) != cudaSuccess) return bail("cudaMalloc maps");
+    cudaMemcpy(t->maps_dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
+    if (cudaMalloc(&t->prog_dev, 2 * sizeof(TfProgram)) != cudaSuccess) return bail("cudaMalloc prog");
+    cudaMemcpy(t->prog_dev, pgs, 2 * sizeof(TfProgram), cudaMemcpyHostToDevice);
+    if (cudaMalloc(&t->err_dev, sizeof(int)) != cudaSuccess) return bail("cudaMalloc err");
+    cudaMemset(t->err_dev, 0, sizeof(int));
+    if (cudaFuncSetAttribute(tc_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES) != cudaSuccess)
+        return bail("cudaFuncSetAttribute(tc_f16_kernel)");
+    if (cudaDeviceSynchronize() != cudaSuccess) return bail("sync after tc_build");
+    return t;
+}
+
+bool tc_has_grad(const TcContext *t) { return t && t->has_grad; }
+
+static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const float *u, int64_t n, float *lnp, float *grad,
+                             cudaStream_t stream)
+{
+    TfArgs a;
+    memset(&a, 0, sizeof a);
+    a.prog = t->prog_dev + pk, a.maps = t->maps_dev, a.c = m->consts;
+    a.in = u, a.lnp = lnp, a.grad = grad, a.masks = t->masks, a.n = n, a.err = t->err_dev;
+    const int64_t pairs = (n + 2 * TF_M - 1) / (2 * TF_M);
+    const int grid = (int)std::min<int64_t>(pairs, t->grid);
+    tc_f16_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t tc_launch_lnp(const linna_model *m, TcContext *t, const float *u, int64_t n, float *lnp, cudaStream_t stream)
+{
+    return tc_launch(m, t, 0, u, n, lnp, nullptr, stream);
+}
+
+cudaError_t tc_launch_grad(const linna_model *m, TcContext *t, const float *u, int64_t n, float *lnp, float *grad,
+                           cudaStream_t stream)
+{
+    return tc_launch(m, t, 1, u, n, lnp, grad, stream);
+}
+
+}  // namespace linna

@@ -1,0 +1,22 @@
+import sys, os, time, numpy as np, torch
+sys.path.insert(0, '/root/repo')
+from linna_b200 import engine, synthetic, arch
+mode = sys.argv[1] if len(sys.argv) > 1 else "lnp"
+ns = [int(a) for a in sys.argv[2:]] or [100000]
+p = synthetic.make_problem(30, 500, seed=0)
+e = engine.engine_from_problem(p, with_likelihood=False)
+m0 = e.predict(np.asarray(p.theta0, np.float32)[None, :], engine.LINNA_OUT_M)[0]
+p.set_data_from_prediction(m0)
+e.set_likelihood(p.priors, np.asarray(p.data, np.float32), p.inv_cov, 1.0)
+e.set_path("tc")
+for n in ns:
+    u = torch.from_numpy(synthetic.walkers(n, 30, scale=0.3, seed=1)).cuda()
+    call = e.lnp if mode == "lnp" else e.lnp_grad
+    for _ in range(3): call(u)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(5): call(u)
+    ev1.record(); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / 5
+    print("SEG", os.environ.get("LINNA_TC_SEG_KC"), mode, "n", n, "ms %.3f  evals/s %.4g" % (ms, n / ms * 1e3), flush=True)

@@ -1,11 +1,15 @@
-"""GPU tests of the EXPERIMENTAL tensor-core (tcgen05 / TMEM / TMA, 3xTF32) lnP kernel.
+"""GPU tests of the tensor-core (tcgen05 / TMEM / TMA, split-fp16) lnP and lnP+gradient kernel.
 
-The kernel is opt-in (``Engine.set_path("tc")``): the tensor core truncates its fp32 accumulator on
-every tcgen05.mma, which leaves a systematic toward-zero bias proportional to the number of
-instructions accumulated in tensor memory (measured here: 6e-6 of chi^2 with plain accumulation,
-1.5e-6 with the default two-level scheme, 4e-7 when draining every k-chunk).  That is outside the
-1e-4-absolute / 4-ulp bar of the FP32 FFMA kernel for |lnL| >~ 100, so the default path stays FFMA and
-these tests hold the tensor-core kernel to the RELATIVE bar  |d lnL| <= 4e-6 |lnL| + 1e-4  instead."""
+The kernel serves large batches (``Engine.set_path("auto")`` sends batches >= tc_min_rows to it,
+``"tc"`` forces it).  Every operand is split into two fp16 halves (22 significant bits) and the
+tensor core's truncating fp32 accumulator is drained into round-to-nearest register accumulators
+every few k-chunks, so the result tracks the FP32 FFMA kernel to a few ulp; the bars below are
+written against a float64 run of the reference modules (tests/golden) / the float64 oracle:
+
+    |d lnL|  <= TC_REL * |lnL| + 1e-4      (1e-4 absolute is north_star's bar; the relative term is
+                                            the float32 resolution of lnL itself)
+    gradient: relative infinity-norm error < 2e-4 (same bar as the FFMA kernel)
+"""
 import numpy as np
 import pytest
 
@@ -13,13 +17,15 @@ torch = pytest.importorskip("torch")
 
 from linna_b200 import arch, engine, synthetic
 from oracle.oracle import Oracle
-from tests.helpers import fixture_problem, lnp_tol, load_golden, problem_from_golden
+from tests.helpers import fixture_problem, load_golden, problem_from_golden
 
 pytestmark = pytest.mark.gpu
 
+TC_REL = 1e-6
+
 
 def tc_tol(lnp):
-    return 4e-6 * np.abs(lnp) + 1e-4
+    return TC_REL * np.abs(lnp) + 1e-4
 
 
 def _dev(a):
@@ -51,6 +57,20 @@ def test_tc_lnp_vs_reference_golden(name):
     assert np.all(np.abs(got - ref_ffma) <= tol)
 
 
+@pytest.mark.parametrize("name", ["tiny", "c1", "c3s", "c3mix", "c4s"])
+def test_tc_grad_vs_reference_golden(name):
+    g = load_golden(name)
+    p = problem_from_golden(g)
+    e = engine.engine_from_problem(p, quad="chol")
+    e.set_path("tc")
+    lnp, grad = e.lnp_grad(_dev(g["u"]))
+    lnp, grad = lnp.cpu().numpy(), grad.cpu().numpy().astype(np.float64)
+    assert np.all(np.abs(lnp - g["f64_lnp"]) <= tc_tol(g["f64_lnp"]))
+    ref = g["f64_grad"]
+    rel = np.max(np.abs(grad - ref), axis=1) / np.max(np.abs(ref), axis=1)
+    assert rel.max() < 2e-4, rel.max()
+
+
 def test_tc_fixture_and_ragged():
     g = load_golden("fixture")
     p = fixture_problem(g)
@@ -59,11 +79,16 @@ def test_tc_fixture_and_ragged():
     got = e.lnp(_dev(g["u"])).cpu().numpy()
     assert np.all(np.abs(got - g["lnp"]) <= tc_tol(g["lnp"]))
     o = Oracle(p, arch)
-    for n in (1, 127, 128, 129, 1000):
+    for n in (1, 127, 128, 129, 255, 256, 257, 1000):
         u = synthetic.walkers(n, 2, scale=1.0, seed=n)
-        ref = o.lnp(u, np.float64)["lnp"]
+        ref = o.lnp(u, np.float64, grad=True)
         out = e.lnp(_dev(u)).cpu().numpy()
-        assert out.shape == (n,) and np.all(np.abs(out - ref) <= tc_tol(ref)), n
+        assert out.shape == (n,) and np.all(np.abs(out - ref["lnp"]) <= tc_tol(ref["lnp"])), n
+        l2, gr = e.lnp_grad(_dev(u))
+        assert np.array_equal(l2.cpu().numpy(), out), n
+        gr = gr.cpu().numpy()
+        assert gr.shape == (n, 2)
+        assert np.max(np.abs(gr - ref["grad"])) <= 2e-4 * np.max(np.abs(ref["grad"])), n
     u = synthetic.walkers(300, 2, seed=3)
     u[7, 1] = np.nan
     out = e.lnp(_dev(u)).cpu().numpy()
@@ -83,9 +108,19 @@ def test_tc_full_size_c3():
     a = e.lnp(ud).cpu().numpy()
     b = e.lnp(ud).cpu().numpy()
     assert np.array_equal(a, b)
+    la, ga = e.lnp_grad(ud)
+    assert np.array_equal(la.cpu().numpy(), a)
     e.set_path("ffma")
     f = e.lnp(ud).cpu().numpy()
     assert np.all(np.abs(a - f) <= tc_tol(f)), np.abs(a - f).max()
+    lf, gf = e.lnp_grad(ud)
+    ga, gf = ga.cpu().numpy(), gf.cpu().numpy()
+    # The gradient is discontinuous where a relu pre-activation crosses zero: a unit whose pre-activation is
+    # within float32 rounding of 0 can come out on either side in two correct float32 evaluations (measured
+    # against the float64 oracle, it is the FFMA kernel as often as this one).  ~4e8 relu units per batch make
+    # that a few dozen rows; everything else has to agree to the usual bar.
+    rel = np.max(np.abs(ga - gf), axis=1) / np.max(np.abs(gf), axis=1)
+    assert np.median(rel) < 1e-5 and np.mean(rel > 2e-4) < 1e-3, (np.median(rel), np.mean(rel > 2e-4))
     idx = np.random.default_rng(0).choice(n, 64, replace=False)
     ref = Oracle(p, arch).lnp(u[idx], np.float64)["lnp"]
     assert np.all(np.abs(a[idx] - ref) <= tc_tol(ref)), np.abs(a[idx] - ref).max()
