@@ -130,13 +130,18 @@ int linna_lnp_grad_host(linna_model_t *m, const float *u, int64_t n, float *lnp,
 
 /* Introspection used by bench.py / tests. */
 int linna_model_info(const linna_model_t *m, int32_t *n_in, int32_t *n_out, int64_t *n_params, int32_t *num_sms);
-/* Kernel selection for linna_lnp: 0 = automatic (tensor-core kernel for n >= tc_min_rows, FP32 FFMA kernel
- * below), 1 = FP32 FFMA kernel only, 2 = tensor-core (tcgen05, 3xTF32) kernel only.  tc_min_rows <= 0 keeps
- * the current threshold. */
+/* Kernel selection for linna_lnp / linna_lnp_grad: 0 = automatic (tensor-core kernel for n >= tc_min_rows,
+ * FP32 FFMA kernel below), 1 = FP32 FFMA kernel only, 2 = tensor-core (tcgen05, split-fp16) kernel only.
+ * tc_min_rows <= 0 keeps the current threshold. */
 int linna_model_set_path(linna_model_t *m, int32_t path, int64_t tc_min_rows);
 /* lnP evaluates the last linear layer, the inverse output transform and the Cholesky product as ONE folded
  * affine map (formed in float64 at pack time); 0 switches the folding off (unfolded reference order). */
 int linna_model_set_fold(linna_model_t *m, int32_t on);
+/* Profiling hook (environment LINNA_TC_DEBUG set when the tensor-core context is built): copies the per-CTA
+ * cycle counters of the last tensor-core launch into out[max_ctas][8] and returns the number of CTAs
+ * (0 when the counters are off).  [0..2] TMA producer: total, waiting for a free stage, waiting for
+ * activations; [3..5] MMA issuer: total, waiting for operands, waiting for the epilogue to drain TMEM. */
+int linna_debug_tc_counters(linna_model_t *m, int64_t *out, int32_t max_ctas);
 /* Force the row-tile height (8, 16 or 32; 0 = automatic) -- test hook for the tiling variants. */
 int linna_model_set_tile_rows(linna_model_t *m, int32_t rows);
 

@@ -27,6 +27,7 @@ cudaError_t tc_launch_lnp(const linna_model *m, TcContext *t, const float *u, in
 cudaError_t tc_launch_grad(const linna_model *m, TcContext *t, const float *u, int64_t n, float *lnp, float *grad,
                            cudaStream_t stream);
 bool tc_has_grad(const TcContext *t);
+int tc_debug_read(TcContext *t, long long *out, int max_ctas);
 }  // namespace linna
 
 static thread_local std::string g_err;
@@ -787,6 +788,12 @@ int linna_model_set_path(linna_model_t *m, int32_t path, int64_t tc_min_rows)
     m->path = path;
     if (tc_min_rows > 0) m->tc_min_rows = tc_min_rows;
     return LINNA_OK;
+}
+
+int linna_debug_tc_counters(linna_model_t *m, int64_t *out, int32_t max_ctas)
+{
+    if (!m || !out) return 0;
+    return tc_debug_read(m->tc, reinterpret_cast<long long *>(out), max_ctas);
 }
 
 int linna_model_set_fold(linna_model_t *m, int32_t on)

@@ -99,6 +99,7 @@ struct TfArgs {
     uint32_t *masks;
     int64_t n;
     int *err;
+    long long *dbg;           // optional [grid][8] cycle counters (LINNA_TC_DEBUG): where the service warps wait
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -142,6 +143,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *e
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 2000000000LL) tf_die(err, code);
     }
+}
+__device__ __forceinline__ void mbar_wait_timed(uint64_t *bar, uint32_t parity, int *err, int code, long long &acc)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 2000000000LL) tf_die(err, code);
+    }
+    acc += clock64() - t0;
 }
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
 {
@@ -374,6 +384,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
         if (lane == 0) {
             int stage = 0;
             uint32_t ph = 0, seen0 = 0, seen1 = 0, pub0 = 0;
+            long long w_empty = 0, w_ready = 0;
+            const long long t_begin = clock64();
             for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, pub0 += total_pub) {
                 for (int si = 0; si < n_steps; ++si) {
                     const TfStep &st = s_steps[si];
@@ -383,7 +395,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
                             const int nk = (st.K[p] + TF_KC - 1) / TF_KC;
                             const CUtensorMap *mb = maps + st.mapB[p];
                             for (int kc = k0; kc < nk; ++kc) {
-                                mbar_wait(&empty_bar[stage], ph ^ 1, args.err, 1);
+                                mbar_wait_timed(&empty_bar[stage], ph ^ 1, args.err, 1, w_empty);
                                 uint8_t *sb = smem + stage * TF_STAGE_BYTES;
                                 mbar_expect_tx(&full_bar[stage], TF_STAGE_BYTES);
                                 tma_load_2d(sb + 4 * TF_TILE_BYTES, mb, &full_bar[stage], kc * TF_KC, n0);
@@ -398,6 +410,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
                                         __nanosleep(64);
                                         if (clock64() - t0 > 2000000000LL) tf_die(args.err, 2);
                                     }
+                                    w_ready += clock64() - t0;
                                     fence_async_all();
                                 }
                                 const int ca = st.src[p] + kc * TF_KC;
@@ -411,12 +424,18 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
                     }
                 }
             }
+            if (args.dbg) {
+                long long *d = args.dbg + (size_t)blockIdx.x * 8;
+                d[0] = clock64() - t_begin, d[1] = w_empty, d[2] = w_ready;
+            }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
             int stage = 0;
             uint32_t ph = 0, g = 0;
+            long long w_full = 0, w_pempty = 0;
+            const long long t_begin = clock64();
             for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
                 for (int si = 0; si < n_steps; ++si) {
                     const TfStep &st = s_steps[si];
@@ -433,11 +452,11 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
                             for (int kc = k0; kc < nk; ++kc) {
                                 if (in_seg == 0) {   // open a fresh pair of accumulator buffers (one per tile)
                                     const int buf = g & 1;
-                                    mbar_wait(&pempty_bar[buf], ((g >> 1) & 1) ^ 1, args.err, 3);
+                                    mbar_wait_timed(&pempty_bar[buf], ((g >> 1) & 1) ^ 1, args.err, 3, w_pempty);
                                     tc_fence_after();
                                     dcol = tmem_base + buf * TF_NC;
                                 }
-                                mbar_wait(&full_bar[stage], ph, args.err, 4);
+                                mbar_wait_timed(&full_bar[stage], ph, args.err, 4, w_full);
                                 tc_fence_after();
                                 const uint32_t sb = smem_u32(smem + stage * TF_STAGE_BYTES);
                                 const uint32_t b_hi = sb + 4 * TF_TILE_BYTES, b_lo = sb + 5 * TF_TILE_BYTES;
@@ -465,6 +484,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
                         }
                     }
                 }
+            }
+            if (args.dbg) {
+                long long *d = args.dbg + (size_t)blockIdx.x * 8;
+                d[3] = clock64() - t_begin, d[4] = w_full, d[5] = w_pempty;
             }
         }
     } else {
@@ -658,6 +681,7 @@ struct TcContext {
     CUtensorMap *maps_dev = nullptr;
     TfProgram *prog_dev = nullptr;   // [0] LNP, [1] GRAD
     int *err_dev = nullptr;
+    long long *dbg_dev = nullptr;
     bool has_grad = false;
     int grid = 0;
     std::string error;
@@ -684,6 +708,7 @@ void tc_destroy(TcContext *t)
     if (t->maps_dev) cudaFree(t->maps_dev);
     if (t->prog_dev) cudaFree(t->prog_dev);
     if (t->err_dev) cudaFree(t->err_dev);
+    if (t->dbg_dev) cudaFree(t->dbg_dev);
     delete t;
 }
 
@@ -1031,6 +1056,10 @@ TcContext *tc_build(const linna_model *m, std::string &why)
     cudaMemcpy(t->prog_dev, pgs, 2 * sizeof(TfProgram), cudaMemcpyHostToDevice);
     if (cudaMalloc(&t->err_dev, sizeof(int)) != cudaSuccess) return bail("cudaMalloc err");
     cudaMemset(t->err_dev, 0, sizeof(int));
+    if (getenv("LINNA_TC_DEBUG")) {
+        if (cudaMalloc(&t->dbg_dev, (size_t)t->grid * 8 * sizeof(long long)) != cudaSuccess) return bail("cudaMalloc dbg");
+        cudaMemset(t->dbg_dev, 0, (size_t)t->grid * 8 * sizeof(long long));
+    }
     if (cudaFuncSetAttribute(tc_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES) != cudaSuccess)
         return bail("cudaFuncSetAttribute(tc_f16_kernel)");
     if (cudaDeviceSynchronize() != cudaSuccess) return bail("sync after tc_build");
@@ -1039,13 +1068,23 @@ TcContext *tc_build(const linna_model *m, std::string &why)
 
 bool tc_has_grad(const TcContext *t) { return t && t->has_grad; }
 
+// LINNA_TC_DEBUG: per-CTA cycle counters of the last launch -> host ([grid][8]); returns the grid size
+int tc_debug_read(TcContext *t, long long *out, int max_ctas)
+{
+    if (!t || !t->dbg_dev) return 0;
+    const int n = std::min(max_ctas, t->grid);
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, t->dbg_dev, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+    return n;
+}
+
 static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const float *u, int64_t n, float *lnp, float *grad,
                              cudaStream_t stream)
 {
     TfArgs a;
     memset(&a, 0, sizeof a);
     a.prog = t->prog_dev + pk, a.maps = t->maps_dev, a.c = m->consts;
-    a.in = u, a.lnp = lnp, a.grad = grad, a.masks = t->masks, a.n = n, a.err = t->err_dev;
+    a.in = u, a.lnp = lnp, a.grad = grad, a.masks = t->masks, a.n = n, a.err = t->err_dev, a.dbg = t->dbg_dev;
     const int64_t pairs = (n + 2 * TF_M - 1) / (2 * TF_M);
     const int grid = (int)std::min<int64_t>(pairs, t->grid);
     tc_f16_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);

@@ -84,6 +84,7 @@ def load_library():
     lib.linna_model_set_tile_rows.argtypes = [vp, i32]
     lib.linna_model_set_path.argtypes = [vp, i32, i64]
     lib.linna_model_set_fold.argtypes = [vp, i32]
+    lib.linna_debug_tc_counters.argtypes = [vp, vp, i32]
     f32 = ctypes.c_float
     lib.linna_train_setup.argtypes = [vp, ctypes.POINTER(TrainDesc)]
     lib.linna_train_num_params.argtypes = [vp]
@@ -213,6 +214,12 @@ class Engine:
         """'auto' | 'ffma' | 'tc' -- which kernel serves lnp()."""
         code = {"auto": 0, "ffma": 1, "tc": 2}[path]
         self._check(self.lib.linna_model_set_path(self.handle, code, int(tc_min_rows)))
+
+    def tc_counters(self, max_ctas=256):
+        """Per-CTA cycle counters of the last tensor-core launch (needs LINNA_TC_DEBUG=1 in the environment)."""
+        buf = np.zeros((max_ctas, 8), np.int64)
+        n = self.lib.linna_debug_tc_counters(self.handle, buf.ctypes.data_as(ctypes.c_void_p), max_ctas)
+        return buf[:n]
 
     def set_fold(self, on):
         """Fold last layer + inverse transform + Cholesky product into one GEMM for lnP (default on)."""

@@ -20,3 +20,9 @@ for n in ns:
     ev1.record(); torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / 5
     print("SEG", os.environ.get("LINNA_TC_SEG_KC"), mode, "n", n, "ms %.3f  evals/s %.4g" % (ms, n / ms * 1e3), flush=True)
+if os.environ.get("LINNA_TC_DEBUG"):
+    cnt = e.tc_counters()
+    if len(cnt):
+        m_ = cnt.mean(axis=0)
+        print("producer: total %.0f  wait_empty %.0f (%.0f%%)  wait_ready %.0f (%.0f%%)" % (m_[0], m_[1], 100*m_[1]/m_[0], m_[2], 100*m_[2]/m_[0]))
+        print("mma     : total %.0f  wait_full %.0f (%.0f%%)  wait_pempty %.0f (%.0f%%)" % (m_[3], m_[4], 100*m_[4]/m_[3], m_[5], 100*m_[5]/m_[3]))
