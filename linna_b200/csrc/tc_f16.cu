@@ -43,13 +43,13 @@
 namespace linna {
 
 constexpr int TF_M = 128;        // walkers per tile
-constexpr int TF_NC = 128;       // accumulator columns per chunk
+constexpr int TF_NC = 256;       // accumulator columns per chunk (two epilogue groups of 128)
 constexpr int TF_KC = 32;        // k-chunk in halves = one 64-byte swizzle row
-constexpr int TF_STAGES = 3;
+constexpr int TF_STAGES = 4;
 constexpr int TF_TILE_BYTES = TF_M * TF_KC * 2;                  // 8 KB operand tile
-constexpr int TF_STAGE_BYTES = 6 * TF_TILE_BYTES;                // A_x hi/lo, A_y hi/lo, B hi/lo = 48 KB
+constexpr int TF_STAGE_BYTES = 4 * TF_TILE_BYTES;                // A hi/lo, B-half hi/lo = 32 KB per CTA
 constexpr int TF_BOX_BYTES = 128 * 64 * 2;                       // staging box: 128 rows x 64 halves = 16 KB
-constexpr int TF_STG_BYTES = 2 * TF_BOX_BYTES;                   // hi + lo per tile
+constexpr int TF_STG_BYTES = 2 * TF_BOX_BYTES;                   // hi + lo per column group
 constexpr int TF_SMEM_BYTES = TF_STAGES * TF_STAGE_BYTES + 2 * TF_STG_BYTES + 1024;
 constexpr int TF_THREADS = 384;  // TMA, MMA, 2 store warps + 2 x 4 epilogue warps
 constexpr int TF_MAX_STEPS = 48;
@@ -63,8 +63,7 @@ struct TfStep {
     int32_t src[2];       // arena column of the hi copy of this phase's A operand; lo copy at + lo_off
     int32_t K[2];
     int32_t mapB[2];      // tensor-map index of the hi weight operand; lo = + 1
-    int32_t src_pub[2];   // output chunks published (per tile pass) before the producer of src's first chunk
-    int32_t src_nch[2];   // number of chunks the producer of src publishes
+    int32_t src_pub[2][2];   // [phase][group]: chunks the group published (per tile pass) before the producer of src
     int32_t N;
     int32_t dst;          // arena column of the output (hi), -1: none
     int32_t dst_pad;      // output width rounded up to 64 (pad columns are written as zeros)
@@ -80,12 +79,12 @@ struct TfStep {
 
 struct TfProgram {
     int32_t n_steps;
-    int32_t total_pub;     // chunks published per tile pass (prologue included)
+    int32_t total_pub[2];  // chunks each column group publishes per tile pass (prologue included)
     int32_t in_col;        // arena column of xhat
     int32_t lo_off;        // column offset from a hi copy to its lo copy
     int32_t seg_kc;        // k-chunks accumulated in tensor memory between two drains
     int32_t mask_words;    // 32-bit words per mask row
-    int32_t pad_[2];
+    int32_t pad_[1];
     TfStep steps[TF_MAX_STEPS];
 };
 
@@ -163,13 +162,32 @@ __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
 {
     asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+// CTA-pair load: the bytes land in this CTA's shared memory, the completion is signalled on the LEADER's
+// barrier (peer bit of the address cleared), as cta_group::2 MMAs consume both CTAs' tiles together.
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
 {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         :
-        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    // plain arrive: a .release.cluster here costs MEMBAR.ALL.GPU + ERRBAR per call; the tensor-memory handoff is
+    // ordered by tcgen05.fence::before_thread_sync / after_thread_sync on the two sides
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const void *smem_src, const CUtensorMap *map, int c0, int c1)
 {
@@ -197,24 +215,26 @@ __device__ __forceinline__ uint64_t make_sdesc64(uint32_t saddr)
     d |= (uint64_t)4 << 61;                  // SWIZZLE_64B
     return d;
 }
-// kind::f16 with fp16 inputs, fp32 accumulate, A and B K-major, M = 128
+// kind::f16 with fp16 inputs, fp32 accumulate, A and B K-major, M = 256 over the CTA pair
 __device__ __forceinline__ uint32_t make_idesc_f16(int n)
 {
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TF_M >> 4) << 24);
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)((2 * TF_M) >> 4) << 24);
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         :
         : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar)
 {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 {
@@ -263,20 +283,23 @@ struct TfEpiCtx {
     double chi;
     uint32_t sidx;              // staging boxes handed to the store warp so far
     int sw;                     // 128-byte swizzle phase of this row
+    long long t_sfree;          // cycles spent waiting for the staging box (LINNA_TC_DEBUG)
 };
 
-// One 128-column chunk: v = acc*scale + bias (clamped below for relu), optional exp / mask / chi^2, split into
-// fp16 hi/lo, written to the swizzled staging box that the store warp sends to the arena.  All flags are
-// compile-time so that each kind of step runs ~6 instructions per element out of a few KB of code.
-// Pad columns (>= N) come out as exact zeros: their accumulators are zero (TMA zero-fills the missing
-// weight rows) and the bias / scale vectors are zero-padded.
+// 128 columns of one output chunk (the columns [c0, c0+128) of the layer, owned by one epilogue group):
+// v = acc*scale + bias (clamped below for relu), optional exp / mask / chi^2, split into fp16 hi/lo, written to
+// the swizzled staging box that the store warp sends to the arena.  All flags are compile-time so that each
+// kind of step runs ~6 instructions per element out of a few KB of code.  Pad columns (>= N) come out as
+// exact zeros: their accumulators are zero (TMA zero-fills the missing weight rows) and the bias / scale
+// vectors are zero-padded.
 template <bool BIAS, bool VSCALE, bool EXPY, bool SAVE, bool APPLY, bool CHI, bool STORE>
-__device__ __forceinline__ void tf_chunk_epilogue(const float (&racc)[128], const TfStep &st, int n0, int ch, TfEpiCtx &x)
+__device__ __forceinline__ void tf_chunk_epilogue(const float (&racc)[128], const TfStep &st, int c0, int mword,
+                                                  const float *bias_s, TfEpiCtx &x)
 {
     uint32_t mw[4] = {0u, 0u, 0u, 0u};
     if (APPLY) {
         if (st.flags & TFF_APPLY_MASK) {
-            const uint4 m4 = *reinterpret_cast<const uint4 *>(x.mask_row + st.mask_word + 4 * ch);
+            const uint4 m4 = *reinterpret_cast<const uint4 *>(x.mask_row + mword);
             mw[0] = m4.x, mw[1] = m4.y, mw[2] = m4.z, mw[3] = m4.w;
         } else {
             mw[0] = mw[1] = mw[2] = mw[3] = 0xffffffffu;
@@ -286,17 +309,17 @@ __device__ __forceinline__ void tf_chunk_epilogue(const float (&racc)[128], cons
     float chi_f = 0.f;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int col0 = n0 + 64 * h;
+        const int col0 = c0 + 64 * h;
         const bool store = STORE && col0 < st.dst_pad;
         if (!store && !(CHI && col0 < st.N)) continue;
-        if (store) mbar_wait(x.sfree, (x.sidx & 1) ^ 1, x.err, 7);   // staging box free again
+        if (store) mbar_wait_timed(x.sfree, (x.sidx & 1) ^ 1, x.err, 7, x.t_sfree);   // staging box free again
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int cb = col0 + 8 * j;
             float b[8], s[8], v[8];
-            if (BIAS) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(st.bias + cb));
-                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(st.bias + cb + 4));
+            if (BIAS) {   // this chunk's 128 bias values were staged in shared memory while the accumulators drained
+                const float4 b0 = *reinterpret_cast<const float4 *>(bias_s + 64 * h + 8 * j);
+                const float4 b1 = *reinterpret_cast<const float4 *>(bias_s + 64 * h + 8 * j + 4);
                 b[0] = b0.x, b[1] = b0.y, b[2] = b0.z, b[3] = b0.w, b[4] = b1.x, b[5] = b1.y, b[6] = b1.z, b[7] = b1.w;
             }
             if (VSCALE) {
@@ -306,7 +329,7 @@ __device__ __forceinline__ void tf_chunk_epilogue(const float (&racc)[128], cons
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int li = 64 * h + 8 * j + e;   // column inside the chunk
+                const int li = 64 * h + 8 * j + e;   // column inside this group's 128
                 float y = fmaf(racc[li], VSCALE ? s[e] : inv_scale, BIAS ? b[e] : 0.f);
                 if (EXPY) y = cb + e < st.N ? expf(y) - __ldg(st.sub + cb + e) : 0.f;
                 y = fmaxf(y, clampv);
@@ -330,16 +353,21 @@ __device__ __forceinline__ void tf_chunk_epilogue(const float (&racc)[128], cons
             ++x.sidx;
         }
     }
-    if (SAVE) *reinterpret_cast<uint4 *>(x.mask_row + st.mask_word + 4 * ch) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+    if (SAVE) *reinterpret_cast<uint4 *>(x.mask_row + mword) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
     if (CHI) x.chi += (double)chi_f;
 }
 
 // ------------------------------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args)
+// One cluster = one CTA pair = 2 x 128 walkers.  CTA rank 0 issues every tcgen05.mma for the pair
+// (cta_group::2, M = 256): each CTA supplies its own 128 activation rows and HALF of the weight tile, and
+// receives its own 128 x N accumulator rows in its own tensor memory.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args)
 {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[TF_STAGES], empty_bar[TF_STAGES], pfull_bar[2], pempty_bar[2];
-    __shared__ __align__(8) uint64_t sfull_bar[2], sfree_bar[2];   // staging buffer of tile X / Y: written / read out
+    __shared__ __align__(8) uint64_t sfull_bar[2], sfree_bar[2];   // staging buffer of column group 0 / 1: written / read out
+    __shared__ __align__(8) double chi_s[TF_M];
+    __shared__ __align__(16) float bias_stage[2][2][128];   // [chunk parity][column group][column]
     __shared__ uint32_t tmem_slot;
     __shared__ uint32_t ready_cnt[2];
     __shared__ TfStep s_steps[TF_MAX_STEPS];
@@ -347,11 +375,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *stg_all = smem + TF_STAGES * TF_STAGE_BYTES;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t cta_rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const bool leader = cta_rank == 0;
     const TfProgram *prog = args.prog;
     const int n_steps = prog->n_steps;
     const int lo_off = prog->lo_off;
     const int seg_kc = prog->seg_kc;
-    const uint32_t total_pub = (uint32_t)prog->total_pub;
     const Consts &c = args.c;
     const CUtensorMap *maps = args.maps;
 
@@ -359,37 +389,41 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
         reinterpret_cast<uint32_t *>(s_steps)[i] = reinterpret_cast<const uint32_t *>(prog->steps)[i];
     if (tid == 0) {
         for (int s = 0; s < TF_STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
-        for (int b = 0; b < 2; ++b) mbar_init(&pfull_bar[b], 1), mbar_init(&pempty_bar[b], 256);
+        for (int b = 0; b < 2; ++b) mbar_init(&pfull_bar[b], 1), mbar_init(&pempty_bar[b], 16);   // 8 warps x 2 CTAs
         for (int b = 0; b < 2; ++b) mbar_init(&sfull_bar[b], 128), mbar_init(&sfree_bar[b], 1);
         ready_cnt[0] = ready_cnt[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512)
                      : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();      // the peer's barriers are initialised before anything is signalled across the pair
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
     const int64_t npairs = (args.n + 2 * TF_M - 1) / (2 * TF_M);
-    const int arena_row0 = blockIdx.x * 2 * TF_M;   // this CTA's rows of the activation arena (X then Y)
+    const int64_t pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+    const int arena_row0 = blockIdx.x * TF_M;   // this CTA's rows of the activation arena
 
     if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(56));
     if (warp == 0) {
-        // =============================== TMA producer ===============================
+        // =============================== TMA producer (both CTAs) ===============================
         if (lane == 0) {
             int stage = 0;
-            uint32_t ph = 0, seen0 = 0, seen1 = 0, pub0 = 0;
+            uint32_t ph = 0, seen0 = 0, seen1 = 0, pubA = 0, pubB = 0;
             long long w_empty = 0, w_ready = 0;
             const long long t_begin = clock64();
-            for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, pub0 += total_pub) {
+            for (int64_t pair = pair0; pair < npairs; pair += pair_step, pubA += prog->total_pub[0], pubB += prog->total_pub[1]) {
                 for (int si = 0; si < n_steps; ++si) {
                     const TfStep &st = s_steps[si];
                     for (int n0 = 0; n0 < st.N; n0 += TF_NC) {
+                        const int nvalid = st.N - n0 < TF_NC ? st.N - n0 : TF_NC;
+                        const int nb = n0 + (int)cta_rank * (((nvalid + 31) & ~31) >> 1);   // this CTA's half of the weight rows
                         const int k0 = (st.flags & TFF_TRI) ? n0 / TF_KC : 0;   // L^T: B[n][k] = 0 for k < n
                         for (int p = 0; p < st.nphase; ++p) {
                             const int nk = (st.K[p] + TF_KC - 1) / TF_KC;
@@ -397,27 +431,27 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
                             for (int kc = k0; kc < nk; ++kc) {
                                 mbar_wait_timed(&empty_bar[stage], ph ^ 1, args.err, 1, w_empty);
                                 uint8_t *sb = smem + stage * TF_STAGE_BYTES;
-                                mbar_expect_tx(&full_bar[stage], TF_STAGE_BYTES);
-                                tma_load_2d(sb + 4 * TF_TILE_BYTES, mb, &full_bar[stage], kc * TF_KC, n0);
-                                tma_load_2d(sb + 5 * TF_TILE_BYTES, mb + 1, &full_bar[stage], kc * TF_KC, n0);
+                                if (leader) mbar_expect_tx(&full_bar[stage], 2 * TF_STAGE_BYTES);   // both CTAs' bytes
+                                tma_load_2d_pair(sb + 2 * TF_TILE_BYTES, mb, &full_bar[stage], kc * TF_KC, nb);
+                                tma_load_2d_pair(sb + 3 * TF_TILE_BYTES, mb + 1, &full_bar[stage], kc * TF_KC, nb);
                                 // the activations this k-chunk reads: wait until their producer chunk is visible
-                                int chunk = (kc * TF_KC + TF_KC - 1) >> 7;
-                                if (chunk > st.src_nch[p] - 1) chunk = st.src_nch[p] - 1;
-                                const uint32_t need = pub0 + (uint32_t)st.src_pub[p] + (uint32_t)chunk + 1u;
-                                if (seen0 < need || seen1 < need) {
+                                const int col = kc * TF_KC;
+                                int chunk = col >> 8;
+                                const int grp = (col >> 7) & 1;
+                                uint32_t need = (grp ? pubB : pubA) + (uint32_t)st.src_pub[p][grp] + (uint32_t)chunk + 1u;
+                                uint32_t &seen = grp ? seen1 : seen0;
+                                if (seen < need) {
                                     const long long t0 = clock64();
-                                    while ((seen0 = ld_acquire_u32(&ready_cnt[0])) < need || (seen1 = ld_acquire_u32(&ready_cnt[1])) < need) {
+                                    while ((seen = ld_acquire_u32(&ready_cnt[grp])) < need) {
                                         __nanosleep(64);
                                         if (clock64() - t0 > 2000000000LL) tf_die(args.err, 2);
                                     }
                                     w_ready += clock64() - t0;
                                     fence_async_all();
                                 }
-                                const int ca = st.src[p] + kc * TF_KC;
-                                tma_load_2d(sb, maps, &full_bar[stage], ca, arena_row0);
-                                tma_load_2d(sb + TF_TILE_BYTES, maps, &full_bar[stage], ca + lo_off, arena_row0);
-                                tma_load_2d(sb + 2 * TF_TILE_BYTES, maps, &full_bar[stage], ca, arena_row0 + TF_M);
-                                tma_load_2d(sb + 3 * TF_TILE_BYTES, maps, &full_bar[stage], ca + lo_off, arena_row0 + TF_M);
+                                const int ca = st.src[p] + col;
+                                tma_load_2d_pair(sb, maps, &full_bar[stage], ca, arena_row0);
+                                tma_load_2d_pair(sb + TF_TILE_BYTES, maps, &full_bar[stage], ca + lo_off, arena_row0);
                                 if (++stage == TF_STAGES) stage = 0, ph ^= 1;
                             }
                         }
@@ -425,18 +459,18 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
                 }
             }
             if (args.dbg) {
-                long long *d = args.dbg + (size_t)blockIdx.x * 8;
+                long long *d = args.dbg + (size_t)blockIdx.x * 16;
                 d[0] = clock64() - t_begin, d[1] = w_empty, d[2] = w_ready;
             }
         }
     } else if (warp == 1) {
-        // =============================== MMA issuer ===============================
-        if (lane == 0) {
+        // =============================== MMA issuer (leader CTA only) ===============================
+        if (lane == 0 && leader) {
             int stage = 0;
             uint32_t ph = 0, g = 0;
             long long w_full = 0, w_pempty = 0;
             const long long t_begin = clock64();
-            for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+            for (int64_t pair = pair0; pair < npairs; pair += pair_step) {
                 for (int si = 0; si < n_steps; ++si) {
                     const TfStep &st = s_steps[si];
                     for (int n0 = 0; n0 < st.N; n0 += TF_NC) {
@@ -450,7 +484,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
                         for (int p = 0; p < st.nphase; ++p) {
                             const int nk = (st.K[p] + TF_KC - 1) / TF_KC;
                             for (int kc = k0; kc < nk; ++kc) {
-                                if (in_seg == 0) {   // open a fresh pair of accumulator buffers (one per tile)
+                                if (in_seg == 0) {   // open a fresh accumulator buffer (in both CTAs)
                                     const int buf = g & 1;
                                     mbar_wait_timed(&pempty_bar[buf], ((g >> 1) & 1) ^ 1, args.err, 3, w_pempty);
                                     tc_fence_after();
@@ -459,24 +493,19 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
                                 mbar_wait_timed(&full_bar[stage], ph, args.err, 4, w_full);
                                 tc_fence_after();
                                 const uint32_t sb = smem_u32(smem + stage * TF_STAGE_BYTES);
-                                const uint32_t b_hi = sb + 4 * TF_TILE_BYTES, b_lo = sb + 5 * TF_TILE_BYTES;
+                                const uint32_t a_hi = sb, a_lo = sb + TF_TILE_BYTES, b_hi = sb + 2 * TF_TILE_BYTES, b_lo = sb + 3 * TF_TILE_BYTES;
 #pragma unroll
-                                for (int t = 0; t < 2; ++t) {
-                                    const uint32_t a_hi = sb + (2 * t) * TF_TILE_BYTES, a_lo = a_hi + TF_TILE_BYTES;
-                                    const uint32_t d = dcol + t * 2 * TF_NC;
-#pragma unroll
-                                    for (int ks = 0; ks < 2; ++ks) {
-                                        const uint32_t o = ks * 32;   // 16 halves = 32 bytes along K inside the swizzle row
-                                        umma_f16(d, make_sdesc64(a_lo + o), make_sdesc64(b_hi + o), idesc, (in_seg | ks) ? 1u : 0u);
-                                        umma_f16(d, make_sdesc64(a_hi + o), make_sdesc64(b_lo + o), idesc, 1u);
-                                        umma_f16(d, make_sdesc64(a_hi + o), make_sdesc64(b_hi + o), idesc, 1u);
-                                    }
+                                for (int ks = 0; ks < 2; ++ks) {
+                                    const uint32_t o = ks * 32;   // 16 halves = 32 bytes along K inside the swizzle row
+                                    umma_f16_pair(dcol, make_sdesc64(a_lo + o), make_sdesc64(b_hi + o), idesc, (in_seg | ks) ? 1u : 0u);
+                                    umma_f16_pair(dcol, make_sdesc64(a_hi + o), make_sdesc64(b_lo + o), idesc, 1u);
+                                    umma_f16_pair(dcol, make_sdesc64(a_hi + o), make_sdesc64(b_hi + o), idesc, 1u);
                                 }
-                                umma_commit(&empty_bar[stage]);   // frees the smem stage when these MMAs retire
+                                umma_commit_pair(&empty_bar[stage]);   // frees the smem stage in both CTAs when these MMAs retire
                                 if (++stage == TF_STAGES) stage = 0, ph ^= 1;
                                 ++done;
                                 if (++in_seg == seg_kc || done == total) {
-                                    umma_commit(&pfull_bar[g & 1]);   // partial tiles complete -> epilogue drains them
+                                    umma_commit_pair(&pfull_bar[g & 1]);   // partial tiles complete -> both epilogues drain them
                                     ++g;
                                     in_seg = 0;
                                 }
@@ -486,41 +515,44 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
                 }
             }
             if (args.dbg) {
-                long long *d = args.dbg + (size_t)blockIdx.x * 8;
+                long long *d = args.dbg + (size_t)blockIdx.x * 16;
                 d[3] = clock64() - t_begin, d[4] = w_full, d[5] = w_pempty;
             }
         }
     } else {
-        // =============================== TMA store issuers (tile X / Y) ===============================
+        // =============================== TMA store issuers (column group 0 / 1) ===============================
         if (lane == 0) {
-            const int t = warp - 2;
-            const int arow = arena_row0 + t * TF_M;
-            uint8_t *stg_hi = stg_all + t * TF_STG_BYTES, *stg_lo = stg_hi + TF_BOX_BYTES;
+            const int gi = warp - 2;
+            uint8_t *stg_hi = stg_all + gi * TF_STG_BYTES, *stg_lo = stg_hi + TF_BOX_BYTES;
             const CUtensorMap *map_st = maps + 1;
             uint32_t sidx = 0, pub = 0;
             auto store_box = [&](int col) {
-                mbar_wait(&sfull_bar[t], sidx & 1, args.err, 6);      // the 128 epilogue threads have written the box
-                tma_store_2d(stg_hi, map_st, col, arow);
-                tma_store_2d(stg_lo, map_st, col + lo_off, arow);
+                mbar_wait(&sfull_bar[gi], sidx & 1, args.err, 6);      // the 128 epilogue threads have written the box
+                tma_store_2d(stg_hi, map_st, col, arena_row0);
+                tma_store_2d(stg_lo, map_st, col + lo_off, arena_row0);
                 bulk_commit();
                 bulk_wait_read();                                      // staging read out: hand it back
-                mbar_arrive(&sfree_bar[t]);
+                mbar_arrive(&sfree_bar[gi]);
                 ++sidx;
             };
             auto publish = [&]() {
                 bulk_wait_all();                                       // the stores have landed
                 fence_async_all();
-                st_release_u32(&ready_cnt[t], ++pub);
+                st_release_u32(&ready_cnt[gi], ++pub);
             };
-            for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-                store_box(prog->in_col);
-                publish();
+            for (int64_t pair = pair0; pair < npairs; pair += pair_step) {
+                if (gi == 0) {
+                    store_box(prog->in_col);
+                    publish();
+                }
                 for (int si = 0; si < n_steps; ++si) {
                     const TfStep &st = s_steps[si];
                     if (st.dst < 0) continue;
                     for (int n0 = 0; n0 < st.N; n0 += TF_NC) {
-                        store_box(st.dst + n0);
-                        if (n0 + 64 < st.dst_pad) store_box(st.dst + n0 + 64);
+                        const int c0 = n0 + 128 * gi;
+                        if (c0 >= st.dst_pad) break;
+                        store_box(st.dst + c0);
+                        if (c0 + 64 < st.dst_pad) store_box(st.dst + c0 + 64);
                         publish();
                     }
                 }
@@ -531,27 +563,31 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
         // =============================== epilogue warps ===============================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(216));
         TfEpiCtx x;
-        const int t = (warp - 4) >> 2;                   // tile: 0 = X, 1 = Y
+        const int gi = (warp - 4) >> 2;                  // column group: columns [128 gi, 128 gi + 128) of every chunk
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;                   // TMEM lane == walker of the tile
-        const uint32_t tmem_tile = tmem_base + ((uint32_t)(q * 32) << 16) + t * 2 * TF_NC;
-        const int arow = arena_row0 + t * TF_M;          // first arena row of this tile
-        x.my_hi = stg_all + t * TF_STG_BYTES + row * 128, x.my_lo = x.my_hi + TF_BOX_BYTES;
+        const uint32_t tmem_grp = tmem_base + ((uint32_t)(q * 32) << 16) + gi * 128;
+        x.my_hi = stg_all + gi * TF_STG_BYTES + row * 128, x.my_lo = x.my_hi + TF_BOX_BYTES;
         x.sw = row & 7;
-        x.sfree = &sfree_bar[t], x.sfull = &sfull_bar[t];
+        x.sfree = &sfree_bar[gi], x.sfull = &sfull_bar[gi];
         x.sidx = 0;
-        x.mask_row = args.masks ? args.masks + (size_t)(arow + row) * prog->mask_words : nullptr;
+        x.mask_row = args.masks ? args.masks + (size_t)(arena_row0 + row) * prog->mask_words : nullptr;
         x.err = args.err;
         x.chi = 0.0;
+        x.t_sfree = 0;
         const int n_in = c.n_in;
-        uint32_t g = 0;
+        uint32_t g = 0, nchunk = 0;
+        long long e_wait = 0, e_drain = 0, e_epi = 0;
+        const long long e_begin = clock64();
+        uint32_t pempty_remote[2];   // the leader's drain barriers, as cluster addresses
+        pempty_remote[0] = map_to_cta(smem_u32(&pempty_bar[0]), 0), pempty_remote[1] = map_to_cta(smem_u32(&pempty_bar[1]), 0);
 
-        for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-            const int64_t grow = (pair * 2 + t) * TF_M + row;
+        for (int64_t pair = pair0; pair < npairs; pair += pair_step) {
+            const int64_t grow = (pair * 2 + cta_rank) * TF_M + row;
             const bool valid = grow < args.n;
-            // ---- prologue: u -> theta -> xhat (util.py:323-347, :483-497), split, stage, TMA store
+            // ---- prologue (group 0): u -> theta -> xhat (util.py:323-347, :483-497), split, stage, TMA store
             float lnprior = 0.f;
-            {
+            if (gi == 0) {
                 mbar_wait(x.sfree, (x.sidx & 1) ^ 1, args.err, 7);
                 const float *u = args.in + grow * n_in;
 #pragma unroll 1
@@ -591,7 +627,11 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
                 for (int ch = 0; ch < nch; ++ch) {
                     const int n0 = ch * TF_NC;
                     const int nvalid = st.N - n0 < TF_NC ? st.N - n0 : TF_NC;
-                    const int nmma = (nvalid + 31) & ~31;
+                    int ncol = ((nvalid + 31) & ~31) - 128 * gi;   // accumulator columns of this group in this chunk
+                    ncol = ncol < 0 ? 0 : (ncol > 128 ? 128 : ncol);
+                    const int c0 = n0 + 128 * gi;
+                    // this thread's share of the chunk's bias vector: fetched now, parked in shared memory after the drain
+                    const float bpre = (st.bias && c0 < st.N + 64) ? __ldg(st.bias + c0 + (tid & 127)) : 0.f;
                     float racc[128];
 #pragma unroll
                     for (int j = 0; j < 128; ++j) racc[j] = 0.f;
@@ -599,33 +639,45 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
 #pragma unroll 1
                     for (int sg = 0; sg < nseg; ++sg) {
                         const int buf = g & 1;
+                        const long long t_a = clock64();
                         mbar_wait(&pfull_bar[buf], (g >> 1) & 1, args.err, 5);
+                        const long long t_b = clock64();
                         tc_fence_after();
 #pragma unroll
                         for (int cb = 0; cb < 128; cb += 32) {
-                            if (cb < nmma) {
+                            if (cb < ncol) {
                                 uint32_t r[32];
-                                tmem_ld32(tmem_tile + buf * TF_NC + cb, r);
+                                tmem_ld32(tmem_grp + buf * TF_NC + cb, r);
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) racc[cb + j] += __uint_as_float(r[j]);
                             }
                         }
                         tc_fence_before();
-                        mbar_arrive(&pempty_bar[buf]);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(pempty_remote[buf]);   // one arrival per warp at the leader
                         ++g;
+                        e_wait += t_b - t_a, e_drain += clock64() - t_b;
                     }
+                    const long long t_c = clock64();
                     // ---------------- chunk epilogue (one compact specialisation per kind of step)
+                    const int mword = st.mask_word + 8 * ch + 4 * gi;
+                    float *bias_s = bias_stage[nchunk & 1][gi];
+                    bias_s[tid & 127] = bpre;
+                    ++nchunk;
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + gi) : "memory");
+                    if (c0 >= st.dst_pad && c0 >= st.N) continue;   // nothing of this chunk belongs to this group
                     switch (st.variant) {
-                    case TFV_ACT: tf_chunk_epilogue<true, false, false, false, false, false, true>(racc, st, n0, ch, x); break;
-                    case TFV_ACT_SAVE: tf_chunk_epilogue<true, false, false, true, false, false, true>(racc, st, n0, ch, x); break;
-                    case TFV_CHI2: tf_chunk_epilogue<true, false, false, false, false, true, false>(racc, st, n0, ch, x); break;
-                    case TFV_CHI2_STORE: tf_chunk_epilogue<true, false, false, false, false, true, true>(racc, st, n0, ch, x); break;
-                    case TFV_BWD: tf_chunk_epilogue<false, false, false, false, true, false, true>(racc, st, n0, ch, x); break;
-                    case TFV_HEAD: tf_chunk_epilogue<true, true, false, false, false, false, true>(racc, st, n0, ch, x); break;
-                    case TFV_HEAD_EXP: tf_chunk_epilogue<true, true, true, false, false, false, true>(racc, st, n0, ch, x); break;
+                    case TFV_ACT: tf_chunk_epilogue<true, false, false, false, false, false, true>(racc, st, c0, mword, bias_s, x); break;
+                    case TFV_ACT_SAVE: tf_chunk_epilogue<true, false, false, true, false, false, true>(racc, st, c0, mword, bias_s, x); break;
+                    case TFV_CHI2: tf_chunk_epilogue<true, false, false, false, false, true, false>(racc, st, c0, mword, bias_s, x); break;
+                    case TFV_CHI2_STORE: tf_chunk_epilogue<true, false, false, false, false, true, true>(racc, st, c0, mword, bias_s, x); break;
+                    case TFV_BWD: tf_chunk_epilogue<false, false, false, false, true, false, true>(racc, st, c0, mword, bias_s, x); break;
+                    case TFV_HEAD: tf_chunk_epilogue<true, true, false, false, false, false, true>(racc, st, c0, mword, bias_s, x); break;
+                    case TFV_HEAD_EXP: tf_chunk_epilogue<true, true, true, false, false, false, true>(racc, st, c0, mword, bias_s, x); break;
                     default: {
-                        // TFV_GRADOUT: chain through xhat = (theta' - mean)/std, theta' = log10(theta), theta = prior(u).
-                        // The accumulators go through this thread's own staging row so that the loop stays rolled.
+                        // TFV_GRADOUT (n_in <= 64: group 0 only): chain through xhat = (theta' - mean)/std,
+                        // theta' = log10(theta), theta = prior(u).  The accumulators go through this thread's own
+                        // staging row so that the loop stays rolled.
                         mbar_wait(x.sfree, (x.sidx & 1) ^ 1, args.err, 7);
                         float *scr_a = reinterpret_cast<float *>(x.my_hi), *scr_b = reinterpret_cast<float *>(x.my_lo);
 #pragma unroll
@@ -651,20 +703,32 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args
                         }
                     } break;
                     }
+                    e_epi += clock64() - t_c;
                 }
             }
-            if (valid && args.lnp) {
-                float l = (float)(-0.5 * x.chi) * c.inv_T + lnprior;                 // util.py:1013
-                if (l != l) l = -INFINITY;                                          // util.py:1015-1016
+            // combine the two column groups of every walker and finish lnP
+            if (gi == 1) chi_s[row] = x.chi;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (gi == 0 && valid && args.lnp) {
+                float l = (float)(-0.5 * (x.chi + chi_s[row])) * c.inv_T + lnprior;   // util.py:1013
+                if (l != l) l = -INFINITY;                                           // util.py:1015-1016
                 args.lnp[grow] = l;
             }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        if (args.dbg && (warp == 4 || warp == 8) && lane == 0) {
+            long long *d = args.dbg + (size_t)blockIdx.x * 16 + (warp == 4 ? 6 : 10);
+            d[0] = clock64() - e_begin, d[1] = e_wait, d[2] = e_drain, d[3] = e_epi;
+            if (warp == 4) args.dbg[(size_t)blockIdx.x * 16 + 14] = x.t_sfree;
+            else args.dbg[(size_t)blockIdx.x * 16 + 15] = x.t_sfree;
         }
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();      // neither CTA frees tensor memory (or exits) while its peer still computes on the pair
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -824,8 +888,8 @@ TcContext *tc_build(const linna_model *m, std::string &why)
         memset(&pg, 0, sizeof pg);
         if (pk == 1 && !has_grad) break;
         const bool grad = pk == 1;
-        int ns = 0, pubs = 1;   // the prologue publishes chunk 0
-        int slot_pub[NSLOT] = {0, 0, 0, 0}, slot_nch[NSLOT] = {1, 1, 1, 1};
+        int ns = 0, pubs[2] = {1, 0};   // the prologue publishes one chunk of column group 0
+        int slot_pub[NSLOT][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
         int mask_words = 0;
         std::vector<int> mask_y(nops, -1), mask_h(nops, -1);
         bool overflow = false;
@@ -839,18 +903,20 @@ TcContext *tc_build(const linna_model *m, std::string &why)
         // src slots are stored in s.src[] as slot ids first and turned into columns once the widths are known
         auto set_phase = [&](TfStep &s, int p, int slot, const MatSrc &ms, int shift) {
             s.src[p] = slot, s.K[p] = ms.K, s.mapB[p] = 2 + 2 * P.put(ms, shift);
-            s.src_pub[p] = slot_pub[slot], s.src_nch[p] = slot_nch[slot];
+            s.src_pub[p][0] = slot_pub[slot][0], s.src_pub[p][1] = slot_pub[slot][1];
         };
         auto set_dst = [&](TfStep &s, int slot) {
             s.dst = slot, s.dst_pad = pad64(s.N);
             slot_w[slot] = std::max(slot_w[slot], s.dst_pad);
-            slot_pub[slot] = pubs, slot_nch[slot] = (s.N + TF_NC - 1) / TF_NC;
-            pubs += slot_nch[slot];
+            for (int g = 0; g < 2; ++g) {   // column group g stores chunk ch iff 256 ch + 128 g < dst_pad
+                slot_pub[slot][g] = pubs[g];
+                for (int n0 = 0; n0 < s.N; n0 += TF_NC) pubs[g] += (n0 + 128 * g < s.dst_pad) ? 1 : 0;
+            }
         };
         auto set_bias = [&](const std::vector<float> &b, float scale, int N) {
             std::vector<float> e(N, 0.f);
             for (size_t i = 0; i < b.size() && (int)i < N; ++i) e[i] = scale * b[i];
-            bias_refs.push_back({pk, ns - 1, 0, P.fput(e, pad64(N) + 64)});
+            bias_refs.push_back({pk, ns - 1, 0, P.fput(e, pad64(N) + 256)});
         };
         // HEAD: y = yhat*y_std + y_mean (exp) ; m = y*sigma ; d = m - data (util.py:532-542, :457-458), handed on
         // as d/sigma = y - data/sigma so that it stays in the fp16 range whatever the units are.  Without exp the
@@ -863,11 +929,11 @@ TcContext *tc_build(const linna_model *m, std::string &why)
                 hb[i] = (float)((double)scale * b[i] * m->y_std[i] + m->y_mean[i] - (m->ypositive ? 0.0 : dos));
                 sub[i] = (float)dos;
             }
-            bias_refs.push_back({pk, ns - 1, 0, P.fput(hb, pad64(N) + 64)});
-            bias_refs.push_back({pk, ns - 1, 1, P.fput(vs, pad64(N) + 64)});
-            bias_refs.push_back({pk, ns - 1, 2, P.fput(sub, pad64(N) + 64)});
+            bias_refs.push_back({pk, ns - 1, 0, P.fput(hb, pad64(N) + 256)});
+            bias_refs.push_back({pk, ns - 1, 1, P.fput(vs, pad64(N) + 256)});
+            bias_refs.push_back({pk, ns - 1, 2, P.fput(sub, pad64(N) + 256)});
         };
-        auto new_mask = [&](int N) { int o = mask_words; mask_words += 4 * ((N + TF_NC - 1) / TF_NC); return o; };
+        auto new_mask = [&](int N) { int o = mask_words; mask_words += 8 * ((N + TF_NC - 1) / TF_NC); return o; };
         auto other = [&](int b) { return b == SLOT_A ? SLOT_B : SLOT_A; };
         int cur = SLOT_X;
         // ------------------------------ forward
@@ -993,7 +1059,7 @@ TcContext *tc_build(const linna_model *m, std::string &why)
             default: s.variant = TFV_GRADOUT; break;
             }
         }
-        pg.n_steps = ns, pg.total_pub = pubs, pg.seg_kc = seg_kc;
+        pg.n_steps = ns, pg.total_pub[0] = pubs[0], pg.total_pub[1] = pubs[1], pg.seg_kc = seg_kc;
         mask_words_total = std::max(mask_words_total, (mask_words + 3) & ~3);
     }
     // ---- arena columns
@@ -1012,13 +1078,13 @@ TcContext *tc_build(const linna_model *m, std::string &why)
 
     TcContext *t = new TcContext();
     auto bail = [&](const std::string &msg) { why = msg; tc_destroy(t); return (TcContext *)nullptr; };
-    t->grid = m->num_sms;
+    t->grid = m->num_sms & ~1;   // whole CTA pairs
     t->has_grad = has_grad;
     if (cudaMalloc(&t->wblob, P.w.size() * sizeof(__half)) != cudaSuccess) return bail("cudaMalloc weights");
     if (cudaMemcpy(t->wblob, P.w.data(), P.w.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) return bail("upload");
     if (cudaMalloc(&t->fblob, std::max<size_t>(P.f.size(), 64) * sizeof(float)) != cudaSuccess) return bail("cudaMalloc biases");
     if (!P.f.empty()) cudaMemcpy(t->fblob, P.f.data(), P.f.size() * sizeof(float), cudaMemcpyHostToDevice);
-    const size_t rows = (size_t)t->grid * 2 * TF_M;
+    const size_t rows = (size_t)t->grid * TF_M;
     if (cudaMalloc(&t->arena, rows * ld * sizeof(__half)) != cudaSuccess) return bail("cudaMalloc arena");
     cudaMemset(t->arena, 0, rows * ld * sizeof(__half));
     if (cudaMalloc(&t->masks, rows * (size_t)pgs[0].mask_words * sizeof(uint32_t)) != cudaSuccess) return bail("cudaMalloc masks");
@@ -1044,9 +1110,9 @@ TcContext *tc_build(const linna_model *m, std::string &why)
         return bail("cuTensorMapEncodeTiled(arena store) failed");
     for (size_t i = 0; i < P.mats.size(); ++i) {
         const Packer::Mat &mt = P.mats[i];
-        if (encode2d(&maps[2 + 2 * i], t->wblob + mt.hi, (uint64_t)mt.K, (uint64_t)mt.N, (uint64_t)mt.ldk * 2, TF_KC, TF_NC,
+        if (encode2d(&maps[2 + 2 * i], t->wblob + mt.hi, (uint64_t)mt.K, (uint64_t)mt.N, (uint64_t)mt.ldk * 2, TF_KC, TF_M,
                      CU_TENSOR_MAP_SWIZZLE_64B) != CUDA_SUCCESS ||
-            encode2d(&maps[3 + 2 * i], t->wblob + mt.lo, (uint64_t)mt.K, (uint64_t)mt.N, (uint64_t)mt.ldk * 2, TF_KC, TF_NC,
+            encode2d(&maps[3 + 2 * i], t->wblob + mt.lo, (uint64_t)mt.K, (uint64_t)mt.N, (uint64_t)mt.ldk * 2, TF_KC, TF_M,
                      CU_TENSOR_MAP_SWIZZLE_64B) != CUDA_SUCCESS)
             return bail("cuTensorMapEncodeTiled(weights) failed");
     }
@@ -1057,8 +1123,8 @@ TcContext *tc_build(const linna_model *m, std::string &why)
     if (cudaMalloc(&t->err_dev, sizeof(int)) != cudaSuccess) return bail("cudaMalloc err");
     cudaMemset(t->err_dev, 0, sizeof(int));
     if (getenv("LINNA_TC_DEBUG")) {
-        if (cudaMalloc(&t->dbg_dev, (size_t)t->grid * 8 * sizeof(long long)) != cudaSuccess) return bail("cudaMalloc dbg");
-        cudaMemset(t->dbg_dev, 0, (size_t)t->grid * 8 * sizeof(long long));
+        if (cudaMalloc(&t->dbg_dev, (size_t)t->grid * 16 * sizeof(long long)) != cudaSuccess) return bail("cudaMalloc dbg");
+        cudaMemset(t->dbg_dev, 0, (size_t)t->grid * 16 * sizeof(long long));
     }
     if (cudaFuncSetAttribute(tc_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES) != cudaSuccess)
         return bail("cudaFuncSetAttribute(tc_f16_kernel)");
@@ -1074,7 +1140,7 @@ int tc_debug_read(TcContext *t, long long *out, int max_ctas)
     if (!t || !t->dbg_dev) return 0;
     const int n = std::min(max_ctas, t->grid);
     cudaDeviceSynchronize();
-    cudaMemcpy(out, t->dbg_dev, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(out, t->dbg_dev, (size_t)n * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
     return n;
 }
 
@@ -1086,7 +1152,7 @@ static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const f
     a.prog = t->prog_dev + pk, a.maps = t->maps_dev, a.c = m->consts;
     a.in = u, a.lnp = lnp, a.grad = grad, a.masks = t->masks, a.n = n, a.err = t->err_dev, a.dbg = t->dbg_dev;
     const int64_t pairs = (n + 2 * TF_M - 1) / (2 * TF_M);
-    const int grid = (int)std::min<int64_t>(pairs, t->grid);
+    const int grid = 2 * (int)std::min<int64_t>(pairs, t->grid / 2);   // one cluster of two CTAs per walker pair
     tc_f16_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
     return cudaGetLastError();
 }
