@@ -137,6 +137,8 @@ int linna_model_set_path(linna_model_t *m, int32_t path, int64_t tc_min_rows);
 /* lnP evaluates the last linear layer, the inverse output transform and the Cholesky product as ONE folded
  * affine map (formed in float64 at pack time); 0 switches the folding off (unfolded reference order). */
 int linna_model_set_fold(linna_model_t *m, int32_t on);
+/* Which kernel served the last launch on this model: 0 none yet, 1 FP32 FFMA kernel, 2 tensor-core kernel. */
+int linna_model_last_kernel(const linna_model_t *m);
 /* Profiling hook (environment LINNA_TC_DEBUG set when the tensor-core context is built): copies the per-CTA
  * cycle counters of the last tensor-core launch into out[max_ctas][16] and returns the number of CTAs
  * (0 when the counters are off).  [0..2] TMA producer: total, waiting for a free stage, waiting for

@@ -790,6 +790,8 @@ int linna_model_set_path(linna_model_t *m, int32_t path, int64_t tc_min_rows)
     return LINNA_OK;
 }
 
+int linna_model_last_kernel(const linna_model_t *m) { return m ? m->last_kernel : 0; }
+
 int linna_debug_tc_counters(linna_model_t *m, int64_t *out, int32_t max_ctas)
 {
     if (!m || !out) return 0;
@@ -838,6 +840,7 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
             if (pk == PROG_LNP) CUDA_TRY(tc_launch_lnp(m, m->tc, in, n, lnp, stream));
             else CUDA_TRY(tc_launch_grad(m, m->tc, in, n, lnp, grad, stream));
             g_launches.fetch_add(1);
+            m->last_kernel = 2;
             CUDA_TRY(cudaEventRecord(m->last_done, stream));
             m->last_stream = stream, m->have_last = true;
             return LINNA_OK;
@@ -879,6 +882,7 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
         }
         CUDA_TRY(launch_fused_ffma(a, rg, grid, stream));
         g_launches.fetch_add(1);
+        m->last_kernel = 1;
         done += take;
     }
     CUDA_TRY(cudaEventRecord(m->last_done, stream));

@@ -72,6 +72,7 @@ struct linna_model {
     linna::TcContext *tc = nullptr;
     bool tc_failed = false;
     int path = 1;                 // 0 auto, 1 FFMA only, 2 tensor core only
+    int last_kernel = 0;          // kernel that served the last launch: 1 FFMA, 2 tensor core
     int64_t tc_min_rows = 8192;
     // host-buffer API staging
     cudaStream_t hstream = nullptr;

@@ -145,8 +145,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *e
 }
 __device__ __forceinline__ void mbar_wait_timed(uint64_t *bar, uint32_t parity, int *err, int code, long long &acc)
 {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    const long long t0 = clock64();   // try_wait itself suspends the thread for a while: time it from the start
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 2000000000LL) tf_die(err, code);
     }
@@ -369,7 +368,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
     __shared__ __align__(8) double chi_s[TF_M];
     __shared__ __align__(16) float bias_stage[2][2][128];   // [chunk parity][column group][column]
     __shared__ uint32_t tmem_slot;
-    __shared__ uint32_t ready_cnt[2];
+    __shared__ uint32_t ready_cnt[2][2];   // [slot][column group]
     __shared__ TfStep s_steps[TF_MAX_STEPS];
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -391,7 +390,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         for (int s = 0; s < TF_STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
         for (int b = 0; b < 2; ++b) mbar_init(&pfull_bar[b], 1), mbar_init(&pempty_bar[b], 16);   // 8 warps x 2 CTAs
         for (int b = 0; b < 2; ++b) mbar_init(&sfull_bar[b], 128), mbar_init(&sfree_bar[b], 1);
-        ready_cnt[0] = ready_cnt[1] = 0;
+        ready_cnt[0][0] = ready_cnt[0][1] = ready_cnt[1][0] = ready_cnt[1][1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -406,8 +405,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
     const uint32_t tmem_base = tmem_slot;
 
     const int64_t npairs = (args.n + 2 * TF_M - 1) / (2 * TF_M);
-    const int64_t pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
-    const int arena_row0 = blockIdx.x * TF_M;   // this CTA's rows of the activation arena
+    // Every cluster works on TWO walker pairs ("slots") at a time, interleaved step by step: while the last
+    // chunk of slot 0's layer goes through epilogue, store and publication, the tensor core already runs the same
+    // layer for slot 1, so the layer-to-layer dependency never idles the MMA pipe.
+    const int64_t pair0 = (int64_t)(blockIdx.x >> 1) * 2, pair_step = (int64_t)(gridDim.x >> 1) * 2;
+    const int arena_row0 = blockIdx.x * 2 * TF_M;   // this CTA's rows of the activation arena (slot 0, then slot 1)
 
     if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(56));
@@ -415,12 +417,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         // =============================== TMA producer (both CTAs) ===============================
         if (lane == 0) {
             int stage = 0;
-            uint32_t ph = 0, seen0 = 0, seen1 = 0, pubA = 0, pubB = 0;
+            uint32_t ph = 0, seen[2][2] = {{0, 0}, {0, 0}}, pubA = 0, pubB = 0;
             long long w_empty = 0, w_ready = 0;
             const long long t_begin = clock64();
             for (int64_t pair = pair0; pair < npairs; pair += pair_step, pubA += prog->total_pub[0], pubB += prog->total_pub[1]) {
+                const int nslots = pair + 1 < npairs ? 2 : 1;
                 for (int si = 0; si < n_steps; ++si) {
                     const TfStep &st = s_steps[si];
+                    for (int slot = 0; slot < nslots; ++slot)
                     for (int n0 = 0; n0 < st.N; n0 += TF_NC) {
                         const int nvalid = st.N - n0 < TF_NC ? st.N - n0 : TF_NC;
                         const int nb = n0 + (int)cta_rank * (((nvalid + 31) & ~31) >> 1);   // this CTA's half of the weight rows
@@ -439,10 +443,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                                 int chunk = col >> 8;
                                 const int grp = (col >> 7) & 1;
                                 uint32_t need = (grp ? pubB : pubA) + (uint32_t)st.src_pub[p][grp] + (uint32_t)chunk + 1u;
-                                uint32_t &seen = grp ? seen1 : seen0;
-                                if (seen < need) {
+                                uint32_t &seen_sg = seen[slot][grp];
+                                if (seen_sg < need) {
                                     const long long t0 = clock64();
-                                    while ((seen = ld_acquire_u32(&ready_cnt[grp])) < need) {
+                                    while ((seen_sg = ld_acquire_u32(&ready_cnt[slot][grp])) < need) {
                                         __nanosleep(64);
                                         if (clock64() - t0 > 2000000000LL) tf_die(args.err, 2);
                                     }
@@ -450,8 +454,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                                     fence_async_all();
                                 }
                                 const int ca = st.src[p] + col;
-                                tma_load_2d_pair(sb, maps, &full_bar[stage], ca, arena_row0);
-                                tma_load_2d_pair(sb + TF_TILE_BYTES, maps, &full_bar[stage], ca + lo_off, arena_row0);
+                                tma_load_2d_pair(sb, maps, &full_bar[stage], ca, arena_row0 + slot * TF_M);
+                                tma_load_2d_pair(sb + TF_TILE_BYTES, maps, &full_bar[stage], ca + lo_off, arena_row0 + slot * TF_M);
                                 if (++stage == TF_STAGES) stage = 0, ph ^= 1;
                             }
                         }
@@ -471,8 +475,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
             long long w_full = 0, w_pempty = 0;
             const long long t_begin = clock64();
             for (int64_t pair = pair0; pair < npairs; pair += pair_step) {
+                const int nslots = pair + 1 < npairs ? 2 : 1;
                 for (int si = 0; si < n_steps; ++si) {
                     const TfStep &st = s_steps[si];
+                    for (int slot = 0; slot < nslots; ++slot)
                     for (int n0 = 0; n0 < st.N; n0 += TF_NC) {
                         const int nvalid = st.N - n0 < TF_NC ? st.N - n0 : TF_NC;
                         // N rounded up to the 32 columns one tcgen05.ld drains: the extra rows of B are TMA zero fill
@@ -525,38 +531,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
             const int gi = warp - 2;
             uint8_t *stg_hi = stg_all + gi * TF_STG_BYTES, *stg_lo = stg_hi + TF_BOX_BYTES;
             const CUtensorMap *map_st = maps + 1;
-            uint32_t sidx = 0, pub = 0;
-            auto store_box = [&](int col) {
+            uint32_t sidx = 0, pub[2] = {0, 0}, pend[2] = {0, 0};
+            // Publication needs the stores to have LANDED (wait_group), which takes far longer than handing the
+            // staging box back (wait_group.read).  Chunks are therefore published lazily, when a later box has been
+            // issued and "all but the newest group complete" costs nothing -- except the last chunk of a layer pass,
+            // whose consumer may be waiting for exactly these columns.
+            auto publish = [&](bool blocking) {
+                if (!(pend[0] | pend[1])) return;
+                if (blocking) bulk_wait_all();
+                else asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+                fence_async_all();
+                for (int sl = 0; sl < 2; ++sl)
+                    if (pend[sl]) {
+                        pub[sl] += pend[sl], pend[sl] = 0;
+                        st_release_u32(&ready_cnt[sl][gi], pub[sl]);
+                    }
+            };
+            auto store_box = [&](int col, int slot) {
                 mbar_wait(&sfull_bar[gi], sidx & 1, args.err, 6);      // the 128 epilogue threads have written the box
-                tma_store_2d(stg_hi, map_st, col, arena_row0);
-                tma_store_2d(stg_lo, map_st, col + lo_off, arena_row0);
+                tma_store_2d(stg_hi, map_st, col, arena_row0 + slot * TF_M);
+                tma_store_2d(stg_lo, map_st, col + lo_off, arena_row0 + slot * TF_M);
                 bulk_commit();
                 bulk_wait_read();                                      // staging read out: hand it back
                 mbar_arrive(&sfree_bar[gi]);
                 ++sidx;
-            };
-            auto publish = [&]() {
-                bulk_wait_all();                                       // the stores have landed
-                fence_async_all();
-                st_release_u32(&ready_cnt[gi], ++pub);
+                publish(false);                                        // everything older than this box has landed
             };
             for (int64_t pair = pair0; pair < npairs; pair += pair_step) {
-                if (gi == 0) {
-                    store_box(prog->in_col);
-                    publish();
-                }
+                const int nslots = pair + 1 < npairs ? 2 : 1;
+                if (gi == 0)
+                    for (int slot = 0; slot < nslots; ++slot) {
+                        store_box(prog->in_col, slot);
+                        ++pend[slot];
+                        publish(true);
+                    }
                 for (int si = 0; si < n_steps; ++si) {
                     const TfStep &st = s_steps[si];
                     if (st.dst < 0) continue;
-                    for (int n0 = 0; n0 < st.N; n0 += TF_NC) {
-                        const int c0 = n0 + 128 * gi;
-                        if (c0 >= st.dst_pad) break;
-                        store_box(st.dst + c0);
-                        if (c0 + 64 < st.dst_pad) store_box(st.dst + c0 + 64);
-                        publish();
-                    }
+                    for (int slot = 0; slot < nslots; ++slot)
+                        for (int n0 = 0; n0 < st.N; n0 += TF_NC) {
+                            const int c0 = n0 + 128 * gi;
+                            if (c0 >= st.dst_pad) break;
+                            store_box(st.dst + c0, slot);
+                            if (c0 + 64 < st.dst_pad) store_box(st.dst + c0 + 64, slot);
+                            ++pend[slot];
+                            const bool last_chunk = c0 + TF_NC >= st.dst_pad;
+                            if (last_chunk && slot == nslots - 1) publish(true);   // the next box may be a whole layer away
+                        }
                 }
             }
+            publish(true);
         }
     }
     } else {
@@ -571,7 +595,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         x.sw = row & 7;
         x.sfree = &sfree_bar[gi], x.sfull = &sfull_bar[gi];
         x.sidx = 0;
-        x.mask_row = args.masks ? args.masks + (size_t)(arena_row0 + row) * prog->mask_words : nullptr;
+        uint32_t *const mask_row0 = args.masks ? args.masks + (size_t)(arena_row0 + row) * prog->mask_words : nullptr;
+        x.mask_row = mask_row0;
         x.err = args.err;
         x.chi = 0.0;
         x.t_sfree = 0;
@@ -583,11 +608,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         pempty_remote[0] = map_to_cta(smem_u32(&pempty_bar[0]), 0), pempty_remote[1] = map_to_cta(smem_u32(&pempty_bar[1]), 0);
 
         for (int64_t pair = pair0; pair < npairs; pair += pair_step) {
-            const int64_t grow = (pair * 2 + cta_rank) * TF_M + row;
-            const bool valid = grow < args.n;
+            const int nslots = pair + 1 < npairs ? 2 : 1;
             // ---- prologue (group 0): u -> theta -> xhat (util.py:323-347, :483-497), split, stage, TMA store
-            float lnprior = 0.f;
-            if (gi == 0) {
+            float lnprior2[2] = {0.f, 0.f};
+            double chi2[2] = {0.0, 0.0};
+            if (gi == 0)
+            for (int slot = 0; slot < nslots; ++slot) {
+                const int64_t grow = ((pair + slot) * 2 + cta_rank) * TF_M + row;
+                const bool valid = grow < args.n;
+                float lnprior = 0.f;
                 mbar_wait(x.sfree, (x.sidx & 1) ^ 1, args.err, 7);
                 const float *u = args.in + grow * n_in;
 #pragma unroll 1
@@ -615,15 +644,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                     *reinterpret_cast<uint4 *>(x.my_hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                     *reinterpret_cast<uint4 *>(x.my_lo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                 }
-                lnprior *= -0.5f;                                                    // util.py:1165
+                lnprior2[slot] = -0.5f * lnprior;                                    // util.py:1165
                 fence_async_smem();
                 mbar_arrive(x.sfull);
                 ++x.sidx;
             }
-            x.chi = 0.0;
             for (int si = 0; si < n_steps; ++si) {
                 const TfStep &st = s_steps[si];
                 const int nch = (st.N + TF_NC - 1) / TF_NC;
+                for (int slot = 0; slot < nslots; ++slot) {
+                const int64_t grow = ((pair + slot) * 2 + cta_rank) * TF_M + row;
+                const bool valid = grow < args.n;
+                x.mask_row = mask_row0 + (size_t)slot * TF_M * prog->mask_words;
+                x.chi = 0.0;
                 for (int ch = 0; ch < nch; ++ch) {
                     const int n0 = ch * TF_NC;
                     const int nvalid = st.N - n0 < TF_NC ? st.N - n0 : TF_NC;
@@ -705,16 +738,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                     }
                     e_epi += clock64() - t_c;
                 }
+                chi2[slot] += x.chi;
+                }
             }
             // combine the two column groups of every walker and finish lnP
-            if (gi == 1) chi_s[row] = x.chi;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (gi == 0 && valid && args.lnp) {
-                float l = (float)(-0.5 * (x.chi + chi_s[row])) * c.inv_T + lnprior;   // util.py:1013
-                if (l != l) l = -INFINITY;                                           // util.py:1015-1016
-                args.lnp[grow] = l;
+            for (int slot = 0; slot < nslots; ++slot) {
+                const int64_t grow = ((pair + slot) * 2 + cta_rank) * TF_M + row;
+                if (gi == 1) chi_s[row] = chi2[slot];
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (gi == 0 && grow < args.n && args.lnp) {
+                    float l = (float)(-0.5 * (chi2[slot] + chi_s[row])) * c.inv_T + lnprior2[slot];   // util.py:1013
+                    if (l != l) l = -INFINITY;                                                     // util.py:1015-1016
+                    args.lnp[grow] = l;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         if (args.dbg && (warp == 4 || warp == 8) && lane == 0) {
             long long *d = args.dbg + (size_t)blockIdx.x * 16 + (warp == 4 ? 6 : 10);
@@ -1084,7 +1122,7 @@ TcContext *tc_build(const linna_model *m, std::string &why)
     if (cudaMemcpy(t->wblob, P.w.data(), P.w.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) return bail("upload");
     if (cudaMalloc(&t->fblob, std::max<size_t>(P.f.size(), 64) * sizeof(float)) != cudaSuccess) return bail("cudaMalloc biases");
     if (!P.f.empty()) cudaMemcpy(t->fblob, P.f.data(), P.f.size() * sizeof(float), cudaMemcpyHostToDevice);
-    const size_t rows = (size_t)t->grid * TF_M;
+    const size_t rows = (size_t)t->grid * 2 * TF_M;   // two slots of 128 walkers per CTA
     if (cudaMalloc(&t->arena, rows * ld * sizeof(__half)) != cudaSuccess) return bail("cudaMalloc arena");
     cudaMemset(t->arena, 0, rows * ld * sizeof(__half));
     if (cudaMalloc(&t->masks, rows * (size_t)pgs[0].mask_words * sizeof(uint32_t)) != cudaSuccess) return bail("cudaMalloc masks");
@@ -1152,7 +1190,8 @@ static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const f
     a.prog = t->prog_dev + pk, a.maps = t->maps_dev, a.c = m->consts;
     a.in = u, a.lnp = lnp, a.grad = grad, a.masks = t->masks, a.n = n, a.err = t->err_dev, a.dbg = t->dbg_dev;
     const int64_t pairs = (n + 2 * TF_M - 1) / (2 * TF_M);
-    const int grid = 2 * (int)std::min<int64_t>(pairs, t->grid / 2);   // one cluster of two CTAs per walker pair
+    // one cluster of two CTAs per two walker pairs (slots)
+    const int grid = 2 * (int)std::min<int64_t>((pairs + 1) / 2, t->grid / 2);
     tc_f16_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
     return cudaGetLastError();
 }

@@ -85,6 +85,7 @@ def load_library():
     lib.linna_model_set_path.argtypes = [vp, i32, i64]
     lib.linna_model_set_fold.argtypes = [vp, i32]
     lib.linna_debug_tc_counters.argtypes = [vp, vp, i32]
+    lib.linna_model_last_kernel.argtypes = [vp]
     f32 = ctypes.c_float
     lib.linna_train_setup.argtypes = [vp, ctypes.POINTER(TrainDesc)]
     lib.linna_train_num_params.argtypes = [vp]
@@ -214,6 +215,10 @@ class Engine:
         """'auto' | 'ffma' | 'tc' -- which kernel serves lnp()."""
         code = {"auto": 0, "ffma": 1, "tc": 2}[path]
         self._check(self.lib.linna_model_set_path(self.handle, code, int(tc_min_rows)))
+
+    def last_kernel(self):
+        """'ffma' | 'tc' | None -- the kernel that served the last launch."""
+        return {0: None, 1: "ffma", 2: "tc"}[int(self.lib.linna_model_last_kernel(self.handle))]
 
     def tc_counters(self, max_ctas=256):
         """Per-CTA cycle counters of the last tensor-core launch (needs LINNA_TC_DEBUG=1 in the environment)."""

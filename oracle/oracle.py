@@ -240,5 +240,78 @@ class NumpyPort:
         return lnp
 
 
+def _port_lnp_grad(self, u):
+    """lnP and d lnP/du of the batched port: forward with saved activations, then the hand-written
+    backward pass (what torch.autograd does for linna/HMCSampler.py:29-32), all in float32 numpy/BLAS."""
+    from scipy.special import erf
+    o = self.o
+    sd = self.sd
+    u = np.asarray(u, np.float32)
+    a1, a2 = o.a1.astype(np.float32), o.a2.astype(np.float32)
+    flat = o.prior_kind == 1
+    theta = u * a2 + a1
+    dtheta = np.broadcast_to(a2, u.shape).copy()
+    if flat.any():
+        uf = u[:, flat]
+        phi = np.float32(0.5) * (1 + erf(uf / np.float32(np.sqrt(2)))).astype(np.float32)
+        theta[:, flat] = phi * (a2 - a1)[flat] + a1[flat]
+        dtheta[:, flat] = (a2 - a1)[flat] * np.float32(0.3989422804014327) * np.exp(np.float32(-0.5) * uf * uf)
+    tp = theta.copy()
+    lg = o.log10 == 1
+    dtp = np.ones_like(theta)
+    if lg.any():
+        tp[:, lg] = np.log10(theta[:, lg])
+        dtp[:, lg] = 1.0 / (theta[:, lg] * np.float32(np.log(10.0)))
+    xhat = ((tp - o.x_mean) / o.x_std).astype(np.float32)
+    # forward, keeping what the backward pass needs
+    saved = []
+    s = xhat
+    for op in self.arch_ops:
+        nm = op["name"]
+        if op["kind"] == "linear":
+            z = s @ sd[nm + ".weight"].T + sd[nm + ".bias"]
+            out = np.maximum(z, 0) if op["act"] == "relu" else z
+            saved.append((op, s, out, None))
+        else:
+            h = np.maximum(s @ sd[nm + ".layer1.weight"].T + sd[nm + ".layer1.bias"], 0)
+            y = (h @ sd[nm + ".layer2.weight"].T + sd[nm + ".layer2.bias"]) * np.float32(op["alpha"])
+            y += s @ sd[nm + ".skip_layer.weight"].T if op["in"] != op["out"] else s
+            out = np.maximum(y, 0)
+            saved.append((op, s, out, h))
+        s = out
+    yhat = s
+    if o_has_linear(o):
+        yhat = yhat + np.float32(1e-3) * (xhat @ sd["linearlayer.weight"].T + sd["linearlayer.bias"])
+    y = yhat * o.y_std + o.y_mean
+    if o.ypositive:
+        y = np.exp(y)
+    d = y * o.sigma - o.data
+    q = d @ o.invcov
+    chi2 = np.einsum("ij,ij->i", q, d)
+    lnp = np.float32(-0.5) * chi2 / np.float32(o.T) - np.float32(0.5) * np.sum(u * u, axis=1)
+    # backward
+    g = (-(q + d @ o.invcov.T) * np.float32(0.5) / np.float32(o.T)) * o.sigma * o.y_std
+    if o.ypositive:
+        g = g * y
+    gx = np.float32(1e-3) * (g @ sd["linearlayer.weight"]) if o_has_linear(o) else 0.0
+    for op, sin, out, h in reversed(saved):
+        nm = op["name"]
+        if op["kind"] == "linear":
+            if op["act"] == "relu":
+                g = g * (out > 0)
+            g = g @ sd[nm + ".weight"]
+        else:
+            g = g * (out > 0)
+            gh = (g @ sd[nm + ".layer2.weight"]) * np.float32(op["alpha"]) * (h > 0)
+            gs = g @ sd[nm + ".skip_layer.weight"] if op["in"] != op["out"] else g
+            g = gh @ sd[nm + ".layer1.weight"] + gs
+    g = (g + gx) / o.x_std * dtp * dtheta - u
+    lnp[np.isnan(lnp)] = -np.inf
+    return lnp, g.astype(np.float32)
+
+
+NumpyPort.lnp_grad = _port_lnp_grad
+
+
 def o_has_linear(o):
     return bool(o.has_linear)

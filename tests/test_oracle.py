@@ -58,6 +58,9 @@ def test_synthetic_f32(name):
     # the batched numpy port (CPU baseline of bench.py) computes the same thing
     lp = NumpyPort(o).lnp(g["u"])
     assert np.all(np.abs(lp - g["f64_lnp"]) <= np.maximum(4 * tol, 4 * err_ref))
+    lp2, gp = NumpyPort(o).lnp_grad(g["u"])                                  # --mode grad baseline
+    assert np.all(np.abs(lp2 - g["f64_lnp"]) <= np.maximum(4 * tol, 4 * err_ref))
+    assert rel_inf(gp, g["f64_grad"]) < 5e-4
 
 
 @pytest.mark.parametrize("name", SYNTH)
