@@ -703,6 +703,8 @@ int linna_model_create(const linna_model_desc_t *d, int device, linna_model_t **
     rc = rebuild(m);
     if (rc) { free_device(m); delete m; return rc; }
     if (cudaStreamCreateWithFlags(&m->hstream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&m->cstream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&m->dstream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->last_done, cudaEventDisableTiming) != cudaSuccess) {
         free_device(m); delete m;
         return fail(LINNA_ECUDA, "cudaStreamCreate/cudaEventCreate failed");
@@ -717,6 +719,10 @@ void linna_model_destroy(linna_model_t *m)
     cudaSetDevice(m->device);
     cudaDeviceSynchronize();
     if (m->hstream) cudaStreamDestroy(m->hstream);
+    if (m->cstream) cudaStreamDestroy(m->cstream);
+    if (m->dstream) cudaStreamDestroy(m->dstream);
+    for (cudaEvent_t e : m->pipe_events) cudaEventDestroy(e);
+    if (m->h_stage) cudaFreeHost(m->h_stage);
     if (m->last_done) cudaEventDestroy(m->last_done);
     if (m->tc) tc_destroy(m->tc);
     if (m->d_in) cudaFree(m->d_in);
@@ -936,20 +942,87 @@ int linna_predict_host(linna_model_t *m, const float *theta, int64_t n, float *o
     return LINNA_OK;
 }
 
+// Host-buffer lnP / lnP+gradient: the batch is cut into chunks of one full wave of the tensor-core kernel
+// (2 walker-pair slots x 256 rows on every CTA pair) and the three legs run on three streams, so that the
+// host->device copy of chunk k+1 and the device->host copy of chunk k-1 hide behind the kernel of chunk k.
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+static int lnp_host_pipelined(linna_model *m, const float *u, int64_t n, float *lnp, float *grad)
+{
+    CUDA_TRY(cudaSetDevice(m->device));
+    int rc;
+    const int n_in = m->n_in;
+    if ((rc = ensure(&m->d_in, &m->d_in_cap, (size_t)n * n_in))) return rc;
+    if ((rc = ensure(&m->d_lnp, &m->d_lnp_cap, (size_t)n))) return rc;
+    if (grad && (rc = ensure(&m->d_grad, &m->d_grad_cap, (size_t)n * n_in))) return rc;
+    // A device->host copy into pageable memory blocks the calling thread until the kernel before it has finished,
+    // which would serialise the pipeline: results for pageable user buffers land in a pinned staging area first
+    // and are copied out by the host while the GPU works on the next chunk.
+    const bool stage = !is_pinned_host(lnp) || (grad && !is_pinned_host(grad));
+    float *s_lnp = lnp, *s_grad = grad;
+    if (stage) {
+        const size_t need = (size_t)n * (1 + (grad ? n_in : 0));
+        if (m->h_stage_cap < need) {
+            if (m->h_stage) cudaFreeHost(m->h_stage);
+            m->h_stage = nullptr, m->h_stage_cap = 0;
+            if (cudaHostAlloc(&m->h_stage, (need + need / 4) * sizeof(float), cudaHostAllocDefault) != cudaSuccess)
+                return fail(LINNA_ENOMEM, "cudaHostAlloc of %zu floats failed", need);
+            m->h_stage_cap = need + need / 4;
+        }
+        s_lnp = m->h_stage, s_grad = m->h_stage + n;
+    }
+    const int64_t wave = (int64_t)(m->num_sms / 2) * 2 * 256;
+    int64_t chunk = n;
+    if (n >= 2 * wave) chunk = wave * ((n / wave + 15) / 16);          // at most 16 chunks
+    const int nchunks = (int)((n + chunk - 1) / chunk);
+    while ((int)m->pipe_events.size() < 3 * nchunks) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        m->pipe_events.push_back(e);
+    }
+    auto copy_out = [&](int k) -> int {   // host side of chunk k: wait for its device->host copy, hand it to the caller
+        const int64_t r0 = (int64_t)k * chunk, rows = std::min(chunk, n - r0);
+        CUDA_TRY(cudaEventSynchronize(m->pipe_events[3 * k + 2]));
+        memcpy(lnp + r0, s_lnp + r0, (size_t)rows * sizeof(float));
+        if (grad) memcpy(grad + r0 * n_in, s_grad + r0 * n_in, (size_t)rows * n_in * sizeof(float));
+        return LINNA_OK;
+    };
+    for (int k = 0; k < nchunks; ++k) {
+        const int64_t r0 = (int64_t)k * chunk, rows = std::min(chunk, n - r0);
+        cudaEvent_t landed = m->pipe_events[3 * k], done = m->pipe_events[3 * k + 1], home = m->pipe_events[3 * k + 2];
+        CUDA_TRY(cudaMemcpyAsync(m->d_in + r0 * n_in, u + r0 * n_in, (size_t)rows * n_in * sizeof(float), cudaMemcpyHostToDevice,
+                                 m->cstream));
+        CUDA_TRY(cudaEventRecord(landed, m->cstream));
+        CUDA_TRY(cudaStreamWaitEvent(m->hstream, landed, 0));
+        rc = grad ? linna_lnp_grad(m, m->d_in + r0 * n_in, rows, m->d_lnp + r0, m->d_grad + r0 * n_in, m->hstream)
+                  : linna_lnp(m, m->d_in + r0 * n_in, rows, m->d_lnp + r0, m->hstream);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(done, m->hstream));
+        CUDA_TRY(cudaStreamWaitEvent(m->dstream, done, 0));
+        CUDA_TRY(cudaMemcpyAsync(s_lnp + r0, m->d_lnp + r0, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost, m->dstream));
+        if (grad)
+            CUDA_TRY(cudaMemcpyAsync(s_grad + r0 * n_in, m->d_grad + r0 * n_in, (size_t)rows * n_in * sizeof(float),
+                                     cudaMemcpyDeviceToHost, m->dstream));
+        CUDA_TRY(cudaEventRecord(home, m->dstream));
+        if (stage && k > 0 && (rc = copy_out(k - 1))) return rc;
+    }
+    if (stage && (rc = copy_out(nchunks - 1))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(m->dstream));
+    CUDA_TRY(cudaStreamSynchronize(m->hstream));
+    return LINNA_OK;
+}
+
 int linna_lnp_host(linna_model_t *m, const float *u, int64_t n, float *lnp)
 {
     if (!m) return fail(LINNA_EINVAL, "null model");
     if (n <= 0) return n == 0 ? LINNA_OK : fail(LINNA_EINVAL, "negative n");
     if (!u || !lnp) return fail(LINNA_EINVAL, "null buffer");
-    CUDA_TRY(cudaSetDevice(m->device));
-    int rc;
-    if ((rc = ensure(&m->d_in, &m->d_in_cap, (size_t)n * m->n_in))) return rc;
-    if ((rc = ensure(&m->d_lnp, &m->d_lnp_cap, (size_t)n))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(m->d_in, u, (size_t)n * m->n_in * sizeof(float), cudaMemcpyHostToDevice, m->hstream));
-    if ((rc = linna_lnp(m, m->d_in, n, m->d_lnp, m->hstream))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(lnp, m->d_lnp, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, m->hstream));
-    CUDA_TRY(cudaStreamSynchronize(m->hstream));
-    return LINNA_OK;
+    return lnp_host_pipelined(m, u, n, lnp, nullptr);
 }
 
 int linna_lnp_grad_host(linna_model_t *m, const float *u, int64_t n, float *lnp, float *grad)
@@ -957,17 +1030,7 @@ int linna_lnp_grad_host(linna_model_t *m, const float *u, int64_t n, float *lnp,
     if (!m) return fail(LINNA_EINVAL, "null model");
     if (n <= 0) return n == 0 ? LINNA_OK : fail(LINNA_EINVAL, "negative n");
     if (!u || !lnp || !grad) return fail(LINNA_EINVAL, "null buffer");
-    CUDA_TRY(cudaSetDevice(m->device));
-    int rc;
-    if ((rc = ensure(&m->d_in, &m->d_in_cap, (size_t)n * m->n_in))) return rc;
-    if ((rc = ensure(&m->d_lnp, &m->d_lnp_cap, (size_t)n))) return rc;
-    if ((rc = ensure(&m->d_grad, &m->d_grad_cap, (size_t)n * m->n_in))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(m->d_in, u, (size_t)n * m->n_in * sizeof(float), cudaMemcpyHostToDevice, m->hstream));
-    if ((rc = linna_lnp_grad(m, m->d_in, n, m->d_lnp, m->d_grad, m->hstream))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(lnp, m->d_lnp, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, m->hstream));
-    CUDA_TRY(cudaMemcpyAsync(grad, m->d_grad, (size_t)n * m->n_in * sizeof(float), cudaMemcpyDeviceToHost, m->hstream));
-    CUDA_TRY(cudaStreamSynchronize(m->hstream));
-    return LINNA_OK;
+    return lnp_host_pipelined(m, u, n, lnp, grad);
 }
 
 // ------------------------------------------------------------------------------------------ training

@@ -75,7 +75,11 @@ struct linna_model {
     int last_kernel = 0;          // kernel that served the last launch: 1 FFMA, 2 tensor core
     int64_t tc_min_rows = 8192;
     // host-buffer API staging
-    cudaStream_t hstream = nullptr;
+    cudaStream_t hstream = nullptr;                  // compute stream of the host-buffer entry points
+    cudaStream_t cstream = nullptr, dstream = nullptr;   // host->device / device->host copy streams (pipelined chunks)
+    std::vector<cudaEvent_t> pipe_events;            // 3 per chunk: input landed, kernel finished, results on the host
+    float *h_stage = nullptr;                        // pinned staging for results that go to pageable user buffers
+    size_t h_stage_cap = 0;
     float *d_in = nullptr, *d_out = nullptr, *d_lnp = nullptr, *d_grad = nullptr;
     size_t d_in_cap = 0, d_out_cap = 0, d_lnp_cap = 0, d_grad_cap = 0;
 };

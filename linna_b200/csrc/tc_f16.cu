@@ -97,6 +97,7 @@ struct TfArgs {
     float *grad;
     uint32_t *masks;
     int64_t n;
+    int32_t slots;            // walker pairs interleaved per cluster: 2, or 1 when the batch cannot fill the GPU twice
     int *err;
     long long *dbg;           // optional [grid][8] cycle counters (LINNA_TC_DEBUG): where the service warps wait
 };
@@ -408,7 +409,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
     // Every cluster works on TWO walker pairs ("slots") at a time, interleaved step by step: while the last
     // chunk of slot 0's layer goes through epilogue, store and publication, the tensor core already runs the same
     // layer for slot 1, so the layer-to-layer dependency never idles the MMA pipe.
-    const int64_t pair0 = (int64_t)(blockIdx.x >> 1) * 2, pair_step = (int64_t)(gridDim.x >> 1) * 2;
+    const int64_t pair0 = (int64_t)(blockIdx.x >> 1) * args.slots, pair_step = (int64_t)(gridDim.x >> 1) * args.slots;
     const int arena_row0 = blockIdx.x * 2 * TF_M;   // this CTA's rows of the activation arena (slot 0, then slot 1)
 
     if (warp < 4) {
@@ -421,7 +422,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
             long long w_empty = 0, w_ready = 0;
             const long long t_begin = clock64();
             for (int64_t pair = pair0; pair < npairs; pair += pair_step, pubA += prog->total_pub[0], pubB += prog->total_pub[1]) {
-                const int nslots = pair + 1 < npairs ? 2 : 1;
+                const int nslots = (args.slots == 2 && pair + 1 < npairs) ? 2 : 1;
                 for (int si = 0; si < n_steps; ++si) {
                     const TfStep &st = s_steps[si];
                     for (int slot = 0; slot < nslots; ++slot)
@@ -475,7 +476,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
             long long w_full = 0, w_pempty = 0;
             const long long t_begin = clock64();
             for (int64_t pair = pair0; pair < npairs; pair += pair_step) {
-                const int nslots = pair + 1 < npairs ? 2 : 1;
+                const int nslots = (args.slots == 2 && pair + 1 < npairs) ? 2 : 1;
                 for (int si = 0; si < n_steps; ++si) {
                     const TfStep &st = s_steps[si];
                     for (int slot = 0; slot < nslots; ++slot)
@@ -558,7 +559,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                 publish(false);                                        // everything older than this box has landed
             };
             for (int64_t pair = pair0; pair < npairs; pair += pair_step) {
-                const int nslots = pair + 1 < npairs ? 2 : 1;
+                const int nslots = (args.slots == 2 && pair + 1 < npairs) ? 2 : 1;
                 if (gi == 0)
                     for (int slot = 0; slot < nslots; ++slot) {
                         store_box(prog->in_col, slot);
@@ -608,7 +609,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         pempty_remote[0] = map_to_cta(smem_u32(&pempty_bar[0]), 0), pempty_remote[1] = map_to_cta(smem_u32(&pempty_bar[1]), 0);
 
         for (int64_t pair = pair0; pair < npairs; pair += pair_step) {
-            const int nslots = pair + 1 < npairs ? 2 : 1;
+            const int nslots = (args.slots == 2 && pair + 1 < npairs) ? 2 : 1;
             // ---- prologue (group 0): u -> theta -> xhat (util.py:323-347, :483-497), split, stage, TMA store
             float lnprior2[2] = {0.f, 0.f};
             double chi2[2] = {0.0, 0.0};
@@ -1190,8 +1191,10 @@ static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const f
     a.prog = t->prog_dev + pk, a.maps = t->maps_dev, a.c = m->consts;
     a.in = u, a.lnp = lnp, a.grad = grad, a.masks = t->masks, a.n = n, a.err = t->err_dev, a.dbg = t->dbg_dev;
     const int64_t pairs = (n + 2 * TF_M - 1) / (2 * TF_M);
-    // one cluster of two CTAs per two walker pairs (slots)
-    const int grid = 2 * (int)std::min<int64_t>((pairs + 1) / 2, t->grid / 2);
+    // one cluster of two CTAs per two walker pairs (slots); small batches spread one pair per cluster instead
+    const int64_t clusters = t->grid / 2;
+    a.slots = pairs > clusters ? 2 : 1;
+    const int grid = 2 * (int)std::min<int64_t>((pairs + a.slots - 1) / a.slots, clusters);
     tc_f16_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
     return cudaGetLastError();
 }
