@@ -118,6 +118,16 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is supposed to use every host thread it can."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=host_threads())
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext()
+
+
 def cpu_port_rate(p, data, n_sample, repeats, grad=False):
     """Time the oracle's batched numpy/BLAS port of the reference arithmetic on the host cores."""
     from oracle.oracle import NumpyPort, Oracle
@@ -126,11 +136,12 @@ def cpu_port_rate(p, data, n_sample, repeats, grad=False):
     port = NumpyPort(o)
     call = port.lnp_grad if grad else port.lnp
     u = synthetic.walkers(n_sample, p.n_in, scale=0.3, seed=11)
-    call(u[:256])
-    t0 = time.perf_counter()
-    for _ in range(repeats):
-        call(u)
-    dt = time.perf_counter() - t0
+    with all_host_threads():
+        call(u[:256])
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            call(u)
+        dt = time.perf_counter() - t0
     return n_sample * repeats / dt, dt
 
 
@@ -151,12 +162,13 @@ def run_reference(args):
     n_sample = min(n, args.ref_sample)
     u = synthetic.walkers(n_sample, p.n_in, scale=0.3, seed=1)
     call = port.lnp_grad if args.mode == "grad" else port.lnp
-    for _ in range(max(args.warmup, 1)):
-        call(u)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        call(u)
-    dt = time.perf_counter() - t0
+    with all_host_threads():
+        for _ in range(max(args.warmup, 1)):
+            call(u)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            call(u)
+        dt = time.perf_counter() - t0
     val = n_sample * args.steps / dt
     cores = host_threads()
     line = {"impl": "reference", "metric": METRIC if args.mode == "lnp" else "emulator log-likelihood+grad evals/sec", "value": val, "unit": "evals/s", "n_gpus": args.gpus,

@@ -1191,9 +1191,12 @@ static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const f
     a.prog = t->prog_dev + pk, a.maps = t->maps_dev, a.c = m->consts;
     a.in = u, a.lnp = lnp, a.grad = grad, a.masks = t->masks, a.n = n, a.err = t->err_dev, a.dbg = t->dbg_dev;
     const int64_t pairs = (n + 2 * TF_M - 1) / (2 * TF_M);
-    // one cluster of two CTAs per two walker pairs (slots); small batches spread one pair per cluster instead
+    // One cluster of two CTAs per walker pair.  LINNA_TC_SLOTS=2 interleaves two pairs per cluster layer by layer
+    // (hides the layer-to-layer dependency bubble, but doubles the activation arena in flight: measured equal on
+    // lnP and 5% slower on lnP+grad at C3 because the L2 hit rate drops from 78% to 58%).
     const int64_t clusters = t->grid / 2;
-    a.slots = pairs > clusters ? 2 : 1;
+    static const int want_slots = getenv("LINNA_TC_SLOTS") ? atoi(getenv("LINNA_TC_SLOTS")) : 1;
+    a.slots = (want_slots == 2 && pairs > clusters) ? 2 : 1;
     const int grid = 2 * (int)std::min<int64_t>((pairs + a.slots - 1) / a.slots, clusters);
     tc_f16_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
     return cudaGetLastError();

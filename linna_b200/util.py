@@ -557,3 +557,5 @@ for _f in (gauss2unif, invgauss2unif, gaussianlogliklihood, lnprior, retrieve_mo
 del _c, _f
 
 from .trainer import train_nn, train_NN  # noqa: E402,F401  (pickled by path linna.util.train_NN, main.py:189-198)
+from .orchestrate import chisqcut_all, generate_training_point, run_mcmc  # noqa: E402,F401  (linna/util.py:1166-1504)
+from .sampler import read_chain_and_cut  # noqa: E402,F401  (linna/util.py:68-94)

@@ -1,0 +1,67 @@
+"""GPU end-to-end tests of ``ml_sampler_core`` (linna/main.py:77-334): the reference's own smoke test
+(tests/test_main.py:8-43 -- 2-D Gaussian, identity theory, ntrain=20) and a posterior-moment check against the
+analytic Gaussian posterior (docs/notebooks/multivariate_gaussian_distribution.ipynb cells 8-9; SURVEY 8c: the
+shipped chain cannot be read without emcee/h5py, so moments are pinned analytically)."""
+import os
+from copy import deepcopy
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from linna.main import ml_sampler_core
+from linna.nn import ChtoModelv2
+
+pytestmark = pytest.mark.gpu
+
+
+def theory(x, outdirs):
+    return deepcopy(x[1])
+
+
+def _priors(ndim, lo, hi):
+    return [{"param": "test_{0}".format(i), "dist": "flat", "arg1": lo, "arg2": hi} for i in range(ndim)]
+
+
+def test_main_reference_smoke(tmp_path):
+    np.random.seed(0)
+    ndim = 2
+    init = np.random.uniform(size=ndim)
+    cov, means = np.diag([0.5, 0.2]), np.array([0.1, 1.0])
+    params = {"trainingoption": 1, "num_epochs": 10, "batch_size": 5}
+    outdir = str(tmp_path / "2dgaussian_Fulltconn") + "/"
+    chain, logprob = ml_sampler_core([20], [5], [1], [2], [0.5], [100], [100], outdir, theory, _priors(ndim, -2.0, 2.0), means,
+                                     cov, init, None, 4, "cuda", None, False, [1.0], omegab2cut=None, docuda=False, tsize=1,
+                                     gpunode=None, nnmodel_in=ChtoModelv2, params=params, method="emcee")
+    it = os.path.join(outdir, "iter_0")
+    for f in ("train_samples_x.txt", "train_samples_y.npy", "val_samples_x.txt", "val_samples_y.npy", "X_transform.pkl",
+              "y_transform.pkl", "y_invtransform_data.pkl", "model_pickle.pkl", "model_args.pkl", "best.pth.tar", "finish.pkl",
+              "chemcee_256.npz"):
+        assert os.path.isfile(os.path.join(it, f)), f
+    assert chain.ndim == 2 and chain.shape[1] == ndim and np.all(np.isfinite(chain))
+    assert np.all(np.abs(chain) <= 2.0)                       # flat prior box
+    assert len(np.asarray(logprob).reshape(-1)) >= len(chain)
+    # a second call finds everything on disk and only reads the chain back
+    chain2, _ = ml_sampler_core([20], [5], [1], [2], [0.5], [100], [100], outdir, theory, _priors(ndim, -2.0, 2.0), means, cov,
+                                init, None, 4, "cuda", None, False, [1.0], params=params, method="emcee")
+    assert np.array_equal(chain, chain2)
+
+
+def test_main_posterior_moments(tmp_path):
+    """Two iterations (T = 4, then 1) on a 3-D Gaussian with an identity theory: the emulator-driven chain has to
+    reproduce the analytic posterior N(means, cov) (flat priors far away)."""
+    np.random.seed(1)
+    torch.manual_seed(1)
+    ndim = 3
+    means = np.array([0.3, -0.5, 0.8])
+    cov = np.diag([0.04, 0.09, 0.0225])
+    params = {"trainingoption": 1, "num_epochs": 80, "batch_size": 200}
+    outdir = str(tmp_path / "gauss3") + "/"
+    chain, logprob = ml_sampler_core([2000, 2000], [200, 200], [4, 8], [10, 25], [0.1, 0.05], [0.3, 0.2], [0.3, 0.2], outdir,
+                                     theory, _priors(ndim, -3.0, 3.0), means, cov, means + 0.05, None, 32, "cuda", None, False,
+                                     [2.0, 1.0], params=params, method="emcee")
+    assert len(chain) > 3000
+    sd = np.sqrt(np.diag(cov))
+    assert np.all(np.abs(chain.mean(axis=0) - means) < 0.15 * sd), (chain.mean(axis=0), means)
+    assert np.all(np.abs(chain.std(axis=0) / sd - 1.0) < 0.15), (chain.std(axis=0), sd)
