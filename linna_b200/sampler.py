@@ -75,7 +75,7 @@ class ChainStore:
     """Chain file with the reference's dataset names (linna/sampler.py:330-339, :572-578)."""
 
     def __init__(self, filename, transform=None):
-        self.base = filename[:-3] if filename.endswith(".h5") else filename
+        self.base = filename[:-3] if filename.endswith(".h5") else filename[:-4] if filename.endswith(".npz") else filename
         self.transform = transform
         self.chain = None           # [steps, walkers, ndim] latent positions
         self.chain_transformed = None
