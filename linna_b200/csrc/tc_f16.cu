@@ -9,8 +9,9 @@
 //     products and fp32 accumulation in tensor memory.  kind::f16 runs at twice the TF32 rate and the
 //     operands are half as wide, so the three passes cost what 1.5 TF32 passes would.
 //   * two-level accumulation.  The tensor core truncates its fp32 accumulator on every tcgen05.mma
-//     (measured: a toward-zero bias of ~0.5 ulp per instruction), so every `seg_kc` k-chunks the partial
-//     tile is drained from tensor memory and added with round-to-nearest into fp32 REGISTER accumulators
+//     (measured: a toward-zero bias of ~0.5 ulp per instruction), so every `seg_kc` k-chunks (default 4 = 128
+//     values of K = 24 instructions; measured max relative lnP error 3.2e-7 at 4, 2.1e-7 at 2, both at the
+//     level of the reference's own float32) the partial tile is drained from tensor memory and added with round-to-nearest into fp32 REGISTER accumulators
 //     by the epilogue warps, while the MMA warp already fills the other TMEM buffer.
 //   * two walker tiles (X, Y: 2 x 128 rows) per CTA share every weight tile that TMA brings into
 //     shared memory: half the L2 weight traffic per walker, and twice the work per pipeline stage.
@@ -63,7 +64,7 @@ struct TfStep {
     int32_t src[2];       // arena column of the hi copy of this phase's A operand; lo copy at + lo_off
     int32_t K[2];
     int32_t mapB[2];      // tensor-map index of the hi weight operand; lo = + 1
-    int32_t src_pub[2][2];   // [phase][group]: chunks the group published (per tile pass) before the producer of src
+    int32_t src_pub[2][2];   // [phase][group]: 64-column boxes the group published (per tile pass) before the producer of src
     int32_t N;
     int32_t dst;          // arena column of the output (hi), -1: none
     int32_t dst_pad;      // output width rounded up to 64 (pad columns are written as zeros)
@@ -79,7 +80,7 @@ struct TfStep {
 
 struct TfProgram {
     int32_t n_steps;
-    int32_t total_pub[2];  // chunks each column group publishes per tile pass (prologue included)
+    int32_t total_pub[2];  // 64-column boxes each column group publishes per tile pass (prologue included)
     int32_t in_col;        // arena column of xhat
     int32_t lo_off;        // column offset from a hi copy to its lo copy
     int32_t seg_kc;        // k-chunks accumulated in tensor memory between two drains
@@ -441,9 +442,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                                 tma_load_2d_pair(sb + 3 * TF_TILE_BYTES, mb + 1, &full_bar[stage], kc * TF_KC, nb);
                                 // the activations this k-chunk reads: wait until their producer chunk is visible
                                 const int col = kc * TF_KC;
-                                int chunk = col >> 8;
                                 const int grp = (col >> 7) & 1;
-                                uint32_t need = (grp ? pubB : pubA) + (uint32_t)st.src_pub[p][grp] + (uint32_t)chunk + 1u;
+                                const uint32_t box = (uint32_t)((col >> 8) * 2 + ((col & 127) >> 6));   // 64-column box of this group
+                                uint32_t need = (grp ? pubB : pubA) + (uint32_t)st.src_pub[p][grp] + box + 1u;
                                 uint32_t &seen_sg = seen[slot][grp];
                                 if (seen_sg < need) {
                                     const long long t0 = clock64();
@@ -557,13 +558,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                 mbar_arrive(&sfree_bar[gi]);
                 ++sidx;
                 publish(false);                                        // everything older than this box has landed
+                ++pend[slot];                                          // publication unit = one 64-column box
             };
             for (int64_t pair = pair0; pair < npairs; pair += pair_step) {
                 const int nslots = (args.slots == 2 && pair + 1 < npairs) ? 2 : 1;
                 if (gi == 0)
                     for (int slot = 0; slot < nslots; ++slot) {
                         store_box(prog->in_col, slot);
-                        ++pend[slot];
                         publish(true);
                     }
                 for (int si = 0; si < n_steps; ++si) {
@@ -575,7 +576,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                             if (c0 >= st.dst_pad) break;
                             store_box(st.dst + c0, slot);
                             if (c0 + 64 < st.dst_pad) store_box(st.dst + c0 + 64, slot);
-                            ++pend[slot];
                             const bool last_chunk = c0 + TF_NC >= st.dst_pad;
                             if (last_chunk && slot == nslots - 1) publish(true);   // the next box may be a whole layer away
                         }
@@ -604,6 +604,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         const int n_in = c.n_in;
         uint32_t g = 0, nchunk = 0;
         long long e_wait = 0, e_drain = 0, e_epi = 0;
+        const bool timing = args.dbg != nullptr;
         const long long e_begin = clock64();
         uint32_t pempty_remote[2];   // the leader's drain barriers, as cluster addresses
         pempty_remote[0] = map_to_cta(smem_u32(&pempty_bar[0]), 0), pempty_remote[1] = map_to_cta(smem_u32(&pempty_bar[1]), 0);
@@ -673,9 +674,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
 #pragma unroll 1
                     for (int sg = 0; sg < nseg; ++sg) {
                         const int buf = g & 1;
-                        const long long t_a = clock64();
+                        const long long t_a = timing ? clock64() : 0;
                         mbar_wait(&pfull_bar[buf], (g >> 1) & 1, args.err, 5);
-                        const long long t_b = clock64();
+                        const long long t_b = timing ? clock64() : 0;
                         tc_fence_after();
 #pragma unroll
                         for (int cb = 0; cb < 128; cb += 32) {
@@ -690,9 +691,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(pempty_remote[buf]);   // one arrival per warp at the leader
                         ++g;
-                        e_wait += t_b - t_a, e_drain += clock64() - t_b;
+                        if (timing) e_wait += t_b - t_a, e_drain += clock64() - t_b;
                     }
-                    const long long t_c = clock64();
+                    const long long t_c = timing ? clock64() : 0;
                     // ---------------- chunk epilogue (one compact specialisation per kind of step)
                     const int mword = st.mask_word + 8 * ch + 4 * gi;
                     float *bias_s = bias_stage[nchunk & 1][gi];
@@ -737,7 +738,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                         }
                     } break;
                     }
-                    e_epi += clock64() - t_c;
+                    if (timing) e_epi += clock64() - t_c;
                 }
                 chi2[slot] += x.chi;
                 }
@@ -797,8 +798,8 @@ static inline int pad8(int n) { return (n + 7) & ~7; }
 static int tc_seg_kc()
 {
     const char *e = getenv("LINNA_TC_SEG_KC");
-    int v = e ? atoi(e) : 2;
-    return v > 0 ? v : 2;
+    int v = e ? atoi(e) : 4;
+    return v > 0 ? v : 4;
 }
 
 void tc_destroy(TcContext *t)
@@ -947,9 +948,10 @@ TcContext *tc_build(const linna_model *m, std::string &why)
         auto set_dst = [&](TfStep &s, int slot) {
             s.dst = slot, s.dst_pad = pad64(s.N);
             slot_w[slot] = std::max(slot_w[slot], s.dst_pad);
-            for (int g = 0; g < 2; ++g) {   // column group g stores chunk ch iff 256 ch + 128 g < dst_pad
+            for (int g = 0; g < 2; ++g) {   // column group g stores the 64-column boxes of [256 ch + 128 g, +128) below dst_pad
                 slot_pub[slot][g] = pubs[g];
-                for (int n0 = 0; n0 < s.N; n0 += TF_NC) pubs[g] += (n0 + 128 * g < s.dst_pad) ? 1 : 0;
+                for (int n0 = 0; n0 < s.N; n0 += TF_NC)
+                    pubs[g] += (n0 + 128 * g < s.dst_pad ? 1 : 0) + (n0 + 128 * g + 64 < s.dst_pad ? 1 : 0);
             }
         };
         auto set_bias = [&](const std::vector<float> &b, float scale, int N) {
@@ -1191,11 +1193,12 @@ static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const f
     a.prog = t->prog_dev + pk, a.maps = t->maps_dev, a.c = m->consts;
     a.in = u, a.lnp = lnp, a.grad = grad, a.masks = t->masks, a.n = n, a.err = t->err_dev, a.dbg = t->dbg_dev;
     const int64_t pairs = (n + 2 * TF_M - 1) / (2 * TF_M);
-    // One cluster of two CTAs per walker pair.  LINNA_TC_SLOTS=2 interleaves two pairs per cluster layer by layer
-    // (hides the layer-to-layer dependency bubble, but doubles the activation arena in flight: measured equal on
-    // lnP and 5% slower on lnP+grad at C3 because the L2 hit rate drops from 78% to 58%).
+    // One cluster of two CTAs per TWO walker pairs ("slots"), interleaved layer by layer: the layer-to-layer
+    // dependency bubble of one pair is filled with the other pair's MMAs (measured +4% on lnP, +1% on lnP+grad at
+    // C3; the activation arena in flight doubles and the L2 hit rate drops from 78% to 58%, which is why it is not
+    // more).  Batches that cannot fill every cluster twice spread one pair per cluster; LINNA_TC_SLOTS=1 forces that.
     const int64_t clusters = t->grid / 2;
-    static const int want_slots = getenv("LINNA_TC_SLOTS") ? atoi(getenv("LINNA_TC_SLOTS")) : 1;
+    static const int want_slots = getenv("LINNA_TC_SLOTS") ? atoi(getenv("LINNA_TC_SLOTS")) : 2;
     a.slots = (want_slots == 2 && pairs > clusters) ? 2 : 1;
     const int grid = 2 * (int)std::min<int64_t>((pairs + a.slots - 1) / a.slots, clusters);
     tc_f16_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
