@@ -71,9 +71,9 @@ struct linna_model {
     // tensor-core (tcgen05) path, built lazily for large batches
     linna::TcContext *tc = nullptr;
     bool tc_failed = false;
-    int path = 1;                 // 0 auto, 1 FFMA only, 2 tensor core only
+    int path = 0;                 // 0 auto (tensor core from tc_min_rows rows on), 1 FFMA only, 2 tensor core only
     int last_kernel = 0;          // kernel that served the last launch: 1 FFMA, 2 tensor core
-    int64_t tc_min_rows = 8192;
+    int64_t tc_min_rows = 1024;   // measured crossover: one tensor-core pass (0.19 ms at C3) beats the FFMA kernel from ~256 rows on
     // host-buffer API staging
     cudaStream_t hstream = nullptr;                  // compute stream of the host-buffer entry points
     cudaStream_t cstream = nullptr, dstream = nullptr;   // host->device / device->host copy streams (pipelined chunks)

@@ -56,7 +56,8 @@ constexpr int TF_THREADS = 384;  // TMA, MMA, 2 store warps + 2 x 4 epilogue war
 constexpr int TF_MAX_STEPS = 48;
 
 enum TfEpi : int32_t { TF_ACT = 0, TF_HEAD = 1, TF_CHI2 = 2, TF_BWD = 3, TF_GRADOUT = 4 };
-enum TfFlags : int32_t { TFF_RELU = 1, TFF_SAVE_MASK = 2, TFF_APPLY_MASK = 4, TFF_TRI = 8 };
+enum TfFlags : int32_t { TFF_RELU = 1, TFF_SAVE_MASK = 2, TFF_APPLY_MASK = 4, TFF_TRI = 8,
+                         TFF_LAST_USE0 = 16, TFF_LAST_USE1 = 32 };   // phase 0 / 1 is the last reader of its activation slot
 enum TfVariant : int32_t { TFV_ACT = 0, TFV_ACT_SAVE, TFV_CHI2, TFV_CHI2_STORE, TFV_BWD, TFV_HEAD, TFV_HEAD_EXP, TFV_GRADOUT };
 
 struct TfStep {
@@ -98,6 +99,7 @@ struct TfArgs {
     float *grad;
     uint32_t *masks;
     int64_t n;
+    int32_t l2_hints;         // 1: TMA loads carry L2 eviction-priority hints (LINNA_TC_L2_HINTS)
     int32_t slots;            // walker pairs interleaved per cluster: 2, or 1 when the batch cannot fill the GPU twice
     int *err;
     long long *dbg;           // optional [grid][8] cycle counters (LINNA_TC_DEBUG): where the service warps wait
@@ -172,6 +174,26 @@ __device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorM
         :
         : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank)
 {
@@ -422,6 +444,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
             uint32_t ph = 0, seen[2][2] = {{0, 0}, {0, 0}}, pubA = 0, pubB = 0;
             long long w_empty = 0, w_ready = 0;
             const long long t_begin = clock64();
+            // L2 policy: weights are re-read by every cluster all the time (keep), an activation line is dead after
+            // its last reader (let it go first) -- the arena in flight is larger than L2
+            const uint64_t pol_keep = l2_policy_evict_last(), pol_dead = l2_policy_evict_first();
+            const bool use_hints = args.l2_hints != 0;
             for (int64_t pair = pair0; pair < npairs; pair += pair_step, pubA += prog->total_pub[0], pubB += prog->total_pub[1]) {
                 const int nslots = (args.slots == 2 && pair + 1 < npairs) ? 2 : 1;
                 for (int si = 0; si < n_steps; ++si) {
@@ -438,8 +464,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                                 mbar_wait_timed(&empty_bar[stage], ph ^ 1, args.err, 1, w_empty);
                                 uint8_t *sb = smem + stage * TF_STAGE_BYTES;
                                 if (leader) mbar_expect_tx(&full_bar[stage], 2 * TF_STAGE_BYTES);   // both CTAs' bytes
-                                tma_load_2d_pair(sb + 2 * TF_TILE_BYTES, mb, &full_bar[stage], kc * TF_KC, nb);
-                                tma_load_2d_pair(sb + 3 * TF_TILE_BYTES, mb + 1, &full_bar[stage], kc * TF_KC, nb);
+                                if (use_hints) {
+                                    tma_load_2d_pair_hint(sb + 2 * TF_TILE_BYTES, mb, &full_bar[stage], kc * TF_KC, nb, pol_keep);
+                                    tma_load_2d_pair_hint(sb + 3 * TF_TILE_BYTES, mb + 1, &full_bar[stage], kc * TF_KC, nb, pol_keep);
+                                } else {
+                                    tma_load_2d_pair(sb + 2 * TF_TILE_BYTES, mb, &full_bar[stage], kc * TF_KC, nb);
+                                    tma_load_2d_pair(sb + 3 * TF_TILE_BYTES, mb + 1, &full_bar[stage], kc * TF_KC, nb);
+                                }
                                 // the activations this k-chunk reads: wait until their producer chunk is visible
                                 const int col = kc * TF_KC;
                                 const int grp = (col >> 7) & 1;
@@ -456,8 +487,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                                     fence_async_all();
                                 }
                                 const int ca = st.src[p] + col;
-                                tma_load_2d_pair(sb, maps, &full_bar[stage], ca, arena_row0 + slot * TF_M);
-                                tma_load_2d_pair(sb + TF_TILE_BYTES, maps, &full_bar[stage], ca + lo_off, arena_row0 + slot * TF_M);
+                                const bool dead = use_hints && (st.flags & (p ? TFF_LAST_USE1 : TFF_LAST_USE0)) && n0 + TF_NC >= st.N;
+                                if (dead) {
+                                    tma_load_2d_pair_hint(sb, maps, &full_bar[stage], ca, arena_row0 + slot * TF_M, pol_dead);
+                                    tma_load_2d_pair_hint(sb + TF_TILE_BYTES, maps, &full_bar[stage], ca + lo_off, arena_row0 + slot * TF_M, pol_dead);
+                                } else {
+                                    tma_load_2d_pair(sb, maps, &full_bar[stage], ca, arena_row0 + slot * TF_M);
+                                    tma_load_2d_pair(sb + TF_TILE_BYTES, maps, &full_bar[stage], ca + lo_off, arena_row0 + slot * TF_M);
+                                }
                                 if (++stage == TF_STAGES) stage = 0, ph ^= 1;
                             }
                         }
@@ -474,7 +511,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         if (lane == 0 && leader) {
             int stage = 0;
             uint32_t ph = 0, g = 0;
-            long long w_full = 0, w_pempty = 0;
+            long long w_full = 0, w_pempty = 0, w_full_head = 0;
             const long long t_begin = clock64();
             for (int64_t pair = pair0; pair < npairs; pair += pair_step) {
                 const int nslots = (args.slots == 2 && pair + 1 < npairs) ? 2 : 1;
@@ -489,6 +526,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                         const int k0 = (st.flags & TFF_TRI) ? n0 / TF_KC : 0;
                         int in_seg = 0, done = 0;
                         uint32_t dcol = 0;
+                        const bool head_chunk = n0 == 0;
                         for (int p = 0; p < st.nphase; ++p) {
                             const int nk = (st.K[p] + TF_KC - 1) / TF_KC;
                             for (int kc = k0; kc < nk; ++kc) {
@@ -498,7 +536,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                                     tc_fence_after();
                                     dcol = tmem_base + buf * TF_NC;
                                 }
-                                mbar_wait_timed(&full_bar[stage], ph, args.err, 4, w_full);
+                                if (head_chunk && done < TF_STAGES) mbar_wait_timed(&full_bar[stage], ph, args.err, 4, w_full_head);
+                                else mbar_wait_timed(&full_bar[stage], ph, args.err, 4, w_full);
                                 tc_fence_after();
                                 const uint32_t sb = smem_u32(smem + stage * TF_STAGE_BYTES);
                                 const uint32_t a_hi = sb, a_lo = sb + TF_TILE_BYTES, b_hi = sb + 2 * TF_TILE_BYTES, b_lo = sb + 3 * TF_TILE_BYTES;
@@ -524,7 +563,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
             }
             if (args.dbg) {
                 long long *d = args.dbg + (size_t)blockIdx.x * 16;
-                d[3] = clock64() - t_begin, d[4] = w_full, d[5] = w_pempty;
+                d[3] = clock64() - t_begin, d[4] = w_full + w_full_head, d[5] = w_pempty, d[14] = w_full_head;
             }
         }
     } else {
@@ -759,8 +798,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         if (args.dbg && (warp == 4 || warp == 8) && lane == 0) {
             long long *d = args.dbg + (size_t)blockIdx.x * 16 + (warp == 4 ? 6 : 10);
             d[0] = clock64() - e_begin, d[1] = e_wait, d[2] = e_drain, d[3] = e_epi;
-            if (warp == 4) args.dbg[(size_t)blockIdx.x * 16 + 14] = x.t_sfree;
-            else args.dbg[(size_t)blockIdx.x * 16 + 15] = x.t_sfree;
+            if (warp == 8) args.dbg[(size_t)blockIdx.x * 16 + 15] = x.t_sfree;
         }
     }
     tc_fence_before();
@@ -1089,6 +1127,19 @@ TcContext *tc_build(const linna_model *m, std::string &why)
             set_bias(std::vector<float>(), 1.f, n_out);
         }
         if (overflow) { why = "too many layers"; return nullptr; }
+        for (int i = 0; i < ns; ++i)        // is phase p of step i the last reader of its slot before it is overwritten?
+            for (int p = 0; p < pg.steps[i].nphase; ++p) {
+                const int slot = pg.steps[i].src[p];
+                bool last = true;
+                for (int p2 = p + 1; p2 < pg.steps[i].nphase; ++p2) last &= pg.steps[i].src[p2] != slot;
+                for (int j = i + 1; j < ns && last; ++j) {
+                    bool reads = false;
+                    for (int p2 = 0; p2 < pg.steps[j].nphase; ++p2) reads |= pg.steps[j].src[p2] == slot;
+                    if (reads) last = false;
+                    if (pg.steps[j].dst == slot) break;
+                }
+                if (last) pg.steps[i].flags |= p ? TFF_LAST_USE1 : TFF_LAST_USE0;
+            }
         for (int i = 0; i < ns; ++i) {
             TfStep &s = pg.steps[i];
             s.clampv = (s.flags & TFF_RELU) ? 0.f : -INFINITY;
@@ -1200,6 +1251,8 @@ static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const f
     const int64_t clusters = t->grid / 2;
     static const int want_slots = getenv("LINNA_TC_SLOTS") ? atoi(getenv("LINNA_TC_SLOTS")) : 2;
     a.slots = (want_slots == 2 && pairs > clusters) ? 2 : 1;
+    static const int want_hints = getenv("LINNA_TC_L2_HINTS") ? atoi(getenv("LINNA_TC_L2_HINTS")) : 0;
+    a.l2_hints = want_hints;
     const int grid = 2 * (int)std::min<int64_t>((pairs + a.slots - 1) / a.slots, clusters);
     tc_f16_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
     return cudaGetLastError();

@@ -29,4 +29,5 @@ if os.environ.get("LINNA_TC_DEBUG"):
         m_ = np.concatenate([m_[:3], lead.mean(axis=0)[3:6], m_[6:]])
         for gname, o in (("epi g0", 6), ("epi g1", 10)):
             print("%s  : total %.0f  wait_pfull %.0f (%.0f%%)  drain %.0f (%.0f%%)  chunk-epilogue %.0f (%.0f%%)" % (gname, m_[o], m_[o+1], 100*m_[o+1]/m_[o], m_[o+2], 100*m_[o+2]/m_[o], m_[o+3], 100*m_[o+3]/m_[o]) + "  of which wait_sfree %.0f" % m_[14 if o == 6 else 15])
+        print("mma wait_full in the first %d stages of a layer pass: %.0f" % (4, lead.mean(axis=0)[14]))
         print("mma     : total %.0f  wait_full %.0f (%.0f%%)  wait_pempty %.0f (%.0f%%)" % (m_[3], m_[4], 100*m_[4]/m_[3], m_[5], 100*m_[5]/m_[3]))

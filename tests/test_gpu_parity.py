@@ -123,6 +123,7 @@ def test_full_size_c3_properties():
     m0 = e.predict(np.asarray(p.theta0, np.float32)[None, :], engine.LINNA_OUT_M)[0]
     p.set_data_from_prediction(m0)
     e.set_likelihood(p.priors, np.asarray(p.data, np.float32), p.inv_cov, 1.0)
+    e.set_path("ffma")          # this test is about the FP32 kernel's tiling; tests/test_gpu_tc.py has the tensor-core twin
     n = 100000
     u = synthetic.walkers(n, 30, scale=0.3, seed=1)
     ud = _dev(u)
