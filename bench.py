@@ -390,12 +390,20 @@ def main():
 
     # ---- e2e: the reference-facing call with HOST buffers (pinned), copies inside the timed region
     pin = [torch.from_numpy(u).pin_memory().numpy() for u in u_host[:4]]
+    # results come back into pinned host buffers too (two sets, alternating), as a high-rate caller would hold them
+    res_l = [torch.empty(n, dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+    res_g = [torch.empty(n, p.n_in, dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+
+    def call_host(s):
+        if args.mode == "grad":
+            return eng.lnp_grad(pin[s % 4], out=res_l[s % 2], out_grad=res_g[s % 2])
+        return eng.lnp(pin[s % 4], out=res_l[s % 2])
     for w in range(2):
-        call(pin[w % 4])
+        call_host(w)
     barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
-        res = call(pin[s % 4])
+        res = call_host(s)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if world > 1:

@@ -305,11 +305,20 @@ class Engine:
                                                self._stream()))
         return out
 
-    def lnp(self, u):
+    @staticmethod
+    def _host_out(out, shape):
+        """Caller-provided result buffer (e.g. pinned memory, which skips the staging copy) or a fresh array."""
+        if out is None:
+            return np.empty(shape, np.float32)
+        if out.dtype != np.float32 or out.shape != tuple(shape) or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous float32 array of shape %r" % (tuple(shape),))
+        return out
+
+    def lnp(self, u, out=None):
         import torch
         if isinstance(u, np.ndarray):
             uu = np.ascontiguousarray(u, np.float32).reshape(-1, self.n_in)
-            out = np.empty(uu.shape[0], np.float32)
+            out = self._host_out(out, (uu.shape[0],))
             self._check(self.lib.linna_lnp_host(self.handle, uu.ctypes.data, uu.shape[0], out.ctypes.data))
             return out
         uu = self._prep_dev(u, self.n_in)
@@ -318,12 +327,12 @@ class Engine:
             self._check(self.lib.linna_lnp(self.handle, uu.data_ptr(), uu.shape[0], out.data_ptr(), self._stream()))
         return out
 
-    def lnp_grad(self, u):
+    def lnp_grad(self, u, out=None, out_grad=None):
         import torch
         if isinstance(u, np.ndarray):
             uu = np.ascontiguousarray(u, np.float32).reshape(-1, self.n_in)
-            out = np.empty(uu.shape[0], np.float32)
-            g = np.empty_like(uu)
+            out = self._host_out(out, (uu.shape[0],))
+            g = self._host_out(out_grad, uu.shape)
             self._check(self.lib.linna_lnp_grad_host(self.handle, uu.ctypes.data, uu.shape[0], out.ctypes.data,
                                                      g.ctypes.data))
             return out, g

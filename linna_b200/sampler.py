@@ -37,20 +37,46 @@ def _autocorr_1d(x):
     return acf / acf[0] if acf[0] != 0 else acf
 
 
+def _mean_acf_torch(chain):
+    """Walker-averaged normalised autocorrelation function per parameter, batched FFT on the GPU:
+    chain [steps, walkers, ndim] (device tensor) -> [steps, ndim] float64 on the host."""
+    nstep = chain.shape[0]
+    n = _next_pow_two(nstep)
+    x = chain.to(torch.float64)
+    x = x - x.mean(dim=0, keepdim=True)
+    f = torch.fft.rfft(x, n=2 * n, dim=0)
+    acf = torch.fft.irfft(f * f.conj(), n=2 * n, dim=0)[:nstep]
+    a0 = acf[0:1]
+    acf = torch.where(a0 != 0, acf / torch.where(a0 != 0, a0, torch.ones_like(a0)), acf)
+    return acf.mean(dim=1).cpu().numpy()
+
+
 def integrated_time(chain, c=5.0):
     """Integrated autocorrelation time per parameter of a chain [steps, walkers, ndim]
-    (autocorrelation averaged over walkers, Sokal window M >= c*tau; always returns an estimate)."""
-    chain = np.asarray(chain, np.float64)
-    if chain.ndim == 2:
+    (autocorrelation averaged over walkers, Sokal window M >= c*tau; always returns an estimate).
+    Device tensors -- and large host chains when a GPU is present -- go through one batched FFT on the GPU
+    (the reference recomputes this every 100 iterations over the whole chain, linna/sampler.py:532-550)."""
+    on_gpu = torch.is_tensor(chain) and chain.is_cuda
+    if not on_gpu:
+        chain = np.asarray(chain, np.float64)
+        if chain.ndim == 2:
+            chain = chain[:, :, None]
+        if chain.size >= (1 << 20) and torch.cuda.is_available():
+            chain, on_gpu = torch.from_numpy(chain).cuda(), True
+    elif chain.dim() == 2:
         chain = chain[:, :, None]
     nstep, nwalk, ndim = chain.shape
+    if on_gpu:
+        macf = _mean_acf_torch(chain)
+    else:
+        macf = np.zeros((nstep, ndim))
+        for d in range(ndim):
+            for w in range(nwalk):
+                macf[:, d] += _autocorr_1d(chain[:, w, d])
+        macf /= nwalk
     tau = np.empty(ndim)
     for d in range(ndim):
-        f = np.zeros(nstep)
-        for w in range(nwalk):
-            f += _autocorr_1d(chain[:, w, d])
-        f /= nwalk
-        taus = 2.0 * np.cumsum(f) - 1.0
+        taus = 2.0 * np.cumsum(macf[:, d]) - 1.0
         m = np.arange(len(taus)) < c * taus
         window = np.argmin(m) if np.any(~m) else len(taus) - 1
         tau[d] = taus[window]

@@ -85,3 +85,19 @@ def test_main_second_iteration_trains_on_the_previous_chain(tmp_path):
     assert np.all(x1.min(axis=0) >= prev.min(axis=0) - 1e-6) and np.all(x1.max(axis=0) <= prev.max(axis=0) + 1e-6)
     assert os.path.isfile(os.path.join(outdir, "iter_1", "best.pth.tar"))
     assert np.all(np.isfinite(chain)) and chain.shape[1] == ndim
+
+
+def test_integrated_time_gpu_matches_host():
+    """The batched-FFT autocorrelation time on the device equals the per-walker host loop (emcee's estimator)."""
+    from linna_b200 import sampler
+    rng = np.random.default_rng(3)
+    n, w, d = 3000, 12, 4
+    x = np.zeros((n, w, d))
+    e = rng.standard_normal((n, w, d))
+    rho = np.array([0.5, 0.8, 0.9, 0.95])
+    for t in range(1, n):
+        x[t] = rho * x[t - 1] + e[t]
+    host = sampler.integrated_time(x)
+    dev = sampler.integrated_time(torch.from_numpy(x).cuda())
+    np.testing.assert_allclose(dev, host, rtol=1e-8)
+    assert np.all(np.abs(host / ((1 + rho) / (1 - rho)) - 1) < 0.25)
