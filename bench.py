@@ -152,6 +152,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if args.workload == "c5":
+        return run_reference_train(args)
     p, n, desc = make_workload(args.workload)
     from oracle.oracle import NumpyPort, Oracle
     o0 = Oracle(p, arch)
@@ -179,6 +181,40 @@ def run_reference(args):
                              "sample": "%d walkers per step, numpy/BLAS batched port of the reference arithmetic "
                                        "(oracle.NumpyPort.%s), %d threads" % (n_sample, call.__name__, cores)},
             "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_reference_train(args):
+    """--impl reference --workload c5: the oracle's C restatement of one training step (forward, loss, backward,
+    AdamW; linna/predictor_gpu.py:268-288) on ONE host core, a bounded number of 500-row steps."""
+    from oracle.oracle import Oracle, normalised_loss_constants
+    p, theta, rng = train_problem()
+    o0 = Oracle(p, arch)
+    m0 = o0.lnp(np.zeros((1, p.n_in), np.float32), want=("m",))["m"][0]
+    p.set_data_from_prediction(m0)
+    o = Oracle(p, arch)
+    B = args.walkers or 500
+    dn, icov = normalised_loss_constants(p.cov, np.asarray(p.sigma, np.float32), p.y_mean, p.y_std, p.data)
+    w = o.w64.astype(np.float32)
+    am, av = np.zeros_like(w), np.zeros_like(w)
+    X = np.ascontiguousarray(theta[:B], np.float32)
+    Y = (np.asarray(p.data, np.float64)[None, :] * (1 + 0.01 * rng.standard_normal((B, p.n_out)))).astype(np.float32)
+    steps = max(1, min(args.steps, 3))
+    o.train_step(w, am, av, 1, X, Y, dn, icov, 1e-3)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        o.train_step(w, am, av, s + 2, X, Y, dn, icov, 1e-3)
+    dt = time.perf_counter() - t0
+    val = B * steps / dt
+    line = {"impl": "reference", "metric": "emulator training rows/sec", "value": val, "unit": "rows/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": 1, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS["c5"][3], "mode": "train"},
+            "cpu_baseline": {"value": val, "unit": "rows/s", "cores": 1, "kind": "port",
+                             "sample": "%d AdamW steps of %d rows through the oracle's C restatement of the training step "
+                                       "(scalar, one core)" % (steps, B)},
+            "e2e": {"value": val, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0
 
