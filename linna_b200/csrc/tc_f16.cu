@@ -690,14 +690,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                 mbar_arrive(x.sfull);
                 ++x.sidx;
             }
+#pragma unroll 1
             for (int si = 0; si < n_steps; ++si) {
                 const TfStep &st = s_steps[si];
                 const int nch = (st.N + TF_NC - 1) / TF_NC;
+#pragma unroll 1
                 for (int slot = 0; slot < nslots; ++slot) {
                 const int64_t grow = ((pair + slot) * 2 + cta_rank) * TF_M + row;
                 const bool valid = grow < args.n;
                 x.mask_row = mask_row0 + (size_t)slot * TF_M * prog->mask_words;
                 x.chi = 0.0;
+#pragma unroll 1
                 for (int ch = 0; ch < nch; ++ch) {
                     const int n0 = ch * TF_NC;
                     const int nvalid = st.N - n0 < TF_NC ? st.N - n0 : TF_NC;
