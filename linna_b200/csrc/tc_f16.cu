@@ -57,7 +57,8 @@ constexpr int TF_MAX_STEPS = 48;
 
 enum TfEpi : int32_t { TF_ACT = 0, TF_HEAD = 1, TF_CHI2 = 2, TF_BWD = 3, TF_GRADOUT = 4 };
 enum TfFlags : int32_t { TFF_RELU = 1, TFF_SAVE_MASK = 2, TFF_APPLY_MASK = 4, TFF_TRI = 8,
-                         TFF_LAST_USE0 = 16, TFF_LAST_USE1 = 32 };   // phase 0 / 1 is the last reader of its activation slot
+                         TFF_LAST_USE0 = 16, TFF_LAST_USE1 = 32,     // phase 0 / 1 is the last reader of its activation slot
+                         TFF_ROWSCALE = 64 };   // first backward step: apply the per-walker power-of-two gradient scale
 enum TfVariant : int32_t { TFV_ACT = 0, TFV_ACT_SAVE, TFV_CHI2, TFV_CHI2_STORE, TFV_BWD, TFV_HEAD, TFV_HEAD_EXP, TFV_GRADOUT };
 
 struct TfStep {
@@ -307,6 +308,7 @@ struct TfEpiCtx {
     uint32_t sidx;              // staging boxes handed to the store warp so far
     int sw;                     // 128-byte swizzle phase of this row
     long long t_sfree;          // cycles spent waiting for the staging box (LINNA_TC_DEBUG)
+    float row_scale;            // 2^-k of this walker's backward pass (k from its chi^2), 1 outside it
 };
 
 // 128 columns of one output chunk (the columns [c0, c0+128) of the layer, owned by one epilogue group):
@@ -328,7 +330,8 @@ __device__ __forceinline__ void tf_chunk_epilogue(const float (&racc)[128], cons
             mw[0] = mw[1] = mw[2] = mw[3] = 0xffffffffu;
         }
     }
-    const float clampv = st.clampv, inv_scale = st.inv_scale;
+    const float clampv = st.clampv;
+    const float inv_scale = (APPLY && (st.flags & TFF_ROWSCALE)) ? st.inv_scale * x.row_scale : st.inv_scale;
     float chi_f = 0.f;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -390,6 +393,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
     __shared__ __align__(8) uint64_t full_bar[TF_STAGES], empty_bar[TF_STAGES], pfull_bar[2], pempty_bar[2];
     __shared__ __align__(8) uint64_t sfull_bar[2], sfree_bar[2];   // staging buffer of column group 0 / 1: written / read out
     __shared__ __align__(8) double chi_s[TF_M];
+    __shared__ __align__(8) double chi_x[2][TF_M];       // chi^2 partials of the two column groups (backward scale)
     __shared__ __align__(16) float bias_stage[2][2][128];   // [chunk parity][column group][column]
     __shared__ uint32_t tmem_slot;
     __shared__ uint32_t ready_cnt[2][2];   // [slot][column group]
@@ -640,6 +644,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         x.err = args.err;
         x.chi = 0.0;
         x.t_sfree = 0;
+        x.row_scale = 1.f;
+        float row_unscale[2] = {1.f, 1.f}, row_scale2[2] = {1.f, 1.f};   // 2^k / 2^-k per walker-pair slot
         const int n_in = c.n_in;
         uint32_t g = 0, nchunk = 0;
         long long e_wait = 0, e_drain = 0, e_epi = 0;
@@ -700,6 +706,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                 const bool valid = grow < args.n;
                 x.mask_row = mask_row0 + (size_t)slot * TF_M * prog->mask_words;
                 x.chi = 0.0;
+                x.row_scale = (st.flags & TFF_ROWSCALE) ? row_scale2[slot] : 1.f;
 #pragma unroll 1
                 for (int ch = 0; ch < nch; ++ch) {
                     const int n0 = ch * TF_NC;
@@ -770,7 +777,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                                 const float uu = __ldg(u + i);
                                 const int kind = c.prior_kind[i];
                                 const float ps = c.prior_scale[i];
-                                float gx = (i < 32 ? scr_a[i] : scr_b[i - 32]) * st.inv_scale / c.x_std[i];
+                                float gx = (i < 32 ? scr_a[i] : scr_b[i - 32]) * (st.inv_scale * row_unscale[slot]) / c.x_std[i];
                                 if (c.log10_flag && c.log10_flag[i])
                                     gx /= (tf_prior_map(uu, kind, ps, c.prior_shift[i]) * 2.30258509299404568f);
                                 float jac = ps;
@@ -783,6 +790,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                     if (timing) e_epi += clock64() - t_c;
                 }
                 chi2[slot] += x.chi;
+                if (st.variant == TFV_CHI2_STORE) {
+                    // The backward pass is linear in r: carry it at unit scale (r / 2^k, k = exponent of |r|) so that a
+                    // walker far from the peak (|r| ~ 1e3) cannot push a gradient past the fp16 range; the last
+                    // epilogue multiplies 2^k back.  Exact: powers of two only.
+                    chi_x[gi][row] = x.chi;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    const double tot = chi_x[0][row] + chi_x[1][row];
+                    int k = (tot > 0.0 && tot < 1e300) ? (ilogb(tot) >> 1) : 0;
+                    k = k < -60 ? -60 : (k > 60 ? 60 : k);
+                    row_scale2[slot] = ldexpf(1.f, -k);
+                    row_unscale[slot] = ldexpf(1.f, k);
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
                 }
             }
             // combine the two column groups of every walker and finish lnP
@@ -1085,6 +1105,7 @@ TcContext *tc_build(const linna_model *m, std::string &why)
                 const int shg = Packer::pick_shift({mg});
                 set_phase(g0, 0, q.dst, mg, shg);
                 g0.N = K, g0.inv_scale = ldexpf(1.f, -shg) * (-1.0f / m->temperature), g0.epi = TF_BWD;
+                g0.flags |= TFF_ROWSCALE;
                 const int pm = prev_mask(nops - 1);
                 if (pm >= 0) g0.flags |= TFF_APPLY_MASK, g0.mask_word = pm;
                 set_dst(g0, sbuf);

@@ -124,3 +124,30 @@ def test_tc_full_size_c3():
     idx = np.random.default_rng(0).choice(n, 64, replace=False)
     ref = Oracle(p, arch).lnp(u[idx], np.float64)["lnp"]
     assert np.all(np.abs(a[idx] - ref) <= tc_tol(ref)), np.abs(a[idx] - ref).max()
+
+
+def test_tc_grad_far_from_the_peak():
+    """A data vector tens of sigma away from everything the emulator predicts (chi^2 ~ 1e6, |r| ~ 50 per element):
+    the backward pass runs at unit scale per walker (a power of two taken from its own chi^2) so that no gradient
+    leaves the fp16 range, and the result still tracks the float64 oracle."""
+    p = synthetic.make_problem(30, 500, seed=0)
+    e = engine.engine_from_problem(p, with_likelihood=False)
+    m0 = e.predict(np.asarray(p.theta0, np.float32)[None, :], engine.LINNA_OUT_M)[0]
+    rng = np.random.default_rng(4)
+    p.data = m0.astype(np.float64) + 60.0 * np.asarray(p.sigma, np.float64) * rng.choice([-1.0, 1.0], size=500)
+    e.set_likelihood(p.priors, np.asarray(p.data, np.float32), p.inv_cov, 1.0)
+    u = np.concatenate([synthetic.walkers(1200, 30, scale=s, seed=7 + i) for i, s in enumerate((0.3, 1.0, 2.0))])
+    e.set_path("tc")
+    lnp, grad = e.lnp_grad(_dev(u))
+    lnp, grad = lnp.cpu().numpy(), grad.cpu().numpy().astype(np.float64)
+    assert np.all(np.isfinite(lnp)) and np.all(np.isfinite(grad))
+    assert -lnp.max() > 1e5                                   # far from the peak indeed
+    idx = np.arange(0, 3600, 60)
+    ref = Oracle(p, arch).lnp(u[idx], np.float64, grad=True)
+    assert np.all(np.abs(lnp[idx] - ref["lnp"]) <= tc_tol(ref["lnp"]))
+    rel = np.max(np.abs(grad[idx] - ref["grad"]), axis=1) / np.max(np.abs(ref["grad"]), axis=1)
+    assert np.median(rel) < 1e-5 and np.mean(rel > 2e-4) <= 0.05, (np.median(rel), rel.max())
+    e.set_path("ffma")
+    lf, gf = e.lnp_grad(_dev(u))
+    relf = np.max(np.abs(grad - gf.cpu().numpy()), axis=1) / np.max(np.abs(gf.cpu().numpy()), axis=1)
+    assert np.median(relf) < 1e-5 and np.mean(relf > 2e-4) < 0.02
