@@ -480,11 +480,12 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        n_sample = min(n, 16384)
-        rate, dt_cpu = cpu_port_rate(p, data, n_sample, 3, grad=args.mode == "grad")
+        n_sample = min(n, 32768)
+        reps = 8 if args.mode == "lnp" else 4          # a few seconds of CPU work on all host threads
+        rate, dt_cpu = cpu_port_rate(p, data, n_sample, reps, grad=args.mode == "grad")
         cpu = {"value": rate, "unit": "evals/s", "cores": host_threads(), "kind": "port",
-               "sample": "3 x %d walkers of the same workload through oracle.NumpyPort (numpy/BLAS batched port of "
-                         "the reference arithmetic, %s), %.1f s" % (n_sample, "lnP+grad" if args.mode == "grad" else "lnP", dt_cpu)}
+               "sample": "%d x %d walkers of the same workload through oracle.NumpyPort (numpy/BLAS batched port of "
+                         "the reference arithmetic, %s), %.1f s" % (reps, n_sample, "lnP+grad" if args.mode == "grad" else "lnP", dt_cpu)}
 
     line = {"metric": METRIC if args.mode == "lnp" else "emulator log-likelihood+grad evals/sec",
             "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,

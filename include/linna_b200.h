@@ -191,6 +191,18 @@ int linna_train_load_params(linna_model_t *m, const float *params, void *stream)
 /* Adopt a flat HOST parameter vector as the model's weights (end of training). */
 int linna_train_commit(linna_model_t *m, const float *params_host);
 
+/* ---- on-device ensemble-sampler step (emcee's stretch move, linna/sampler.py:493-503, 530) ---------------
+ * One half-ensemble update is propose -> linna_lnp(y) -> accept, all on device pointers.
+ * propose: for i < ns: partner = second[randint(n_second)], z ~ g(z) on [1/a, a],
+ *          y[i,:] = x[partner,:] + z (x[first[i],:] - x[partner,:]);  z[i] is kept for the acceptance.
+ * accept:  ln q = (d-1) ln z + lnp_y - lnp[first];  accept iff ln U < ln q and lnp_y is finite; accepted walkers
+ *          get x[first[i],:] = y[i,:], lnp[first[i]] = lnp_y[i], naccepted[first[i]] += 1.
+ * Random numbers are Philox4x32-10 streams keyed by (seed, i, offset): pass a different offset per call. */
+int linna_stretch_propose(const float *x, int32_t d, const int64_t *first, const int64_t *second, int64_t ns,
+                          int64_t n_second, float a, uint64_t seed, uint64_t offset, float *y, float *z, void *stream);
+int linna_stretch_accept(float *x, float *lnp, float *naccepted, int32_t d, const int64_t *first, int64_t ns, const float *y,
+                         const float *lnp_y, const float *z, uint64_t seed, uint64_t offset, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

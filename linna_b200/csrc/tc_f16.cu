@@ -436,7 +436,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
     // Every cluster works on TWO walker pairs ("slots") at a time, interleaved step by step: while the last
     // chunk of slot 0's layer goes through epilogue, store and publication, the tensor core already runs the same
     // layer for slot 1, so the layer-to-layer dependency never idles the MMA pipe.
-    const int64_t pair0 = (int64_t)(blockIdx.x >> 1) * args.slots, pair_step = (int64_t)(gridDim.x >> 1) * args.slots;
+    // Cluster c owns the walker pairs c, c + C, c + 2C, ... and walks through them `slots` at a time (the last
+    // visit takes whatever is left), so every cluster gets floor or ceil of pairs / clusters whatever `slots` is.
+    const int64_t n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+    const int64_t my_pairs = cluster_id < npairs ? (npairs - cluster_id + n_clusters - 1) / n_clusters : 0;
+    const int64_t pair0 = 0, pair_step = args.slots;   // `pair` below counts this cluster's own pairs
     const int arena_row0 = blockIdx.x * 2 * TF_M;   // this CTA's rows of the activation arena (slot 0, then slot 1)
 
     if (warp < 4) {
@@ -452,8 +456,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
             // its last reader (let it go first) -- the arena in flight is larger than L2
             const uint64_t pol_keep = l2_policy_evict_last(), pol_dead = l2_policy_evict_first();
             const bool use_hints = args.l2_hints != 0;
-            for (int64_t pair = pair0; pair < npairs; pair += pair_step, pubA += prog->total_pub[0], pubB += prog->total_pub[1]) {
-                const int nslots = (args.slots == 2 && pair + 1 < npairs) ? 2 : 1;
+            for (int64_t pair = pair0; pair < my_pairs; pair += pair_step, pubA += prog->total_pub[0], pubB += prog->total_pub[1]) {
+                const int nslots = (args.slots == 2 && pair + 1 < my_pairs) ? 2 : 1;
                 for (int si = 0; si < n_steps; ++si) {
                     const TfStep &st = s_steps[si];
                     for (int slot = 0; slot < nslots; ++slot)
@@ -517,8 +521,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
             uint32_t ph = 0, g = 0;
             long long w_full = 0, w_pempty = 0, w_full_head = 0;
             const long long t_begin = clock64();
-            for (int64_t pair = pair0; pair < npairs; pair += pair_step) {
-                const int nslots = (args.slots == 2 && pair + 1 < npairs) ? 2 : 1;
+            for (int64_t pair = pair0; pair < my_pairs; pair += pair_step) {
+                const int nslots = (args.slots == 2 && pair + 1 < my_pairs) ? 2 : 1;
                 for (int si = 0; si < n_steps; ++si) {
                     const TfStep &st = s_steps[si];
                     for (int slot = 0; slot < nslots; ++slot)
@@ -603,8 +607,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                 publish(false);                                        // everything older than this box has landed
                 ++pend[slot];                                          // publication unit = one 64-column box
             };
-            for (int64_t pair = pair0; pair < npairs; pair += pair_step) {
-                const int nslots = (args.slots == 2 && pair + 1 < npairs) ? 2 : 1;
+            for (int64_t pair = pair0; pair < my_pairs; pair += pair_step) {
+                const int nslots = (args.slots == 2 && pair + 1 < my_pairs) ? 2 : 1;
                 if (gi == 0)
                     for (int slot = 0; slot < nslots; ++slot) {
                         store_box(prog->in_col, slot);
@@ -654,14 +658,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         uint32_t pempty_remote[2];   // the leader's drain barriers, as cluster addresses
         pempty_remote[0] = map_to_cta(smem_u32(&pempty_bar[0]), 0), pempty_remote[1] = map_to_cta(smem_u32(&pempty_bar[1]), 0);
 
-        for (int64_t pair = pair0; pair < npairs; pair += pair_step) {
-            const int nslots = (args.slots == 2 && pair + 1 < npairs) ? 2 : 1;
+        for (int64_t pair = pair0; pair < my_pairs; pair += pair_step) {
+            const int nslots = (args.slots == 2 && pair + 1 < my_pairs) ? 2 : 1;
             // ---- prologue (group 0): u -> theta -> xhat (util.py:323-347, :483-497), split, stage, TMA store
             float lnprior2[2] = {0.f, 0.f};
             double chi2[2] = {0.0, 0.0};
             if (gi == 0)
             for (int slot = 0; slot < nslots; ++slot) {
-                const int64_t grow = ((pair + slot) * 2 + cta_rank) * TF_M + row;
+                const int64_t grow = ((cluster_id + (pair + slot) * n_clusters) * 2 + cta_rank) * TF_M + row;
                 const bool valid = grow < args.n;
                 float lnprior = 0.f;
                 mbar_wait(x.sfree, (x.sidx & 1) ^ 1, args.err, 7);
@@ -702,7 +706,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                 const int nch = (st.N + TF_NC - 1) / TF_NC;
 #pragma unroll 1
                 for (int slot = 0; slot < nslots; ++slot) {
-                const int64_t grow = ((pair + slot) * 2 + cta_rank) * TF_M + row;
+                const int64_t grow = ((cluster_id + (pair + slot) * n_clusters) * 2 + cta_rank) * TF_M + row;
                 const bool valid = grow < args.n;
                 x.mask_row = mask_row0 + (size_t)slot * TF_M * prog->mask_words;
                 x.chi = 0.0;
@@ -807,7 +811,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
             }
             // combine the two column groups of every walker and finish lnP
             for (int slot = 0; slot < nslots; ++slot) {
-                const int64_t grow = ((pair + slot) * 2 + cta_rank) * TF_M + row;
+                const int64_t grow = ((cluster_id + (pair + slot) * n_clusters) * 2 + cta_rank) * TF_M + row;
                 if (gi == 1) chi_s[row] = chi2[slot];
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (gi == 0 && grow < args.n && args.lnp) {
@@ -1277,7 +1281,7 @@ static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const f
     a.slots = (want_slots == 2 && pairs > clusters) ? 2 : 1;
     static const int want_hints = getenv("LINNA_TC_L2_HINTS") ? atoi(getenv("LINNA_TC_L2_HINTS")) : 0;
     a.l2_hints = want_hints;
-    const int grid = 2 * (int)std::min<int64_t>((pairs + a.slots - 1) / a.slots, clusters);
+    const int grid = 2 * (int)std::min<int64_t>(pairs, clusters);
     tc_f16_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
     return cudaGetLastError();
 }

@@ -86,6 +86,9 @@ def load_library():
     lib.linna_model_set_fold.argtypes = [vp, i32]
     lib.linna_debug_tc_counters.argtypes = [vp, vp, i32]
     lib.linna_model_last_kernel.argtypes = [vp]
+    u64 = ctypes.c_uint64
+    lib.linna_stretch_propose.argtypes = [vp, i32, vp, vp, i64, i64, ctypes.c_float, u64, u64, vp, vp, vp]
+    lib.linna_stretch_accept.argtypes = [vp, vp, vp, i32, vp, i64, vp, vp, vp, u64, u64, vp]
     f32 = ctypes.c_float
     lib.linna_train_setup.argtypes = [vp, ctypes.POINTER(TrainDesc)]
     lib.linna_train_num_params.argtypes = [vp]
@@ -99,6 +102,35 @@ def load_library():
         raise LinnaError("linna_b200: ABI version mismatch")
     _lib = lib
     return lib
+
+
+def stretch_propose(x, first, second, a, seed, offset):
+    """Stretch-move proposal for the walkers ``first`` against the complementary set ``second`` (device tensors:
+    x [W, d] float32, index tensors int64).  Returns (y [ns, d], z [ns]).  linna/sampler.py:493-503 via emcee."""
+    import torch
+    lib = load_library()
+    ns, d = int(first.numel()), int(x.shape[1])
+    y = torch.empty((ns, d), dtype=torch.float32, device=x.device)
+    z = torch.empty(ns, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.linna_stretch_propose(x.data_ptr(), d, first.data_ptr(), second.data_ptr(), ns, int(second.numel()), float(a),
+                                       int(seed), int(offset), y.data_ptr(), z.data_ptr(),
+                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        raise LinnaError("linna_stretch_propose failed (%d)" % rc)
+    return y, z
+
+
+def stretch_accept(x, lnp, naccepted, first, y, lnp_y, z, seed, offset):
+    """Accept / reject the proposals in place (x, lnp, naccepted are updated for the accepted walkers)."""
+    import torch
+    lib = load_library()
+    with torch.cuda.device(x.device):
+        rc = lib.linna_stretch_accept(x.data_ptr(), lnp.data_ptr(), naccepted.data_ptr(), int(x.shape[1]), first.data_ptr(),
+                                      int(first.numel()), y.data_ptr(), lnp_y.data_ptr(), z.data_ptr(), int(seed), int(offset),
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        raise LinnaError("linna_stretch_accept failed (%d)" % rc)
 
 
 def launch_count():

@@ -21,6 +21,8 @@ import os
 import numpy as np
 import torch
 
+from . import engine as _engine
+
 
 # ---------------------------------------------------------------------------------------- statistics
 def _next_pow_two(n):
@@ -185,7 +187,9 @@ class EnsembleSampler:
         self.nwalkers, self.ndim, self.a = int(nwalkers), int(ndim), float(a)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.gen = torch.Generator(device=self.device)
-        self.gen.manual_seed(int(seed) if seed is not None else int(np.random.randint(0, 2 ** 31 - 1)))
+        self.seed = int(seed) if seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+        self.gen.manual_seed(self.seed)
+        self._calls = 0               # Philox offsets 8c (proposal: 4 numbers) and 8c + 4 (acceptance: 1 number)
         self._lp = log_prob
         self.reset()
 
@@ -208,25 +212,19 @@ class EnsembleSampler:
         """Generator over iterations (like ``emcee.EnsembleSampler.sample``); yields (x, lnp) device tensors."""
         x = torch.as_tensor(np.asarray(x0), dtype=torch.float32).to(self.device).clone() if not torch.is_tensor(x0) \
             else x0.to(self.device, torch.float32).clone()
-        lnp = self._eval(x) if lnp0 is None else lnp0.clone()
+        x = x.contiguous()
+        lnp = (self._eval(x) if lnp0 is None else lnp0.clone()).to(torch.float32).contiguous()
         W, d, a = self.nwalkers, self.ndim, self.a
         half = W // 2
         for _ in range(int(iterations)):
             perm = torch.randperm(W, device=self.device, generator=self.gen)
             for first, second in ((perm[:half], perm[half:]), (perm[half:], perm[:half])):
-                ns = first.numel()
-                partners = second[torch.randint(0, second.numel(), (ns,), device=self.device, generator=self.gen)]
-                u = torch.rand(ns, device=self.device, generator=self.gen)
-                z = ((a - 1.0) * u + 1.0) ** 2 / a
-                xs, cs = x[first], x[partners]
-                y = cs + z[:, None] * (xs - cs)
-                lnp_y = self._eval(y)
-                lnq = (d - 1.0) * torch.log(z) + lnp_y - lnp[first]
-                acc = torch.log(torch.rand(ns, device=self.device, generator=self.gen)) < lnq
-                acc &= torch.isfinite(lnp_y)
-                x[first] = torch.where(acc[:, None], y, xs)
-                lnp[first] = torch.where(acc, lnp_y, lnp[first])
-                self.naccepted[first] += acc.float()
+                # proposal and accept/reject are one CUDA kernel each (csrc/sampler_kernels.cu)
+                first, second = first.contiguous(), second.contiguous()
+                y, z = _engine.stretch_propose(x, first, second, a, self.seed, 8 * self._calls)
+                lnp_y = self._eval(y).contiguous()
+                _engine.stretch_accept(x, lnp, self.naccepted, first, y, lnp_y, z, self.seed, 8 * self._calls + 4)
+                self._calls += 1
             self.iteration += 1
             if store:
                 self._chain.append(x.clone())
