@@ -830,6 +830,9 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
     if (m->have_last && m->last_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, m->last_done, 0));
     // Large lnP / lnP+gradient batches go to the tensor-core (tcgen05) kernel; everything else stays on the
     // FP32 FFMA kernel.
+    if ((pk == PROG_LNP || pk == PROG_GRAD) && !proto && m->path == 2 && (m->tc_failed || m->has_extra))
+        return fail(LINNA_EINVAL, "tensor-core path unavailable: %s",
+                    m->has_extra ? "extra linear branch not supported on the tensor-core path" : m->tc_why.c_str());
     if ((pk == PROG_LNP || pk == PROG_GRAD) && !proto && m->path != 1 && !m->has_extra && !m->tc_failed &&
         (m->path == 2 || n >= m->tc_min_rows)) {
         if (!m->tc) {
@@ -837,6 +840,7 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
             m->tc = tc_build(m, why);
             if (!m->tc) {
                 m->tc_failed = true;
+                m->tc_why = why;
                 if (m->path == 2) return fail(LINNA_EINVAL, "tensor-core path unavailable: %s", why.c_str());
             }
         }

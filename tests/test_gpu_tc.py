@@ -151,3 +151,39 @@ def test_tc_grad_far_from_the_peak():
     lf, gf = e.lnp_grad(_dev(u))
     relf = np.max(np.abs(grad - gf.cpu().numpy()), axis=1) / np.max(np.abs(gf.cpu().numpy()), axis=1)
     assert np.median(relf) < 1e-5 and np.mean(relf > 2e-4) < 0.02
+
+
+@pytest.mark.parametrize("n_in,n_out", [(3, 37), (64, 40), (17, 129), (8, 257)])
+def test_tc_odd_shapes(n_in, n_out):
+    """Widths that are not multiples of anything: K / N padding, a 2-chunk last layer (257), the widest input the
+    tensor-core prologue takes (64)."""
+    p = synthetic.make_problem(n_in, n_out, seed=11, priors="mixed")
+    e = engine.engine_from_problem(p, with_likelihood=False)
+    m0 = e.predict(np.asarray(p.theta0, np.float32)[None, :], engine.LINNA_OUT_M)[0]
+    p.set_data_from_prediction(m0)
+    e.set_likelihood(p.priors, np.asarray(p.data, np.float32), p.inv_cov, p.temperature)
+    u = synthetic.walkers(300, n_in, scale=0.5, seed=5)
+    ref = Oracle(p, arch).lnp(u, np.float64, grad=True)
+    e.set_path("tc")
+    lnp, grad = e.lnp_grad(_dev(u))
+    assert e.last_kernel() == "tc"
+    lnp, grad = lnp.cpu().numpy(), grad.cpu().numpy().astype(np.float64)
+    assert np.all(np.abs(lnp - ref["lnp"]) <= tc_tol(ref["lnp"])), np.abs(lnp - ref["lnp"]).max()
+    rel = np.max(np.abs(grad - ref["grad"]), axis=1) / np.max(np.abs(ref["grad"]), axis=1)
+    assert np.median(rel) < 1e-5 and rel.max() < 2e-4, rel.max()
+    assert np.array_equal(e.lnp(_dev(u)).cpu().numpy(), lnp)
+
+
+def test_tc_falls_back_when_the_shape_is_not_supported():
+    p = synthetic.make_problem(70, 20, seed=3)       # 70 input parameters: wider than the tensor-core prologue
+    e = engine.engine_from_problem(p, with_likelihood=False)
+    m0 = e.predict(np.asarray(p.theta0, np.float32)[None, :], engine.LINNA_OUT_M)[0]
+    p.set_data_from_prediction(m0)
+    e.set_likelihood(p.priors, np.asarray(p.data, np.float32), p.inv_cov, 1.0)
+    u = synthetic.walkers(2048, 70, scale=0.3, seed=1)
+    ref = Oracle(p, arch).lnp(u[:32], np.float64)["lnp"]
+    out = e.lnp(_dev(u)).cpu().numpy()                # automatic selection: FP32 kernel
+    assert e.last_kernel() == "ffma" and np.all(np.abs(out[:32] - ref) <= tc_tol(ref))
+    e.set_path("tc")
+    with pytest.raises(engine.LinnaError, match="64 input"):
+        e.lnp(_dev(u))
