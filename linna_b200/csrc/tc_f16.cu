@@ -623,8 +623,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                             if (c0 >= st.dst_pad) break;
                             store_box(st.dst + c0, slot);
                             if (c0 + 64 < st.dst_pad) store_box(st.dst + c0 + 64, slot);
-                            const bool last_chunk = c0 + TF_NC >= st.dst_pad;
-                            if (last_chunk && slot == nslots - 1) publish(true);   // the next box may be a whole layer away
+                            // The next box of this group is a whole chunk of MMAs away: flush now (the store warp has nothing
+                            // else to do), so that the consumer layer can prefetch these columns at once.  Only between the
+                            // two boxes of a chunk is publication lazy.
+                            publish(true);
                         }
                 }
             }
