@@ -237,12 +237,15 @@ class EnsembleSampler:
             pass
         return x, lnp
 
-    def get_chain(self, flat=False):
-        c = torch.stack(self._chain).cpu().numpy().astype(np.float64)
+    def get_chain(self, flat=False, start=0):
+        """Stored positions [steps, walkers, ndim] on the host, from iteration ``start`` on."""
+        part = self._chain[start:]
+        c = (torch.stack(part).cpu().numpy().astype(np.float64) if part else np.zeros((0, self.nwalkers, self.ndim)))
         return c.reshape(-1, self.ndim) if flat else c
 
-    def get_log_prob(self, flat=False):
-        l = torch.stack(self._lnp).cpu().numpy().astype(np.float64)
+    def get_log_prob(self, flat=False, start=0):
+        part = self._lnp[start:]
+        l = torch.stack(part).cpu().numpy().astype(np.float64) if part else np.zeros((0, self.nwalkers))
         return l.reshape(-1) if flat else l
 
     def get_autocorr_time(self, tol=0, **kw):
@@ -304,10 +307,8 @@ class HMCSampler:
             it = self.sampler.iteration
             if it % check_every:
                 continue
-            chain = self.sampler.get_chain()
-            lp = self.sampler.get_log_prob()
-            store.extend(chain[saved:], lp[saved:])
-            saved = len(chain)
+            store.extend(self.sampler.get_chain(start=saved), self.sampler.get_log_prob(start=saved))   # only the new steps
+            saved = it
             store.save()
             tau = integrated_time(store.chain)
             if np.isnan(np.sum(tau)) and it > 10:
@@ -323,8 +324,7 @@ class HMCSampler:
                 break
             old_tau = tau
         if self.sampler.iteration > saved:
-            chain, lp = self.sampler.get_chain(), self.sampler.get_log_prob()
-            store.extend(chain[saved:], lp[saved:])
+            store.extend(self.sampler.get_chain(start=saved), self.sampler.get_log_prob(start=saved))
             store.save()
         self.sampler = None
         return store

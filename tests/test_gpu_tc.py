@@ -110,6 +110,9 @@ def test_tc_full_size_c3():
     assert np.array_equal(a, b)
     la, ga = e.lnp_grad(ud)
     assert np.array_equal(la.cpu().numpy(), a)
+    # a walker's value does not depend on what else is in the batch, nor on where in the batch it sits
+    idx = np.sort(np.random.default_rng(1).choice(n, 3000, replace=False))
+    assert np.array_equal(e.lnp(_dev(u[idx])).cpu().numpy(), a[idx])
     e.set_path("ffma")
     f = e.lnp(ud).cpu().numpy()
     assert np.all(np.abs(a - f) <= tc_tol(f)), np.abs(a - f).max()
