@@ -101,6 +101,9 @@ struct TfArgs {
     uint32_t *masks;
     int64_t n;
     int32_t l2_hints;         // 1: TMA loads carry L2 eviction-priority hints (LINNA_TC_L2_HINTS)
+    int32_t discard;          // 1: dead activation lines are dropped from L2 instead of being written back (LINNA_TC_DISCARD)
+    int32_t arena_ld;         // arena row pitch in halves
+    __half *arena;
     int32_t slots;            // walker pairs interleaved per cluster: 2, or 1 when the batch cannot fill the GPU twice
     int *err;
     long long *dbg;           // optional [grid][8] cycle counters (LINNA_TC_DEBUG): where the service warps wait
@@ -796,6 +799,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                     if (timing) e_epi += clock64() - t_c;
                 }
                 chi2[slot] += x.chi;
+                if (args.discard) {
+                    // Every MMA of this layer pass has retired (its last accumulator segment was drained above), so the
+                    // activations it was the last reader of are dead: drop this walker's lines from L2 rather than let
+                    // them be written back to HBM when they are evicted -- the arena in flight is as large as L2, and a
+                    // dead dirty line pushes out a live one.  Group 0 drops the hi copy, group 1 the lo copy.
+#pragma unroll 1
+                    for (int p = 0; p < st.nphase; ++p) {
+                        if (!(st.flags & (p ? TFF_LAST_USE1 : TFF_LAST_USE0))) continue;
+                        const __half *base = args.arena + (size_t)(arena_row0 + slot * TF_M + row) * args.arena_ld + st.src[p] +
+                                             (gi ? lo_off : 0);
+                        const int nlines = (st.K[p] + 63) >> 6;   // 64 halves = one 128-byte line
+#pragma unroll 1
+                        for (int l = 0; l < nlines; ++l)
+                            asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + 64 * l) : "memory");
+                    }
+                    fence_async_all();   // ordered before the TMA stores that will reuse these columns (they follow an mbarrier
+                                         // hand-off from this thread to the store warp)
+                }
                 if (st.variant == TFV_CHI2_STORE) {
                     // The backward pass is linear in r: carry it at unit scale (r / 2^k, k = exponent of |r|) so that a
                     // walker far from the peak (|r| ~ 1e3) cannot push a gradient past the fp16 range; the last
@@ -848,6 +869,7 @@ struct TcContext {
     __half *wblob = nullptr;      // packed hi/lo weight operands
     float *fblob = nullptr;       // effective biases
     __half *arena = nullptr;
+    int ld = 0;                   // arena row pitch in halves
     uint32_t *masks = nullptr;
     CUtensorMap *maps_dev = nullptr;
     TfProgram *prog_dev = nullptr;   // [0] LNP, [1] GRAD
@@ -1201,6 +1223,7 @@ TcContext *tc_build(const linna_model *m, std::string &why)
     TcContext *t = new TcContext();
     auto bail = [&](const std::string &msg) { why = msg; tc_destroy(t); return (TcContext *)nullptr; };
     t->grid = m->num_sms & ~1;   // whole CTA pairs
+    t->ld = ld;
     t->has_grad = has_grad;
     if (cudaMalloc(&t->wblob, P.w.size() * sizeof(__half)) != cudaSuccess) return bail("cudaMalloc weights");
     if (cudaMemcpy(t->wblob, P.w.data(), P.w.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) return bail("upload");
@@ -1283,6 +1306,8 @@ static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const f
     a.slots = (want_slots == 2 && pairs > clusters) ? 2 : 1;
     static const int want_hints = getenv("LINNA_TC_L2_HINTS") ? atoi(getenv("LINNA_TC_L2_HINTS")) : 0;
     a.l2_hints = want_hints;
+    static const int want_discard = getenv("LINNA_TC_DISCARD") ? atoi(getenv("LINNA_TC_DISCARD")) : 0;
+    a.discard = want_discard, a.arena = t->arena, a.arena_ld = t->ld;
     const int grid = 2 * (int)std::min<int64_t>(pairs, clusters);
     tc_f16_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
     return cudaGetLastError();
