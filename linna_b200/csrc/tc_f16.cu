@@ -1,7 +1,7 @@
-// Tensor-core emulator-likelihood kernel for large walker batches (sm_100a: tcgen05 + TMEM + TMA).
+// Tensor-core emulator-likelihood kernel (sm_100a: tcgen05 + TMEM + TMA), lnP and lnP+gradient.
 //
 // Same step program as the FFMA kernel (linna/nn.py:45-56, :110-133; linna/util.py:953-955, :990-1021), but
-// every GEMM  D[128 walkers][N] = A[128][K] . B[N][K]^T  runs on the 5th-generation tensor cores:
+// every GEMM  D[256 walkers][N] = A[256][K] . B[N][K]^T  runs on the 5th-generation tensor cores:
 //
 //   * split-fp16 product.  Every fp32 operand x is stored as two halves, hi = fp16(x), lo = fp16(x - hi)
 //     (22 significant bits; weights are pre-scaled by a power of two per step so that they sit in the
@@ -11,24 +11,32 @@
 //   * two-level accumulation.  The tensor core truncates its fp32 accumulator on every tcgen05.mma
 //     (measured: a toward-zero bias of ~0.5 ulp per instruction), so every `seg_kc` k-chunks (default 4 = 128
 //     values of K = 24 instructions; measured max relative lnP error 3.2e-7 at 4, 2.1e-7 at 2, both at the
-//     level of the reference's own float32) the partial tile is drained from tensor memory and added with round-to-nearest into fp32 REGISTER accumulators
-//     by the epilogue warps, while the MMA warp already fills the other TMEM buffer.
-//   * two walker tiles (X, Y: 2 x 128 rows) per CTA share every weight tile that TMA brings into
-//     shared memory: half the L2 weight traffic per walker, and twice the work per pipeline stage.
-//   * operands are K-major 64-byte-swizzled tiles filled by TMA (cp.async.bulk.tensor) from the packed
-//     hi/lo weights and from the row-major hi/lo activation arena of this CTA; layer outputs go back to the
-//     arena through a swizzled staging buffer and TMA stores.  The producer tracks, per tile, how many
-//     128-column output chunks have become visible, so the next layer starts on the first columns of an
-//     activation while the epilogue is still writing the last ones.
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM allocator, warps 2 / 3 = TMA
-//     store issuers of tile X / Y (they also publish the chunks), warps 4-7 / 8-11 = epilogue of tile
-//     X / Y: every thread owns one walker (TMEM lane) and all 128 columns of a chunk, so the chi^2
-//     reduction, the relu masks of the backward pass and the final Jacobian need no cross-thread traffic
-//     at all.  setmaxnreg moves registers from the four service warps to the epilogue warps, whose 128
-//     fp32 accumulators per thread are the second accumulation level.
+//     level of the reference's own float32) the partial tile is drained from tensor memory and added with
+//     round-to-nearest into fp32 REGISTER accumulators by the epilogue warps, while the MMA warp already
+//     fills the other TMEM buffer.
+//   * CTA pairs.  One cluster = two CTAs = 2 x 128 walkers; rank 0 issues every MMA for the pair
+//     (cta_group::2, M = 256, N <= 256).  Each CTA supplies its own 128 activation rows and HALF of the weight
+//     tile and receives its own 128 x N accumulator rows: half the L2 weight traffic per walker, and the MMA
+//     is off the shared-memory bandwidth limit a 128 x 128 single-CTA instruction sits on.
+//   * operands are K-major 64-byte-swizzled tiles (4 stages x 32 KB) filled by TMA (cp.async.bulk.tensor,
+//     completion on the leader's mbarrier) from the packed hi/lo weights and from the row-major hi/lo
+//     activation arena of this CTA; layer outputs go back to the arena through a 128-byte-swizzled staging box
+//     and TMA stores.  The store warps publish, per 64-column box, how far a layer's output is visible, and the
+//     producer fetches a k-chunk as soon as ITS columns are there, so the next layer starts on the first
+//     columns of an activation while the epilogue is still writing the last ones.
+//   * every cluster interleaves two walker pairs ("slots") layer by layer, so that the layer-to-layer
+//     dependency bubble of one pair is filled with the other pair's MMAs.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread, leader CTA) + TMEM allocator, warps 2 / 3
+//     = TMA store issuers of column group 0 / 1, warps 4-7 / 8-11 = epilogue of column group 0 / 1 (columns
+//     [0,128) / [128,256) of every 256-column chunk): an epilogue thread owns one walker (TMEM lane) and 128
+//     columns, so the chi^2 reduction, the relu masks of the backward pass and the final Jacobian need no
+//     cross-thread traffic beyond one exchange of the two groups' chi^2 partials.  setmaxnreg moves registers
+//     from the four service warps to the epilogue warps, whose 128 fp32 accumulators per thread are the
+//     second accumulation level.
 //
 // Two programs: LNP (forward, chi^2) and GRAD (forward with saved relu masks, backward-data through every
-// layer with the transposed weights, prior-map Jacobian in the last epilogue).
+// layer with the transposed weights at a per-walker power-of-two scale, prior-map Jacobian in the last
+// epilogue).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
