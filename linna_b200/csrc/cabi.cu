@@ -1,5 +1,5 @@
 // C-ABI of linna_b200 (see include/linna_b200.h): model packing, step-program construction and
-// kernel dispatch.  Host code only; the kernels live in fused_ffma.cu (and later tc_*.cu).
+// kernel dispatch.  Host code only; the kernels live in fused_ffma.cu, tc_f16.cu, train_kernels.cu and sampler_kernels.cu.
 #include <algorithm>
 #include <atomic>
 #include <cmath>

@@ -1,4 +1,4 @@
-// Host-side model state shared by the C-ABI translation units (cabi.cu, tc_mlp.cu).
+// Host-side model state shared by the C-ABI translation units (cabi.cu, tc_f16.cu).
 #pragma once
 #include <cstdint>
 #include <string>
@@ -10,7 +10,7 @@
 using namespace linna;
 
 namespace linna {
-struct TcContext;   // tensor-core path state (tc_mlp.cu)
+struct TcContext;   // tensor-core path state (tc_f16.cu)
 }
 
 static inline int pad4(int n) { return (n + 3) & ~3; }
