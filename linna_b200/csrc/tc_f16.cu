@@ -18,10 +18,13 @@
 //     (cta_group::2, M = 256, N <= 256).  Each CTA supplies its own 128 activation rows and HALF of the weight
 //     tile and receives its own 128 x N accumulator rows: half the L2 weight traffic per walker, and the MMA
 //     is off the shared-memory bandwidth limit a 128 x 128 single-CTA instruction sits on.
-//   * operands are K-major 64-byte-swizzled tiles (4 stages x 32 KB) filled by TMA (cp.async.bulk.tensor,
-//     completion on the leader's mbarrier) from the packed hi/lo weights and from the row-major hi/lo
-//     activation arena of this CTA; layer outputs go back to the arena through a 128-byte-swizzled staging box
-//     and TMA stores.  The store warps publish, per 64-column box, how far a layer's output is visible, and the
+//   * operands are K-major 128-byte-swizzled tiles (4 stages x 32 KB) filled by TMA (cp.async.bulk.tensor,
+//     completion on the leader's mbarrier) from the packed weights and from the row-major activation arena of
+//     this CTA.  Both keep the hi and lo halves of a k-chunk of 32 values side by side ([32 hi | 32 lo] = 128
+//     contiguous bytes per row), so that one TMA box row is one full cache line and a stage is two TMA
+//     instructions (A tile, B half tile) rather than four of half-line rows; the MMA descriptors pick the hi or
+//     lo half of the swizzle row by a 64-byte offset of the start address.  Layer outputs go back to the arena
+//     through staging boxes of the same format and TMA stores.  The store warps publish, per 64-column box, how far a layer's output is visible, and the
 //     producer fetches a k-chunk as soon as ITS columns are there, so the next layer starts on the first
 //     columns of an activation while the epilogue is still writing the last ones.
 //   * every cluster interleaves two walker pairs ("slots") layer by layer, so that the layer-to-layer
@@ -53,12 +56,12 @@ namespace linna {
 
 constexpr int TF_M = 128;        // walkers per tile
 constexpr int TF_NC = 256;       // accumulator columns per chunk (two epilogue groups of 128)
-constexpr int TF_KC = 32;        // k-chunk in halves = one 64-byte swizzle row
+constexpr int TF_KC = 32;        // k-chunk: 32 values of K = [32 hi halves | 32 lo halves] = one 128-byte swizzle row
 constexpr int TF_STAGES = 4;
-constexpr int TF_TILE_BYTES = TF_M * TF_KC * 2;                  // 8 KB operand tile
-constexpr int TF_STAGE_BYTES = 4 * TF_TILE_BYTES;                // A hi/lo, B-half hi/lo = 32 KB per CTA
-constexpr int TF_BOX_BYTES = 128 * 64 * 2;                       // staging box: 128 rows x 64 halves = 16 KB
-constexpr int TF_STG_BYTES = 2 * TF_BOX_BYTES;                   // hi + lo per column group
+constexpr int TF_TILE_BYTES = TF_M * 2 * TF_KC * 2;              // 16 KB operand tile (hi and lo of one k-chunk, interleaved)
+constexpr int TF_STAGE_BYTES = 2 * TF_TILE_BYTES;                // A tile + B-half tile = 32 KB per CTA
+constexpr int TF_BOX_BYTES = 128 * 64 * 2;                       // staging box: 128 rows x 64 halves = 16 KB = one k-chunk, hi | lo
+constexpr int TF_STG_BYTES = 2 * TF_BOX_BYTES;                   // two k-chunks (64 activation columns) per column group
 constexpr int TF_SMEM_BYTES = TF_STAGES * TF_STAGE_BYTES + 2 * TF_STG_BYTES + 1024;
 constexpr int TF_THREADS = 384;  // TMA, MMA, 2 store warps + 2 x 4 epilogue warps
 constexpr int TF_MAX_STEPS = 48;
@@ -71,12 +74,12 @@ enum TfVariant : int32_t { TFV_ACT = 0, TFV_ACT_SAVE, TFV_CHI2, TFV_CHI2_STORE, 
 
 struct TfStep {
     int32_t nphase;
-    int32_t src[2];       // arena column of the hi copy of this phase's A operand; lo copy at + lo_off
+    int32_t src[2];       // arena column (in halves: 2 x the activation column) of this phase's A operand
     int32_t K[2];
-    int32_t mapB[2];      // tensor-map index of the hi weight operand; lo = + 1
+    int32_t mapB[2];      // tensor-map index of the weight operand
     int32_t src_pub[2][2];   // [phase][group]: 64-column boxes the group published (per tile pass) before the producer of src
     int32_t N;
-    int32_t dst;          // arena column of the output (hi), -1: none
+    int32_t dst;          // arena column (in halves) of the output, -1: none
     int32_t dst_pad;      // output width rounded up to 64 (pad columns are written as zeros)
     int32_t epi, flags;
     int32_t mask_word;    // first 32-bit word of this layer's relu bits inside a mask row
@@ -91,8 +94,8 @@ struct TfStep {
 struct TfProgram {
     int32_t n_steps;
     int32_t total_pub[2];  // 64-column boxes each column group publishes per tile pass (prologue included)
-    int32_t in_col;        // arena column of xhat
-    int32_t lo_off;        // column offset from a hi copy to its lo copy
+    int32_t in_col;        // arena column (in halves) of xhat
+    int32_t pad0_;
     int32_t seg_kc;        // k-chunks accumulated in tensor memory between two drains
     int32_t mask_words;    // 32-bit words per mask row
     int32_t pad_[1];
@@ -101,7 +104,7 @@ struct TfProgram {
 
 struct TfArgs {
     const TfProgram *prog;
-    const CUtensorMap *maps;  // [0] arena load, [1] arena store, then hi/lo per weight operand
+    const CUtensorMap *maps;  // [0] arena load, [1] arena store, then one per weight operand
     Consts c;
     const float *in;
     float *lnp;
@@ -109,9 +112,6 @@ struct TfArgs {
     uint32_t *masks;
     int64_t n;
     int32_t l2_hints;         // 1: TMA loads carry L2 eviction-priority hints (LINNA_TC_L2_HINTS)
-    int32_t discard;          // 1: dead activation lines are dropped from L2 instead of being written back (LINNA_TC_DISCARD)
-    int32_t arena_ld;         // arena row pitch in halves
-    __half *arena;
     int32_t slots;            // walker pairs interleaved per cluster: 2, or 1 when the batch cannot fill the GPU twice
     int *err;
     long long *dbg;           // optional [grid][8] cycle counters (LINNA_TC_DEBUG): where the service warps wait
@@ -239,15 +239,17 @@ __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.as
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major operand tile, 64-byte swizzle: rows are 64 B apart, 8-row groups 512 B apart.
-__device__ __forceinline__ uint64_t make_sdesc64(uint32_t saddr)
+// K-major operand tile, 128-byte swizzle: rows are 128 B apart, 8-row groups 1024 B apart.  A row holds the hi
+// halves of its k-chunk in bytes [0, 64) and the lo halves in [64, 128): a K = 16 slice of either is a 32-byte
+// step of the start address inside the swizzle row.
+__device__ __forceinline__ uint64_t make_sdesc128(uint32_t saddr)
 {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);  // start address, 16-byte units
     d |= (uint64_t)1 << 16;                  // leading byte offset (unused with swizzle)
-    d |= (uint64_t)(512 >> 4) << 32;         // stride byte offset between 8-row groups
+    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset between 8-row groups
     d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
-    d |= (uint64_t)4 << 61;                  // SWIZZLE_64B
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
     return d;
 }
 // kind::f16 with fp16 inputs, fp32 accumulate, A and B K-major, M = 256 over the CTA pair
@@ -311,7 +313,7 @@ __device__ __forceinline__ int tf_chunk_stages(const TfStep &st, int n0)
 
 // ------------------------------------------------------------------------------------------ chunk epilogue
 struct TfEpiCtx {
-    uint8_t *my_hi, *my_lo;     // this thread's 128-byte rows of the hi / lo staging boxes
+    uint8_t *my_x, *my_y;       // this thread's 128-byte rows of the two staging boxes (k-chunk 0 / 1 of 64 columns)
     uint64_t *sfree, *sfull;
     uint32_t *mask_row;
     int *err;
@@ -379,9 +381,10 @@ __device__ __forceinline__ void tf_chunk_epilogue(const float (&racc)[128], cons
                 uint32_t hw[4], lw[4];
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) split2(v[e], v[e + 1], hw[e >> 1], lw[e >> 1]);
-                const int o = (j ^ x.sw) << 4;
-                *reinterpret_cast<uint4 *>(x.my_hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *reinterpret_cast<uint4 *>(x.my_lo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                // columns [8j, 8j+8) of the box: 16-byte unit j&3 of the hi half, 4 + (j&3) of the lo half
+                uint8_t *bx = (j & 4) ? x.my_y : x.my_x;
+                *reinterpret_cast<uint4 *>(bx + (((j & 3) ^ x.sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4 *>(bx + (((4 + (j & 3)) ^ x.sw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
         }
         if (store) {
@@ -418,7 +421,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
     const bool leader = cta_rank == 0;
     const TfProgram *prog = args.prog;
     const int n_steps = prog->n_steps;
-    const int lo_off = prog->lo_off;
     const int seg_kc = prog->seg_kc;
     const Consts &c = args.c;
     const CUtensorMap *maps = args.maps;
@@ -483,13 +485,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                                 mbar_wait_timed(&empty_bar[stage], ph ^ 1, args.err, 1, w_empty);
                                 uint8_t *sb = smem + stage * TF_STAGE_BYTES;
                                 if (leader) mbar_expect_tx(&full_bar[stage], 2 * TF_STAGE_BYTES);   // both CTAs' bytes
-                                if (use_hints) {
-                                    tma_load_2d_pair_hint(sb + 2 * TF_TILE_BYTES, mb, &full_bar[stage], kc * TF_KC, nb, pol_keep);
-                                    tma_load_2d_pair_hint(sb + 3 * TF_TILE_BYTES, mb + 1, &full_bar[stage], kc * TF_KC, nb, pol_keep);
-                                } else {
-                                    tma_load_2d_pair(sb + 2 * TF_TILE_BYTES, mb, &full_bar[stage], kc * TF_KC, nb);
-                                    tma_load_2d_pair(sb + 3 * TF_TILE_BYTES, mb + 1, &full_bar[stage], kc * TF_KC, nb);
-                                }
+                                if (use_hints) tma_load_2d_pair_hint(sb + TF_TILE_BYTES, mb, &full_bar[stage], kc * 2 * TF_KC, nb, pol_keep);
+                                else tma_load_2d_pair(sb + TF_TILE_BYTES, mb, &full_bar[stage], kc * 2 * TF_KC, nb);
                                 // the activations this k-chunk reads: wait until their producer chunk is visible
                                 const int col = kc * TF_KC;
                                 const int grp = (col >> 7) & 1;
@@ -505,15 +502,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                                     w_ready += clock64() - t0;
                                     fence_async_all();
                                 }
-                                const int ca = st.src[p] + col;
+                                const int ca = st.src[p] + 2 * col;
                                 const bool dead = use_hints && (st.flags & (p ? TFF_LAST_USE1 : TFF_LAST_USE0)) && n0 + TF_NC >= st.N;
-                                if (dead) {
-                                    tma_load_2d_pair_hint(sb, maps, &full_bar[stage], ca, arena_row0 + slot * TF_M, pol_dead);
-                                    tma_load_2d_pair_hint(sb + TF_TILE_BYTES, maps, &full_bar[stage], ca + lo_off, arena_row0 + slot * TF_M, pol_dead);
-                                } else {
-                                    tma_load_2d_pair(sb, maps, &full_bar[stage], ca, arena_row0 + slot * TF_M);
-                                    tma_load_2d_pair(sb + TF_TILE_BYTES, maps, &full_bar[stage], ca + lo_off, arena_row0 + slot * TF_M);
-                                }
+                                if (dead) tma_load_2d_pair_hint(sb, maps, &full_bar[stage], ca, arena_row0 + slot * TF_M, pol_dead);
+                                else tma_load_2d_pair(sb, maps, &full_bar[stage], ca, arena_row0 + slot * TF_M);
                                 if (++stage == TF_STAGES) stage = 0, ph ^= 1;
                             }
                         }
@@ -559,13 +551,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                                 else mbar_wait_timed(&full_bar[stage], ph, args.err, 4, w_full);
                                 tc_fence_after();
                                 const uint32_t sb = smem_u32(smem + stage * TF_STAGE_BYTES);
-                                const uint32_t a_hi = sb, a_lo = sb + TF_TILE_BYTES, b_hi = sb + 2 * TF_TILE_BYTES, b_lo = sb + 3 * TF_TILE_BYTES;
+                                const uint32_t a_hi = sb, a_lo = sb + 64, b_hi = sb + TF_TILE_BYTES, b_lo = b_hi + 64;
 #pragma unroll
                                 for (int ks = 0; ks < 2; ++ks) {
                                     const uint32_t o = ks * 32;   // 16 halves = 32 bytes along K inside the swizzle row
-                                    umma_f16_pair(dcol, make_sdesc64(a_lo + o), make_sdesc64(b_hi + o), idesc, (in_seg | ks) ? 1u : 0u);
-                                    umma_f16_pair(dcol, make_sdesc64(a_hi + o), make_sdesc64(b_lo + o), idesc, 1u);
-                                    umma_f16_pair(dcol, make_sdesc64(a_hi + o), make_sdesc64(b_hi + o), idesc, 1u);
+                                    umma_f16_pair(dcol, make_sdesc128(a_lo + o), make_sdesc128(b_hi + o), idesc, (in_seg | ks) ? 1u : 0u);
+                                    umma_f16_pair(dcol, make_sdesc128(a_hi + o), make_sdesc128(b_lo + o), idesc, 1u);
+                                    umma_f16_pair(dcol, make_sdesc128(a_hi + o), make_sdesc128(b_hi + o), idesc, 1u);
                                 }
                                 umma_commit_pair(&empty_bar[stage]);   // frees the smem stage in both CTAs when these MMAs retire
                                 if (++stage == TF_STAGES) stage = 0, ph ^= 1;
@@ -589,7 +581,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         // =============================== TMA store issuers (column group 0 / 1) ===============================
         if (lane == 0) {
             const int gi = warp - 2;
-            uint8_t *stg_hi = stg_all + gi * TF_STG_BYTES, *stg_lo = stg_hi + TF_BOX_BYTES;
+            uint8_t *stg_x = stg_all + gi * TF_STG_BYTES, *stg_y = stg_x + TF_BOX_BYTES;
             const CUtensorMap *map_st = maps + 1;
             uint32_t sidx = 0, pub[2] = {0, 0}, pend[2] = {0, 0};
             // Publication needs the stores to have LANDED (wait_group), which takes far longer than handing the
@@ -609,8 +601,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
             };
             auto store_box = [&](int col, int slot) {
                 mbar_wait(&sfull_bar[gi], sidx & 1, args.err, 6);      // the 128 epilogue threads have written the box
-                tma_store_2d(stg_hi, map_st, col, arena_row0 + slot * TF_M);
-                tma_store_2d(stg_lo, map_st, col + lo_off, arena_row0 + slot * TF_M);
+                tma_store_2d(stg_x, map_st, col, arena_row0 + slot * TF_M);          // k-chunk 0 of the 64 columns: hi | lo
+                tma_store_2d(stg_y, map_st, col + 64, arena_row0 + slot * TF_M);     // k-chunk 1
                 bulk_commit();
                 bulk_wait_read();                                      // staging read out: hand it back
                 mbar_arrive(&sfree_bar[gi]);
@@ -632,8 +624,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                         for (int n0 = 0; n0 < st.N; n0 += TF_NC) {
                             const int c0 = n0 + 128 * gi;
                             if (c0 >= st.dst_pad) break;
-                            store_box(st.dst + c0, slot);
-                            if (c0 + 64 < st.dst_pad) store_box(st.dst + c0 + 64, slot);
+                            store_box(st.dst + 2 * c0, slot);
+                            if (c0 + 64 < st.dst_pad) store_box(st.dst + 2 * (c0 + 64), slot);
                             // The next box of this group is a whole chunk of MMAs away: flush now (the store warp has nothing
                             // else to do), so that the consumer layer can prefetch these columns at once.  Only between the
                             // two boxes of a chunk is publication lazy.
@@ -652,7 +644,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;                   // TMEM lane == walker of the tile
         const uint32_t tmem_grp = tmem_base + ((uint32_t)(q * 32) << 16) + gi * 128;
-        x.my_hi = stg_all + gi * TF_STG_BYTES + row * 128, x.my_lo = x.my_hi + TF_BOX_BYTES;
+        x.my_x = stg_all + gi * TF_STG_BYTES + row * 128, x.my_y = x.my_x + TF_BOX_BYTES;
         x.sw = row & 7;
         x.sfree = &sfree_bar[gi], x.sfull = &sfull_bar[gi];
         x.sidx = 0;
@@ -704,9 +696,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                         }
                         split2(xv[0], xv[1], hw[e >> 1], lw[e >> 1]);
                     }
-                    const int o = (j ^ x.sw) << 4;
-                    *reinterpret_cast<uint4 *>(x.my_hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                    *reinterpret_cast<uint4 *>(x.my_lo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    uint8_t *bx = (j & 4) ? x.my_y : x.my_x;
+                    *reinterpret_cast<uint4 *>(bx + (((j & 3) ^ x.sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4 *>(bx + (((4 + (j & 3)) ^ x.sw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                 }
                 lnprior2[slot] = -0.5f * lnprior;                                    // util.py:1165
                 fence_async_smem();
@@ -780,7 +772,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                         // theta' = log10(theta), theta = prior(u).  The accumulators go through this thread's own
                         // staging row so that the loop stays rolled.
                         mbar_wait(x.sfree, (x.sidx & 1) ^ 1, args.err, 7);
-                        float *scr_a = reinterpret_cast<float *>(x.my_hi), *scr_b = reinterpret_cast<float *>(x.my_lo);
+                        float *scr_a = reinterpret_cast<float *>(x.my_x), *scr_b = reinterpret_cast<float *>(x.my_y);
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             *reinterpret_cast<float4 *>(scr_a + i) = make_float4(racc[i], racc[i + 1], racc[i + 2], racc[i + 3]);
@@ -807,24 +799,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                     if (timing) e_epi += clock64() - t_c;
                 }
                 chi2[slot] += x.chi;
-                if (args.discard) {
-                    // Every MMA of this layer pass has retired (its last accumulator segment was drained above), so the
-                    // activations it was the last reader of are dead: drop this walker's lines from L2 rather than let
-                    // them be written back to HBM when they are evicted -- the arena in flight is as large as L2, and a
-                    // dead dirty line pushes out a live one.  Group 0 drops the hi copy, group 1 the lo copy.
-#pragma unroll 1
-                    for (int p = 0; p < st.nphase; ++p) {
-                        if (!(st.flags & (p ? TFF_LAST_USE1 : TFF_LAST_USE0))) continue;
-                        const __half *base = args.arena + (size_t)(arena_row0 + slot * TF_M + row) * args.arena_ld + st.src[p] +
-                                             (gi ? lo_off : 0);
-                        const int nlines = (st.K[p] + 63) >> 6;   // 64 halves = one 128-byte line
-#pragma unroll 1
-                        for (int l = 0; l < nlines; ++l)
-                            asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + 64 * l) : "memory");
-                    }
-                    fence_async_all();   // ordered before the TMA stores that will reuse these columns (they follow an mbarrier
-                                         // hand-off from this thread to the store warp)
-                }
                 if (st.variant == TFV_CHI2_STORE) {
                     // The backward pass is linear in r: carry it at unit scale (r / 2^k, k = exponent of |r|) so that a
                     // walker far from the peak (|r| ~ 1e3) cannot push a gradient past the fp16 range; the last
@@ -889,7 +863,6 @@ struct TcContext {
 };
 
 static inline int pad64(int n) { return (n + 63) & ~63; }
-static inline int pad8(int n) { return (n + 7) & ~7; }
 
 // k-chunks (of 32) accumulated in tensor memory between two promotions to the register accumulators
 static int tc_seg_kc()
@@ -923,7 +896,7 @@ struct MatSrc {
 struct Packer {
     std::vector<__half> w;       // weight blob (halves)
     std::vector<float> f;        // float blob (biases)
-    struct Mat { size_t hi, lo; int N, K, ldk; };
+    struct Mat { size_t off; int N, K, ldk; };   // row n: per k-chunk of 32, [32 hi halves | 32 lo halves]
     std::vector<Mat> mats;
     size_t walloc(size_t n) { size_t o = (w.size() + 127) / 128 * 128; w.resize(o + n, __float2half_rn(0.f)); return o; }
     size_t fput(const std::vector<float> &v, int padded)
@@ -956,15 +929,16 @@ struct Packer {
     int put(const MatSrc &s, int shift)
     {
         Mat mt;
-        mt.N = s.N, mt.K = s.K, mt.ldk = pad8(s.K);
-        mt.hi = walloc((size_t)s.N * mt.ldk), mt.lo = walloc((size_t)s.N * mt.ldk);
+        mt.N = s.N, mt.K = s.K, mt.ldk = 2 * TF_KC * ((s.K + TF_KC - 1) / TF_KC);
+        mt.off = walloc((size_t)s.N * mt.ldk);
         const float sc = ldexpf(1.f, shift);
         for (int n = 0; n < s.N; ++n)
             for (int k = 0; k < s.K; ++k) {
                 const float x = at(s, n, k) * sc;
                 const __half hi = __float2half_rn(x);
-                w[mt.hi + (size_t)n * mt.ldk + k] = hi;
-                w[mt.lo + (size_t)n * mt.ldk + k] = __float2half_rn(x - __half2float(hi));
+                const size_t o = mt.off + (size_t)n * mt.ldk + 2 * TF_KC * (k / TF_KC) + k % TF_KC;
+                w[o] = hi;
+                w[o + TF_KC] = __float2half_rn(x - __half2float(hi));
             }
         mats.push_back(mt);
         return (int)mats.size() - 1;
@@ -1039,7 +1013,7 @@ TcContext *tc_build(const linna_model *m, std::string &why)
         };
         // src slots are stored in s.src[] as slot ids first and turned into columns once the widths are known
         auto set_phase = [&](TfStep &s, int p, int slot, const MatSrc &ms, int shift) {
-            s.src[p] = slot, s.K[p] = ms.K, s.mapB[p] = 2 + 2 * P.put(ms, shift);
+            s.src[p] = slot, s.K[p] = ms.K, s.mapB[p] = 2 + P.put(ms, shift);
             s.src_pub[p][0] = slot_pub[slot][0], s.src_pub[p][1] = slot_pub[slot][1];
         };
         auto set_dst = [&](TfStep &s, int slot) {
@@ -1217,14 +1191,14 @@ TcContext *tc_build(const linna_model *m, std::string &why)
     // ---- arena columns
     int slot_col[NSLOT], ncol = 0;
     for (int s = 0; s < NSLOT; ++s) slot_col[s] = ncol, ncol += slot_w[s];
-    const int lo_off = ncol, ld = 2 * ncol;
+    const int ld = 2 * ncol;   // halves per arena row: every activation column is a (hi, lo) pair
     for (int pk = 0; pk < 2; ++pk) {
         TfProgram &pg = pgs[pk];
-        pg.in_col = slot_col[SLOT_X], pg.lo_off = lo_off, pg.mask_words = std::max(mask_words_total, 4);
+        pg.in_col = 2 * slot_col[SLOT_X], pg.mask_words = std::max(mask_words_total, 4);
         for (int i = 0; i < pg.n_steps; ++i) {
             TfStep &s = pg.steps[i];
-            for (int p = 0; p < s.nphase; ++p) s.src[p] = slot_col[s.src[p]];
-            if (s.dst >= 0) s.dst = slot_col[s.dst];
+            for (int p = 0; p < s.nphase; ++p) s.src[p] = 2 * slot_col[s.src[p]];
+            if (s.dst >= 0) s.dst = 2 * slot_col[s.dst];
         }
     }
 
@@ -1247,7 +1221,7 @@ TcContext *tc_build(const linna_model *m, std::string &why)
     }
 
     // ---- tensor maps
-    std::vector<CUtensorMap> maps(2 + 2 * P.mats.size());
+    std::vector<CUtensorMap> maps(2 + P.mats.size());
     auto encode2d = [&](CUtensorMap *mp, void *base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner,
                         uint32_t box_outer, CUtensorMapSwizzle sw) {
         cuuint64_t dims[2] = {inner, outer};
@@ -1257,16 +1231,14 @@ TcContext *tc_build(const linna_model *m, std::string &why)
         return encode(mp, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     };
-    if (encode2d(&maps[0], t->arena, (uint64_t)ld, rows, (uint64_t)ld * 2, TF_KC, TF_M, CU_TENSOR_MAP_SWIZZLE_64B) != CUDA_SUCCESS)
+    if (encode2d(&maps[0], t->arena, (uint64_t)ld, rows, (uint64_t)ld * 2, 2 * TF_KC, TF_M, CU_TENSOR_MAP_SWIZZLE_128B) != CUDA_SUCCESS)
         return bail("cuTensorMapEncodeTiled(arena load) failed");
     if (encode2d(&maps[1], t->arena, (uint64_t)ld, rows, (uint64_t)ld * 2, 64, TF_M, CU_TENSOR_MAP_SWIZZLE_128B) != CUDA_SUCCESS)
         return bail("cuTensorMapEncodeTiled(arena store) failed");
     for (size_t i = 0; i < P.mats.size(); ++i) {
         const Packer::Mat &mt = P.mats[i];
-        if (encode2d(&maps[2 + 2 * i], t->wblob + mt.hi, (uint64_t)mt.K, (uint64_t)mt.N, (uint64_t)mt.ldk * 2, TF_KC, TF_M,
-                     CU_TENSOR_MAP_SWIZZLE_64B) != CUDA_SUCCESS ||
-            encode2d(&maps[3 + 2 * i], t->wblob + mt.lo, (uint64_t)mt.K, (uint64_t)mt.N, (uint64_t)mt.ldk * 2, TF_KC, TF_M,
-                     CU_TENSOR_MAP_SWIZZLE_64B) != CUDA_SUCCESS)
+        if (encode2d(&maps[2 + i], t->wblob + mt.off, (uint64_t)mt.ldk, (uint64_t)mt.N, (uint64_t)mt.ldk * 2, 2 * TF_KC, TF_M,
+                     CU_TENSOR_MAP_SWIZZLE_128B) != CUDA_SUCCESS)
             return bail("cuTensorMapEncodeTiled(weights) failed");
     }
     if (cudaMalloc(&t->maps_dev, maps.size() * sizeof(CUtensorMap)) != cudaSuccess) return bail("cudaMalloc maps");
@@ -1314,8 +1286,6 @@ static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const f
     a.slots = (want_slots == 2 && pairs > clusters) ? 2 : 1;
     static const int want_hints = getenv("LINNA_TC_L2_HINTS") ? atoi(getenv("LINNA_TC_L2_HINTS")) : 0;
     a.l2_hints = want_hints;
-    static const int want_discard = getenv("LINNA_TC_DISCARD") ? atoi(getenv("LINNA_TC_DISCARD")) : 0;
-    a.discard = want_discard, a.arena = t->arena, a.arena_ld = t->ld;
     const int grid = 2 * (int)std::min<int64_t>(pairs, clusters);
     tc_f16_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
     return cudaGetLastError();
