@@ -159,13 +159,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *e
         if (clock64() - t0 > 2000000000LL) tf_die(err, code);
     }
 }
+// DBG (LINNA_TC_DEBUG) instantiation only: the same wait with its duration added to a cycle counter.  The
+// production kernel does not read the clock on its service warps' critical path.
+template <bool DBG>
 __device__ __forceinline__ void mbar_wait_timed(uint64_t *bar, uint32_t parity, int *err, int code, long long &acc)
 {
+    if (!DBG) {
+        mbar_wait(bar, parity, err, code);
+        return;
+    }
     const long long t0 = clock64();   // try_wait itself suspends the thread for a while: time it from the start
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 2000000000LL) tf_die(err, code);
     }
     acc += clock64() - t0;
+}
+// One lane of a converged warp.  Issuing tcgen05 / TMA instructions from `if (elect_one())` inside warp-uniform
+// control flow keeps the service loops free of the per-instruction serialisation loops that the compiler has
+// to wrap around uniform-datapath instructions in divergent code (`if (lane == 0)`).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
 {
@@ -252,20 +272,30 @@ __device__ __forceinline__ uint64_t make_sdesc128(uint32_t saddr)
     d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
     return d;
 }
+// The six MMAs of one k-chunk (two K = 16 slices x three split-fp16 passes) from the descriptors of the A and
+// B-half tiles of a stage: a slice is +32 bytes, the lo half +64 bytes (descriptor address units are 16 bytes;
+// the tiles are 1024-byte aligned, so the additions never carry out of the address field).
+__device__ __forceinline__ void umma_f16_pair_x6(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, t;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, %4, %4;\n\t"
+        "add.u64 a1, %1, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 a3, %1, 6;\n\t"
+        "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a2, %2, %3, p;\n\t"     // A_lo . B_hi, K slice 0
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, b2, %3, t;\n\t"     // A_hi . B_lo
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, t;\n\t"     // A_hi . B_hi
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b1, %3, t;\n\t"     // K slice 1
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b3, %3, t;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, t;\n\t}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // kind::f16 with fp16 inputs, fp32 accumulate, A and B K-major, M = 256 over the CTA pair
 __device__ __forceinline__ uint32_t make_idesc_f16(int n)
 {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)((2 * TF_M) >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        :
-        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
 }
 __device__ __forceinline__ void umma_commit_pair(uint64_t *bar)
 {
@@ -322,6 +352,7 @@ struct TfEpiCtx {
     int sw;                     // 128-byte swizzle phase of this row
     long long t_sfree;          // cycles spent waiting for the staging box (LINNA_TC_DEBUG)
     float row_scale;            // 2^-k of this walker's backward pass (k from its chi^2), 1 outside it
+    bool timing;                // LINNA_TC_DEBUG instantiation
 };
 
 // 128 columns of one output chunk (the columns [c0, c0+128) of the layer, owned by one epilogue group):
@@ -351,7 +382,10 @@ __device__ __forceinline__ void tf_chunk_epilogue(const float (&racc)[128], cons
         const int col0 = c0 + 64 * h;
         const bool store = STORE && col0 < st.dst_pad;
         if (!store && !(CHI && col0 < st.N)) continue;
-        if (store) mbar_wait_timed(x.sfree, (x.sidx & 1) ^ 1, x.err, 7, x.t_sfree);   // staging box free again
+        if (store) {   // staging box free again
+            if (x.timing) mbar_wait_timed<true>(x.sfree, (x.sidx & 1) ^ 1, x.err, 7, x.t_sfree);
+            else mbar_wait(x.sfree, (x.sidx & 1) ^ 1, x.err, 7);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int cb = col0 + 8 * j;
@@ -401,6 +435,7 @@ __device__ __forceinline__ void tf_chunk_epilogue(const float (&racc)[128], cons
 // One cluster = one CTA pair = 2 x 128 walkers.  CTA rank 0 issues every tcgen05.mma for the pair
 // (cta_group::2, M = 256): each CTA supplies its own 128 activation rows and HALF of the weight tile, and
 // receives its own 128 x N accumulator rows in its own tensor memory.
+template <bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -460,11 +495,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(56));
     if (warp == 0) {
         // =============================== TMA producer (both CTAs) ===============================
-        if (lane == 0) {
+        // The whole warp walks the program (warp-uniform control flow, every lane waits on the barriers); one
+        // elected lane issues the TMA instructions.
+        {
             int stage = 0;
             uint32_t ph = 0, seen[2][2] = {{0, 0}, {0, 0}}, pubA = 0, pubB = 0;
             long long w_empty = 0, w_ready = 0;
-            const long long t_begin = clock64();
+            const long long t_begin = DBG ? clock64() : 0;
             // L2 policy: weights are re-read by every cluster all the time (keep), an activation line is dead after
             // its last reader (let it go first) -- the arena in flight is larger than L2
             const uint64_t pol_keep = l2_policy_evict_last(), pol_dead = l2_policy_evict_first();
@@ -473,25 +510,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                 const int nslots = (args.slots == 2 && pair + 1 < my_pairs) ? 2 : 1;
                 for (int si = 0; si < n_steps; ++si) {
                     const TfStep &st = s_steps[si];
+                    const int st_N = st.N, st_flags = st.flags, st_nphase = st.nphase;
                     for (int slot = 0; slot < nslots; ++slot)
-                    for (int n0 = 0; n0 < st.N; n0 += TF_NC) {
-                        const int nvalid = st.N - n0 < TF_NC ? st.N - n0 : TF_NC;
+                    for (int n0 = 0; n0 < st_N; n0 += TF_NC) {
+                        const int nvalid = st_N - n0 < TF_NC ? st_N - n0 : TF_NC;
                         const int nb = n0 + (int)cta_rank * (((nvalid + 31) & ~31) >> 1);   // this CTA's half of the weight rows
-                        const int k0 = (st.flags & TFF_TRI) ? n0 / TF_KC : 0;   // L^T: B[n][k] = 0 for k < n
-                        for (int p = 0; p < st.nphase; ++p) {
+                        const int k0 = (st_flags & TFF_TRI) ? n0 / TF_KC : 0;   // L^T: B[n][k] = 0 for k < n
+                        const int arow = arena_row0 + slot * TF_M;
+                        for (int p = 0; p < st_nphase; ++p) {
                             const int nk = (st.K[p] + TF_KC - 1) / TF_KC;
                             const CUtensorMap *mb = maps + st.mapB[p];
+                            const int src_col = st.src[p];
+                            const uint32_t base_pub[2] = {pubA + (uint32_t)st.src_pub[p][0] + 1u, pubB + (uint32_t)st.src_pub[p][1] + 1u};
+                            const bool dead = use_hints && (st_flags & (p ? TFF_LAST_USE1 : TFF_LAST_USE0)) && n0 + TF_NC >= st_N;
                             for (int kc = k0; kc < nk; ++kc) {
-                                mbar_wait_timed(&empty_bar[stage], ph ^ 1, args.err, 1, w_empty);
+                                mbar_wait_timed<DBG>(&empty_bar[stage], ph ^ 1, args.err, 1, w_empty);
                                 uint8_t *sb = smem + stage * TF_STAGE_BYTES;
-                                if (leader) mbar_expect_tx(&full_bar[stage], 2 * TF_STAGE_BYTES);   // both CTAs' bytes
-                                if (use_hints) tma_load_2d_pair_hint(sb + TF_TILE_BYTES, mb, &full_bar[stage], kc * 2 * TF_KC, nb, pol_keep);
-                                else tma_load_2d_pair(sb + TF_TILE_BYTES, mb, &full_bar[stage], kc * 2 * TF_KC, nb);
+                                if (elect_one()) {
+                                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * TF_STAGE_BYTES);   // both CTAs' bytes
+                                    if (use_hints) tma_load_2d_pair_hint(sb + TF_TILE_BYTES, mb, &full_bar[stage], kc * 2 * TF_KC, nb, pol_keep);
+                                    else tma_load_2d_pair(sb + TF_TILE_BYTES, mb, &full_bar[stage], kc * 2 * TF_KC, nb);
+                                }
                                 // the activations this k-chunk reads: wait until their producer chunk is visible
                                 const int col = kc * TF_KC;
                                 const int grp = (col >> 7) & 1;
                                 const uint32_t box = (uint32_t)((col >> 8) * 2 + ((col & 127) >> 6));   // 64-column box of this group
-                                uint32_t need = (grp ? pubB : pubA) + (uint32_t)st.src_pub[p][grp] + box + 1u;
+                                const uint32_t need = base_pub[grp] + box;
                                 uint32_t &seen_sg = seen[slot][grp];
                                 if (seen_sg < need) {
                                     const long long t0 = clock64();
@@ -499,80 +543,75 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                                         __nanosleep(64);
                                         if (clock64() - t0 > 2000000000LL) tf_die(args.err, 2);
                                     }
-                                    w_ready += clock64() - t0;
+                                    if (DBG) w_ready += clock64() - t0;
+                                    seen_sg = __shfl_sync(0xffffffffu, seen_sg, 0);   // every lane made its own acquire; keep the count warp-uniform
                                     fence_async_all();
                                 }
-                                const int ca = st.src[p] + 2 * col;
-                                const bool dead = use_hints && (st.flags & (p ? TFF_LAST_USE1 : TFF_LAST_USE0)) && n0 + TF_NC >= st.N;
-                                if (dead) tma_load_2d_pair_hint(sb, maps, &full_bar[stage], ca, arena_row0 + slot * TF_M, pol_dead);
-                                else tma_load_2d_pair(sb, maps, &full_bar[stage], ca, arena_row0 + slot * TF_M);
+                                if (elect_one()) {
+                                    const int ca = src_col + 2 * col;
+                                    if (dead) tma_load_2d_pair_hint(sb, maps, &full_bar[stage], ca, arow, pol_dead);
+                                    else tma_load_2d_pair(sb, maps, &full_bar[stage], ca, arow);
+                                }
                                 if (++stage == TF_STAGES) stage = 0, ph ^= 1;
                             }
                         }
                     }
                 }
             }
-            if (args.dbg) {
+            if (DBG && lane == 0) {
                 long long *d = args.dbg + (size_t)blockIdx.x * 16;
                 d[0] = clock64() - t_begin, d[1] = w_empty, d[2] = w_ready;
             }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer (leader CTA only) ===============================
-        if (lane == 0 && leader) {
+        // Warp-uniform loop as above; the elected lane issues the tcgen05.mma / tcgen05.commit instructions.
+        if (leader) {
             int stage = 0;
             uint32_t ph = 0, g = 0;
             long long w_full = 0, w_pempty = 0, w_full_head = 0;
-            const long long t_begin = clock64();
+            const long long t_begin = DBG ? clock64() : 0;
+            const uint64_t desc0 = make_sdesc128(smem_u32(smem));
             for (int64_t pair = pair0; pair < my_pairs; pair += pair_step) {
                 const int nslots = (args.slots == 2 && pair + 1 < my_pairs) ? 2 : 1;
                 for (int si = 0; si < n_steps; ++si) {
                     const TfStep &st = s_steps[si];
+                    const int st_N = st.N, st_flags = st.flags, st_nphase = st.nphase;
+                    int nk_p[2];
+                    nk_p[0] = (st.K[0] + TF_KC - 1) / TF_KC, nk_p[1] = st_nphase > 1 ? (st.K[1] + TF_KC - 1) / TF_KC : 0;
                     for (int slot = 0; slot < nslots; ++slot)
-                    for (int n0 = 0; n0 < st.N; n0 += TF_NC) {
-                        const int nvalid = st.N - n0 < TF_NC ? st.N - n0 : TF_NC;
+                    for (int n0 = 0; n0 < st_N; n0 += TF_NC) {
+                        const int nvalid = st_N - n0 < TF_NC ? st_N - n0 : TF_NC;
                         // N rounded up to the 32 columns one tcgen05.ld drains: the extra rows of B are TMA zero fill
                         const uint32_t idesc = make_idesc_f16((nvalid + 31) & ~31);
-                        const int total = tf_chunk_stages(st, n0);
-                        const int k0 = (st.flags & TFF_TRI) ? n0 / TF_KC : 0;
-                        int in_seg = 0, done = 0;
+                        const int k0 = (st_flags & TFF_TRI) ? n0 / TF_KC : 0;
+                        const int total = nk_p[0] - k0 + (st_nphase > 1 ? nk_p[1] - k0 : 0);
+                        int in_seg = 0;
                         uint32_t dcol = 0;
-                        const bool head_chunk = n0 == 0;
-                        for (int p = 0; p < st.nphase; ++p) {
-                            const int nk = (st.K[p] + TF_KC - 1) / TF_KC;
-                            for (int kc = k0; kc < nk; ++kc) {
-                                if (in_seg == 0) {   // open a fresh accumulator buffer (in both CTAs)
-                                    const int buf = g & 1;
-                                    mbar_wait_timed(&pempty_bar[buf], ((g >> 1) & 1) ^ 1, args.err, 3, w_pempty);
-                                    tc_fence_after();
-                                    dcol = tmem_base + buf * TF_NC;
-                                }
-                                if (head_chunk && done < TF_STAGES) mbar_wait_timed(&full_bar[stage], ph, args.err, 4, w_full_head);
-                                else mbar_wait_timed(&full_bar[stage], ph, args.err, 4, w_full);
-                                tc_fence_after();
-                                const uint32_t sb = smem_u32(smem + stage * TF_STAGE_BYTES);
-                                const uint32_t a_hi = sb, a_lo = sb + 64, b_hi = sb + TF_TILE_BYTES, b_lo = b_hi + 64;
-#pragma unroll
-                                for (int ks = 0; ks < 2; ++ks) {
-                                    const uint32_t o = ks * 32;   // 16 halves = 32 bytes along K inside the swizzle row
-                                    umma_f16_pair(dcol, make_sdesc128(a_lo + o), make_sdesc128(b_hi + o), idesc, (in_seg | ks) ? 1u : 0u);
-                                    umma_f16_pair(dcol, make_sdesc128(a_hi + o), make_sdesc128(b_lo + o), idesc, 1u);
-                                    umma_f16_pair(dcol, make_sdesc128(a_hi + o), make_sdesc128(b_hi + o), idesc, 1u);
-                                }
-                                umma_commit_pair(&empty_bar[stage]);   // frees the smem stage in both CTAs when these MMAs retire
-                                if (++stage == TF_STAGES) stage = 0, ph ^= 1;
-                                ++done;
-                                if (++in_seg == seg_kc || done == total) {
-                                    umma_commit_pair(&pfull_bar[g & 1]);   // partial tiles complete -> both epilogues drain them
-                                    ++g;
-                                    in_seg = 0;
-                                }
+                        for (int done = 0; done < total; ++done) {
+                            if (in_seg == 0) {   // open a fresh accumulator buffer (in both CTAs)
+                                const int buf = g & 1;
+                                mbar_wait_timed<DBG>(&pempty_bar[buf], ((g >> 1) & 1) ^ 1, args.err, 3, w_pempty);
+                                dcol = tmem_base + buf * TF_NC;
                             }
+                            if (DBG && n0 == 0 && done < TF_STAGES) mbar_wait_timed<DBG>(&full_bar[stage], ph, args.err, 4, w_full_head);
+                            else mbar_wait_timed<DBG>(&full_bar[stage], ph, args.err, 4, w_full);
+                            tc_fence_after();
+                            ++in_seg;
+                            const bool seg_end = in_seg == seg_kc || done + 1 == total;
+                            if (elect_one()) {
+                                const uint64_t adesc = desc0 + (uint64_t)(stage * (TF_STAGE_BYTES >> 4));
+                                umma_f16_pair_x6(dcol, adesc, adesc + (TF_TILE_BYTES >> 4), idesc, in_seg > 1 ? 1u : 0u);
+                                umma_commit_pair(&empty_bar[stage]);   // frees the smem stage in both CTAs when these MMAs retire
+                                if (seg_end) umma_commit_pair(&pfull_bar[g & 1]);   // partial tiles complete -> both epilogues drain them
+                            }
+                            if (seg_end) ++g, in_seg = 0;
+                            if (++stage == TF_STAGES) stage = 0, ph ^= 1;
                         }
                     }
                 }
             }
-            if (args.dbg) {
+            if (DBG && lane == 0) {
                 long long *d = args.dbg + (size_t)blockIdx.x * 16;
                 d[3] = clock64() - t_begin, d[4] = w_full + w_full_head, d[5] = w_pempty, d[14] = w_full_head;
             }
@@ -658,7 +697,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         const int n_in = c.n_in;
         uint32_t g = 0, nchunk = 0;
         long long e_wait = 0, e_drain = 0, e_epi = 0;
-        const bool timing = args.dbg != nullptr;
+        constexpr bool timing = DBG;
+        x.timing = DBG;
         const long long e_begin = clock64();
         uint32_t pempty_remote[2];   // the leader's drain barriers, as cluster addresses
         pempty_remote[0] = map_to_cta(smem_u32(&pempty_bar[0]), 0), pempty_remote[1] = map_to_cta(smem_u32(&pempty_bar[1]), 0);
@@ -827,7 +867,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
-        if (args.dbg && (warp == 4 || warp == 8) && lane == 0) {
+        if (DBG && (warp == 4 || warp == 8) && lane == 0) {
             long long *d = args.dbg + (size_t)blockIdx.x * 16 + (warp == 4 ? 6 : 10);
             d[0] = clock64() - e_begin, d[1] = e_wait, d[2] = e_drain, d[3] = e_epi;
             if (warp == 8) args.dbg[(size_t)blockIdx.x * 16 + 15] = x.t_sfree;
@@ -1251,7 +1291,8 @@ TcContext *tc_build(const linna_model *m, std::string &why)
         if (cudaMalloc(&t->dbg_dev, (size_t)t->grid * 16 * sizeof(long long)) != cudaSuccess) return bail("cudaMalloc dbg");
         cudaMemset(t->dbg_dev, 0, (size_t)t->grid * 16 * sizeof(long long));
     }
-    if (cudaFuncSetAttribute(tc_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES) != cudaSuccess)
         return bail("cudaFuncSetAttribute(tc_f16_kernel)");
     if (cudaDeviceSynchronize() != cudaSuccess) return bail("sync after tc_build");
     return t;
@@ -1287,7 +1328,8 @@ static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const f
     static const int want_hints = getenv("LINNA_TC_L2_HINTS") ? atoi(getenv("LINNA_TC_L2_HINTS")) : 0;
     a.l2_hints = want_hints;
     const int grid = 2 * (int)std::min<int64_t>(pairs, clusters);
-    tc_f16_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
+    if (a.dbg) tc_f16_kernel<true><<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
+    else tc_f16_kernel<false><<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
     return cudaGetLastError();
 }
 
