@@ -76,7 +76,9 @@ struct TfStep {
     int32_t nphase;
     int32_t src[2];       // arena column (in halves: 2 x the activation column) of this phase's A operand
     int32_t K[2];
-    int32_t mapB[2];      // tensor-map index of the weight operand
+    int32_t mapB[2];      // tensor-map index of the weight operand, box of 128 rows (full 256-column chunks)
+    int32_t mapBt[2];     // the same matrix with a box of `tail_rows` rows, for the last chunk of the step
+    int32_t tail_rows;    // weight rows each CTA supplies to the last chunk: round32(N - n0_last) / 2
     int32_t src_pub[2][2];   // [phase][group]: 64-column boxes the group published (per tile pass) before the producer of src
     int32_t N;
     int32_t dst;          // arena column (in halves) of the output, -1: none
@@ -499,7 +501,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         // elected lane issues the TMA instructions.
         {
             int stage = 0;
-            uint32_t ph = 0, seen[2][2] = {{0, 0}, {0, 0}}, pubA = 0, pubB = 0;
+            uint32_t ph = 0, pubA = 0, pubB = 0;
+            uint32_t seen00 = 0, seen01 = 0, seen10 = 0, seen11 = 0;   // [slot][group]: publications seen so far (registers, not a local array)
             long long w_empty = 0, w_ready = 0;
             const long long t_begin = DBG ? clock64() : 0;
             // L2 policy: weights are re-read by every cluster all the time (keep), an activation line is dead after
@@ -513,44 +516,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                     const int st_N = st.N, st_flags = st.flags, st_nphase = st.nphase;
                     for (int slot = 0; slot < nslots; ++slot)
                     for (int n0 = 0; n0 < st_N; n0 += TF_NC) {
-                        const int nvalid = st_N - n0 < TF_NC ? st_N - n0 : TF_NC;
-                        const int nb = n0 + (int)cta_rank * (((nvalid + 31) & ~31) >> 1);   // this CTA's half of the weight rows
+                        // this CTA's half of the weight rows; the last chunk of a step uses a tensor map whose box is just
+                        // that tall (a bottleneck layer of 16 columns loads 8 rows per CTA, not 128 rows of zero fill)
+                        const bool tail = n0 + TF_NC >= st_N;
+                        const int brows = tail ? st.tail_rows : TF_M;
+                        const int nb = n0 + (int)cta_rank * brows;
+                        const uint32_t stage_tx = 2u * (uint32_t)(TF_TILE_BYTES + brows * 4 * TF_KC);   // both CTAs' bytes
                         const int k0 = (st_flags & TFF_TRI) ? n0 / TF_KC : 0;   // L^T: B[n][k] = 0 for k < n
                         const int arow = arena_row0 + slot * TF_M;
                         for (int p = 0; p < st_nphase; ++p) {
                             const int nk = (st.K[p] + TF_KC - 1) / TF_KC;
-                            const CUtensorMap *mb = maps + st.mapB[p];
+                            const CUtensorMap *mb = maps + (tail ? st.mapBt[p] : st.mapB[p]);
                             const int src_col = st.src[p];
-                            const uint32_t base_pub[2] = {pubA + (uint32_t)st.src_pub[p][0] + 1u, pubB + (uint32_t)st.src_pub[p][1] + 1u};
+                            const uint32_t base_pub0 = pubA + (uint32_t)st.src_pub[p][0] + 1u, base_pub1 = pubB + (uint32_t)st.src_pub[p][1] + 1u;
                             const bool dead = use_hints && (st_flags & (p ? TFF_LAST_USE1 : TFF_LAST_USE0)) && n0 + TF_NC >= st_N;
                             for (int kc = k0; kc < nk; ++kc) {
                                 mbar_wait_timed<DBG>(&empty_bar[stage], ph ^ 1, args.err, 1, w_empty);
                                 uint8_t *sb = smem + stage * TF_STAGE_BYTES;
-                                if (elect_one()) {
-                                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * TF_STAGE_BYTES);   // both CTAs' bytes
-                                    if (use_hints) tma_load_2d_pair_hint(sb + TF_TILE_BYTES, mb, &full_bar[stage], kc * 2 * TF_KC, nb, pol_keep);
-                                    else tma_load_2d_pair(sb + TF_TILE_BYTES, mb, &full_bar[stage], kc * 2 * TF_KC, nb);
-                                }
-                                // the activations this k-chunk reads: wait until their producer chunk is visible
+                                uint64_t *fb = &full_bar[stage];
+                                // the activations this k-chunk reads must be visible: their producer chunk is published per
+                                // 64-column box of its column group
                                 const int col = kc * TF_KC;
                                 const int grp = (col >> 7) & 1;
-                                const uint32_t box = (uint32_t)((col >> 8) * 2 + ((col & 127) >> 6));   // 64-column box of this group
-                                const uint32_t need = base_pub[grp] + box;
-                                uint32_t &seen_sg = seen[slot][grp];
-                                if (seen_sg < need) {
+                                const uint32_t box = (uint32_t)((col >> 8) * 2 + ((col & 127) >> 6));
+                                const uint32_t need = (grp ? base_pub1 : base_pub0) + box;
+                                const uint32_t seen_v = slot ? (grp ? seen11 : seen10) : (grp ? seen01 : seen00);
+                                const int ca = src_col + 2 * col;
+                                if (seen_v >= need) {   // the usual case: one elected lane issues the whole stage
+                                    if (elect_one()) {
+                                        if (leader) mbar_expect_tx(fb, stage_tx);
+                                        if (use_hints) {
+                                            tma_load_2d_pair_hint(sb + TF_TILE_BYTES, mb, fb, kc * 2 * TF_KC, nb, pol_keep);
+                                            tma_load_2d_pair_hint(sb, maps, fb, ca, arow, dead ? pol_dead : pol_keep);
+                                        } else {
+                                            tma_load_2d_pair(sb + TF_TILE_BYTES, mb, fb, kc * 2 * TF_KC, nb);
+                                            tma_load_2d_pair(sb, maps, fb, ca, arow);
+                                        }
+                                    }
+                                } else {                // weights now, activations once they are published
+                                    if (elect_one()) {
+                                        if (leader) mbar_expect_tx(fb, stage_tx);
+                                        tma_load_2d_pair(sb + TF_TILE_BYTES, mb, fb, kc * 2 * TF_KC, nb);
+                                    }
                                     const long long t0 = clock64();
-                                    while ((seen_sg = ld_acquire_u32(&ready_cnt[slot][grp])) < need) {
+                                    uint32_t sv;
+                                    while ((sv = ld_acquire_u32(&ready_cnt[slot][grp])) < need) {
                                         __nanosleep(64);
                                         if (clock64() - t0 > 2000000000LL) tf_die(args.err, 2);
                                     }
                                     if (DBG) w_ready += clock64() - t0;
-                                    seen_sg = __shfl_sync(0xffffffffu, seen_sg, 0);   // every lane made its own acquire; keep the count warp-uniform
+                                    sv = __shfl_sync(0xffffffffu, sv, 0);   // every lane made its own acquire; keep the count warp-uniform
+                                    if (slot) { if (grp) seen11 = sv; else seen10 = sv; }
+                                    else { if (grp) seen01 = sv; else seen00 = sv; }
                                     fence_async_all();
-                                }
-                                if (elect_one()) {
-                                    const int ca = src_col + 2 * col;
-                                    if (dead) tma_load_2d_pair_hint(sb, maps, &full_bar[stage], ca, arow, pol_dead);
-                                    else tma_load_2d_pair(sb, maps, &full_bar[stage], ca, arow);
+                                    if (elect_one()) tma_load_2d_pair(sb, maps, fb, ca, arow);
                                 }
                                 if (++stage == TF_STAGES) stage = 0, ph ^= 1;
                             }
@@ -1053,7 +1072,7 @@ TcContext *tc_build(const linna_model *m, std::string &why)
         };
         // src slots are stored in s.src[] as slot ids first and turned into columns once the widths are known
         auto set_phase = [&](TfStep &s, int p, int slot, const MatSrc &ms, int shift) {
-            s.src[p] = slot, s.K[p] = ms.K, s.mapB[p] = 2 + P.put(ms, shift);
+            s.src[p] = slot, s.K[p] = ms.K, s.mapB[p] = P.put(ms, shift);   // matrix index; turned into tensor-map indices below
             s.src_pub[p][0] = slot_pub[slot][0], s.src_pub[p][1] = slot_pub[slot][1];
         };
         auto set_dst = [&](TfStep &s, int slot) {
@@ -1261,7 +1280,19 @@ TcContext *tc_build(const linna_model *m, std::string &why)
     }
 
     // ---- tensor maps
-    std::vector<CUtensorMap> maps(2 + P.mats.size());
+    // per weight matrix: a 128-row box for full chunks and a box as tall as one CTA's share of the last chunk
+    auto tail_rows_of = [](int N) { const int last = N - (N - 1) / TF_NC * TF_NC; return ((last + 31) & ~31) / 2; };
+    std::vector<CUtensorMap> maps(2 + 2 * P.mats.size());
+    for (int pk = 0; pk < 2; ++pk)
+        for (int i = 0; i < pgs[pk].n_steps; ++i) {
+            TfStep &s = pgs[pk].steps[i];
+            s.tail_rows = tail_rows_of(s.N);
+            for (int p = 0; p < s.nphase; ++p) {
+                const int mi = s.mapB[p];
+                if (P.mats[mi].N != s.N) return bail("internal: operand rows != step columns");
+                s.mapB[p] = 2 + 2 * mi, s.mapBt[p] = 3 + 2 * mi;
+            }
+        }
     auto encode2d = [&](CUtensorMap *mp, void *base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner,
                         uint32_t box_outer, CUtensorMapSwizzle sw) {
         cuuint64_t dims[2] = {inner, outer};
@@ -1277,8 +1308,10 @@ TcContext *tc_build(const linna_model *m, std::string &why)
         return bail("cuTensorMapEncodeTiled(arena store) failed");
     for (size_t i = 0; i < P.mats.size(); ++i) {
         const Packer::Mat &mt = P.mats[i];
-        if (encode2d(&maps[2 + i], t->wblob + mt.off, (uint64_t)mt.ldk, (uint64_t)mt.N, (uint64_t)mt.ldk * 2, 2 * TF_KC, TF_M,
-                     CU_TENSOR_MAP_SWIZZLE_128B) != CUDA_SUCCESS)
+        if (encode2d(&maps[2 + 2 * i], t->wblob + mt.off, (uint64_t)mt.ldk, (uint64_t)mt.N, (uint64_t)mt.ldk * 2, 2 * TF_KC, TF_M,
+                     CU_TENSOR_MAP_SWIZZLE_128B) != CUDA_SUCCESS ||
+            encode2d(&maps[3 + 2 * i], t->wblob + mt.off, (uint64_t)mt.ldk, (uint64_t)mt.N, (uint64_t)mt.ldk * 2, 2 * TF_KC,
+                     (uint32_t)tail_rows_of(mt.N), CU_TENSOR_MAP_SWIZZLE_128B) != CUDA_SUCCESS)
             return bail("cuTensorMapEncodeTiled(weights) failed");
     }
     if (cudaMalloc(&t->maps_dev, maps.size() * sizeof(CUtensorMap)) != cudaSuccess) return bail("cudaMalloc maps");
