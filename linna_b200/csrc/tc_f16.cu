@@ -65,6 +65,9 @@ constexpr int TF_STG_BYTES = 2 * TF_BOX_BYTES;                   // two k-chunks
 constexpr int TF_SMEM_BYTES = TF_STAGES * TF_STAGE_BYTES + 2 * TF_STG_BYTES + 1024;
 constexpr int TF_THREADS = 384;  // TMA, MMA, 2 store warps + 2 x 4 epilogue warps
 constexpr int TF_MAX_STEPS = 48;
+// LINNA_TC_DEBUG counters per CTA: 16 role counters, then per program step the cycles of the MMA warp [16, 40), of
+// epilogue group 0 [40, 64), and of that group's waits for accumulators [64, 88) and chunk epilogues [88, 112)
+constexpr int TF_DBG_STRIDE = 128;
 
 enum TfEpi : int32_t { TF_ACT = 0, TF_HEAD = 1, TF_CHI2 = 2, TF_BWD = 3, TF_GRADOUT = 4 };
 enum TfFlags : int32_t { TFF_RELU = 1, TFF_SAVE_MASK = 2, TFF_APPLY_MASK = 4, TFF_TRI = 8,
@@ -578,7 +581,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                 }
             }
             if (DBG && lane == 0) {
-                long long *d = args.dbg + (size_t)blockIdx.x * 16;
+                long long *d = args.dbg + (size_t)blockIdx.x * TF_DBG_STRIDE;
                 d[0] = clock64() - t_begin, d[1] = w_empty, d[2] = w_ready;
             }
         }
@@ -596,6 +599,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                 for (int si = 0; si < n_steps; ++si) {
                     const TfStep &st = s_steps[si];
                     const int st_N = st.N, st_flags = st.flags, st_nphase = st.nphase;
+                    const long long t_step = DBG ? clock64() : 0;
                     int nk_p[2];
                     nk_p[0] = (st.K[0] + TF_KC - 1) / TF_KC, nk_p[1] = st_nphase > 1 ? (st.K[1] + TF_KC - 1) / TF_KC : 0;
                     for (int slot = 0; slot < nslots; ++slot)
@@ -628,10 +632,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                             if (++stage == TF_STAGES) stage = 0, ph ^= 1;
                         }
                     }
+                    if (DBG && lane == 0 && si < 24) args.dbg[(size_t)blockIdx.x * TF_DBG_STRIDE + 16 + si] += clock64() - t_step;
                 }
             }
             if (DBG && lane == 0) {
-                long long *d = args.dbg + (size_t)blockIdx.x * 16;
+                long long *d = args.dbg + (size_t)blockIdx.x * TF_DBG_STRIDE;
                 d[3] = clock64() - t_begin, d[4] = w_full + w_full_head, d[5] = w_pempty, d[14] = w_full_head;
             }
         }
@@ -768,6 +773,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
             for (int si = 0; si < n_steps; ++si) {
                 const TfStep &st = s_steps[si];
                 const int nch = (st.N + TF_NC - 1) / TF_NC;
+                const long long t_step = timing ? clock64() : 0, w_step = e_wait, p_step = e_epi;
 #pragma unroll 1
                 for (int slot = 0; slot < nslots; ++slot) {
                 const int64_t grow = ((cluster_id + (pair + slot) * n_clusters) * 2 + cta_rank) * TF_M + row;
@@ -872,6 +878,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
                 }
+                if (timing && tid == 128 && si < 24) {
+                    long long *d = args.dbg + (size_t)blockIdx.x * TF_DBG_STRIDE;
+                    d[40 + si] += clock64() - t_step, d[64 + si] += e_wait - w_step, d[88 + si] += e_epi - p_step;
+                }
             }
             // combine the two column groups of every walker and finish lnP
             for (int slot = 0; slot < nslots; ++slot) {
@@ -887,9 +897,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
             }
         }
         if (DBG && (warp == 4 || warp == 8) && lane == 0) {
-            long long *d = args.dbg + (size_t)blockIdx.x * 16 + (warp == 4 ? 6 : 10);
+            long long *d = args.dbg + (size_t)blockIdx.x * TF_DBG_STRIDE + (warp == 4 ? 6 : 10);
             d[0] = clock64() - e_begin, d[1] = e_wait, d[2] = e_drain, d[3] = e_epi;
-            if (warp == 8) args.dbg[(size_t)blockIdx.x * 16 + 15] = x.t_sfree;
+            if (warp == 8) args.dbg[(size_t)blockIdx.x * TF_DBG_STRIDE + 15] = x.t_sfree;
         }
     }
     tc_fence_before();
@@ -1321,8 +1331,8 @@ TcContext *tc_build(const linna_model *m, std::string &why)
     if (cudaMalloc(&t->err_dev, sizeof(int)) != cudaSuccess) return bail("cudaMalloc err");
     cudaMemset(t->err_dev, 0, sizeof(int));
     if (getenv("LINNA_TC_DEBUG")) {
-        if (cudaMalloc(&t->dbg_dev, (size_t)t->grid * 16 * sizeof(long long)) != cudaSuccess) return bail("cudaMalloc dbg");
-        cudaMemset(t->dbg_dev, 0, (size_t)t->grid * 16 * sizeof(long long));
+        if (cudaMalloc(&t->dbg_dev, (size_t)t->grid * TF_DBG_STRIDE * sizeof(long long)) != cudaSuccess) return bail("cudaMalloc dbg");
+        cudaMemset(t->dbg_dev, 0, (size_t)t->grid * TF_DBG_STRIDE * sizeof(long long));
     }
     if (cudaFuncSetAttribute(tc_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(tc_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES) != cudaSuccess)
@@ -1339,7 +1349,7 @@ int tc_debug_read(TcContext *t, long long *out, int max_ctas)
     if (!t || !t->dbg_dev) return 0;
     const int n = std::min(max_ctas, t->grid);
     cudaDeviceSynchronize();
-    cudaMemcpy(out, t->dbg_dev, (size_t)n * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(out, t->dbg_dev, (size_t)n * TF_DBG_STRIDE * sizeof(long long), cudaMemcpyDeviceToHost);
     return n;
 }
 
@@ -1361,6 +1371,7 @@ static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const f
     static const int want_hints = getenv("LINNA_TC_L2_HINTS") ? atoi(getenv("LINNA_TC_L2_HINTS")) : 0;
     a.l2_hints = want_hints;
     const int grid = 2 * (int)std::min<int64_t>(pairs, clusters);
+    if (a.dbg) cudaMemsetAsync(t->dbg_dev, 0, (size_t)t->grid * TF_DBG_STRIDE * sizeof(long long), stream);
     if (a.dbg) tc_f16_kernel<true><<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
     else tc_f16_kernel<false><<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
     return cudaGetLastError();

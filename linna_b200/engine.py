@@ -254,7 +254,7 @@ class Engine:
 
     def tc_counters(self, max_ctas=256):
         """Per-CTA cycle counters of the last tensor-core launch (needs LINNA_TC_DEBUG=1 in the environment)."""
-        buf = np.zeros((max_ctas, 16), np.int64)
+        buf = np.zeros((max_ctas, 128), np.int64)
         n = self.lib.linna_debug_tc_counters(self.handle, buf.ctypes.data_as(ctypes.c_void_p), max_ctas)
         return buf[:n]
 

@@ -31,3 +31,9 @@ if os.environ.get("LINNA_TC_DEBUG"):
             print("%s  : total %.0f  wait_pfull %.0f (%.0f%%)  drain %.0f (%.0f%%)  chunk-epilogue %.0f (%.0f%%)" % (gname, m_[o], m_[o+1], 100*m_[o+1]/m_[o], m_[o+2], 100*m_[o+2]/m_[o], m_[o+3], 100*m_[o+3]/m_[o]) + "  of which wait_sfree %.0f" % m_[14 if o == 6 else 15])
         print("mma wait_full in the first %d stages of a layer pass: %.0f" % (4, lead.mean(axis=0)[14]))
         print("mma     : total %.0f  wait_full %.0f (%.0f%%)  wait_pempty %.0f (%.0f%%)" % (m_[3], m_[4], 100*m_[4]/m_[3], m_[5], 100*m_[5]/m_[3]))
+        ns_ = 24
+        f = lambda a: " ".join("%d" % v for v in a)
+        print("per-step cycles, MMA warp (leader)       :", f(lead.mean(axis=0)[16:16+ns_]))
+        print("per-step cycles, epilogue group 0        :", f(cnt.mean(axis=0)[40:40+ns_]))
+        print("   of which waiting for accumulators     :", f(cnt.mean(axis=0)[64:64+ns_]))
+        print("   of which chunk epilogues              :", f(cnt.mean(axis=0)[88:88+ns_]))
