@@ -59,7 +59,13 @@ constexpr int TF_NC = 256;       // accumulator columns per chunk (two epilogue 
 constexpr int TF_KC = 32;        // k-chunk: 32 values of K = [32 hi halves | 32 lo halves] = one 128-byte swizzle row
 constexpr int TF_STAGES = 4;
 constexpr int TF_TILE_BYTES = TF_M * 2 * TF_KC * 2;              // 16 KB operand tile (hi and lo of one k-chunk, interleaved)
-constexpr int TF_STAGE_BYTES = 2 * TF_TILE_BYTES;                // A tile + B-half tile = 32 KB per CTA
+constexpr int TF_NARROW_B = 2048;                                // B-half tile of a narrow step: 16 rows x 128 bytes
+// One operand stage: [A tile 16 KB][B-half tile 16 KB][4 KB].  A "narrow" step (N <= 32: the bottleneck layer of a
+// res-block, the last backward step) needs 16 weight rows per CTA and k-chunk, and its k-loop is pure latency (one
+// TMA round trip per four stages in flight, next to no MMA work): it packs TWO k-chunks into a stage -- the second
+// A tile in the place of the B-half tile, the two 2 KB weight tiles in the last 4 KB -- so that twice as much of
+// the k-loop is in flight.
+constexpr int TF_STAGE_BYTES = 2 * TF_TILE_BYTES + 2 * TF_NARROW_B;   // 36 KB per CTA
 constexpr int TF_BOX_BYTES = 128 * 64 * 2;                       // staging box: 128 rows x 64 halves = 16 KB = one k-chunk, hi | lo
 constexpr int TF_STG_BYTES = 2 * TF_BOX_BYTES;                   // two k-chunks (64 activation columns) per column group
 constexpr int TF_SMEM_BYTES = TF_STAGES * TF_STAGE_BYTES + 2 * TF_STG_BYTES + 1024;
@@ -116,7 +122,6 @@ struct TfArgs {
     float *grad;
     uint32_t *masks;
     int64_t n;
-    int32_t l2_hints;         // 1: TMA loads carry L2 eviction-priority hints (LINNA_TC_L2_HINTS)
     int32_t slots;            // walker pairs interleaved per cluster: 2, or 1 when the batch cannot fill the GPU twice
     int *err;
     long long *dbg;           // optional [grid][8] cycle counters (LINNA_TC_DEBUG): where the service warps wait
@@ -211,26 +216,6 @@ __device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorM
         :
         : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
         : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair_hint(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint64_t policy)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-        :
-        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(policy)
-        : "memory");
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first()
-{
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last()
-{
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
 }
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank)
 {
@@ -336,6 +321,12 @@ __device__ __forceinline__ float tf_prior_map(float u, int kind, float scale, fl
     float t = u;
     if (kind == LINNA_PRIOR_FLAT) t = 0.5f * (1.0f + erff(u / 1.41421356237309515f));  // gauss2unif, util.py:300
     return t * scale + shift;
+}
+// k-chunks the next operand stage of a narrow step takes (producer and MMA issuer decide alike): two when both
+// belong to the same 64-column publication box, the same phase and the same accumulation segment.
+__device__ __forceinline__ int tf_stage_take(bool narrow, int kc, int nk, int in_seg, int seg_kc)
+{
+    return (narrow && !(kc & 1) && kc + 1 < nk && in_seg + 2 <= seg_kc) ? 2 : 1;
 }
 // stages (k-chunks over all phases) of output chunk n0 of a step
 __device__ __forceinline__ int tf_chunk_stages(const TfStep &st, int n0)
@@ -508,10 +499,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
             uint32_t seen00 = 0, seen01 = 0, seen10 = 0, seen11 = 0;   // [slot][group]: publications seen so far (registers, not a local array)
             long long w_empty = 0, w_ready = 0;
             const long long t_begin = DBG ? clock64() : 0;
-            // L2 policy: weights are re-read by every cluster all the time (keep), an activation line is dead after
-            // its last reader (let it go first) -- the arena in flight is larger than L2
-            const uint64_t pol_keep = l2_policy_evict_last(), pol_dead = l2_policy_evict_first();
-            const bool use_hints = args.l2_hints != 0;
             for (int64_t pair = pair0; pair < my_pairs; pair += pair_step, pubA += prog->total_pub[0], pubB += prog->total_pub[1]) {
                 const int nslots = (args.slots == 2 && pair + 1 < my_pairs) ? 2 : 1;
                 for (int si = 0; si < n_steps; ++si) {
@@ -527,52 +514,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                         const uint32_t stage_tx = 2u * (uint32_t)(TF_TILE_BYTES + brows * 4 * TF_KC);   // both CTAs' bytes
                         const int k0 = (st_flags & TFF_TRI) ? n0 / TF_KC : 0;   // L^T: B[n][k] = 0 for k < n
                         const int arow = arena_row0 + slot * TF_M;
+                        const bool narrow = st_N <= 32;   // one chunk, 16 weight rows per CTA
+                        int in_seg = 0;
                         for (int p = 0; p < st_nphase; ++p) {
                             const int nk = (st.K[p] + TF_KC - 1) / TF_KC;
                             const CUtensorMap *mb = maps + (tail ? st.mapBt[p] : st.mapB[p]);
                             const int src_col = st.src[p];
                             const uint32_t base_pub0 = pubA + (uint32_t)st.src_pub[p][0] + 1u, base_pub1 = pubB + (uint32_t)st.src_pub[p][1] + 1u;
-                            const bool dead = use_hints && (st_flags & (p ? TFF_LAST_USE1 : TFF_LAST_USE0)) && n0 + TF_NC >= st_N;
-                            for (int kc = k0; kc < nk; ++kc) {
+                            for (int kc = k0, take; kc < nk; kc += take) {
+                                take = tf_stage_take(narrow, kc, nk, in_seg, seg_kc);
+                                in_seg += take;
+                                if (in_seg >= seg_kc) in_seg = 0;
                                 mbar_wait_timed<DBG>(&empty_bar[stage], ph ^ 1, args.err, 1, w_empty);
                                 uint8_t *sb = smem + stage * TF_STAGE_BYTES;
                                 uint64_t *fb = &full_bar[stage];
-                                // the activations this k-chunk reads must be visible: their producer chunk is published per
+                                // the activations this stage reads must be visible: their producer chunk is published per
                                 // 64-column box of its column group
                                 const int col = kc * TF_KC;
                                 const int grp = (col >> 7) & 1;
                                 const uint32_t box = (uint32_t)((col >> 8) * 2 + ((col & 127) >> 6));
                                 const uint32_t need = (grp ? base_pub1 : base_pub0) + box;
-                                const uint32_t seen_v = slot ? (grp ? seen11 : seen10) : (grp ? seen01 : seen00);
+                                uint32_t seen_v = slot ? (grp ? seen11 : seen10) : (grp ? seen01 : seen00);
                                 const int ca = src_col + 2 * col;
-                                if (seen_v >= need) {   // the usual case: one elected lane issues the whole stage
-                                    if (elect_one()) {
-                                        if (leader) mbar_expect_tx(fb, stage_tx);
-                                        if (use_hints) {
-                                            tma_load_2d_pair_hint(sb + TF_TILE_BYTES, mb, fb, kc * 2 * TF_KC, nb, pol_keep);
-                                            tma_load_2d_pair_hint(sb, maps, fb, ca, arow, dead ? pol_dead : pol_keep);
-                                        } else {
-                                            tma_load_2d_pair(sb + TF_TILE_BYTES, mb, fb, kc * 2 * TF_KC, nb);
-                                            tma_load_2d_pair(sb, maps, fb, ca, arow);
-                                        }
-                                    }
-                                } else {                // weights now, activations once they are published
-                                    if (elect_one()) {
-                                        if (leader) mbar_expect_tx(fb, stage_tx);
+                                const bool wait_pub = seen_v < need;
+                                if (elect_one()) {   // the weights, and in the usual case (activations published) the whole stage
+                                    if (leader) mbar_expect_tx(fb, take == 2 ? 2 * stage_tx : stage_tx);
+                                    if (narrow) {
+                                        tma_load_2d_pair(sb + 2 * TF_TILE_BYTES, mb, fb, kc * 2 * TF_KC, nb);
+                                        if (take == 2) tma_load_2d_pair(sb + 2 * TF_TILE_BYTES + TF_NARROW_B, mb, fb, (kc + 1) * 2 * TF_KC, nb);
+                                    } else {
                                         tma_load_2d_pair(sb + TF_TILE_BYTES, mb, fb, kc * 2 * TF_KC, nb);
                                     }
+                                    if (!wait_pub) {
+                                        tma_load_2d_pair(sb, maps, fb, ca, arow);
+                                        if (take == 2) tma_load_2d_pair(sb + TF_TILE_BYTES, maps, fb, ca + 2 * TF_KC, arow);
+                                    }
+                                }
+                                if (wait_pub) {
                                     const long long t0 = clock64();
-                                    uint32_t sv;
-                                    while ((sv = ld_acquire_u32(&ready_cnt[slot][grp])) < need) {
+                                    while ((seen_v = ld_acquire_u32(&ready_cnt[slot][grp])) < need) {
                                         __nanosleep(64);
                                         if (clock64() - t0 > 2000000000LL) tf_die(args.err, 2);
                                     }
                                     if (DBG) w_ready += clock64() - t0;
-                                    sv = __shfl_sync(0xffffffffu, sv, 0);   // every lane made its own acquire; keep the count warp-uniform
-                                    if (slot) { if (grp) seen11 = sv; else seen10 = sv; }
-                                    else { if (grp) seen01 = sv; else seen00 = sv; }
+                                    seen_v = __shfl_sync(0xffffffffu, seen_v, 0);   // every lane made its own acquire; keep the count warp-uniform
+                                    if (slot) { if (grp) seen11 = seen_v; else seen10 = seen_v; }
+                                    else { if (grp) seen01 = seen_v; else seen00 = seen_v; }
                                     fence_async_all();
-                                    if (elect_one()) tma_load_2d_pair(sb, maps, fb, ca, arow);
+                                    if (elect_one()) {
+                                        tma_load_2d_pair(sb, maps, fb, ca, arow);
+                                        if (take == 2) tma_load_2d_pair(sb + TF_TILE_BYTES, maps, fb, ca + 2 * TF_KC, arow);
+                                    }
                                 }
                                 if (++stage == TF_STAGES) stage = 0, ph ^= 1;
                             }
@@ -609,27 +601,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                         const uint32_t idesc = make_idesc_f16((nvalid + 31) & ~31);
                         const int k0 = (st_flags & TFF_TRI) ? n0 / TF_KC : 0;
                         const int total = nk_p[0] - k0 + (st_nphase > 1 ? nk_p[1] - k0 : 0);
-                        int in_seg = 0;
+                        const bool narrow = st_N <= 32;
+                        int in_seg = 0, done = 0, nstage = 0;
                         uint32_t dcol = 0;
-                        for (int done = 0; done < total; ++done) {
-                            if (in_seg == 0) {   // open a fresh accumulator buffer (in both CTAs)
-                                const int buf = g & 1;
-                                mbar_wait_timed<DBG>(&pempty_bar[buf], ((g >> 1) & 1) ^ 1, args.err, 3, w_pempty);
-                                dcol = tmem_base + buf * TF_NC;
+                        for (int p = 0; p < st_nphase; ++p) {
+                            const int nk = nk_p[p];
+                            for (int kc = k0, take; kc < nk; kc += take, ++nstage) {
+                                take = tf_stage_take(narrow, kc, nk, in_seg, seg_kc);
+                                if (in_seg == 0) {   // open a fresh accumulator buffer (in both CTAs)
+                                    const int buf = g & 1;
+                                    mbar_wait_timed<DBG>(&pempty_bar[buf], ((g >> 1) & 1) ^ 1, args.err, 3, w_pempty);
+                                    dcol = tmem_base + buf * TF_NC;
+                                }
+                                if (DBG && n0 == 0 && nstage < TF_STAGES) mbar_wait_timed<DBG>(&full_bar[stage], ph, args.err, 4, w_full_head);
+                                else mbar_wait_timed<DBG>(&full_bar[stage], ph, args.err, 4, w_full);
+                                tc_fence_after();
+                                const uint32_t acc = in_seg > 0 ? 1u : 0u;
+                                in_seg += take, done += take;
+                                const bool seg_end = in_seg >= seg_kc || done == total;
+                                if (elect_one()) {
+                                    const uint64_t adesc = desc0 + (uint64_t)(stage * (TF_STAGE_BYTES >> 4));
+                                    if (narrow) {   // [A(kc)][A(kc+1)][B(kc) 2 KB][B(kc+1) 2 KB]
+                                        umma_f16_pair_x6(dcol, adesc, adesc + (2 * TF_TILE_BYTES >> 4), idesc, acc);
+                                        if (take == 2)
+                                            umma_f16_pair_x6(dcol, adesc + (TF_TILE_BYTES >> 4), adesc + ((2 * TF_TILE_BYTES + TF_NARROW_B) >> 4), idesc, 1u);
+                                    } else {
+                                        umma_f16_pair_x6(dcol, adesc, adesc + (TF_TILE_BYTES >> 4), idesc, acc);
+                                    }
+                                    umma_commit_pair(&empty_bar[stage]);   // frees the smem stage in both CTAs when these MMAs retire
+                                    if (seg_end) umma_commit_pair(&pfull_bar[g & 1]);   // partial tiles complete -> both epilogues drain them
+                                }
+                                if (seg_end) ++g, in_seg = 0;
+                                if (++stage == TF_STAGES) stage = 0, ph ^= 1;
                             }
-                            if (DBG && n0 == 0 && done < TF_STAGES) mbar_wait_timed<DBG>(&full_bar[stage], ph, args.err, 4, w_full_head);
-                            else mbar_wait_timed<DBG>(&full_bar[stage], ph, args.err, 4, w_full);
-                            tc_fence_after();
-                            ++in_seg;
-                            const bool seg_end = in_seg == seg_kc || done + 1 == total;
-                            if (elect_one()) {
-                                const uint64_t adesc = desc0 + (uint64_t)(stage * (TF_STAGE_BYTES >> 4));
-                                umma_f16_pair_x6(dcol, adesc, adesc + (TF_TILE_BYTES >> 4), idesc, in_seg > 1 ? 1u : 0u);
-                                umma_commit_pair(&empty_bar[stage]);   // frees the smem stage in both CTAs when these MMAs retire
-                                if (seg_end) umma_commit_pair(&pfull_bar[g & 1]);   // partial tiles complete -> both epilogues drain them
-                            }
-                            if (seg_end) ++g, in_seg = 0;
-                            if (++stage == TF_STAGES) stage = 0, ph ^= 1;
                         }
                     }
                     if (DBG && lane == 0 && si < 24) args.dbg[(size_t)blockIdx.x * TF_DBG_STRIDE + 16 + si] += clock64() - t_step;
@@ -1368,8 +1372,6 @@ static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const f
     const int64_t clusters = t->grid / 2;
     static const int want_slots = getenv("LINNA_TC_SLOTS") ? atoi(getenv("LINNA_TC_SLOTS")) : 2;
     a.slots = (want_slots == 2 && pairs > clusters) ? 2 : 1;
-    static const int want_hints = getenv("LINNA_TC_L2_HINTS") ? atoi(getenv("LINNA_TC_L2_HINTS")) : 0;
-    a.l2_hints = want_hints;
     const int grid = 2 * (int)std::min<int64_t>(pairs, clusters);
     if (a.dbg) cudaMemsetAsync(t->dbg_dev, 0, (size_t)t->grid * TF_DBG_STRIDE * sizeof(long long), stream);
     if (a.dbg) tc_f16_kernel<true><<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
