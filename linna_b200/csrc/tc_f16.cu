@@ -328,6 +328,25 @@ __device__ __forceinline__ int tf_stage_take(bool narrow, int kc, int nk, int in
 {
     return (narrow && !(kc & 1) && kc + 1 < nk && in_seg + 2 <= seg_kc) ? 2 : 1;
 }
+// Tensor memory is a ring of four 128-column accumulator entries.  A segment of a chunk of up to 128 columns takes
+// one entry, a wider one an even-aligned pair -- so the narrow steps, whose k-loops are chains of short segments, have
+// four accumulator buffers in flight instead of two.  The MMA issuer and the epilogue warps walk the ring alike:
+// `r` is the next entry, bit e of `par` the parity of the uses of entry e so far.
+struct TfAccRing {
+    uint32_t r = 0, par = 0;
+    // entry of the next segment (`wide`: two entries)
+    __device__ __forceinline__ uint32_t open(bool wide)
+    {
+        if (wide && (r & 1u)) r = (r + 1u) & 3u;
+        return r;
+    }
+    __device__ __forceinline__ uint32_t parity(uint32_t e) const { return (par >> e) & 1u; }
+    __device__ __forceinline__ void close(uint32_t e, bool wide)
+    {
+        par ^= wide ? (3u << e) : (1u << e);
+        r = (e + (wide ? 2u : 1u)) & 3u;
+    }
+};
 // stages (k-chunks over all phases) of output chunk n0 of a step
 __device__ __forceinline__ int tf_chunk_stages(const TfStep &st, int n0)
 {
@@ -435,7 +454,7 @@ template <bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f16_kernel(const TfArgs args)
 {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[TF_STAGES], empty_bar[TF_STAGES], pfull_bar[2], pempty_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[TF_STAGES], empty_bar[TF_STAGES], pfull_bar[4], pempty_bar[4];
     __shared__ __align__(8) uint64_t sfull_bar[2], sfree_bar[2];   // staging buffer of column group 0 / 1: written / read out
     __shared__ __align__(8) double chi_s[TF_M];
     __shared__ __align__(8) double chi_x[2][TF_M];       // chi^2 partials of the two column groups (backward scale)
@@ -460,7 +479,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         reinterpret_cast<uint32_t *>(s_steps)[i] = reinterpret_cast<const uint32_t *>(prog->steps)[i];
     if (tid == 0) {
         for (int s = 0; s < TF_STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
-        for (int b = 0; b < 2; ++b) mbar_init(&pfull_bar[b], 1), mbar_init(&pempty_bar[b], 16);   // 8 warps x 2 CTAs
+        for (int b = 0; b < 4; ++b) mbar_init(&pfull_bar[b], 1), mbar_init(&pempty_bar[b], 16);   // 8 warps x 2 CTAs
         for (int b = 0; b < 2; ++b) mbar_init(&sfull_bar[b], 128), mbar_init(&sfree_bar[b], 1);
         ready_cnt[0][0] = ready_cnt[0][1] = ready_cnt[1][0] = ready_cnt[1][1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -582,7 +601,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         // Warp-uniform loop as above; the elected lane issues the tcgen05.mma / tcgen05.commit instructions.
         if (leader) {
             int stage = 0;
-            uint32_t ph = 0, g = 0;
+            uint32_t ph = 0, acc_e = 0;
+            TfAccRing ring;
             long long w_full = 0, w_pempty = 0, w_full_head = 0;
             const long long t_begin = DBG ? clock64() : 0;
             const uint64_t desc0 = make_sdesc128(smem_u32(smem));
@@ -602,6 +622,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                         const int k0 = (st_flags & TFF_TRI) ? n0 / TF_KC : 0;
                         const int total = nk_p[0] - k0 + (st_nphase > 1 ? nk_p[1] - k0 : 0);
                         const bool narrow = st_N <= 32;
+                        const bool wide = ((nvalid + 31) & ~31) > 128;   // accumulator columns of this chunk: one ring entry or two
                         int in_seg = 0, done = 0, nstage = 0;
                         uint32_t dcol = 0;
                         for (int p = 0; p < st_nphase; ++p) {
@@ -609,9 +630,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                             for (int kc = k0, take; kc < nk; kc += take, ++nstage) {
                                 take = tf_stage_take(narrow, kc, nk, in_seg, seg_kc);
                                 if (in_seg == 0) {   // open a fresh accumulator buffer (in both CTAs)
-                                    const int buf = g & 1;
-                                    mbar_wait_timed<DBG>(&pempty_bar[buf], ((g >> 1) & 1) ^ 1, args.err, 3, w_pempty);
-                                    dcol = tmem_base + buf * TF_NC;
+                                    acc_e = ring.open(wide);
+                                    mbar_wait_timed<DBG>(&pempty_bar[acc_e], ring.parity(acc_e) ^ 1, args.err, 3, w_pempty);
+                                    if (wide) mbar_wait_timed<DBG>(&pempty_bar[acc_e + 1], ring.parity(acc_e + 1) ^ 1, args.err, 3, w_pempty);
+                                    dcol = tmem_base + acc_e * 128;
                                 }
                                 if (DBG && n0 == 0 && nstage < TF_STAGES) mbar_wait_timed<DBG>(&full_bar[stage], ph, args.err, 4, w_full_head);
                                 else mbar_wait_timed<DBG>(&full_bar[stage], ph, args.err, 4, w_full);
@@ -629,9 +651,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                                         umma_f16_pair_x6(dcol, adesc, adesc + (TF_TILE_BYTES >> 4), idesc, acc);
                                     }
                                     umma_commit_pair(&empty_bar[stage]);   // frees the smem stage in both CTAs when these MMAs retire
-                                    if (seg_end) umma_commit_pair(&pfull_bar[g & 1]);   // partial tiles complete -> both epilogues drain them
+                                    if (seg_end) {   // partial tiles complete -> both epilogues drain them
+                                        umma_commit_pair(&pfull_bar[acc_e]);
+                                        if (wide) umma_commit_pair(&pfull_bar[acc_e + 1]);
+                                    }
                                 }
-                                if (seg_end) ++g, in_seg = 0;
+                                if (seg_end) ring.close(acc_e, wide), in_seg = 0;
                                 if (++stage == TF_STAGES) stage = 0, ph ^= 1;
                             }
                         }
@@ -710,7 +735,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         const int gi = (warp - 4) >> 2;                  // column group: columns [128 gi, 128 gi + 128) of every chunk
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;                   // TMEM lane == walker of the tile
-        const uint32_t tmem_grp = tmem_base + ((uint32_t)(q * 32) << 16) + gi * 128;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);   // this warp's lane quarter
         x.my_x = stg_all + gi * TF_STG_BYTES + row * 128, x.my_y = x.my_x + TF_BOX_BYTES;
         x.sw = row & 7;
         x.sfree = &sfree_bar[gi], x.sfull = &sfull_bar[gi];
@@ -723,13 +748,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         x.row_scale = 1.f;
         float row_unscale[2] = {1.f, 1.f}, row_scale2[2] = {1.f, 1.f};   // 2^k / 2^-k per walker-pair slot
         const int n_in = c.n_in;
-        uint32_t g = 0, nchunk = 0;
+        uint32_t nchunk = 0;
+        TfAccRing ring;
         long long e_wait = 0, e_drain = 0, e_epi = 0;
         constexpr bool timing = DBG;
         x.timing = DBG;
         const long long e_begin = clock64();
-        uint32_t pempty_remote[2];   // the leader's drain barriers, as cluster addresses
-        pempty_remote[0] = map_to_cta(smem_u32(&pempty_bar[0]), 0), pempty_remote[1] = map_to_cta(smem_u32(&pempty_bar[1]), 0);
+        const uint32_t pempty_remote0 = map_to_cta(smem_u32(&pempty_bar[0]), 0);   // the leader's drain barriers, as cluster addresses
 
         for (int64_t pair = pair0; pair < my_pairs; pair += pair_step) {
             const int nslots = (args.slots == 2 && pair + 1 < my_pairs) ? 2 : 1;
@@ -789,6 +814,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                 for (int ch = 0; ch < nch; ++ch) {
                     const int n0 = ch * TF_NC;
                     const int nvalid = st.N - n0 < TF_NC ? st.N - n0 : TF_NC;
+                    const bool wide = ((nvalid + 31) & ~31) > 128;   // two ring entries (see TfAccRing)
                     int ncol = ((nvalid + 31) & ~31) - 128 * gi;   // accumulator columns of this group in this chunk
                     ncol = ncol < 0 ? 0 : (ncol > 128 ? 128 : ncol);
                     const int c0 = n0 + 128 * gi;
@@ -800,24 +826,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                     const int nseg = (tf_chunk_stages(st, n0) + seg_kc - 1) / seg_kc;
 #pragma unroll 1
                     for (int sg = 0; sg < nseg; ++sg) {
-                        const int buf = g & 1;
+                        const uint32_t acc_e = ring.open(wide);
                         const long long t_a = timing ? clock64() : 0;
-                        mbar_wait(&pfull_bar[buf], (g >> 1) & 1, args.err, 5);
+                        mbar_wait(&pfull_bar[acc_e], ring.parity(acc_e), args.err, 5);
+                        if (wide) mbar_wait(&pfull_bar[acc_e + 1], ring.parity(acc_e + 1), args.err, 5);
                         const long long t_b = timing ? clock64() : 0;
                         tc_fence_after();
 #pragma unroll
                         for (int cb = 0; cb < 128; cb += 32) {
                             if (cb < ncol) {
                                 uint32_t r[32];
-                                tmem_ld32(tmem_grp + buf * TF_NC + cb, r);
+                                tmem_ld32(tmem_lane + acc_e * 128 + gi * 128 + cb, r);
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) racc[cb + j] += __uint_as_float(r[j]);
                             }
                         }
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(pempty_remote[buf]);   // one arrival per warp at the leader
-                        ++g;
+                        if (lane == 0) {   // one arrival per warp at the leader
+                            mbar_arrive_cluster(pempty_remote0 + 8 * acc_e);
+                            if (wide) mbar_arrive_cluster(pempty_remote0 + 8 * (acc_e + 1));
+                        }
+                        ring.close(acc_e, wide);
                         if (timing) e_wait += t_b - t_a, e_drain += clock64() - t_b;
                     }
                     const long long t_c = timing ? clock64() : 0;
