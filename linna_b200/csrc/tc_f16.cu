@@ -758,18 +758,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
 
         for (int64_t pair = pair0; pair < my_pairs; pair += pair_step) {
             const int nslots = (args.slots == 2 && pair + 1 < my_pairs) ? 2 : 1;
-            // ---- prologue (group 0): u -> theta -> xhat (util.py:323-347, :483-497), split, stage, TMA store
+            // ---- prologue: u -> theta -> xhat (util.py:323-347, :483-497), split, staged in group 0's boxes, TMA store.
+            // Both column groups share the work (erf, log10 and a division per parameter: 8 k cycles on one group alone):
+            // group g converts the parameters [16 j + 8 g, +8) of its walker.
             float lnprior2[2] = {0.f, 0.f};
             double chi2[2] = {0.0, 0.0};
-            if (gi == 0)
             for (int slot = 0; slot < nslots; ++slot) {
                 const int64_t grow = ((cluster_id + (pair + slot) * n_clusters) * 2 + cta_rank) * TF_M + row;
                 const bool valid = grow < args.n;
                 float lnprior = 0.f;
-                mbar_wait(x.sfree, (x.sidx & 1) ^ 1, args.err, 7);
+                if (gi == 0) mbar_wait(x.sfree, (x.sidx & 1) ^ 1, args.err, 7);
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // group 0's staging boxes are free
+                uint8_t *px = stg_all + row * 128, *py = px + TF_BOX_BYTES;
                 const float *u = args.in + grow * n_in;
 #pragma unroll 1
-                for (int j = 0; j < 8; ++j) {
+                for (int j = gi; j < 8; j += 2) {
                     uint32_t hw[4], lw[4];
 #pragma unroll
                     for (int e = 0; e < 8; e += 2) {
@@ -789,14 +792,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                         }
                         split2(xv[0], xv[1], hw[e >> 1], lw[e >> 1]);
                     }
-                    uint8_t *bx = (j & 4) ? x.my_y : x.my_x;
+                    uint8_t *bx = (j & 4) ? py : px;
                     *reinterpret_cast<uint4 *>(bx + (((j & 3) ^ x.sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                     *reinterpret_cast<uint4 *>(bx + (((4 + (j & 3)) ^ x.sw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                 }
-                lnprior2[slot] = -0.5f * lnprior;                                    // util.py:1165
+                if (gi == 1) chi_s[row] = (double)lnprior;
                 fence_async_smem();
-                mbar_arrive(x.sfull);
-                ++x.sidx;
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // both halves of the row are written
+                if (gi == 0) {
+                    lnprior2[slot] = -0.5f * (lnprior + (float)chi_s[row]);           // util.py:1165
+                    mbar_arrive(x.sfull);
+                    ++x.sidx;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // chi_s may be reused
             }
 #pragma unroll 1
             for (int si = 0; si < n_steps; ++si) {
