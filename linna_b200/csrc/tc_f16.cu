@@ -1408,7 +1408,7 @@ static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const f
     // C3; the activation arena in flight doubles and the L2 hit rate drops from 78% to 58%, which is why it is not
     // more).  Batches that cannot fill every cluster twice spread one pair per cluster; LINNA_TC_SLOTS=1 forces that.
     const int64_t clusters = t->grid / 2;
-    static const int want_slots = getenv("LINNA_TC_SLOTS") ? atoi(getenv("LINNA_TC_SLOTS")) : 2;
+    const int want_slots = getenv("LINNA_TC_SLOTS") ? atoi(getenv("LINNA_TC_SLOTS")) : 2;
     a.slots = (want_slots == 2 && pairs > clusters) ? 2 : 1;
     const int grid = 2 * (int)std::min<int64_t>(pairs, clusters);
     if (a.dbg) cudaMemsetAsync(t->dbg_dev, 0, (size_t)t->grid * TF_DBG_STRIDE * sizeof(long long), stream);

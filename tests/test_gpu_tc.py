@@ -190,3 +190,30 @@ def test_tc_falls_back_when_the_shape_is_not_supported():
     e.set_path("tc")
     with pytest.raises(engine.LinnaError, match="64 input"):
         e.lnp(_dev(u))
+
+
+@pytest.mark.parametrize("seg_kc,slots", [(2, 2), (3, 2), (5, 1), (8, 2)])
+def test_tc_segment_lengths_and_slots(monkeypatch, seg_kc, slots):
+    """The producer and the MMA issuer decide alike how many k-chunks a stage of a narrow step takes (two, unless
+    that would cross an accumulation segment) and all roles walk the four-entry tensor-memory ring alike: any
+    segment length (odd ones included) and either number of walker pairs per cluster give the same answer.  A
+    protocol mismatch would trap (bounded mbarrier waits) rather than hang."""
+    monkeypatch.setenv("LINNA_TC_SEG_KC", str(seg_kc))
+    monkeypatch.setenv("LINNA_TC_SLOTS", str(slots))
+    g = load_golden("c3s")
+    p = problem_from_golden(g)
+    e = engine.engine_from_problem(p, quad="chol")
+    e.set_path("tc")
+    reps = 1600                                        # 76 800 rows = 300 walker pairs: several visits of every cluster
+    u = np.tile(g["u"], (reps, 1))
+    lnp, grad = e.lnp_grad(_dev(u))
+    assert e.last_kernel() == "tc"
+    lnp, grad = lnp.cpu().numpy(), grad.cpu().numpy().astype(np.float64)
+    n = g["u"].shape[0]
+    tol = tc_tol(g["f64_lnp"]) * (2.0 if seg_kc > 4 else 1.0)   # longer segments: more truncated accumulations
+    for r in (0, reps // 2, reps - 1):
+        sl = slice(r * n, (r + 1) * n)
+        assert np.all(np.abs(lnp[sl] - g["f64_lnp"]) <= tol), np.abs(lnp[sl] - g["f64_lnp"]).max()
+        rel = np.max(np.abs(grad[sl] - g["f64_grad"]), axis=1) / np.max(np.abs(g["f64_grad"]), axis=1)
+        assert rel.max() < 2e-4, rel.max()
+    assert np.array_equal(lnp[:n], lnp[-n:])           # batch position does not matter
