@@ -867,8 +867,8 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
             const int64_t g32 = (int64_t)m->num_sms * m->occ[2] * 32, g16 = (int64_t)m->num_sms * m->occ[1] * 16;
             if (left >= g32) rows = 32, take = left / g32 * g32;
             else if (left >= g16) rows = 16, take = left / g16 * g16;
-            else if (left > (int64_t)m->num_sms * 16) rows = 16;
-            else rows = 8;
+            else if (left > (int64_t)m->num_sms * 8 * m->occ[0]) rows = 16;
+            else rows = 8;   // every tile resident at once: the deep-ring 8-row kernel (one CTA per SM)
         }
         const int rg = rows / 8;
         const int occ = m->occ[rg == 4 ? 2 : rg == 2 ? 1 : 0];

@@ -13,7 +13,10 @@
 // {4CG+4cg..}), so the inner loop is 4 LDS.128 per 64 FFMA for every layer width: narrow layers
 // trade column groups for k-slices (split-K inside the CTA, reduced through shared memory).
 // Weights ([k][n] packed) and activations ([feature][row] in the per-CTA L2-resident arena) are
-// streamed through a 3-stage cp.async ring.
+// streamed through a cp.async ring of 24 KB stages.  A tile of 8*RG walkers uses every weight 8*RG times, so the
+// CTA needs 64/RG bytes per clock from L2 at the full FFMA rate, and the bytes in flight decide what it gets
+// (an L2 round trip is ~2000 cycles): the 8-row kernel (small batches, training; one CTA per SM) runs an
+// 8-stage ring (112 KB in flight), the 16- and 32-row kernels 4 stages with two CTAs per SM.
 #include "linna_device.cuh"
 #include "../../include/linna_b200.h"
 
@@ -43,6 +46,7 @@ struct Cfg {
     static constexpr int BK_LOG2 = (RG == 4) ? 3 : (RG == 2) ? 2 : 1;
     static constexpr int CGMAX_LOG2 = (RG == 4) ? 6 : (RG == 2) ? 7 : 8;  // 256/RG column groups at most
     static constexpr int CGMIN_LOG2 = CGMAX_LOG2 - 3;                     // at most 8 k-slices
+    static constexpr int STAGES = (RG == 1) ? 8 : 4;                      // cp.async ring depth
 };
 
 template <int RG>
@@ -70,7 +74,7 @@ template <int RG, int CGL>
 __device__ __forceinline__ void gemm_phase(float (&acc)[8][8], float *smem, const float *__restrict__ A,
                                            const float *__restrict__ Wt, int K, int ldw, int n0, int tid)
 {
-    constexpr int BM = Cfg<RG>::BM, BK = Cfg<RG>::BK, BKL = Cfg<RG>::BK_LOG2;
+    constexpr int BM = Cfg<RG>::BM, BK = Cfg<RG>::BK, BKL = Cfg<RG>::BK_LOG2, kStages = Cfg<RG>::STAGES;
     constexpr int CG = 1 << CGL, KSL = Cfg<RG>::CGMAX_LOG2 - CGL, KS = 1 << KSL, NCH = 8 * CG;
     constexpr int R4L = BKL;              // log2(BM/4) == log2(BK)
     constexpr int NA4 = KS * BK * (BM / 4);  // float4 copies of the activation slab
@@ -237,12 +241,12 @@ __device__ __forceinline__ float prior_map(float u, int kind, float scale, float
 }
 
 template <int RG>
-__global__ void __launch_bounds__(kThreads, 2) fused_ffma_kernel(const KernelArgs args)
+__global__ void __launch_bounds__(kThreads, RG == 1 ? 1 : 2) fused_ffma_kernel(const KernelArgs args)
 {
     constexpr int BM = 8 * RG;
     extern __shared__ float4 smem4[];
     float *smem = reinterpret_cast<float *>(smem4);
-    double *chi_part = reinterpret_cast<double *>(smem + kStages * kStageFloats);  // [RG*nsub<=8][8]
+    double *chi_part = reinterpret_cast<double *>(smem + Cfg<RG>::STAGES * kStageFloats);  // [RG*nsub<=8][8]
     double *chi_acc = chi_part + 64;                                               // [BM]
     float *lnprior = reinterpret_cast<float *>(chi_acc + 32);                      // [BM]
 
@@ -510,12 +514,16 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ffma_kernel(const KernelArg
     }
 }
 
-static size_t fused_smem_bytes() { return (size_t)kStages * kStageFloats * sizeof(float) + 64 * 8 + 32 * 8 + 32 * 4; }
+static size_t fused_smem_bytes(int rg)
+{
+    const int stages = rg == 1 ? Cfg<1>::STAGES : rg == 2 ? Cfg<2>::STAGES : Cfg<4>::STAGES;
+    return (size_t)stages * kStageFloats * sizeof(float) + 64 * 8 + 32 * 8 + 32 * 4;
+}
 
 cudaError_t launch_fused_ffma(const KernelArgs &args, int rg, int grid, cudaStream_t stream)
 {
     static bool attr_set[3] = {false, false, false};
-    const size_t smem = fused_smem_bytes();
+    const size_t smem = fused_smem_bytes(rg);
     cudaError_t e = cudaSuccess;
 #define LINNA_LAUNCH(RGV, IDX)                                                                                  \
     {                                                                                                           \
@@ -537,7 +545,7 @@ cudaError_t launch_fused_ffma(const KernelArgs &args, int rg, int grid, cudaStre
 int fused_ffma_max_ctas_per_sm(int rg)
 {
     int nb = 0;
-    const size_t smem = fused_smem_bytes();
+    const size_t smem = fused_smem_bytes(rg);
     if (rg == 4) {
         cudaFuncSetAttribute(fused_ffma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fused_ffma_kernel<4>, kThreads, smem);

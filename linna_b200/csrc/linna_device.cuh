@@ -16,8 +16,7 @@ constexpr int kThreads = 256;        // threads per CTA of the fused FFMA kernel
 constexpr int kMaxSteps = 64;
 constexpr int kStageWFloats = 4096;  // weight slab per pipeline stage (16 KB)
 constexpr int kStageAFloats = 2048;  // activation slab per pipeline stage (<= 8 KB)
-constexpr int kStageFloats = kStageWFloats + kStageAFloats;
-constexpr int kStages = 3;
+constexpr int kStageFloats = kStageWFloats + kStageAFloats;   // ring depth: Cfg<RG>::STAGES (fused_ffma.cu)
 
 enum Epilogue : int32_t {
     EPI_ACT = 0,   // v (+relu) -> dst ; optionally save relu mask bits

@@ -74,7 +74,7 @@ struct linna_model {
     std::string tc_why;           // why the tensor-core program could not be built for this model
     int path = 0;                 // 0 auto (tensor core from tc_min_rows rows on), 1 FFMA only, 2 tensor core only
     int last_kernel = 0;          // kernel that served the last launch: 1 FFMA, 2 tensor core
-    int64_t tc_min_rows = 1024;   // measured crossover: one tensor-core pass (0.19 ms at C3) beats the FFMA kernel from ~256 rows on
+    int64_t tc_min_rows = 256;    // one full walker pair; one tensor-core pass (0.14 ms at C3) beats the FFMA kernel (0.20 ms) at every size (scratch/crossover.py)
     // host-buffer API staging
     cudaStream_t hstream = nullptr;                  // compute stream of the host-buffer entry points
     cudaStream_t cstream = nullptr, dstream = nullptr;   // host->device / device->host copy streams (pipelined chunks)
