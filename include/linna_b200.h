@@ -141,11 +141,13 @@ int linna_model_set_fold(linna_model_t *m, int32_t on);
 /* Which kernel served the last launch on this model: 0 none yet, 1 FP32 FFMA kernel, 2 tensor-core kernel. */
 int linna_model_last_kernel(const linna_model_t *m);
 /* Profiling hook (environment LINNA_TC_DEBUG set when the tensor-core context is built): copies the per-CTA
- * cycle counters of the last tensor-core launch into out[max_ctas][16] and returns the number of CTAs
+ * cycle counters of the last tensor-core launch into out[max_ctas][128] and returns the number of CTAs
  * (0 when the counters are off).  [0..2] TMA producer: total, waiting for a free stage, waiting for
  * activations; [3..5] MMA issuer (leader CTA of a pair): total, waiting for operands, waiting for the
  * epilogue to drain TMEM; [6..9] / [10..13] first epilogue warp of column group 0 / 1: total, waiting for
- * the MMAs, draining TMEM, chunk epilogues. */
+ * the MMAs, draining TMEM, chunk epilogues; then per program step (up to 24): [16..] cycles of the MMA
+ * issuer, [40..] of epilogue group 0, [64..] of which waiting for accumulators, [88..] of which chunk
+ * epilogues. */
 int linna_debug_tc_counters(linna_model_t *m, int64_t *out, int32_t max_ctas);
 /* Force the row-tile height (8, 16 or 32; 0 = automatic) -- test hook for the tiling variants. */
 int linna_model_set_tile_rows(linna_model_t *m, int32_t rows);
