@@ -131,7 +131,7 @@ int linna_lnp_grad_host(linna_model_t *m, const float *u, int64_t n, float *lnp,
 /* Introspection used by bench.py / tests. */
 int linna_model_info(const linna_model_t *m, int32_t *n_in, int32_t *n_out, int64_t *n_params, int32_t *num_sms);
 /* Kernel selection for linna_lnp / linna_lnp_grad: 0 = automatic (the default: tensor-core kernel for
- * n >= tc_min_rows, default 1024, FP32 FFMA kernel below and wherever the tensor-core program does not apply),
+ * n >= tc_min_rows, default 256, FP32 FFMA kernel below and wherever the tensor-core program does not apply),
  * 1 = FP32 FFMA kernel only, 2 = tensor-core (tcgen05, split-fp16) kernel only.  tc_min_rows <= 0 keeps the
  * current threshold. */
 int linna_model_set_path(linna_model_t *m, int32_t path, int64_t tc_min_rows);
