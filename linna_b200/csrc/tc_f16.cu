@@ -9,9 +9,10 @@
 //     products and fp32 accumulation in tensor memory.  kind::f16 runs at twice the TF32 rate and the
 //     operands are half as wide, so the three passes cost what 1.5 TF32 passes would.
 //   * two-level accumulation.  The tensor core truncates its fp32 accumulator on every tcgen05.mma
-//     (measured: a toward-zero bias of ~0.5 ulp per instruction), so every `seg_kc` k-chunks (default 4 = 128
-//     values of K = 24 instructions; measured max relative lnP error 3.2e-7 at 4, 2.1e-7 at 2, both at the
-//     level of the reference's own float32) the partial tile is drained from tensor memory and added with
+//     (measured: a toward-zero bias of ~0.5 ulp per instruction), so every `seg_kc` k-chunks (default 6 = 192
+//     values of K = 36 instructions; measured max relative lnP error over the goldens 2.7e-7 at 6, 3.2e-7 at 4,
+//     3.7e-7 at 8, all at the level of the reference's own float32, 2.0e-7; mean relative error 6e-8 at 6) the
+//     partial tile is drained from tensor memory and added with
 //     round-to-nearest into fp32 REGISTER accumulators by the epilogue warps, while the MMA warp already
 //     fills the other TMEM buffer.
 //   * CTA pairs.  One cluster = two CTAs = 2 x 128 walkers; rank 0 issues every MMA for the pair
@@ -979,8 +980,8 @@ static inline int pad64(int n) { return (n + 63) & ~63; }
 static int tc_seg_kc()
 {
     const char *e = getenv("LINNA_TC_SEG_KC");
-    int v = e ? atoi(e) : 4;
-    return v > 0 ? v : 4;
+    int v = e ? atoi(e) : 6;
+    return v > 0 ? v : 6;
 }
 
 void tc_destroy(TcContext *t)

@@ -192,7 +192,7 @@ def test_tc_falls_back_when_the_shape_is_not_supported():
         e.lnp(_dev(u))
 
 
-@pytest.mark.parametrize("seg_kc,slots", [(2, 2), (3, 2), (5, 1), (8, 2)])
+@pytest.mark.parametrize("seg_kc,slots", [(2, 2), (3, 2), (4, 2), (5, 1), (8, 2)])
 def test_tc_segment_lengths_and_slots(monkeypatch, seg_kc, slots):
     """The producer and the MMA issuer decide alike how many k-chunks a stage of a narrow step takes (two, unless
     that would cross an accumulation segment) and all roles walk the four-entry tensor-memory ring alike: any
@@ -210,7 +210,7 @@ def test_tc_segment_lengths_and_slots(monkeypatch, seg_kc, slots):
     assert e.last_kernel() == "tc"
     lnp, grad = lnp.cpu().numpy(), grad.cpu().numpy().astype(np.float64)
     n = g["u"].shape[0]
-    tol = tc_tol(g["f64_lnp"]) * (2.0 if seg_kc > 4 else 1.0)   # longer segments: more truncated accumulations
+    tol = tc_tol(g["f64_lnp"]) * (2.0 if seg_kc > 6 else 1.0)   # longer segments: more truncated accumulations
     for r in (0, reps // 2, reps - 1):
         sl = slice(r * n, (r + 1) * n)
         assert np.all(np.abs(lnp[sl] - g["f64_lnp"]) <= tol), np.abs(lnp[sl] - g["f64_lnp"]).max()
