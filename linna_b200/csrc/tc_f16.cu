@@ -204,6 +204,10 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
     asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
 {
     asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
@@ -360,6 +364,7 @@ __device__ __forceinline__ int tf_chunk_stages(const TfStep &st, int n0)
 // ------------------------------------------------------------------------------------------ chunk epilogue
 struct TfEpiCtx {
     uint8_t *my_x, *my_y;       // this thread's 128-byte rows of the two staging boxes (k-chunk 0 / 1 of 64 columns)
+    uint32_t sx, sw16;          // shared-space address of my_x (my_y = + TF_BOX_BYTES); swizzle phase << 4
     uint64_t *sfree, *sfull;
     uint32_t *mask_row;
     int *err;
@@ -432,9 +437,10 @@ __device__ __forceinline__ void tf_chunk_epilogue(const float (&racc)[128], cons
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) split2(v[e], v[e + 1], hw[e >> 1], lw[e >> 1]);
                 // columns [8j, 8j+8) of the box: 16-byte unit j&3 of the hi half, 4 + (j&3) of the lo half
-                uint8_t *bx = (j & 4) ? x.my_y : x.my_x;
-                *reinterpret_cast<uint4 *>(bx + (((j & 3) ^ x.sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *reinterpret_cast<uint4 *>(bx + (((4 + (j & 3)) ^ x.sw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                // (32-bit shared-space stores: no generic-address arithmetic in the hot loop)
+                const uint32_t bx = x.sx + ((j & 4) ? (uint32_t)TF_BOX_BYTES : 0u);
+                st_shared_v4(bx + ((uint32_t)((j & 3) << 4) ^ x.sw16), hw[0], hw[1], hw[2], hw[3]);
+                st_shared_v4(bx + ((uint32_t)((4 + (j & 3)) << 4) ^ x.sw16), lw[0], lw[1], lw[2], lw[3]);
             }
         }
         if (store) {
@@ -738,6 +744,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
         const int row = q * 32 + lane;                   // TMEM lane == walker of the tile
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);   // this warp's lane quarter
         x.my_x = stg_all + gi * TF_STG_BYTES + row * 128, x.my_y = x.my_x + TF_BOX_BYTES;
+        x.sx = smem_u32(x.my_x), x.sw16 = (uint32_t)(row & 7) << 4;
         x.sw = row & 7;
         x.sfree = &sfree_bar[gi], x.sfull = &sfull_bar[gi];
         x.sidx = 0;
