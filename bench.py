@@ -185,28 +185,34 @@ def run_reference(args):
     return 0
 
 
-def run_reference_train(args):
-    """--impl reference --workload c5: the oracle's C restatement of one training step (forward, loss, backward,
-    AdamW; linna/predictor_gpu.py:268-288) on ONE host core, a bounded number of 500-row steps."""
+def cpu_train_rate(B, steps):
+    """Time `steps` AdamW steps of B rows through the oracle's C restatement of the training step (forward, loss,
+    backward, AdamW; linna/predictor_gpu.py:268-288) on ONE host core.  Returns (rows/s, seconds)."""
     from oracle.oracle import Oracle, normalised_loss_constants
     p, theta, rng = train_problem()
     o0 = Oracle(p, arch)
     m0 = o0.lnp(np.zeros((1, p.n_in), np.float32), want=("m",))["m"][0]
     p.set_data_from_prediction(m0)
     o = Oracle(p, arch)
-    B = args.walkers or 500
     dn, icov = normalised_loss_constants(p.cov, np.asarray(p.sigma, np.float32), p.y_mean, p.y_std, p.data)
     w = o.w64.astype(np.float32)
     am, av = np.zeros_like(w), np.zeros_like(w)
     X = np.ascontiguousarray(theta[:B], np.float32)
     Y = (np.asarray(p.data, np.float64)[None, :] * (1 + 0.01 * rng.standard_normal((B, p.n_out)))).astype(np.float32)
-    steps = max(1, min(args.steps, 3))
     o.train_step(w, am, av, 1, X, Y, dn, icov, 1e-3)
     t0 = time.perf_counter()
     for s in range(steps):
         o.train_step(w, am, av, s + 2, X, Y, dn, icov, 1e-3)
     dt = time.perf_counter() - t0
-    val = B * steps / dt
+    return B * steps / dt, dt
+
+
+def run_reference_train(args):
+    """--impl reference --workload c5: the oracle's C restatement of one training step on ONE host core, a bounded
+    number of 500-row steps."""
+    B = args.walkers or 500
+    steps = max(1, min(args.steps, 3))
+    val, dt = cpu_train_rate(B, steps)
     line = {"impl": "reference", "metric": "emulator training rows/sec", "value": val, "unit": "rows/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": 1, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -323,6 +329,13 @@ def run_train(args):
         flops_row = 6 * macs + 500 * 501
         achieved = flops_row * B / ((ms * 1e-3) / args.steps) / 1e12
         lh = losses.cpu().numpy()
+        ffma_peak = 148 * 128 * 2 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e12
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, dt_cpu = cpu_train_rate(B, 2)
+            cpu = {"value": rate, "unit": "rows/s", "cores": 1, "kind": "port",
+                   "sample": "2 AdamW steps of %d rows through the oracle's C restatement of the training step "
+                             "(scalar, one core), %.1f s" % (B, dt_cpu)}
         line = {"metric": "emulator training rows/sec", "value": value, "unit": "rows/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -338,8 +351,11 @@ def run_train(args):
                              "frac": achieved / peaks["bf16_tflops"], "traffic": None,
                              "kernel": "fused_ffma_kernel<1> (fwd+loss+bwd-data) + wgrad_kernel (+AdamW)",
                              "peak_source": peaks["source"],
-                             "note": "FP32 FFMA path; step is latency-bound at B=500 (63 row tiles on 148 SMs)"},
-                "cpu_baseline": None}
+                             "note": "FP32 FFMA path: %.1f %% of the %.1f TFLOP/s FP32 FFMA peak of 148 SMs at the sampled clock; "
+                                     "at B=500 the step runs 63 row tiles of 8 rows on 148 SMs and is bound by "
+                                     "instruction issue and barriers inside those CTAs (profiles/r1_ncu_ffma_train_v2_summary.csv)"
+                                     % (100.0 * achieved / ffma_peak, ffma_peak)},
+                "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
