@@ -495,7 +495,7 @@ def main():
                 "kernel": kernel, "peak_source": peaks["source"], "note": note}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:   # reported at N=1 only (the reference arm covers the other N)
         n_sample = min(n, 32768)
         reps = 8 if args.mode == "lnp" else 4          # a few seconds of CPU work on all host threads
         rate, dt_cpu = cpu_port_rate(p, data, n_sample, reps, grad=args.mode == "grad")
