@@ -12,25 +12,27 @@
 //     (measured: a toward-zero bias of ~0.5 ulp per instruction), so every `seg_kc` k-chunks (default 6 = 192
 //     values of K = 36 instructions; measured max relative lnP error over the goldens 2.7e-7 at 6, 3.2e-7 at 4,
 //     3.7e-7 at 8, all at the level of the reference's own float32, 2.0e-7; mean relative error 6e-8 at 6) the
-//     partial tile is drained from tensor memory and added with
-//     round-to-nearest into fp32 REGISTER accumulators by the epilogue warps, while the MMA warp already
-//     fills the other TMEM buffer.
+//     partial tile is drained from tensor memory and added with round-to-nearest into fp32 REGISTER
+//     accumulators by the epilogue warps, while the MMA warp already fills another TMEM buffer (tensor memory
+//     is a ring of four 128-column entries, TfAccRing: a chunk of more than 128 columns takes an aligned pair).
 //   * CTA pairs.  One cluster = two CTAs = 2 x 128 walkers; rank 0 issues every MMA for the pair
 //     (cta_group::2, M = 256, N <= 256).  Each CTA supplies its own 128 activation rows and HALF of the weight
 //     tile and receives its own 128 x N accumulator rows: half the L2 weight traffic per walker, and the MMA
 //     is off the shared-memory bandwidth limit a 128 x 128 single-CTA instruction sits on.
-//   * operands are K-major 128-byte-swizzled tiles (4 stages x 32 KB) filled by TMA (cp.async.bulk.tensor,
+//   * operands are K-major 128-byte-swizzled tiles (4 stages x 36 KB) filled by TMA (cp.async.bulk.tensor,
 //     completion on the leader's mbarrier) from the packed weights and from the row-major activation arena of
 //     this CTA.  Both keep the hi and lo halves of a k-chunk of 32 values side by side ([32 hi | 32 lo] = 128
 //     contiguous bytes per row), so that one TMA box row is one full cache line and a stage is two TMA
 //     instructions (A tile, B half tile) rather than four of half-line rows; the MMA descriptors pick the hi or
 //     lo half of the swizzle row by a 64-byte offset of the start address.  Layer outputs go back to the arena
-//     through staging boxes of the same format and TMA stores.  The store warps publish, per 64-column box, how far a layer's output is visible, and the
-//     producer fetches a k-chunk as soon as ITS columns are there, so the next layer starts on the first
-//     columns of an activation while the epilogue is still writing the last ones.
+//     through staging boxes of the same format and TMA stores.  The store warps publish, per 64-column box,
+//     how far a layer's output is visible, and the producer fetches a k-chunk as soon as ITS columns are
+//     there, so the next layer starts on the first columns of an activation while the epilogue is still
+//     writing the last ones.  A narrow step (N <= 32) packs two k-chunks into one stage (TF_STAGE_BYTES).
 //   * every cluster interleaves two walker pairs ("slots") layer by layer, so that the layer-to-layer
 //     dependency bubble of one pair is filled with the other pair's MMAs.
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread, leader CTA) + TMEM allocator, warps 2 / 3
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA) + TMEM allocator -- both walk the program
+//     warp-uniformly and issue from one elected lane --, warps 2 / 3
 //     = TMA store issuers of column group 0 / 1, warps 4-7 / 8-11 = epilogue of column group 0 / 1 (columns
 //     [0,128) / [128,256) of every 256-column chunk): an epilogue thread owns one walker (TMEM lane) and 128
 //     columns, so the chi^2 reduction, the relu masks of the backward pass and the final Jacobian need no
