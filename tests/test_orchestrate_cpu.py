@@ -106,6 +106,15 @@ def test_checkmeanstd_and_chain_store(tmp_path):
     assert sampler.checkmeanstd(good, 0.2, 0.15)
     drift = good + np.linspace(0, 3, 400)[:, None, None]
     assert not sampler.checkmeanstd(drift, 0.2, 0.15)
+    # the tensor path (what runs on the GPU for large chains) computes the same two statistics
+    import torch
+    for x in (good, drift, rng.standard_normal((41, 5, 4))):
+        half = len(x) // 2
+        a, b = x[:half].reshape(-1, x.shape[-1]), x[half:].reshape(-1, x.shape[-1])
+        sb = b.std(axis=0)
+        ref = (np.median(np.abs(a.mean(axis=0) - b.mean(axis=0)) / sb), np.median((a.std(axis=0) - sb) / sb))
+        np.testing.assert_allclose(sampler._halves_shift_torch(torch.from_numpy(x)), ref, rtol=1e-10, atol=1e-13)
+        assert sampler.checkmeanstd(torch.from_numpy(x), 0.2, 0.15) == sampler.checkmeanstd(x, 0.2, 0.15)
     name = str(tmp_path / "chemcee_256.h5")
     st = sampler.ChainStore(name, transform=lambda c: 2.0 * c)
     st.extend(good[:100], np.zeros((100, 6)))
