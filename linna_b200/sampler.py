@@ -39,6 +39,18 @@ def _autocorr_1d(x):
     return acf / acf[0] if acf[0] != 0 else acf
 
 
+def _mean_acf_numpy(chain):
+    """Host twin of _mean_acf_torch: one batched FFT over every (walker, parameter) series."""
+    nstep = chain.shape[0]
+    n = _next_pow_two(nstep)
+    x = chain - chain.mean(axis=0, keepdims=True)
+    f = np.fft.rfft(x, n=2 * n, axis=0)
+    acf = np.fft.irfft(f * np.conjugate(f), n=2 * n, axis=0)[:nstep]
+    a0 = acf[0:1]
+    acf = np.where(a0 != 0, acf / np.where(a0 != 0, a0, 1.0), acf)
+    return acf.mean(axis=1)
+
+
 def _mean_acf_torch(chain):
     """Walker-averaged normalised autocorrelation function per parameter, batched FFT on the GPU:
     chain [steps, walkers, ndim] (device tensor) -> [steps, ndim] float64 on the host."""
@@ -71,11 +83,7 @@ def integrated_time(chain, c=5.0):
     if on_gpu:
         macf = _mean_acf_torch(chain)
     else:
-        macf = np.zeros((nstep, ndim))
-        for d in range(ndim):
-            for w in range(nwalk):
-                macf[:, d] += _autocorr_1d(chain[:, w, d])
-        macf /= nwalk
+        macf = _mean_acf_numpy(chain)
     tau = np.empty(ndim)
     for d in range(ndim):
         taus = 2.0 * np.cumsum(macf[:, d]) - 1.0
