@@ -27,6 +27,8 @@ cudaError_t tc_launch_lnp(const linna_model *m, TcContext *t, const float *u, in
 cudaError_t tc_launch_grad(const linna_model *m, TcContext *t, const float *u, int64_t n, float *lnp, float *grad,
                            cudaStream_t stream);
 bool tc_has_grad(const TcContext *t);
+void tc_fix_buffers(TcContext *t, const int32_t **rows, const int32_t **count, int32_t **next_count);
+void tc_launch_done(TcContext *t);
 int tc_debug_read(TcContext *t, long long *out, int max_ctas);
 }  // namespace linna
 
@@ -850,6 +852,20 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
             if (pk == PROG_LNP) CUDA_TRY(tc_launch_lnp(m, m->tc, in, n, lnp, stream));
             else CUDA_TRY(tc_launch_grad(m, m->tc, in, n, lnp, grad, stream));
             g_launches.fetch_add(1);
+            {
+                // Fix-up: rows that came out NaN on the tensor-core path (an activation beyond the fp16 range) are redone
+                // by the FP32 kernel, which has the reference's own range.  The row list and its length stay on the
+                // device; with nothing flagged the launch is a few idle CTAs.
+                KernelArgs a;
+                memset(&a, 0, sizeof a);
+                a.prog = m->prog_dev + pk, a.c = m->consts, a.in = in, a.lnp = lnp, a.grad = grad;
+                a.arena = m->arena, a.masks = m->masks, a.n = n;
+                tc_fix_buffers(m->tc, &a.row_index, &a.n_dev, &a.zero_me);
+                const int grid = (int)std::min<int64_t>((n + 7) / 8, std::min(m->num_sms, 32));
+                CUDA_TRY(launch_fused_ffma(a, 1, grid, stream));
+                tc_launch_done(m->tc);
+                g_launches.fetch_add(1);
+            }
             m->last_kernel = 2;
             CUDA_TRY(cudaEventRecord(m->last_done, stream));
             m->last_stream = stream, m->have_last = true;

@@ -258,7 +258,11 @@ __global__ void __launch_bounds__(kThreads, RG == 1 ? 1 : 2) fused_ffma_kernel(c
     float *arena = args.arena + (size_t)blockIdx.x * prog->arena_features * BM;
     uint8_t *masks = args.masks + (size_t)blockIdx.x * prog->mask_features * RG;
     const int n_in = c.n_in, n_out = c.n_out;
-    const int64_t ntiles = (args.n + BM - 1) / BM;
+    // indexed launch: the row count lives in device memory (rows flagged by the tensor-core kernel)
+    const int64_t n_rows = args.n_dev ? ((int64_t)__ldg(args.n_dev) < args.n ? (int64_t)__ldg(args.n_dev) : args.n) : args.n;
+    const int32_t *__restrict__ ridx = args.row_index;
+    if (args.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *args.zero_me = 0;
+    const int64_t ntiles = (n_rows + BM - 1) / BM;
     const int n_steps = prog->n_steps;
     {
         const int nwords = n_steps * (int)(sizeof(Step) / 4);
@@ -270,17 +274,19 @@ __global__ void __launch_bounds__(kThreads, RG == 1 ? 1 : 2) fused_ffma_kernel(c
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t row0 = tile * BM;
-        const int nrows = (int)((args.n - row0) < BM ? (args.n - row0) : BM);
+        const int nrows = (int)((n_rows - row0) < BM ? (n_rows - row0) : BM);
+        // global row of tile row r (only dereferenced for r < nrows)
+        auto grow = [&](int r) -> int64_t { return ridx ? (int64_t)ridx[row0 + r] : row0 + r; };
 
         // ---------------- prologue: u -> theta -> xhat (feature-major) ----------------
         {
             float *xb = arena + (size_t)prog->in_buf * BM;
-            const float *in = args.in + row0 * n_in;
+            const float *in = args.in;
             for (int e = tid; e < BM * n_in; e += kThreads) {
                 int r = e / n_in, i = e - r * n_in;
                 float th = 0.f;
                 if (r < nrows) {
-                    float u = in[e];
+                    float u = in[grow(r) * n_in + i];
                     th = args.input_theta ? u : prior_map(u, c.prior_kind[i], c.prior_scale[i], c.prior_shift[i]);
                     if (c.log10_flag && c.log10_flag[i]) th = log10f(th);            // util.py:491-496
                     th = (th - c.x_mean[i]) / c.x_std[i];                             // util.py:497
@@ -291,8 +297,10 @@ __global__ void __launch_bounds__(kThreads, RG == 1 ? 1 : 2) fused_ffma_kernel(c
             }
             if (tid < BM) {
                 float s = 0.f;
-                if (tid < nrows && !args.input_theta)
-                    for (int i = 0; i < n_in; ++i) { float u = in[tid * n_in + i]; s = fmaf(u, u, s); }
+                if (tid < nrows && !args.input_theta) {
+                    const float *ur = in + grow(tid) * n_in;
+                    for (int i = 0; i < n_in; ++i) { float u = ur[i]; s = fmaf(u, u, s); }
+                }
                 lnprior[tid] = -0.5f * s;                                             // util.py:1165
                 chi_acc[tid] = 0.0;
             }
@@ -464,12 +472,13 @@ __global__ void __launch_bounds__(kThreads, RG == 1 ? 1 : 2) fused_ffma_kernel(c
                             for (int i = 0; i < 8; ++i) {
                                 int r = row_base + i;
                                 if (r < nrows) {
-                                    float u = args.in[(row0 + r) * n_in + cidx];
+                                    const int64_t gr = grow(r);
+                                    float u = args.in[gr * n_in + cidx];
                                     float gx = v[i] * inv_std;
                                     if (lg) gx /= (prior_map(u, kind, ps, psh) * 2.30258509299404568f);
                                     float jac = ps;
                                     if (kind == LINNA_PRIOR_FLAT) jac *= 0.398942280401432678f * expf(-0.5f * u * u);
-                                    args.grad[(row0 + r) * n_in + cidx] = gx * jac - u;
+                                    args.grad[gr * n_in + cidx] = gx * jac - u;
                                 }
                             }
                         }
@@ -502,12 +511,12 @@ __global__ void __launch_bounds__(kThreads, RG == 1 ? 1 : 2) fused_ffma_kernel(c
             }
             if (st.epi == EPI_LOSSQ && tid < nrows && args.lnp) {
                 const double chi = chi_acc[tid];
-                args.lnp[row0 + tid] = args.cmd ? (float)chi / __ldg(args.cmd + row0 + tid) : (float)chi;   // util.py:1087
+                args.lnp[grow(tid)] = args.cmd ? (float)chi / __ldg(args.cmd + row0 + tid) : (float)chi;   // util.py:1087
             }
             if (st.epi == EPI_CHI2 && tid < nrows && args.lnp) {
                 float l = (float)(-0.5 * chi_acc[tid]) * c.inv_T + lnprior[tid];       // util.py:1013
                 if (l != l) l = -INFINITY;                                            // util.py:1015-1016
-                args.lnp[row0 + tid] = l;
+                args.lnp[grow(tid)] = l;
             }
         }
         __syncthreads();

@@ -99,6 +99,11 @@ struct KernelArgs {
     float loss_inv_B;     // 1 / (rows in the optimiser batch)
     int64_t rm_row0;      // row index of this launch's first row inside the row-major store
     int32_t delta_kind;   // 0: target - pred (chi2_M,nn)  1: target - data (chi2_M,d)  2: pred - data (chi2_nn,d)
+    // indexed launch (fix-up of the rows the tensor-core kernel flagged): row r of the launch is walker row_index[r] of
+    // `in` / `lnp` / `grad`, and the number of rows is read from device memory (no host synchronisation)
+    const int32_t *row_index;   // or nullptr: row r is row r
+    const int32_t *n_dev;       // or nullptr: args.n rows; else min(*n_dev, args.n)
+    int32_t *zero_me;           // counter of the NEXT tensor-core launch, cleared by this one
 };
 
 // ---- weight-gradient / AdamW kernels --------------------------------------------------------

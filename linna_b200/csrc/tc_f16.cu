@@ -128,6 +128,11 @@ struct TfArgs {
     int32_t slots;            // walker pairs interleaved per cluster: 2, or 1 when the batch cannot fill the GPU twice
     int *err;
     long long *dbg;           // optional [grid][8] cycle counters (LINNA_TC_DEBUG): where the service warps wait
+    // rows whose result came out NaN (an activation beyond the fp16 range, |x| > 65504, turns into inf - inf): their
+    // indices are appended here and the FP32 FFMA kernel recomputes exactly these rows right after this launch
+    int32_t *fix_count;
+    int32_t *fix_rows;
+    int32_t fix_cap;
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -323,6 +328,13 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
     hi = *reinterpret_cast<const uint32_t *>(&h);
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
+// max that PROPAGATES NaN (fmaxf returns the other operand): a relu must not turn the NaN of an fp16 overflow into 0
+__device__ __forceinline__ float max_nan(float a, float b)
+{
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
 __device__ __forceinline__ float tf_prior_map(float u, int kind, float scale, float shift)
 {
     float t = u;
@@ -428,7 +440,7 @@ __device__ __forceinline__ void tf_chunk_epilogue(const float (&racc)[128], cons
                 const int li = 64 * h + 8 * j + e;   // column inside this group's 128
                 float y = fmaf(racc[li], VSCALE ? s[e] : inv_scale, BIAS ? b[e] : 0.f);
                 if (EXPY) y = cb + e < st.N ? expf(y) - __ldg(st.sub + cb + e) : 0.f;
-                y = fmaxf(y, clampv);
+                y = max_nan(y, clampv);
                 if (APPLY) y = ((mw[li >> 5] >> (li & 31)) & 1u) ? y : 0.f;
                 if (SAVE) mw[li >> 5] |= (y > 0.f ? 1u : 0u) << (li & 31);
                 if (CHI) chi_f = fmaf(y, y, chi_f);
@@ -942,7 +954,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (gi == 0 && grow < args.n && args.lnp) {
                     float l = (float)(-0.5 * (chi2[slot] + chi_s[row])) * c.inv_T + lnprior2[slot];   // util.py:1013
-                    if (l != l) l = -INFINITY;                                                     // util.py:1015-1016
+                    if (l != l) {
+                        l = -INFINITY;                                                             // util.py:1015-1016
+                        if (args.fix_rows) {   // fp16 overflow or a NaN input: the FP32 kernel decides (it redoes this row)
+                            const int k = atomicAdd(args.fix_count, 1);
+                            if (k < args.fix_cap) args.fix_rows[k] = (int32_t)grow;
+                        }
+                    }
                     args.lnp[grow] = l;
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -978,6 +996,10 @@ struct TcContext {
     TfProgram *prog_dev = nullptr;   // [0] LNP, [1] GRAD
     int *err_dev = nullptr;
     long long *dbg_dev = nullptr;
+    int32_t *fix_count = nullptr;     // [2]: ping-pong counters of flagged rows (launch k uses [k & 1])
+    int32_t *fix_rows = nullptr;      // [fix_cap]
+    int64_t fix_cap = 0;
+    uint64_t launches = 0;
     bool has_grad = false;
     int grid = 0;
     std::string error;
@@ -1004,6 +1026,8 @@ void tc_destroy(TcContext *t)
     if (t->prog_dev) cudaFree(t->prog_dev);
     if (t->err_dev) cudaFree(t->err_dev);
     if (t->dbg_dev) cudaFree(t->dbg_dev);
+    if (t->fix_count) cudaFree(t->fix_count);
+    if (t->fix_rows) cudaFree(t->fix_rows);
     delete t;
 }
 
@@ -1382,6 +1406,8 @@ TcContext *tc_build(const linna_model *m, std::string &why)
     cudaMemcpy(t->prog_dev, pgs, 2 * sizeof(TfProgram), cudaMemcpyHostToDevice);
     if (cudaMalloc(&t->err_dev, sizeof(int)) != cudaSuccess) return bail("cudaMalloc err");
     cudaMemset(t->err_dev, 0, sizeof(int));
+    if (cudaMalloc(&t->fix_count, 2 * sizeof(int32_t)) != cudaSuccess) return bail("cudaMalloc fix_count");
+    cudaMemset(t->fix_count, 0, 2 * sizeof(int32_t));
     if (getenv("LINNA_TC_DEBUG")) {
         if (cudaMalloc(&t->dbg_dev, (size_t)t->grid * TF_DBG_STRIDE * sizeof(long long)) != cudaSuccess) return bail("cudaMalloc dbg");
         cudaMemset(t->dbg_dev, 0, (size_t)t->grid * TF_DBG_STRIDE * sizeof(long long));
@@ -1405,11 +1431,28 @@ int tc_debug_read(TcContext *t, long long *out, int max_ctas)
     return n;
 }
 
+// Where the launch that is about to be made will list its NaN rows: (rows, count of this launch, count of the next
+// launch -- the fix-up kernel clears it).
+void tc_fix_buffers(TcContext *t, const int32_t **rows, const int32_t **count, int32_t **next_count)
+{
+    *rows = t->fix_rows, *count = t->fix_count + (t->launches & 1), *next_count = t->fix_count + ((t->launches + 1) & 1);
+}
+
 static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const float *u, int64_t n, float *lnp, float *grad,
                              cudaStream_t stream)
 {
+    if (t->fix_cap < n) {   // stream-ordered with every launch that used the old list (one model, chained launches)
+        if (t->fix_rows) cudaFreeAsync(t->fix_rows, stream);
+        t->fix_rows = nullptr, t->fix_cap = 0;
+        const int64_t want = n + n / 4 + 1024;
+        cudaError_t e = cudaMallocAsync(&t->fix_rows, (size_t)want * sizeof(int32_t), stream);
+        if (e != cudaSuccess) return e;
+        t->fix_cap = want;
+    }
     TfArgs a;
     memset(&a, 0, sizeof a);
+    a.fix_count = t->fix_count + (t->launches & 1), a.fix_rows = t->fix_rows;
+    a.fix_cap = (int32_t)std::min<int64_t>(t->fix_cap, 0x7fffffff);
     a.prog = t->prog_dev + pk, a.maps = t->maps_dev, a.c = m->consts;
     a.in = u, a.lnp = lnp, a.grad = grad, a.masks = t->masks, a.n = n, a.err = t->err_dev, a.dbg = t->dbg_dev;
     const int64_t pairs = (n + 2 * TF_M - 1) / (2 * TF_M);
@@ -1426,6 +1469,9 @@ static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const f
     else tc_f16_kernel<false><<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(a);
     return cudaGetLastError();
 }
+
+// the launch has been followed by its fix-up kernel: the next one uses the other counter
+void tc_launch_done(TcContext *t) { ++t->launches; }
 
 cudaError_t tc_launch_lnp(const linna_model *m, TcContext *t, const float *u, int64_t n, float *lnp, cudaStream_t stream)
 {

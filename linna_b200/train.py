@@ -85,6 +85,10 @@ class FusedTrainer:
                                    self.weight_decay, fuse_adam=True, loss_mean=out)
         return out
 
+    def kernel_path(self):
+        """'tc' when the optimiser step runs on the tensor-core (tcgen05) training kernels, else 'ffma'."""
+        return "ffma"
+
     # -- validation metric (Val_metric_fn, linna/util.py:1118-1127) ------------------------
     def val_metric(self, X, Y, cmd):
         mnn = self.engine.train_chisq(X, Y, 0)

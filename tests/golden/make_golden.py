@@ -78,7 +78,7 @@ def build_reference_objects(p, dtype=torch.float32):
     return pred, yinv, transform
 
 
-def eval_reference(p, u, dtype=torch.float32, want_m_rows=8):
+def eval_reference(p, u, dtype=torch.float32, want_m_rows=8, want_hess_rows=2):
     pred, yinv, transform = build_reference_objects(p, dtype)
     data = torch.tensor(p.data.astype(np.float32)).to(dtype)
     invcov = torch.tensor(p.inv_cov.astype(np.float32)).to(dtype)
@@ -93,6 +93,14 @@ def eval_reference(p, u, dtype=torch.float32, want_m_rows=8):
         g = torch.autograd.grad(val, x)[0]
         lnp.append(val.item())
         grad.append(g.detach().numpy().astype(np.float64))
+    # Hessian of lnP at the first rows by double backward: the body of the reference's Ddlnp.__call__
+    # (util.py:1043-1051; its constructor is broken at HEAD, SURVEY Q2, so the Log_prob above is used directly)
+    hess = []
+    for row in u[:want_hess_rows]:
+        x = torch.tensor(row, dtype=dtype).clone().requires_grad_()
+        val = lp(x, returntorch=True, inputnumpy=False)
+        g1 = torch.autograd.grad(val, x, create_graph=True)[0]
+        hess.append(torch.stack([torch.autograd.grad(g1[i], x, retain_graph=True)[0] for i in range(len(g1))]).detach().numpy())
     # batched predict through the reference's own Predictor (predictor_gpu.py:461-504)
     ub = torch.tensor(u[:want_m_rows], dtype=dtype)
     theta = transform(ub, inputnumpy=False, returnnumpy=False).reshape(-1, p.n_in)
@@ -102,7 +110,7 @@ def eval_reference(p, u, dtype=torch.float32, want_m_rows=8):
         y = pred.predict(theta, no_grad=True)
         m = yinv(y)
     return dict(lnp=np.array(lnp), grad=np.array(grad), theta=theta.detach().numpy(),
-                yhat=yhat.numpy(), y=y.numpy(), m=m.detach().numpy())
+                yhat=yhat.numpy(), y=y.numpy(), m=m.detach().numpy(), hess=np.array(hess, dtype=np.float64))
 
 
 def pack_problem(p):
@@ -277,11 +285,49 @@ def train_case(name, n_in, n_out, batch, nsteps, kind="ChtoModelv2", store_full=
         losses.append(loss.item())
     out["losses"] = np.array(losses)
     out["keys"] = np.array(keys)
+    # the same steps with the same (float32-valued) constants and inputs, every operation in float64: the error budget
+    # the float32 reference itself spends (tests hold the CUDA step to a small multiple of it)
+    pred64, _, _ = build_reference_objects(p, torch.float64)
+    ytd64 = U.Y_transform_data(p.sigma, device)
+    ytd64.sigma = ytd64.sigma.detach().double()
+    data64 = data_t.double()
+    yinvt64 = U.Y_invtransform_class(torch.tensor(p.y_mean).double(), torch.tensor(p.y_std).double(), data64, device,
+                                     ypositive=ypositive)
+    loss64 = U.Loss_fn(data64, torch.tensor(p.cov), torch.tensor(p.inv_cov), ytd64, yinvt64, device)
+    aux64 = loss64.auxileryfunction
+    aux64.inv_transformed_cov = torch.inverse(aux64.transformed_cov).detach()      # the reference casts this one to float32
+    aux64.inv_transformed_cov = aux64.inv_transformed_cov.float().double()         # same float32-valued constant, float64 math
+    aux64.data_in = aux64.data_in.float().double()
+    model64 = pred64.model
+    model64.train()
+    opt64 = torch.optim.AdamW(params=model64.parameters(), lr=lr, weight_decay=1e-4)
+    losses64 = []
+    for s in range(nsteps):
+        X = torch.tensor(theta[s * batch:(s + 1) * batch], dtype=torch.float32).double()
+        Y = torch.tensor(target[s * batch:(s + 1) * batch], dtype=torch.float32).double()
+        opt64.zero_grad()
+        y_pred = model64(pred64.X_transform(X))
+        loss = loss64(y_pred, Y)
+        loss.backward()
+        if s == 0:
+            grads64 = {k: prm.grad.detach().numpy().copy() for k, prm in model64.named_parameters()}
+            with torch.no_grad():
+                l_, cmd_, cnd_ = aux64(y_pred.detach(), Y)
+                out["f64_loss_rows"], out["f64_chisqMd"], out["f64_chisqnnd"] = l_.numpy(), cmd_.numpy(), cnd_.numpy()
+        opt64.step()
+        losses64.append(loss.item())
+    out["f64_losses"] = np.array(losses64)
+    sd64 = model64.state_dict()
+    # what the float32 reference itself loses against float64 (max-norm relative, per tensor)
+    out["f32_grad0_err"] = np.array([float(np.max(np.abs(grads[k] - grads64[k])) / max(np.max(np.abs(grads64[k])), 1e-300)) for k in keys])
+    out["f32_final_err"] = np.array([float(np.max(np.abs(model.state_dict()[k].numpy() - sd64[k].numpy()))) for k in keys])
     sd = model.state_dict()
     if store_full:
         for k in keys:
             out["grad0_" + k] = grads[k]
             out["final_" + k] = sd[k].numpy()
+            out["f64_grad0_" + k] = grads64[k]
+            out["f64_final_" + k] = sd64[k].numpy()
     else:
         out["grad0_sum"] = np.array([float(grads[k].astype(np.float64).sum()) for k in keys])
         out["grad0_norm"] = np.array([float(np.linalg.norm(grads[k].astype(np.float64))) for k in keys])
@@ -291,8 +337,13 @@ def train_case(name, n_in, n_out, batch, nsteps, kind="ChtoModelv2", store_full=
         out["final_layer8_row0"] = sd["layer8.weight"][0].numpy()
         out["grad0_layer1"] = grads["layer1.weight"]
         out["final_layer1"] = sd["layer1.weight"].numpy()
+        out["f64_grad0_norm"] = np.array([float(np.linalg.norm(grads64[k])) for k in keys])
+        out["f64_final_norm"] = np.array([float(sd64[k].norm()) for k in keys])
+        out["f64_grad0_layer8_row0"] = grads64["layer8.weight"][0]
+        out["f64_grad0_layer1"] = grads64["layer1.weight"]
+        out["f64_final_layer1"] = sd64["layer1.weight"].numpy()
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-    print(name, "losses", losses, flush=True)
+    print(name, "losses", losses, "f64", losses64, "f32 grad err", out["f32_grad0_err"].max(), "final", out["f32_final_err"].max(), flush=True)
 
 
 if __name__ == "__main__":

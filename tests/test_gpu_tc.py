@@ -6,9 +6,15 @@ tensor core's truncating fp32 accumulator is drained into round-to-nearest regis
 every few k-chunks, so the result tracks the FP32 FFMA kernel to a few ulp; the bars below are
 written against a float64 run of the reference modules (tests/golden) / the float64 oracle:
 
-    |d lnL|  <= TC_REL * |lnL| + 1e-4      (1e-4 absolute is north_star's bar; the relative term is
-                                            the float32 resolution of lnL itself)
+    |d lnL|  <= max(1e-4, 4 ulp_f32(|lnL|))   -- tests.helpers.lnp_tol, the SAME bar the exact-FP32 kernel is held to
+                                            (1e-4 absolute is north_star's bar; below |lnL| ~ 400 it is the binding
+                                            term, above it float32 resolution of lnL itself is: the reference returns
+                                            float32 and is itself 0.6 - 0.75 of this bar away from float64 on these
+                                            goldens, profiles/r2_parity_probe.txt)
     gradient: relative infinity-norm error < 2e-4 (same bar as the FFMA kernel)
+
+Rows in which an activation leaves the fp16 range come out NaN on the tensor-core path (the relu clamp propagates
+NaN) and are recomputed by the FP32 kernel in a fix-up launch: `test_tc_fp16_overflow_rows_are_fixed_up`.
 """
 import numpy as np
 import pytest
@@ -17,15 +23,13 @@ torch = pytest.importorskip("torch")
 
 from linna_b200 import arch, engine, synthetic
 from oracle.oracle import Oracle
-from tests.helpers import fixture_problem, load_golden, problem_from_golden
+from tests.helpers import fixture_problem, lnp_tol, load_golden, problem_from_golden
 
 pytestmark = pytest.mark.gpu
 
-TC_REL = 1e-6
-
 
 def tc_tol(lnp):
-    return TC_REL * np.abs(lnp) + 1e-4
+    return lnp_tol(lnp)
 
 
 def _dev(a):
@@ -156,6 +160,51 @@ def test_tc_grad_far_from_the_peak():
     assert np.median(relf) < 1e-5 and np.mean(relf > 2e-4) < 0.02
 
 
+def test_tc_fp16_overflow_rows_are_fixed_up():
+    """An input normalisation with a tiny X_std puts xhat (and the first activations) of some walkers beyond the fp16
+    range (65 504): the reference, in float32, returns a finite lnP for them.  On the tensor-core path such a row turns
+    into NaN, is flagged, and the FP32 kernel recomputes exactly those rows in the fix-up launch -- value and gradient
+    agree with the float64 oracle like any other row, and the neighbours are untouched."""
+    p = synthetic.make_problem(12, 40, seed=21)
+    p.X_std = p.X_std.copy()
+    p.X_std[3] = 2e-5                                   # theta_3 in [-5, 5]  ->  |xhat_3| up to 2.5e5
+    e = engine.engine_from_problem(p, with_likelihood=False)
+    m0 = e.predict(np.asarray(p.theta0, np.float32)[None, :], engine.LINNA_OUT_M)[0]
+    p.set_data_from_prediction(m0)
+    e.set_likelihood(p.priors, np.asarray(p.data, np.float32), p.inv_cov, 1.0)
+    n = 3000
+    u = synthetic.walkers(n, 12, scale=0.3, seed=2)
+    u[:, 3] *= 1e-4                                     # most walkers: |xhat_3| <~ 4e3, inside the fp16 range
+    hot = np.arange(5, n, 97)
+    u[hot, 3] = np.linspace(0.4, 1.2, hot.size) * np.where(np.arange(hot.size) % 2, 1, -1)   # |xhat_3| ~ 0.8e5 .. 2e5
+    o = Oracle(p, arch)
+    ref = o.lnp(u, np.float64, grad=True)
+    assert np.all(np.isfinite(ref["lnp"]))
+    e.set_path("tc")
+    l0 = engine.launch_count()
+    lnp, grad = e.lnp_grad(_dev(u))
+    lnp, grad = lnp.cpu().numpy(), grad.cpu().numpy().astype(np.float64)
+    assert e.last_kernel() == "tc" and engine.launch_count() - l0 == 2     # tensor-core launch + fix-up launch
+    assert np.all(np.isfinite(lnp)), np.where(~np.isfinite(lnp))[0][:10]
+    err = np.abs(lnp - ref["lnp"]) / tc_tol(ref["lnp"])
+    cold = np.setdiff1d(np.arange(n), hot)
+    assert err[cold].max() <= 1.0, (err[cold].max(), cold[np.argmax(err[cold])])
+    # the fixed-up rows sit at chi^2 ~ 1e8 .. 1e10: the FP32 kernel's own accuracy there (a few 1e-6 relative)
+    assert np.all(np.abs(lnp[hot] - ref["lnp"][hot]) <= 5e-6 * np.abs(ref["lnp"][hot])), np.abs(lnp[hot] / ref["lnp"][hot] - 1).max()
+    e.set_path("ffma")
+    ff = e.lnp(_dev(u)).cpu().numpy()[hot].astype(np.float64)     # they ARE FP32-kernel rows (8-row tiles in the fix-up)
+    assert np.all(np.abs(ff - lnp[hot]) <= 2e-6 * np.abs(ff))
+    e.set_path("tc")
+    rel = np.max(np.abs(grad - ref["grad"]), axis=1) / np.max(np.abs(ref["grad"]), axis=1)
+    assert np.median(rel) < 1e-5 and rel[cold].max() < 2e-4 and rel[hot].max() < 1e-3, (np.median(rel), rel[cold].max(), rel[hot].max())
+    assert np.array_equal(e.lnp(_dev(u)).cpu().numpy(), lnp.astype(np.float32))
+    # a NaN input is still -inf (util.py:1015-1016) after the fix-up
+    u2 = u.copy()
+    u2[11, 0] = np.nan
+    out = e.lnp(_dev(u2)).cpu().numpy()
+    assert np.isneginf(out[11]) and np.all(np.isfinite(np.delete(out, 11)))
+
+
 @pytest.mark.parametrize("n_in,n_out", [(3, 37), (64, 40), (17, 129), (8, 257)])
 def test_tc_odd_shapes(n_in, n_out):
     """Widths that are not multiples of anything: K / N padding, a 2-chunk last layer (257), the widest input the
@@ -210,7 +259,7 @@ def test_tc_segment_lengths_and_slots(monkeypatch, seg_kc, slots):
     assert e.last_kernel() == "tc"
     lnp, grad = lnp.cpu().numpy(), grad.cpu().numpy().astype(np.float64)
     n = g["u"].shape[0]
-    tol = tc_tol(g["f64_lnp"]) * (2.0 if seg_kc > 6 else 1.0)   # longer segments: more truncated accumulations
+    tol = tc_tol(g["f64_lnp"]) * (2.0 if seg_kc != 6 else 1.0)   # 6 is what ships; other lengths are protocol tests
     for r in (0, reps // 2, reps - 1):
         sl = slice(r * n, (r + 1) * n)
         assert np.all(np.abs(lnp[sl] - g["f64_lnp"]) <= tol), np.abs(lnp[sl] - g["f64_lnp"]).max()
