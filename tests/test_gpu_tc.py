@@ -119,7 +119,8 @@ def test_tc_full_size_c3():
     assert np.array_equal(e.lnp(_dev(u[idx])).cpu().numpy(), a[idx])
     e.set_path("ffma")
     f = e.lnp(ud).cpu().numpy()
-    assert np.all(np.abs(a - f) <= tc_tol(f)), np.abs(a - f).max()
+    # two float32 results that are each within the bar of the float64 value can be two bars apart
+    assert np.all(np.abs(a - f) <= 2 * tc_tol(f)), np.abs(a - f).max()
     lf, gf = e.lnp_grad(ud)
     ga, gf = ga.cpu().numpy(), gf.cpu().numpy()
     # The gradient is discontinuous where a relu pre-activation crosses zero: a unit whose pre-activation is
@@ -128,9 +129,10 @@ def test_tc_full_size_c3():
     # that a few dozen rows; everything else has to agree to the usual bar.
     rel = np.max(np.abs(ga - gf), axis=1) / np.max(np.abs(gf), axis=1)
     assert np.median(rel) < 1e-5 and np.mean(rel > 2e-4) < 1e-3, (np.median(rel), np.mean(rel > 2e-4))
-    idx = np.random.default_rng(0).choice(n, 64, replace=False)
+    idx = np.random.default_rng(0).choice(n, 2048, replace=False)
     ref = Oracle(p, arch).lnp(u[idx], np.float64)["lnp"]
     assert np.all(np.abs(a[idx] - ref) <= tc_tol(ref)), np.abs(a[idx] - ref).max()
+    assert np.all(np.abs(f[idx] - ref) <= tc_tol(ref)), np.abs(f[idx] - ref).max()
 
 
 def test_tc_grad_far_from_the_peak():

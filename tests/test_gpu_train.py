@@ -1,5 +1,12 @@
 """GPU parity of the fused training step (forward + loss + backward + AdamW) against goldens made
-by the reference's own Loss_fn / autograd / torch.optim.AdamW (tests/golden/make_golden.py)."""
+by the reference's own Loss_fn / autograd / torch.optim.AdamW (tests/golden/make_golden.py).
+
+Bars.  Every golden holds the reference's float32 result AND a float64 run of the same reference modules on the same
+float32-valued constants, so the error the reference itself spends is known per quantity (`f32_grad0_err`: 3.5e-6 /
+3.1e-6 max-norm relative for the well-conditioned cases, 0.2 for the log-normal `ypositive` case, whose normalised
+covariance is ill-conditioned).  The CUDA step has to (a) agree with the reference's float32 numbers to 2e-5 -- a hundred
+times tighter than round 1's 2e-3 and ~5x what was measured (profiles/r2_parity_probe.txt: 6.6e-7 .. 3.9e-6) -- and
+(b) be no further from float64 than max(4 x the reference's own float32 error, 1e-5)."""
 import numpy as np
 import pytest
 
@@ -36,28 +43,39 @@ def test_loss_and_gradients(name, full):
     Y = torch.from_numpy(g["target"][:B].astype(np.float32)).cuda()
     cmd_raw = e.train_chisq(X, Y, 1)
     cmd = torch.clamp(cmd_raw, min=0.5 * p.n_out)                      # util.py:1086
-    np.testing.assert_allclose(cmd.cpu().numpy(), g["chisqMd"], rtol=2e-4)
-    np.testing.assert_allclose(e.train_chisq(X, Y, 2).cpu().numpy(), g["chisqnnd"], rtol=2e-3)
+    np.testing.assert_allclose(cmd.cpu().numpy(), g["chisqMd"], rtol=3e-6)
+    nnd = e.train_chisq(X, Y, 2)
+    np.testing.assert_allclose(nnd.cpu().numpy(), g["chisqnnd"], rtol=3e-6)
     mnn = e.train_chisq(X, Y, 0)
-    np.testing.assert_allclose((mnn / cmd).cpu().numpy(), g["loss_rows"], rtol=2e-3, atol=1e-9)
+    np.testing.assert_allclose((mnn / cmd).cpu().numpy(), g["loss_rows"], rtol=3e-5, atol=1e-10)
+    # Val_metric_fn (linna/util.py:1124-1127) through FusedTrainer.val_metric, against the reference's own output
+    import types
+    from linna_b200.train import FusedTrainer
+    vm = FusedTrainer.val_metric(types.SimpleNamespace(engine=e), X, Y, cmd).cpu().numpy()
+    np.testing.assert_allclose(vm[0], g["val_metric"][0], rtol=1e-5)
+    np.testing.assert_allclose(vm[1:], g["val_metric"][1:], rtol=3e-4)     # |chi2_nn,d / chi2_M,d - 1|: a difference of near-equal numbers
     grads = torch.zeros_like(w)
     loss, rows = e.train_step(X, Y, cmd, None, None, None, grads, 1, float(g["lr"]), fuse_adam=False)
     torch.cuda.synchronize()
-    assert abs(float(loss) - g["losses"][0]) <= 2e-3 * abs(g["losses"][0])
-    np.testing.assert_allclose(rows.cpu().numpy(), g["loss_rows"], rtol=2e-3, atol=1e-9)
+    assert abs(float(loss) - g["losses"][0]) <= 3e-6 * abs(g["losses"][0])
+    np.testing.assert_allclose(rows.cpu().numpy(), g["loss_rows"], rtol=3e-5, atol=1e-10)
     gd = unflatten(grads.cpu().numpy(), shapes)
     keys = [str(k) for k in g["keys"]]
+    budget = max(4.0 * float(g["f32_grad0_err"].max()), 1e-5)   # what the reference's own float32 spends, x 4
+
+    def check(got, ref32, ref64, what):
+        scale = np.max(np.abs(ref64))
+        assert np.max(np.abs(got - ref32)) <= 2e-5 * scale + 1e-12, (what, np.max(np.abs(got - ref32)) / scale)
+        assert np.max(np.abs(got - ref64)) <= budget * scale + 1e-12, (what, np.max(np.abs(got - ref64)) / scale)
     if full:
         for k in keys:
-            ref = g["grad0_" + k]
-            assert np.max(np.abs(gd[k] - ref)) <= 2e-3 * np.max(np.abs(ref)) + 1e-12, k
+            check(gd[k], g["grad0_" + k], g["f64_grad0_" + k], k)
     else:
         norms = np.array([np.linalg.norm(gd[k].astype(np.float64)) for k in keys])
-        np.testing.assert_allclose(norms, g["grad0_norm"], rtol=2e-3)
-        ref = g["grad0_layer1"]
-        assert np.max(np.abs(gd["layer1.weight"] - ref)) <= 2e-3 * np.max(np.abs(ref))
-        ref = g["grad0_layer8_row0"]
-        assert np.max(np.abs(gd["layer8.weight"][0] - ref)) <= 2e-3 * np.max(np.abs(ref))
+        np.testing.assert_allclose(norms, g["grad0_norm"], rtol=5e-6)
+        np.testing.assert_allclose(norms, g["f64_grad0_norm"], rtol=5e-6)
+        check(gd["layer1.weight"], g["grad0_layer1"], g["f64_grad0_layer1"], "layer1.weight")
+        check(gd["layer8.weight"][0], g["grad0_layer8_row0"], g["f64_grad0_layer8_row0"], "layer8.weight[0]")
 
 
 @pytest.mark.parametrize("name,full", [("train_small", True), ("train_ypos", True), ("train_c3", False)])
