@@ -185,6 +185,12 @@ int linna_train_step(linna_model_t *m, const float *X, const float *Y, const flo
                      float *adam_m, float *adam_v, float *grads, int64_t step, float lr, float beta1, float beta2,
                      float eps, float weight_decay, int32_t fuse_adam, float *loss_rows, float *loss_mean,
                      void *stream);
+/* Which kernels run linna_train_step / linna_train_chisq: 0 = automatic (the default: the tensor-core (tcgen05, bf16x3
+ * split) kernels whenever the network shape is covered -- LINEAR / RES ops with a skip matrix, LINEAR last layer --, the
+ * FP32 FFMA kernels otherwise), 1 = FP32 FFMA kernels only, 2 = tensor-core only (LINNA_EINVAL when unavailable). */
+int linna_train_set_path(linna_model_t *m, int32_t path);
+/* Kernel family that served the last training call on this model: 0 none yet, 1 FP32 FFMA, 2 tensor core. */
+int linna_train_last_kernel(const linna_model_t *m);
 /* torch.optim.AdamW update from an (all-reduced) flat gradient; refreshes the packed weights. */
 int linna_train_adamw(linna_model_t *m, float *params, float *adam_m, float *adam_v, const float *grads, int64_t step,
                       float lr, float beta1, float beta2, float eps, float weight_decay, void *stream);

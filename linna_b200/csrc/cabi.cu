@@ -1,6 +1,7 @@
 // C-ABI of linna_b200 (see include/linna_b200.h): model packing, step-program construction and
 // kernel dispatch.  Host code only; the kernels live in fused_ffma.cu, tc_f16.cu, train_kernels.cu and sampler_kernels.cu.
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -30,6 +31,13 @@ bool tc_has_grad(const TcContext *t);
 void tc_fix_buffers(TcContext *t, const int32_t **rows, const int32_t **count, int32_t **next_count);
 void tc_launch_done(TcContext *t);
 int tc_debug_read(TcContext *t, long long *out, int max_ctas);
+TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> &flat_off,
+                    const std::vector<std::array<const float *, 2>> &bias_ptr, std::string &why);
+void tg_destroy(TgContext *t);
+cudaError_t tg_repack(TgContext *t, const float *params, cudaStream_t stream);
+int tg_train_step(const linna_model *m, TgContext *t, const float *X, const float *Y, const float *cmd, int64_t B, const AdamArgs &ad,
+                  float *loss_rows, float *loss_mean, cudaStream_t stream);
+int tg_chisq(const linna_model *m, TgContext *t, const float *X, const float *Y, int64_t n, int kind, float *chi2, cudaStream_t stream);
 }  // namespace linna
 
 static thread_local std::string g_err;
@@ -105,6 +113,7 @@ static void free_device(linna_model *m)
     if (m->wg_tiles_dev) cudaFree(m->wg_tiles_dev);
     if (m->map_fwd_dev) cudaFree(m->map_fwd_dev);
     if (m->map_bwd_dev) cudaFree(m->map_bwd_dev);
+    if (m->tg) { tg_destroy(m->tg); m->tg = nullptr; }
     m->blob = nullptr, m->prog_dev = nullptr, m->arena = nullptr, m->masks = nullptr, m->rm = nullptr;
     m->wg_layers_dev = nullptr, m->wg_tiles_dev = nullptr, m->map_fwd_dev = nullptr, m->map_bwd_dev = nullptr;
 }
@@ -115,6 +124,7 @@ static int rebuild(linna_model *m)
     CUDA_TRY(cudaSetDevice(m->device));
     CUDA_TRY(cudaDeviceSynchronize());  // no launch may still be reading the blob we are about to replace
     if (m->tc) { tc_destroy(m->tc); m->tc = nullptr; }
+    if (m->tg) { tg_destroy(m->tg); m->tg = nullptr; }
     m->tc_failed = false;
     const int n_in = m->n_in, n_out = m->n_out;
     Builder B;
@@ -611,6 +621,19 @@ static int rebuild(linna_model *m)
         }
     }
     CUDA_TRY(cudaDeviceSynchronize());
+    if (m->has_train) {
+        // tensor-core training kernels (tg_gemm.cu); the FP32 kernels above stay as the path for shapes they do not cover
+        std::vector<std::array<int, 5>> flat_off(m->ops.size());
+        std::vector<std::array<const float *, 2>> bias_ptr(m->ops.size());
+        for (size_t i = 0; i < m->ops.size(); ++i) {
+            flat_off[i] = {fo[i].w, fo[i].b, fo[i].w2, fo[i].b2, fo[i].ws};
+            bias_ptr[i] = {P(off[i].b), m->ops[i].kind == LINNA_OP_RES ? P(off[i].b2) : nullptr};
+        }
+        m->tg_why.clear();
+        if (!getenv("LINNA_TRAIN_NO_TC")) m->tg = tg_build(m, flat_off, bias_ptr, m->tg_why);
+        else m->tg_why = "LINNA_TRAIN_NO_TC set";
+        cudaGetLastError();
+    }
     return LINNA_OK;
 }
 
@@ -1082,6 +1105,21 @@ int linna_train_chisq(linna_model_t *m, const float *X, const float *Y, int64_t 
     if (!m || !m->has_train) return fail(LINNA_ESTATE, "linna_train_setup has not been called");
     if (kind < 0 || kind > 2) return fail(LINNA_EINVAL, "bad kind");
     if (n > 0 && (!Y || !chi2)) return fail(LINNA_EINVAL, "null buffer");
+    if (m->train_path == 2 && !m->tg) return fail(LINNA_EINVAL, "tensor-core training path unavailable: %s", m->tg_why.c_str());
+    if (m->tg && m->train_path != 1 && n > 0) {
+        if (!X) return fail(LINNA_EINVAL, "null input");
+        CUDA_TRY(cudaSetDevice(m->device));
+        cudaStream_t st = (cudaStream_t)stream;
+        if (m->have_last && m->last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, m->last_done, 0));
+        const int l = tg_chisq(m, m->tg, X, Y, n, kind, chi2, st);
+        if (l < 0) return fail(LINNA_ECUDA, "tensor-core chi^2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        g_launches.fetch_add(l);
+        m->last_train_kernel = 2;
+        CUDA_TRY(cudaEventRecord(m->last_done, st));
+        m->last_stream = st, m->have_last = true;
+        return LINNA_OK;
+    }
+    m->last_train_kernel = 1;
     KernelArgs p;
     memset(&p, 0, sizeof p);
     p.target = Y, p.delta_kind = kind, p.loss_inv_B = 1.f;
@@ -1112,6 +1150,21 @@ int linna_train_step(linna_model_t *m, const float *X, const float *Y, const flo
     if (fuse_adam ? (!params || !adam_m || !adam_v) : !grads) return fail(LINNA_EINVAL, "null optimiser buffer");
     if (step < 1) return fail(LINNA_EINVAL, "step counts from 1");
     cudaStream_t st = (cudaStream_t)stream;
+    if (m->train_path == 2 && !m->tg) return fail(LINNA_EINVAL, "tensor-core training path unavailable: %s", m->tg_why.c_str());
+    if (m->tg && m->train_path != 1) {
+        // tensor-core path: one launch per layer (forward, loss, backward-data), one for every weight gradient + AdamW
+        CUDA_TRY(cudaSetDevice(m->device));
+        if (m->have_last && m->last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, m->last_done, 0));
+        AdamArgs a = adam_args(m, params, adam_m, adam_v, grads, step, lr, beta1, beta2, eps, weight_decay, fuse_adam ? 1 : 0);
+        const int l = tg_train_step(m, m->tg, X, Y, cmd, B, a, loss_rows, loss_mean, st);
+        if (l < 0) return fail(LINNA_ECUDA, "tensor-core training launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        g_launches.fetch_add(l);
+        m->last_train_kernel = 2;
+        CUDA_TRY(cudaEventRecord(m->last_done, st));
+        m->last_stream = st, m->have_last = true;
+        return LINNA_OK;
+    }
+    m->last_train_kernel = 1;
     KernelArgs p;
     memset(&p, 0, sizeof p);
     p.target = Y, p.cmd = cmd, p.rm_base = m->rm, p.loss_inv_B = 1.0f / (float)B, p.delta_kind = 0;
@@ -1125,8 +1178,19 @@ int linna_train_step(linna_model_t *m, const float *X, const float *Y, const flo
         g_launches.fetch_add(1);
     }
     CUDA_TRY(cudaEventRecord(m->last_done, st));
+    m->last_stream = st, m->have_last = true;
     return LINNA_OK;
 }
+
+int linna_train_set_path(linna_model_t *m, int32_t path)
+{
+    if (!m || path < 0 || path > 2) return fail(LINNA_EINVAL, "path must be 0 (auto), 1 (FFMA) or 2 (tensor core)");
+    if (path == 2 && m->has_train && !m->tg) return fail(LINNA_EINVAL, "tensor-core training path unavailable: %s", m->tg_why.c_str());
+    m->train_path = path;
+    return LINNA_OK;
+}
+
+int linna_train_last_kernel(const linna_model_t *m) { return m ? m->last_train_kernel : 0; }
 
 int linna_train_adamw(linna_model_t *m, float *params, float *adam_m, float *adam_v, const float *grads, int64_t step,
                       float lr, float beta1, float beta2, float eps, float weight_decay, void *stream)
@@ -1139,6 +1203,10 @@ int linna_train_adamw(linna_model_t *m, float *params, float *adam_m, float *ada
     AdamArgs a = adam_args(m, params, adam_m, adam_v, const_cast<float *>(grads), step, lr, beta1, beta2, eps, weight_decay, 1);
     CUDA_TRY(launch_adamw(a, (int)m->n_params, m->num_sms, st));
     g_launches.fetch_add(1);
+    if (m->tg) {   // the tensor-core kernels' packed planes follow the flat vector
+        CUDA_TRY(tg_repack(m->tg, params, st));
+        g_launches.fetch_add(1);
+    }
     CUDA_TRY(cudaEventRecord(m->last_done, st));
     m->last_stream = st, m->have_last = true;
     return LINNA_OK;
@@ -1153,6 +1221,10 @@ int linna_train_load_params(linna_model_t *m, const float *params, void *stream)
     if (m->have_last && m->last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, m->last_done, 0));
     CUDA_TRY(launch_scatter_params(params, m->blob, m->map_fwd_dev, m->map_bwd_dev, (int)m->n_params, st));
     g_launches.fetch_add(1);
+    if (m->tg) {
+        CUDA_TRY(tg_repack(m->tg, params, st));
+        g_launches.fetch_add(1);
+    }
     CUDA_TRY(cudaEventRecord(m->last_done, st));
     m->last_stream = st, m->have_last = true;
     return LINNA_OK;

@@ -10,7 +10,8 @@
 using namespace linna;
 
 namespace linna {
-struct TcContext;   // tensor-core path state (tc_f16.cu)
+struct TcContext;   // tensor-core likelihood path state (tc_f16.cu)
+struct TgContext;   // tensor-core training path state (tg_gemm.cu)
 }
 
 static inline int pad4(int n) { return (n + 3) & ~3; }
@@ -50,6 +51,11 @@ struct linna_model {
     WgradTile *wg_tiles_dev = nullptr;
     int n_wg_tiles = 0;
     int32_t *map_fwd_dev = nullptr, *map_bwd_dev = nullptr;
+    // tensor-core (tcgen05, bf16x3) training kernels: built with the training constants when the network shape is covered
+    linna::TgContext *tg = nullptr;
+    std::string tg_why;            // why not
+    int train_path = 0;            // 0 auto (tensor core when available), 1 FP32 FFMA kernels, 2 tensor core only
+    int last_train_kernel = 0;     // 1 FFMA, 2 tensor core
     // device state
     float *blob = nullptr;
     size_t blob_floats = 0;

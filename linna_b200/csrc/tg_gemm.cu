@@ -1,0 +1,1022 @@
+// Tensor-core emulator TRAINING kernels (sm_100a: tcgen05 + TMEM + TMA): the forward pass, the loss, backward-data and
+// the weight gradients (+ AdamW) of Predictor.train's inner loop (linna/predictor_gpu.py:273-288) as tiled GEMMs.
+//
+// The sampling kernel (tc_f16.cu) gives every CTA pair whole walkers and walks all layers on them; a training batch
+// is only B = 500 rows, so here every LAYER is spread over the chip instead: one launch per layer, one CTA per
+// 128 x 64 output tile (4 row tiles x N/64 column tiles; the weight-gradient launch covers every layer's 128 x 64
+// tiles of dW at once, ~200 CTAs).
+//
+//   * bf16x3 products.  Every fp32 operand x is kept as three bf16 planes, h = bf16(x), m = bf16(x - h),
+//     l = bf16(x - h - m) (24 significant bits, fp32's exponent range: gradients of any magnitude and weights that
+//     drift during training need no scaling), and  D += A_m.B_m + A_h.B_l + A_l.B_h + A_h.B_m + A_m.B_h + A_h.B_h
+//     with exact bf16 x bf16 products and fp32 accumulation in tensor memory.
+//   * two-level accumulation as in tc_f16.cu: the tensor core truncates its fp32 accumulator on every instruction
+//     (~0.5 ulp of the accumulator, toward zero), so every k-chunk (64 values of K = 24 instructions) is drained from
+//     tensor memory and added with round-to-nearest into 64 register accumulators per epilogue thread -- and the three
+//     orders of magnitude of the split go to three SEPARATE tensor-memory accumulators (h.h | h.m + m.h | m.m + h.l +
+//     l.h), so that the 20 small-term instructions of a chunk truncate at THEIR magnitude (2^-8, 2^-16 of the sum) and
+//     only 4 instructions per chunk touch the leading accumulator (two buffers of 3 x 64 columns).
+//   * operands are 128-byte-swizzled tiles filled by TMA (3 stages x 72 KB): forward / backward-data read
+//     activations [batch][features] and weights [out][in] (or the transposed copy) K-major; the weight-gradient GEMM
+//     dW[n][k] = sum_b gz[b][n] x[b][k] contracts over the BATCH and reads the very same activation planes as
+//     MN-major operands (instruction-descriptor transpose bits), so no transposed activation copy exists.  The
+//     bias gradient is the extra column k == K of x, which every producer epilogue sets to 1.
+//   * epilogues (one thread = one output row, 64 columns): bias + relu + mask bits + bf16x3 split (forward), the
+//     normalised-space residual (loss head), chi^2 partials and d loss / d yhat (loss), relu-mask backward, and
+//     AdamW with the refresh of every packed copy of the weight (weight gradients).
+//   * warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2-5 = epilogue.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "linna_host.hpp"
+
+namespace linna {
+
+constexpr int TG_BM = 128, TG_BN = 64, TG_KC = 64;            // output tile; k-chunk = 64 bf16 = one 128-byte swizzle row
+constexpr int TG_STAGES = 3;
+constexpr int TG_A_PLANE = TG_BM * 128;                        // 16 KB: 128 rows (or 2 x 64 contraction rows) x 128 B
+constexpr int TG_B_PLANE = TG_BN * 128;                        // 8 KB
+constexpr int TG_STAGE_BYTES = 3 * (TG_A_PLANE + TG_B_PLANE);  // 72 KB
+constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_BYTES + 1024;
+constexpr int TG_THREADS = 192;
+
+enum TgEpi : int32_t { TG_ACT = 0, TG_HEAD = 1, TG_LOSSQ = 2, TG_BWD = 3 };
+
+struct TgStep {
+    int32_t epi, nphase;
+    int32_t mapA[2], mapB[2];     // tensor maps: A box 64 x 128 rows, B box 64 x 64 rows (both K-major)
+    int32_t rowsA[2], rowsB[2];   // rows per bf16 plane of the operand (plane p starts at row p * rows)
+    int32_t K[2];
+    int32_t N;                    // valid output columns
+    int32_t n_tiles;              // column tiles of 64
+    int64_t out_off;              // element offset of the output's plane 0 inside the activation blob
+    int32_t out_ld, out_rows;     // row pitch (elements) and rows per plane of the output
+    int32_t write_ones;           // column N of the output is the bias column of the next layer's input
+    int32_t relu, save_mask, apply_mask;
+    int64_t mask_off;             // word offset of this layer's relu bits (save) / of the producer's bits (apply)
+    int32_t mask_ld;              // words per row
+    float bias_scale;
+    const float *bias;            // [N] fp32 bias inside the model's FP32 blob (kept current by every AdamW path), or nullptr
+};
+
+struct TgWLayer {
+    int32_t mapA, mapB;           // gz planes / x planes as MN-major operands (box 64 x 64 batch rows)
+    int32_t N, K;
+    int32_t w_flat, b_flat;       // offsets into the flat parameter vector (b_flat < 0: no bias)
+    float gscale, pack_scale;     // alpha of a res-block's second layer (gradient and packed copies), else 1
+    int64_t wf_off, wb_off;       // plane 0 of the packed forward [N][K] / backward [K][N] copy (elements of the weight blob)
+    int32_t wf_ld, wf_rows, wb_ld, wb_rows;
+};
+struct TgWTile {
+    int32_t layer, m0, n0, pad_;
+};
+
+struct TgArgs {
+    const CUtensorMap *maps;
+    const TgStep *step;
+    __nv_bfloat16 *act;           // activation / gradient planes
+    uint32_t *masks;
+    int32_t B, B_pad;
+    int32_t B_eff;                // rows the layer launches of this step covered: 128 x row tiles (contraction of the weight-gradient GEMM)
+    // loss
+    const float *target;          // [B][n_out] physical targets
+    const float *cmd;             // [B] clamped chi2(target, data), or nullptr (chi^2 only)
+    float *delta32;               // [B_pad][dld] fp32 copy of the residual
+    int32_t dld;
+    float *chi_part;              // [B_pad][chi_ld] chi^2 partial of every column tile
+    int32_t chi_ld;
+    Consts c;
+    int32_t delta_kind;
+    float loss_inv_B;
+    int32_t want_grad;            // LOSSQ: also emit d loss / d yhat
+    // weight gradients
+    const TgWLayer *wlayers;
+    const TgWTile *wtiles;
+    __nv_bfloat16 *wblob;         // packed weight planes
+    AdamArgs adam;
+    int *err;
+};
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t tg_smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void tg_mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tg_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tg_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tg_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tg_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tg_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool tg_mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(tg_smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (and report) instead of hanging the GPU.
+__device__ __forceinline__ void tg_mbar_wait(uint64_t *bar, uint32_t parity, int *err, int code)
+{
+    if (tg_mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!tg_mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 2000000000LL) {
+            if (err) atomicExch(err, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ bool tg_elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tg_tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(tg_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(tg_smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tg_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tg_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, 128-byte swizzle.  K-major operand: rows are 128 B apart, 8-row groups 1024 B
+// (SBO); a K = 16 slice is a 32-byte step of the start address inside the swizzle row.  MN-major operand (the
+// weight-gradient GEMM: a tile row is one CONTRACTION index holding 64 consecutive M/N values): 8 contraction rows
+// are 1024 B (SBO), the next 64 M/N values are the next TMA box, `lbo` bytes further, and a K = 16 slice is 16 rows
+// = 2048 B.
+__device__ __forceinline__ uint64_t tg_sdesc(uint32_t saddr, uint32_t lbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16, bf16 inputs, fp32 accumulation, M = 128, N = 64; `mn_major`: both operands transposed (MN-major)
+__device__ __forceinline__ uint32_t tg_idesc(bool mn_major)
+{
+    uint32_t d = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TG_BN >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
+    if (mn_major) d |= (1u << 15) | (1u << 16);
+    return d;
+}
+__device__ __forceinline__ void tg_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tg_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tg_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tg_tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// x = h + m + l, three bf16 values; two numbers per call (packed bf16x2 words)
+__device__ __forceinline__ void tg_split3(float a, float b, uint32_t &h, uint32_t &m, uint32_t &l)
+{
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(hh);
+    const float ra = a - hf.x, rb = b - hf.y;
+    const __nv_bfloat162 mm = __floats2bfloat162_rn(ra, rb);
+    const float2 mf = __bfloat1622float2(mm);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(ra - mf.x, rb - mf.y);
+    h = *reinterpret_cast<const uint32_t *>(&hh);
+    m = *reinterpret_cast<const uint32_t *>(&mm);
+    l = *reinterpret_cast<const uint32_t *>(&ll);
+}
+
+// ------------------------------------------------------------------------------------------ GEMM core
+// One 128 x 64 output tile: sum over phases of A_p . B_p^T, result in `racc` of the epilogue threads (thread = tile
+// row (warp & 3) * 32 + lane).  K-major: A box (kc, plane * rowsA + m0) of 128 rows, B box (kc, plane * rowsB + n0)
+// of 64 rows.  MN-major (weight gradients): A boxes (m0 + 64 g, plane * rows + kc) for g = 0, 1, B box (n0, plane *
+// rows + kc), 64 contraction rows each.
+struct TgTileDesc {
+    const CUtensorMap *mapA[2], *mapB[2];
+    int32_t rowsA[2], rowsB[2], K[2];
+    int32_t nphase, m0, n0;
+    bool mn_major;
+};
+
+struct TgPipe {
+    uint64_t full_bar[TG_STAGES], empty_bar[TG_STAGES], tfull_bar[2], tempty_bar[2];
+    uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ void tg_gemm_tile(const TgTileDesc &t, uint8_t *smem, TgPipe &pp, float (&racc)[TG_BN], int *err)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TG_STAGES; ++s) tg_mbar_init(&pp.full_bar[s], 1), tg_mbar_init(&pp.empty_bar[s], 1);
+        for (int b = 0; b < 2; ++b) tg_mbar_init(&pp.tfull_bar[b], 1), tg_mbar_init(&pp.tempty_bar[b], 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tg_smem_u32(&pp.tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tg_fence_before();
+    __syncthreads();
+    tg_fence_after();
+    const uint32_t tmem_base = pp.tmem_slot;
+    int nk[2];
+    nk[0] = (t.K[0] + TG_KC - 1) / TG_KC, nk[1] = t.nphase > 1 ? (t.K[1] + TG_KC - 1) / TG_KC : 0;
+    const int total = nk[0] + nk[1];
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int p = 0; p < t.nphase; ++p)
+            for (int kc = 0; kc < nk[p]; ++kc) {
+                tg_mbar_wait(&pp.empty_bar[stage], ph ^ 1, err, 21);
+                if (tg_elect_one()) {
+                    uint8_t *sa = smem + stage * TG_STAGE_BYTES, *sb = sa + 3 * TG_A_PLANE;
+                    tg_mbar_expect_tx(&pp.full_bar[stage], TG_STAGE_BYTES);
+#pragma unroll
+                    for (int pl = 0; pl < 3; ++pl) {
+                        if (!t.mn_major) {
+                            tg_tma_load_2d(sa + pl * TG_A_PLANE, t.mapA[p], &pp.full_bar[stage], kc * TG_KC, pl * t.rowsA[p] + t.m0);
+                            tg_tma_load_2d(sb + pl * TG_B_PLANE, t.mapB[p], &pp.full_bar[stage], kc * TG_KC, pl * t.rowsB[p] + t.n0);
+                        } else {
+                            tg_tma_load_2d(sa + pl * TG_A_PLANE, t.mapA[p], &pp.full_bar[stage], t.m0, pl * t.rowsA[p] + kc * TG_KC);
+                            tg_tma_load_2d(sa + pl * TG_A_PLANE + TG_A_PLANE / 2, t.mapA[p], &pp.full_bar[stage], t.m0 + 64,
+                                           pl * t.rowsA[p] + kc * TG_KC);
+                            tg_tma_load_2d(sb + pl * TG_B_PLANE, t.mapB[p], &pp.full_bar[stage], t.n0, pl * t.rowsB[p] + kc * TG_KC);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (++stage == TG_STAGES) stage = 0, ph ^= 1;
+            }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        int stage = 0;
+        uint32_t ph = 0;
+        const uint32_t idesc = tg_idesc(t.mn_major);
+        const uint32_t kstep = t.mn_major ? (2048u >> 4) : (32u >> 4);   // descriptor start-address step of a K = 16 slice
+        for (int it = 0; it < total; ++it) {
+            const int buf = it & 1;
+            tg_mbar_wait(&pp.tempty_bar[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u, err, 23);
+            tg_mbar_wait(&pp.full_bar[stage], ph, err, 22);
+            tg_fence_after();
+            if (tg_elect_one()) {
+                const uint32_t sa = tg_smem_u32(smem + stage * TG_STAGE_BYTES), sb = sa + 3 * TG_A_PLANE;
+                const uint64_t ah = tg_sdesc(sa, TG_A_PLANE / 2), am = tg_sdesc(sa + TG_A_PLANE, TG_A_PLANE / 2),
+                               al = tg_sdesc(sa + 2 * TG_A_PLANE, TG_A_PLANE / 2);
+                const uint64_t bh = tg_sdesc(sb, TG_B_PLANE), bm = tg_sdesc(sb + TG_B_PLANE, TG_B_PLANE),
+                               bl = tg_sdesc(sb + 2 * TG_B_PLANE, TG_B_PLANE);
+                const uint32_t d0 = tmem_base + buf * (3 * TG_BN), d1 = d0 + TG_BN, d2 = d1 + TG_BN;   // h.h | 2^-8 | 2^-16 terms
+#pragma unroll
+                for (int ks = 0; ks < TG_KC / 16; ++ks) {
+                    const uint64_t o = (uint64_t)(ks * kstep);
+                    const uint32_t acc = ks > 0 ? 1u : 0u;
+                    tg_mma(d2, am + o, bm + o, idesc, acc);
+                    tg_mma(d2, ah + o, bl + o, idesc, 1u);
+                    tg_mma(d2, al + o, bh + o, idesc, 1u);
+                    tg_mma(d1, ah + o, bm + o, idesc, acc);
+                    tg_mma(d1, am + o, bh + o, idesc, 1u);
+                    tg_mma(d0, ah + o, bh + o, idesc, acc);
+                }
+                tg_commit(&pp.empty_bar[stage]);    // the operand stage is free when these MMAs retire
+                tg_commit(&pp.tfull_bar[buf]);      // and the partial tile can be drained
+            }
+            __syncwarp();
+            if (++stage == TG_STAGES) stage = 0, ph ^= 1;
+        }
+    } else {
+        // =============================== epilogue warps: drain every k-chunk ===============================
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll
+        for (int j = 0; j < TG_BN; ++j) racc[j] = 0.f;
+        for (int it = 0; it < total; ++it) {
+            const int buf = it & 1;
+            tg_mbar_wait(&pp.tfull_bar[buf], (uint32_t)(it >> 1) & 1u, err, 24);
+            tg_fence_after();
+#pragma unroll
+            for (int cb = 0; cb < TG_BN; cb += 32) {
+                uint32_t r0[32], r1[32], r2[32];
+                tg_tmem_ld32(tmem_lane + buf * (3 * TG_BN) + cb, r0);
+                tg_tmem_ld32(tmem_lane + buf * (3 * TG_BN) + TG_BN + cb, r1);
+                tg_tmem_ld32(tmem_lane + buf * (3 * TG_BN) + 2 * TG_BN + cb, r2);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    racc[cb + j] += (__uint_as_float(r2[j]) + __uint_as_float(r1[j])) + __uint_as_float(r0[j]);
+            }
+            tg_fence_before();
+            __syncwarp();
+            if (lane == 0) tg_mbar_arrive(&pp.tempty_bar[buf]);
+        }
+    }
+}
+
+__device__ __forceinline__ void tg_gemm_finish(TgPipe &pp)
+{
+    tg_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 1) {
+        tg_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(pp.tmem_slot), "r"(512) : "memory");
+    }
+}
+
+// 64 output values of one row -> the three bf16 planes of a row-major matrix (128 contiguous bytes per plane)
+__device__ __forceinline__ void tg_store_planes(__nv_bfloat16 *base, int64_t plane_stride, int64_t elem_off, const float (&v)[TG_BN])
+{
+#pragma unroll
+    for (int j = 0; j < TG_BN; j += 8) {
+        uint32_t h[4], m[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) tg_split3(v[j + e], v[j + e + 1], h[e >> 1], m[e >> 1], l[e >> 1]);
+        *reinterpret_cast<uint4 *>(base + elem_off + j) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(base + plane_stride + elem_off + j) = make_uint4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<uint4 *>(base + 2 * plane_stride + elem_off + j) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ layer kernel
+__global__ void __launch_bounds__(TG_THREADS, 1) tg_layer_kernel(const TgArgs args)
+{
+    extern __shared__ uint8_t tg_smem_raw[];
+    __shared__ TgPipe pp;
+    __shared__ TgStep st;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tg_smem_raw) + 1023) & ~(uintptr_t)1023);
+    for (int i = threadIdx.x; i < (int)(sizeof(TgStep) / 4); i += TG_THREADS)
+        reinterpret_cast<uint32_t *>(&st)[i] = reinterpret_cast<const uint32_t *>(args.step)[i];
+    __syncthreads();
+    TgTileDesc t;
+    t.nphase = st.nphase, t.mn_major = false;
+    for (int p = 0; p < 2; ++p) {
+        t.mapA[p] = args.maps + st.mapA[p], t.mapB[p] = args.maps + st.mapB[p];
+        t.rowsA[p] = st.rowsA[p], t.rowsB[p] = st.rowsB[p], t.K[p] = st.K[p];
+    }
+    const int nt = blockIdx.x % st.n_tiles, mt = blockIdx.x / st.n_tiles;
+    t.m0 = mt * TG_BM, t.n0 = nt * TG_BN;
+    float racc[TG_BN];
+    tg_gemm_tile(t, smem, pp, racc, args.err);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= 2) {
+        const int row = (warp & 3) * 32 + lane;
+        const int grow = t.m0 + row;
+        const bool valid = grow < args.B;
+        const int N = st.N, n0 = t.n0;
+        const Consts &c = args.c;
+        float v[TG_BN];
+        if (st.epi == TG_ACT || st.epi == TG_BWD) {
+            uint32_t mw[2] = {0u, 0u};
+            if (st.apply_mask) {
+                const uint2 m2 = *reinterpret_cast<const uint2 *>(args.masks + st.mask_off + (size_t)grow * st.mask_ld + (n0 >> 5));
+                mw[0] = m2.x, mw[1] = m2.y;
+            }
+            uint32_t sw[2] = {0u, 0u};
+#pragma unroll
+            for (int j = 0; j < TG_BN; ++j) {
+                const int col = n0 + j;
+                float y = racc[j];
+                if (st.bias && col < N) y += st.bias_scale * __ldg(st.bias + col);
+                if (st.relu) y = fmaxf(y, 0.f);
+                if (st.apply_mask) y = ((mw[j >> 5] >> (j & 31)) & 1u) ? y : 0.f;
+                if (st.save_mask) sw[j >> 5] |= (y > 0.f ? 1u : 0u) << (j & 31);
+                if (!(valid && col < N)) y = (valid && col == N && st.write_ones) ? 1.f : 0.f;
+                v[j] = y;
+            }
+            if (st.save_mask)
+                *reinterpret_cast<uint2 *>(args.masks + st.mask_off + (size_t)grow * st.mask_ld + (n0 >> 5)) = make_uint2(sw[0], sw[1]);
+            tg_store_planes(args.act + st.out_off, (int64_t)st.out_rows * st.out_ld, (int64_t)grow * st.out_ld + n0, v);
+        } else if (st.epi == TG_HEAD) {
+            // v = yhat; residual in normalised space (Auxilleryfunc, linna/util.py:1070-1088)
+            uint32_t okw[2] = {0u, 0u};
+#pragma unroll
+            for (int j = 0; j < TG_BN; ++j) {
+                const int col = n0 + j;
+                float dv = 0.f;
+                if (valid && col < N) {
+                    const float yh = racc[j] + (st.bias ? st.bias_scale * __ldg(st.bias + col) : 0.f);
+                    const float ys = __ldg(c.y_std + col), ym = __ldg(c.y_mean + col);
+                    const float sg = c.sigma ? __ldg(c.sigma + col) : 1.f;
+                    const float dh = __ldg(c.data_hat + col);
+                    const float Y = __ldg(args.target + (size_t)grow * N + col);
+                    float tt = Y / sg;                                              // util.py:432
+                    if (c.ypositive) tt = logf(tt);                                 // util.py:567-568
+                    tt = (tt - ym) / ys;                                            // util.py:570
+                    const bool ok = !(Y == 1e-30f || Y == 1e10f || dh == 1e-30f);    // util.py:1072
+                    dv = args.delta_kind == 0 ? tt - yh : args.delta_kind == 1 ? tt - dh : yh - dh;
+                    if (!ok) dv = 0.f;
+                    okw[j >> 5] |= (ok ? 1u : 0u) << (j & 31);
+                }
+                v[j] = dv;
+            }
+            *reinterpret_cast<uint2 *>(args.masks + st.mask_off + (size_t)grow * st.mask_ld + (n0 >> 5)) = make_uint2(okw[0], okw[1]);
+#pragma unroll
+            for (int j = 0; j < TG_BN; j += 4)
+                *reinterpret_cast<float4 *>(args.delta32 + (size_t)grow * args.dld + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            tg_store_planes(args.act + st.out_off, (int64_t)st.out_rows * st.out_ld, (int64_t)grow * st.out_ld + n0, v);
+        } else {   // TG_LOSSQ: q = delta @ Chat^-1 ; chi2 += q . delta ; g_yhat = -2 q ok / (cmd B)
+            const uint2 ok2 = *reinterpret_cast<const uint2 *>(args.masks + st.mask_off + (size_t)grow * st.mask_ld + (n0 >> 5));
+            const uint32_t okw[2] = {ok2.x, ok2.y};
+            const float rs = (valid && args.cmd) ? -2.0f * args.loss_inv_B / __ldg(args.cmd + grow) : 0.f;
+            float part = 0.f;
+#pragma unroll
+            for (int j = 0; j < TG_BN; j += 4) {
+                const float4 d4 = *reinterpret_cast<const float4 *>(args.delta32 + (size_t)grow * args.dld + n0 + j);
+                const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = n0 + j + e;
+                    const float q = (valid && col < N) ? racc[j + e] : 0.f;
+                    part = fmaf(q, dd[e], part);
+                    v[j + e] = ((okw[(j + e) >> 5] >> ((j + e) & 31)) & 1u) ? q * rs : 0.f;
+                }
+            }
+            args.chi_part[(size_t)grow * args.chi_ld + (n0 / TG_BN)] = part;
+            if (args.want_grad)
+                tg_store_planes(args.act + st.out_off, (int64_t)st.out_rows * st.out_ld, (int64_t)grow * st.out_ld + n0, v);
+        }
+    }
+    tg_gemm_finish(pp);
+}
+
+// ------------------------------------------------------------------------------------------ weight gradients + AdamW
+__device__ __forceinline__ float tg_adamw(const AdamArgs &a, int idx, float g)
+{
+    float p = a.params[idx], m = a.m[idx], v = a.v[idx];
+    p *= 1.0f - a.lr * a.wd;                       // decoupled weight decay (torch.optim.AdamW, predictor_gpu.py:267)
+    m = m + (1.0f - a.beta1) * (g - m);
+    v = v * a.beta2 + (1.0f - a.beta2) * g * g;
+    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+    p = p - (a.lr / a.bc1) * (m / denom);
+    a.params[idx] = p, a.m[idx] = m, a.v[idx] = v;
+    a.blob[a.map_fwd[idx]] = p;                    // the FP32 kernel's packed copies (predict / chi^2 calls between steps)
+    const int mb = a.map_bwd[idx];
+    if (mb >= 0) a.blob[mb] = p;
+    return p;
+}
+
+// bf16x3 planes of one weight into the packed forward [n][k] and backward [k][n] copies
+__device__ __forceinline__ void tg_pack_weight(__nv_bfloat16 *wblob, const TgWLayer &L, int n, int k, float p)
+{
+    const float x = p * L.pack_scale;
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+    const int64_t pf = (int64_t)L.wf_rows * L.wf_ld, of = L.wf_off + (int64_t)n * L.wf_ld + k;
+    wblob[of] = h, wblob[of + pf] = m, wblob[of + 2 * pf] = l;
+    const int64_t pb = (int64_t)L.wb_rows * L.wb_ld, ob = L.wb_off + (int64_t)k * L.wb_ld + n;
+    wblob[ob] = h, wblob[ob + pb] = m, wblob[ob + 2 * pb] = l;
+}
+
+__global__ void __launch_bounds__(TG_THREADS, 1) tg_wgrad_kernel(const TgArgs args)
+{
+    extern __shared__ uint8_t tg_smem_raw[];
+    __shared__ TgPipe pp;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tg_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const TgWTile wt = args.wtiles[blockIdx.x];
+    const TgWLayer L = args.wlayers[wt.layer];
+    TgTileDesc t;
+    t.nphase = 1, t.mn_major = true;
+    t.mapA[0] = t.mapA[1] = args.maps + L.mapA, t.mapB[0] = t.mapB[1] = args.maps + L.mapB;
+    t.rowsA[0] = t.rowsA[1] = t.rowsB[0] = t.rowsB[1] = args.B_pad;
+    t.K[0] = args.B_eff, t.K[1] = 0;
+    t.m0 = wt.m0, t.n0 = wt.n0;
+    float racc[TG_BN];
+    tg_gemm_tile(t, smem, pp, racc, args.err);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= 2) {
+        const int n = wt.m0 + (warp & 3) * 32 + lane;
+        if (n < L.N) {
+#pragma unroll
+            for (int j = 0; j < TG_BN; ++j) {
+                const int k = wt.n0 + j;
+                const float g = L.gscale * racc[j];
+                if (k < L.K) {
+                    const int idx = L.w_flat + n * L.K + k;
+                    if (args.adam.fuse) tg_pack_weight(args.wblob, L, n, k, tg_adamw(args.adam, idx, g));
+                    else args.adam.grads[idx] = g;
+                } else if (k == L.K && L.b_flat >= 0) {
+                    const int idx = L.b_flat + n;
+                    if (args.adam.fuse) tg_adamw(args.adam, idx, g);
+                    else args.adam.grads[idx] = g;
+                }
+            }
+        }
+    }
+    tg_gemm_finish(pp);
+}
+
+// params -> packed bf16x3 planes of every weight matrix (set-up, load_state_dict, after the stand-alone AdamW)
+__global__ void tg_repack_kernel(const float *__restrict__ params, __nv_bfloat16 *wblob, const TgWLayer *__restrict__ layers)
+{
+    const TgWLayer L = layers[blockIdx.y];
+    const int total = L.N * L.K;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int n = e / L.K, k = e - n * L.K;
+        tg_pack_weight(wblob, L, n, k, params[L.w_flat + e]);
+    }
+}
+
+// physical parameters -> xhat = (theta' - mean)/std (util.py:483-497) as bf16x3 planes, bias column set to 1
+__global__ void tg_input_kernel(const float *__restrict__ X, int B, int B_pad, int n_in, int ld, Consts c, __nv_bfloat16 *planes)
+{
+    const int64_t plane = (int64_t)B_pad * ld;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < B_pad * ld; e += gridDim.x * blockDim.x) {
+        const int r = e / ld, i = e - r * ld;
+        float x = 0.f;
+        if (r < B) {
+            if (i < n_in) {
+                float th = X[(size_t)r * n_in + i];
+                if (c.log10_flag && c.log10_flag[i]) th = log10f(th);
+                x = (th - c.x_mean[i]) / c.x_std[i];
+            } else if (i == n_in)
+                x = 1.f;
+        }
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        const float r1 = x - __bfloat162float(h);
+        const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+        planes[e] = h, planes[e + plane] = m, planes[e + 2 * plane] = __float2bfloat16_rn(r1 - __bfloat162float(m));
+    }
+}
+
+// loss rows and their mean from the per-tile chi^2 partials (fixed summation order: deterministic)
+__global__ void tg_loss_kernel(const float *__restrict__ chi_part, int chi_ld, int n_tiles, const float *__restrict__ cmd, int B,
+                               float *__restrict__ rows, float *__restrict__ mean)
+{
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int b = threadIdx.x; b < B; b += 256) {
+        double chi = 0.0;
+        for (int t = 0; t < n_tiles; ++t) chi += (double)chi_part[(size_t)b * chi_ld + t];
+        const float l = cmd ? (float)chi / cmd[b] : (float)chi;                      // util.py:1087
+        rows[b] = l;
+        s += (double)l;
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && mean) mean[0] = (float)(sh[0] / (double)B);              // util.py:1114-1115
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*TgEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TgContext {
+    int B_pad = 0, n_in = 0, n_out = 0;
+    __nv_bfloat16 *act = nullptr, *wblob = nullptr;
+    uint32_t *masks = nullptr;
+    float *delta32 = nullptr, *chi_part = nullptr;
+    int dld = 0, chi_ld = 0;
+    CUtensorMap *maps_dev = nullptr;
+    TgStep *steps_dev = nullptr;
+    TgWLayer *wlayers_dev = nullptr;
+    TgWTile *wtiles_dev = nullptr;
+    int *err_dev = nullptr;
+    std::vector<TgStep> steps;         // forward ..., HEAD, LOSSQ, backward ...
+    int n_fwd = 0, i_head = 0, i_lossq = 0, n_steps = 0;
+    int n_wlayers = 0, n_wtiles = 0;
+    int64_t in_off = 0;
+    int in_ld = 0;
+    int lossq_tiles = 0;
+    int64_t max_wn = 0;
+};
+
+cudaError_t tg_repack(TgContext *t, const float *params, cudaStream_t stream);
+
+void tg_destroy(TgContext *t)
+{
+    if (!t) return;
+    cudaFree(t->act), cudaFree(t->wblob), cudaFree(t->masks), cudaFree(t->delta32), cudaFree(t->chi_part);
+    cudaFree(t->maps_dev), cudaFree(t->steps_dev), cudaFree(t->wlayers_dev), cudaFree(t->wtiles_dev), cudaFree(t->err_dev);
+    delete t;
+}
+
+static inline int tg_pad(int n, int q) { return (n + q - 1) / q * q; }
+
+// Build the tensor-core training context: plane buffers, tensor maps, the layer-step list and the weight-gradient
+// tile table.  `flat_off` gives, per op, the offsets of (w, b, w2, b2, ws) in the flat parameter vector.  Returns
+// nullptr and fills `why` when the network shape is not covered (identity skips, extra linear branch).
+TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> &flat_off,
+                    const std::vector<std::array<const float *, 2>> &bias_ptr, std::string &why)
+{
+    if (m->has_extra) { why = "extra linear branch"; return nullptr; }
+    for (const OpHost &op : m->ops)
+        if (op.kind == LINNA_OP_RES && !op.has_ws) { why = "identity skip"; return nullptr; }
+    if (m->ops.back().kind != LINNA_OP_LINEAR || m->ops.back().act != LINNA_ACT_NONE) { why = "last layer must be linear"; return nullptr; }
+    TgEncodeFn encode = nullptr;
+    {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+            qres != cudaDriverEntryPointSuccess) {
+            why = "cuTensorMapEncodeTiled not available";
+            return nullptr;
+        }
+        encode = reinterpret_cast<TgEncodeFn>(fn);
+    }
+    TgContext *t = new TgContext();
+    auto bail = [&](const std::string &msg) { why = msg; tg_destroy(t); return (TgContext *)nullptr; };
+    const int nops = (int)m->ops.size();
+    const int B_pad = tg_pad(m->max_batch, 128);
+    t->B_pad = B_pad, t->n_in = m->n_in, t->n_out = m->n_out;
+
+    // ---- activation / gradient matrices: [3 planes][B_pad][ld], ld = pad64(width + 1) (the +1 is the bias column)
+    struct Mat { int64_t off; int ld; int mapA, mapMN; };
+    int64_t act_elems = 0;
+    std::vector<Mat> mats;
+    auto new_mat = [&](int width) {
+        Mat a;
+        a.ld = tg_pad(width + 1, 64), a.off = act_elems, a.mapA = a.mapMN = -1;
+        act_elems += 3 * (int64_t)B_pad * a.ld;
+        mats.push_back(a);
+        return (int)mats.size() - 1;
+    };
+    const int mX = new_mat(m->n_in);
+    std::vector<int> mAct(nops), mHid(nops, -1), mGz(nops), mGzh(nops, -1);
+    for (int i = 0; i < nops; ++i) {
+        mAct[i] = new_mat(m->ops[i].out);      // output of op i (for the last op: the residual delta)
+        mGz[i] = new_mat(m->ops[i].out);       // d loss / d (pre-activation of op i's output)
+        if (m->ops[i].kind == LINNA_OP_RES) mHid[i] = new_mat(m->ops[i].mid), mGzh[i] = new_mat(m->ops[i].mid);
+    }
+    // ---- packed weights: forward [N_pad64][pad64(K)] and backward [K_pad64][pad64(N)], three planes each
+    struct WMat { int64_t off; int ld, rows; int map; };
+    int64_t w_elems = 0;
+    auto new_w = [&](int rows, int cols) {
+        WMat w;
+        w.ld = tg_pad(cols, 64), w.rows = tg_pad(rows, 64), w.off = w_elems, w.map = -1;
+        w_elems += 3 * (int64_t)w.rows * w.ld;
+        return w;
+    };
+    struct OpW { WMat f, b, f2, b2, fs, bs; };
+    std::vector<OpW> ow(nops);
+    for (int i = 0; i < nops; ++i) {
+        const OpHost &op = m->ops[i];
+        if (op.kind == LINNA_OP_LINEAR) {
+            ow[i].f = new_w(op.out, op.in), ow[i].b = new_w(op.in, op.out);
+        } else {
+            ow[i].f = new_w(op.mid, op.in), ow[i].b = new_w(op.in, op.mid);
+            ow[i].f2 = new_w(op.out, op.mid), ow[i].b2 = new_w(op.mid, op.out);
+            ow[i].fs = new_w(op.out, op.in), ow[i].bs = new_w(op.in, op.out);
+        }
+    }
+    WMat wQ = new_w(m->n_out, m->n_out);   // Chat^-1 (symmetrised): q = delta @ Chat^-1, B[n][k] = Chat^-1[k][n] = itself
+
+    if (cudaMalloc(&t->act, act_elems * sizeof(__nv_bfloat16)) != cudaSuccess) return bail("cudaMalloc activations");
+    cudaMemset(t->act, 0, act_elems * sizeof(__nv_bfloat16));
+    if (cudaMalloc(&t->wblob, w_elems * sizeof(__nv_bfloat16)) != cudaSuccess) return bail("cudaMalloc weights");
+    cudaMemset(t->wblob, 0, w_elems * sizeof(__nv_bfloat16));
+
+    // ---- tensor maps
+    std::vector<CUtensorMap> maps;
+    auto add_map = [&](void *base, int ld, int rows_total, int box_rows) -> int {
+        CUtensorMap mp;
+        cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows_total};
+        cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+        cuuint32_t estr[2] = {1, 1};
+        if (encode(&mp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return -1;
+        maps.push_back(mp);
+        return (int)maps.size() - 1;
+    };
+    for (Mat &a : mats) {
+        a.mapA = add_map(t->act + a.off, a.ld, 3 * B_pad, 128);
+        a.mapMN = add_map(t->act + a.off, a.ld, 3 * B_pad, 64);
+        if (a.mapA < 0 || a.mapMN < 0) return bail("cuTensorMapEncodeTiled(activations) failed");
+    }
+    auto map_w = [&](WMat &w) { w.map = add_map(t->wblob + w.off, w.ld, 3 * w.rows, 64); return w.map >= 0; };
+    for (int i = 0; i < nops; ++i) {
+        bool ok = map_w(ow[i].f) && map_w(ow[i].b);
+        if (m->ops[i].kind == LINNA_OP_RES) ok = ok && map_w(ow[i].f2) && map_w(ow[i].b2) && map_w(ow[i].fs) && map_w(ow[i].bs);
+        if (!ok) return bail("cuTensorMapEncodeTiled(weights) failed");
+    }
+    if (!map_w(wQ)) return bail("cuTensorMapEncodeTiled(Chat^-1) failed");
+
+    // ---- masks: relu bits of every forward output (+ the ok bits of the loss), words per row
+    int64_t mask_words = 0;
+    std::vector<int64_t> mkY(nops, -1), mkH(nops, -1);
+    std::vector<int> mkYld(nops, 0), mkHld(nops, 0);
+    auto new_mask = [&](int width, int &ld) {
+        ld = tg_pad(width + 1, 64) / 32;
+        int64_t o = mask_words;
+        mask_words += (int64_t)B_pad * ld;
+        return o;
+    };
+    for (int i = 0; i < nops; ++i) {
+        mkY[i] = new_mask(m->ops[i].out, mkYld[i]);
+        if (m->ops[i].kind == LINNA_OP_RES) mkH[i] = new_mask(m->ops[i].mid, mkHld[i]);
+    }
+    if (cudaMalloc(&t->masks, std::max<int64_t>(mask_words, 64) * sizeof(uint32_t)) != cudaSuccess) return bail("cudaMalloc masks");
+    cudaMemset(t->masks, 0, std::max<int64_t>(mask_words, 64) * sizeof(uint32_t));
+    t->dld = tg_pad(m->n_out + 1, 64);
+    t->chi_ld = t->dld / 64;
+    if (cudaMalloc(&t->delta32, (size_t)B_pad * t->dld * sizeof(float)) != cudaSuccess) return bail("cudaMalloc delta");
+    if (cudaMalloc(&t->chi_part, (size_t)B_pad * t->chi_ld * sizeof(float)) != cudaSuccess) return bail("cudaMalloc chi");
+    cudaMemset(t->delta32, 0, (size_t)B_pad * t->dld * sizeof(float));
+    cudaMemset(t->chi_part, 0, (size_t)B_pad * t->chi_ld * sizeof(float));
+
+    // ---- steps
+    auto base_step = [&](int epi, int out_mat, int N) {
+        TgStep s;
+        memset(&s, 0, sizeof s);
+        s.epi = epi, s.nphase = 1, s.N = N, s.bias = nullptr, s.bias_scale = 1.f;
+        s.out_off = mats[out_mat].off, s.out_ld = mats[out_mat].ld, s.out_rows = B_pad;
+        s.n_tiles = mats[out_mat].ld / 64;
+        return s;
+    };
+    auto set_phase = [&](TgStep &s, int p, int a_mat, const WMat &w, int K) {
+        s.mapA[p] = mats[a_mat].mapA, s.rowsA[p] = B_pad, s.mapB[p] = w.map, s.rowsB[p] = w.rows, s.K[p] = K;
+    };
+    auto producer_mask = [&](int i, int64_t &off, int &ld) -> bool {   // relu bits of the producer of op i's input
+        if (i <= 0) return false;
+        const OpHost &pv = m->ops[i - 1];
+        if (!(pv.kind == LINNA_OP_RES || pv.act == LINNA_ACT_RELU)) return false;
+        off = mkY[i - 1], ld = mkYld[i - 1];
+        return true;
+    };
+    int cur = mX;
+    for (int i = 0; i < nops; ++i) {
+        const OpHost &op = m->ops[i];
+        const bool last = i + 1 == nops;
+        if (op.kind == LINNA_OP_LINEAR) {
+            TgStep s = base_step(last ? TG_HEAD : TG_ACT, mAct[i], op.out);
+            set_phase(s, 0, cur, ow[i].f, op.in);
+            s.bias = bias_ptr[i][0], s.relu = (!last && op.act == LINNA_ACT_RELU) ? 1 : 0, s.save_mask = s.relu, s.write_ones = last ? 0 : 1;
+            s.mask_off = mkY[i], s.mask_ld = mkYld[i];     // HEAD: the ok bits of the loss live in the last op's mask
+            t->steps.push_back(s);
+        } else {
+            TgStep h = base_step(TG_ACT, mHid[i], op.mid);
+            set_phase(h, 0, cur, ow[i].f, op.in);
+            h.bias = bias_ptr[i][0], h.relu = 1, h.save_mask = 1, h.write_ones = 1, h.mask_off = mkH[i], h.mask_ld = mkHld[i];
+            t->steps.push_back(h);
+            TgStep y = base_step(TG_ACT, mAct[i], op.out);
+            y.nphase = 2;
+            set_phase(y, 0, cur, ow[i].fs, op.in);
+            set_phase(y, 1, mHid[i], ow[i].f2, op.mid);
+            y.bias = bias_ptr[i][1], y.bias_scale = op.alpha, y.relu = 1, y.save_mask = 1, y.write_ones = 1;
+            y.mask_off = mkY[i], y.mask_ld = mkYld[i];
+            t->steps.push_back(y);
+        }
+        cur = mAct[i];
+    }
+    t->n_fwd = (int)t->steps.size() - 1;
+    t->i_head = t->n_fwd;
+    {   // q = delta @ Chat^-1
+        TgStep q = base_step(TG_LOSSQ, mGz[nops - 1], m->n_out);
+        set_phase(q, 0, mAct[nops - 1], wQ, m->n_out);
+        q.mask_off = mkY[nops - 1], q.mask_ld = mkYld[nops - 1];
+        t->i_lossq = (int)t->steps.size();
+        t->lossq_tiles = q.n_tiles;
+        t->steps.push_back(q);
+    }
+    for (int i = nops - 1; i >= 1; --i) {   // backward-data; d loss / d xhat is not needed
+        const OpHost &op = m->ops[i];
+        int64_t moff = 0;
+        int mld = 0;
+        const bool pm = producer_mask(i, moff, mld);
+        if (op.kind == LINNA_OP_LINEAR) {
+            TgStep s = base_step(TG_BWD, mGz[i - 1], op.in);
+            set_phase(s, 0, mGz[i], ow[i].b, op.out);
+            if (pm) s.apply_mask = 1, s.mask_off = moff, s.mask_ld = mld;
+            t->steps.push_back(s);
+        } else {
+            TgStep h = base_step(TG_BWD, mGzh[i], op.mid);
+            set_phase(h, 0, mGz[i], ow[i].b2, op.out);
+            h.apply_mask = 1, h.mask_off = mkH[i], h.mask_ld = mkHld[i];
+            t->steps.push_back(h);
+            TgStep x = base_step(TG_BWD, mGz[i - 1], op.in);
+            x.nphase = 2;
+            set_phase(x, 0, mGz[i], ow[i].bs, op.out);
+            set_phase(x, 1, mGzh[i], ow[i].b, op.mid);
+            if (pm) x.apply_mask = 1, x.mask_off = moff, x.mask_ld = mld;
+            t->steps.push_back(x);
+        }
+    }
+    if (m->ops[0].kind == LINNA_OP_RES) {   // the hidden gradient of a leading res-block is still needed for its weights
+        const OpHost &op = m->ops[0];
+        TgStep h = base_step(TG_BWD, mGzh[0], op.mid);
+        set_phase(h, 0, mGz[0], ow[0].b2, op.out);
+        h.apply_mask = 1, h.mask_off = mkH[0], h.mask_ld = mkHld[0];
+        t->steps.push_back(h);
+    }
+    t->n_steps = (int)t->steps.size();
+    t->in_off = mats[mX].off, t->in_ld = mats[mX].ld;
+
+    // ---- weight-gradient layers and tiles
+    std::vector<TgWLayer> wl;
+    auto add_wl = [&](int gz_mat, int x_mat, int N, int K, int wf, int bf, float gs, const WMat &f, const WMat &b) {
+        TgWLayer L;
+        memset(&L, 0, sizeof L);
+        L.mapA = mats[gz_mat].mapMN, L.mapB = mats[x_mat].mapMN, L.N = N, L.K = K, L.w_flat = wf, L.b_flat = bf;
+        L.gscale = gs, L.pack_scale = gs;
+        L.wf_off = f.off, L.wf_ld = f.ld, L.wf_rows = f.rows, L.wb_off = b.off, L.wb_ld = b.ld, L.wb_rows = b.rows;
+        wl.push_back(L);
+    };
+    for (int i = 0; i < nops; ++i) {
+        const OpHost &op = m->ops[i];
+        const int xin = i == 0 ? mX : mAct[i - 1];
+        if (op.kind == LINNA_OP_LINEAR) {
+            add_wl(mGz[i], xin, op.out, op.in, flat_off[i][0], flat_off[i][1], 1.f, ow[i].f, ow[i].b);
+        } else {
+            add_wl(mGzh[i], xin, op.mid, op.in, flat_off[i][0], flat_off[i][1], 1.f, ow[i].f, ow[i].b);
+            add_wl(mGz[i], mHid[i], op.out, op.mid, flat_off[i][2], flat_off[i][3], op.alpha, ow[i].f2, ow[i].b2);
+            add_wl(mGz[i], xin, op.out, op.in, flat_off[i][4], -1, 1.f, ow[i].fs, ow[i].bs);
+        }
+    }
+    std::vector<TgWTile> tiles;
+    for (size_t l = 0; l < wl.size(); ++l) {
+        const int kmax = wl[l].K + (wl[l].b_flat >= 0 ? 1 : 0);
+        for (int m0 = 0; m0 < wl[l].N; m0 += TG_BM)
+            for (int n0 = 0; n0 < kmax; n0 += TG_BN) tiles.push_back(TgWTile{(int32_t)l, m0, n0, 0});
+    }
+    // large tiles first: the 64 tiles of the widest skip layer should not start last
+    std::stable_sort(tiles.begin(), tiles.end(), [&](const TgWTile &a, const TgWTile &b) {
+        return (int64_t)wl[a.layer].N * wl[a.layer].K > (int64_t)wl[b.layer].N * wl[b.layer].K;
+    });
+    t->n_wlayers = (int)wl.size(), t->n_wtiles = (int)tiles.size();
+    for (const TgWLayer &L : wl) t->max_wn = std::max<int64_t>(t->max_wn, (int64_t)L.N * L.K);
+
+    // Chat^-1 planes (constant): B[n][k] = Chat^-1[k][n]
+    {
+        std::vector<__nv_bfloat16> h((size_t)3 * wQ.rows * wQ.ld, __float2bfloat16_rn(0.f));
+        const int n = m->n_out;
+        for (int r = 0; r < n; ++r)
+            for (int k = 0; k < n; ++k) {
+                const float x = m->icov_hat[(size_t)k * n + r];
+                const __nv_bfloat16 a = __float2bfloat16_rn(x);
+                const float r1 = x - __bfloat162float(a);
+                const __nv_bfloat16 b = __float2bfloat16_rn(r1);
+                const size_t o = (size_t)r * wQ.ld + k, pl = (size_t)wQ.rows * wQ.ld;
+                h[o] = a, h[o + pl] = b, h[o + 2 * pl] = __float2bfloat16_rn(r1 - __bfloat162float(b));
+            }
+        cudaMemcpy(t->wblob + wQ.off, h.data(), h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
+    }
+    if (cudaMalloc(&t->maps_dev, maps.size() * sizeof(CUtensorMap)) != cudaSuccess) return bail("cudaMalloc maps");
+    cudaMemcpy(t->maps_dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
+    if (cudaMalloc(&t->steps_dev, t->steps.size() * sizeof(TgStep)) != cudaSuccess) return bail("cudaMalloc steps");
+    cudaMemcpy(t->steps_dev, t->steps.data(), t->steps.size() * sizeof(TgStep), cudaMemcpyHostToDevice);
+    if (cudaMalloc(&t->wlayers_dev, wl.size() * sizeof(TgWLayer)) != cudaSuccess) return bail("cudaMalloc wlayers");
+    cudaMemcpy(t->wlayers_dev, wl.data(), wl.size() * sizeof(TgWLayer), cudaMemcpyHostToDevice);
+    if (cudaMalloc(&t->wtiles_dev, tiles.size() * sizeof(TgWTile)) != cudaSuccess) return bail("cudaMalloc wtiles");
+    cudaMemcpy(t->wtiles_dev, tiles.data(), tiles.size() * sizeof(TgWTile), cudaMemcpyHostToDevice);
+    if (cudaMalloc(&t->err_dev, sizeof(int)) != cudaSuccess) return bail("cudaMalloc err");
+    cudaMemset(t->err_dev, 0, sizeof(int));
+    if (cudaFuncSetAttribute(tg_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(tg_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES) != cudaSuccess)
+        return bail("cudaFuncSetAttribute(tg kernels)");
+    {   // initial packed planes from the host copies of the weights (flat state_dict order)
+        size_t nflat = 0;
+        for (const OpHost &op : m->ops) nflat += op.w.size() + op.b.size() + op.w2.size() + op.b2.size() + op.ws.size();
+        std::vector<float> flat;
+        flat.reserve(nflat);
+        for (const OpHost &op : m->ops) {
+            flat.insert(flat.end(), op.w.begin(), op.w.end()), flat.insert(flat.end(), op.b.begin(), op.b.end());
+            if (op.kind == LINNA_OP_RES) {
+                flat.insert(flat.end(), op.w2.begin(), op.w2.end()), flat.insert(flat.end(), op.b2.begin(), op.b2.end());
+                if (op.has_ws) flat.insert(flat.end(), op.ws.begin(), op.ws.end());
+            }
+        }
+        float *tmp = nullptr;
+        if (cudaMalloc(&tmp, flat.size() * sizeof(float)) != cudaSuccess) return bail("cudaMalloc flat params");
+        cudaMemcpy(tmp, flat.data(), flat.size() * sizeof(float), cudaMemcpyHostToDevice);
+        cudaError_t e = tg_repack(t, tmp, 0);
+        cudaDeviceSynchronize();
+        cudaFree(tmp);
+        if (e != cudaSuccess) return bail("initial weight pack failed");
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) return bail("sync after tg_build");
+    return t;
+}
+
+// packed planes <- flat parameter vector (device)
+cudaError_t tg_repack(TgContext *t, const float *params, cudaStream_t stream)
+{
+    const int bx = (int)std::min<int64_t>((t->max_wn + 255) / 256, 256);
+    tg_repack_kernel<<<dim3(bx, t->n_wlayers), 256, 0, stream>>>(params, t->wblob, t->wlayers_dev);
+    return cudaGetLastError();
+}
+
+static TgArgs tg_args(const linna_model *m, TgContext *t, int64_t B)
+{
+    TgArgs a;
+    memset(&a, 0, sizeof a);
+    a.maps = t->maps_dev, a.act = t->act, a.masks = t->masks, a.B = (int)B, a.B_pad = t->B_pad;
+    a.B_eff = (int)((B + TG_BM - 1) / TG_BM) * TG_BM;
+    a.delta32 = t->delta32, a.dld = t->dld, a.chi_part = t->chi_part, a.chi_ld = t->chi_ld, a.c = m->consts;
+    a.wlayers = t->wlayers_dev, a.wtiles = t->wtiles_dev, a.wblob = t->wblob, a.err = t->err_dev;
+    return a;
+}
+
+// forward + loss head + quadratic form over B <= max_batch rows; `want_grad` also leaves d loss / d yhat for the
+// backward pass.  Returns the number of kernels launched (negative: CUDA error).
+static int tg_forward_loss(const linna_model *m, TgContext *t, const float *X, const float *Y, const float *cmd,
+                           int64_t B, int delta_kind, bool want_grad, float *rows, float *mean, cudaStream_t stream)
+{
+    TgArgs a = tg_args(m, t, B);
+    a.target = Y, a.cmd = cmd, a.delta_kind = delta_kind, a.loss_inv_B = 1.0f / (float)B, a.want_grad = want_grad ? 1 : 0;
+    const int m_tiles = (int)((B + TG_BM - 1) / TG_BM);
+    int launches = 0;
+    {
+        const int total = t->B_pad * t->in_ld;
+        tg_input_kernel<<<(total + 255) / 256, 256, 0, stream>>>(X, (int)B, t->B_pad, t->n_in, t->in_ld, m->consts, t->act + t->in_off);
+        ++launches;
+    }
+    // delta_kind 1 (target vs data) does not need the network at all, but the chi^2 calls are not hot: same path
+    for (int si = 0; si <= t->i_lossq; ++si) {
+        a.step = t->steps_dev + si;
+        tg_layer_kernel<<<m_tiles * t->steps[si].n_tiles, TG_THREADS, TG_SMEM_BYTES, stream>>>(a);
+        ++launches;
+    }
+    tg_loss_kernel<<<1, 256, 0, stream>>>(t->chi_part, t->chi_ld, t->lossq_tiles, cmd, (int)B, rows, mean);
+    ++launches;
+    return cudaGetLastError() == cudaSuccess ? launches : -1;
+}
+
+int tg_train_step(const linna_model *m, TgContext *t, const float *X, const float *Y, const float *cmd, int64_t B, const AdamArgs &ad,
+                  float *loss_rows, float *loss_mean, cudaStream_t stream)
+{
+    int launches = tg_forward_loss(m, t, X, Y, cmd, B, 0, true, loss_rows, loss_mean, stream);
+    if (launches < 0) return -1;
+    TgArgs a = tg_args(m, t, B);
+    const int m_tiles = (int)((B + TG_BM - 1) / TG_BM);
+    for (int si = t->i_lossq + 1; si < t->n_steps; ++si) {
+        a.step = t->steps_dev + si;
+        tg_layer_kernel<<<m_tiles * t->steps[si].n_tiles, TG_THREADS, TG_SMEM_BYTES, stream>>>(a);
+        ++launches;
+    }
+    a.adam = ad;
+    tg_wgrad_kernel<<<t->n_wtiles, TG_THREADS, TG_SMEM_BYTES, stream>>>(a);
+    ++launches;
+    return cudaGetLastError() == cudaSuccess ? launches : -1;
+}
+
+int tg_chisq(const linna_model *m, TgContext *t, const float *X, const float *Y, int64_t n, int kind, float *chi2,
+             cudaStream_t stream)
+{
+    int launches = 0;
+    for (int64_t done = 0; done < n; done += m->max_batch) {
+        const int64_t B = std::min<int64_t>(m->max_batch, n - done);
+        const int l = tg_forward_loss(m, t, X + done * m->n_in, Y + done * m->n_out, nullptr, B, kind, false, chi2 + done, nullptr,
+                                      stream);
+        if (l < 0) return -1;
+        launches += l;
+    }
+    return launches;
+}
+
+int tg_check(TgContext *t)
+{
+    int e = 0;
+    cudaMemcpy(&e, t->err_dev, sizeof(int), cudaMemcpyDeviceToHost);
+    return e;
+}
+
+}  // namespace linna

@@ -98,6 +98,8 @@ def load_library():
     lib.linna_train_adamw.argtypes = [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp]
     lib.linna_train_load_params.argtypes = [vp, vp, vp]
     lib.linna_train_commit.argtypes = [vp, vp]
+    lib.linna_train_set_path.argtypes = [vp, i32]
+    lib.linna_train_last_kernel.argtypes = [vp]
     if lib.linna_abi_version() != 1:
         raise LinnaError("linna_b200: ABI version mismatch")
     _lib = lib
@@ -385,6 +387,13 @@ class Engine:
         d.data_hat, d.icov_hat, d.max_batch = _fp(dh), _fp(ic), int(max_batch)
         self._check(self.lib.linna_train_setup(self.handle, ctypes.byref(d)))
         self.n_params = int(self.lib.linna_train_num_params(self.handle))
+
+    def set_train_path(self, path):
+        """'auto' | 'ffma' | 'tc' -- which kernels run train_step / train_chisq."""
+        self._check(self.lib.linna_train_set_path(self.handle, {"auto": 0, "ffma": 1, "tc": 2}[path]))
+
+    def last_train_kernel(self):
+        return {0: None, 1: "ffma", 2: "tc"}[int(self.lib.linna_train_last_kernel(self.handle))]
 
     def train_chisq(self, X, Y, kind):
         """Per-row chi^2 of the loss (kind 0: target/pred, 1: target/data, 2: pred/data); CUDA tensors."""

@@ -87,7 +87,7 @@ class FusedTrainer:
 
     def kernel_path(self):
         """'tc' when the optimiser step runs on the tensor-core (tcgen05) training kernels, else 'ffma'."""
-        return "ffma"
+        return self.engine.last_train_kernel() or "none"
 
     # -- validation metric (Val_metric_fn, linna/util.py:1118-1127) ------------------------
     def val_metric(self, X, Y, cmd):

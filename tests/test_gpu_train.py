@@ -19,7 +19,10 @@ from tests.helpers import load_golden
 pytestmark = pytest.mark.gpu
 
 
-def _setup(name):
+PATHS = ["ffma", "tc"]     # the FP32 FFMA kernels and the tensor-core (tcgen05, bf16x3) kernels: same bars
+
+
+def _setup(name, path="auto"):
     g = load_golden(name)
     p = synthetic.make_problem(int(g["n_in"]), int(g["n_out"]), kind=str(g["kind"]), ypositive=bool(g["ypositive"]), seed=4)
     p.data = g["data"].astype(np.float64)
@@ -30,15 +33,17 @@ def _setup(name):
     e = engine.engine_from_problem(p, with_likelihood=False)
     B = int(g["batch"])
     e.train_setup(dn, icov, B)
+    e.set_train_path(path)
     shapes = arch.state_dict_shapes(p.kind, p.n_in, p.n_out)
     w = torch.from_numpy(flatten_state_dict(p.state_dict, shapes).astype(np.float32)).cuda()
     assert w.numel() == e.n_params
     return g, p, e, shapes, w, B
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("name,full", [("train_small", True), ("train_ypos", True), ("train_c3", False)])
-def test_loss_and_gradients(name, full):
-    g, p, e, shapes, w, B = _setup(name)
+def test_loss_and_gradients(name, full, path):
+    g, p, e, shapes, w, B = _setup(name, path)
     X = torch.from_numpy(g["theta"][:B].astype(np.float32)).cuda()
     Y = torch.from_numpy(g["target"][:B].astype(np.float32)).cuda()
     cmd_raw = e.train_chisq(X, Y, 1)
@@ -57,6 +62,7 @@ def test_loss_and_gradients(name, full):
     grads = torch.zeros_like(w)
     loss, rows = e.train_step(X, Y, cmd, None, None, None, grads, 1, float(g["lr"]), fuse_adam=False)
     torch.cuda.synchronize()
+    assert e.last_train_kernel() == path
     assert abs(float(loss) - g["losses"][0]) <= 3e-6 * abs(g["losses"][0])
     np.testing.assert_allclose(rows.cpu().numpy(), g["loss_rows"], rtol=3e-5, atol=1e-10)
     gd = unflatten(grads.cpu().numpy(), shapes)
@@ -80,8 +86,9 @@ def test_loss_and_gradients(name, full):
 
 @pytest.mark.parametrize("name,full", [("train_small", True), ("train_ypos", True), ("train_c3", False)])
 @pytest.mark.parametrize("fused", [True, False])
-def test_adamw_steps_match_reference(name, full, fused):
-    g, p, e, shapes, w, B = _setup(name)
+@pytest.mark.parametrize("path", PATHS)
+def test_adamw_steps_match_reference(name, full, fused, path):
+    g, p, e, shapes, w, B = _setup(name, path)
     m, v, grads = torch.zeros_like(w), torch.zeros_like(w), torch.zeros_like(w)
     lr = float(g["lr"])
     for s in range(int(g["nsteps"])):
@@ -96,13 +103,22 @@ def test_adamw_steps_match_reference(name, full, fused):
         assert abs(float(loss) - g["losses"][s]) <= 3e-3 * abs(g["losses"][s]) + 1e-9, (s, float(loss), g["losses"][s])
     wd = unflatten(w.cpu().numpy(), shapes)
     keys = [str(k) for k in g["keys"]]
+    # AdamW divides by sqrt(v): where a gradient is within rounding of zero the update is +-lr whatever its size, so two
+    # correct float32 evaluations can differ by ~lr in single weights.  The goldens record how far the reference's own
+    # float32 result is from its float64 run per tensor (`f32_final_err`: up to 1.4e-3 at the C3 shape, lr = 2e-3); the
+    # CUDA result may be as far from the float32 reference as that, and no further.
+    spread = dict(zip(keys, g["f32_final_err"]))
     if full:
         for k in keys:
             ref = g["final_" + k]
-            assert np.max(np.abs(wd[k] - ref)) <= 1e-4 * max(np.max(np.abs(ref)), 1e-3) + 3e-5, k
+            assert np.max(np.abs(wd[k] - ref)) <= max(1e-4 * max(np.max(np.abs(ref)), 1e-3) + 3e-5, 1.5 * spread[k]), k
+            assert np.max(np.abs(wd[k] - g["f64_final_" + k])) <= max(1e-4 * max(np.max(np.abs(ref)), 1e-3) + 3e-5, 1.5 * spread[k]), k
     else:
         ref = g["final_layer1"]
-        assert np.max(np.abs(wd["layer1.weight"] - ref)) <= 1e-4 * np.max(np.abs(ref)) + 3e-5
+        bar = max(1e-4 * np.max(np.abs(ref)) + 3e-5, 1.5 * spread["layer1.weight"])
+        assert np.max(np.abs(wd["layer1.weight"] - ref)) <= bar
+        assert np.max(np.abs(wd["layer1.weight"] - g["f64_final_layer1"])) <= bar
+        assert np.mean(np.abs(wd["layer1.weight"] - ref) > 1e-4 * np.max(np.abs(ref)) + 3e-5) < 2e-3     # and only in a few weights
         np.testing.assert_allclose([float(np.linalg.norm(wd[k].astype(np.float64))) for k in keys], g["final_norm"], rtol=1e-4)
     # the packed weights inside the engine follow the flat vector: predictions use the updated weights
     th = g["theta"][:4].astype(np.float32)
