@@ -149,6 +149,11 @@ int linna_model_last_kernel(const linna_model_t *m);
  * issuer, [40..] of epilogue group 0, [64..] of which waiting for accumulators, [88..] of which chunk
  * epilogues. */
 int linna_debug_tc_counters(linna_model_t *m, int64_t *out, int32_t max_ctas);
+/* Profiling hook of the tensor-core training kernels (environment LINNA_TG_DEBUG set at linna_train_setup): clock64 stamps
+ * of CTA 0 of every layer launch of the last step, out[step][8] = {kernel entry, set-up done, predecessor complete
+ * (griddepcontrol.wait), first segment drained, contraction done, epilogue done, tensor memory freed, 0}; returns the
+ * number of steps (0 when off). */
+int linna_debug_tg_counters(linna_model_t *m, int64_t *out, int32_t max_steps);
 /* Force the row-tile height (8, 16 or 32; 0 = automatic) -- test hook for the tiling variants. */
 int linna_model_set_tile_rows(linna_model_t *m, int32_t rows);
 

@@ -32,12 +32,14 @@ void tc_fix_buffers(TcContext *t, const int32_t **rows, const int32_t **count, i
 void tc_launch_done(TcContext *t);
 int tc_debug_read(TcContext *t, long long *out, int max_ctas);
 TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> &flat_off,
-                    const std::vector<std::array<const float *, 2>> &bias_ptr, std::string &why);
+                    const std::vector<std::array<const float *, 2>> &bias_ptr, const std::vector<std::array<int64_t, 8>> &blob_off,
+                    std::string &why);
 void tg_destroy(TgContext *t);
 cudaError_t tg_repack(TgContext *t, const float *params, cudaStream_t stream);
 int tg_train_step(const linna_model *m, TgContext *t, const float *X, const float *Y, const float *cmd, int64_t B, const AdamArgs &ad,
                   float *loss_rows, float *loss_mean, cudaStream_t stream);
 int tg_chisq(const linna_model *m, TgContext *t, const float *X, const float *Y, int64_t n, int kind, float *chi2, cudaStream_t stream);
+int tg_debug_read(TgContext *t, long long *out, int max_steps);
 }  // namespace linna
 
 static thread_local std::string g_err;
@@ -625,12 +627,17 @@ static int rebuild(linna_model *m)
         // tensor-core training kernels (tg_gemm.cu); the FP32 kernels above stay as the path for shapes they do not cover
         std::vector<std::array<int, 5>> flat_off(m->ops.size());
         std::vector<std::array<const float *, 2>> bias_ptr(m->ops.size());
+        std::vector<std::array<int64_t, 8>> blob_off(m->ops.size());
         for (size_t i = 0; i < m->ops.size(); ++i) {
+            const bool res = m->ops[i].kind == LINNA_OP_RES;
             flat_off[i] = {fo[i].w, fo[i].b, fo[i].w2, fo[i].b2, fo[i].ws};
-            bias_ptr[i] = {P(off[i].b), m->ops[i].kind == LINNA_OP_RES ? P(off[i].b2) : nullptr};
+            bias_ptr[i] = {P(off[i].b), res ? P(off[i].b2) : nullptr};
+            blob_off[i] = {(int64_t)off[i].w_f, (int64_t)off[i].w_b, (int64_t)off[i].b, res ? (int64_t)off[i].w2_f : -1,
+                           res ? (int64_t)off[i].w2_b : -1, res ? (int64_t)off[i].b2 : -1,
+                           res && m->ops[i].has_ws ? (int64_t)off[i].ws_f : -1, res && m->ops[i].has_ws ? (int64_t)off[i].ws_b : -1};
         }
         m->tg_why.clear();
-        if (!getenv("LINNA_TRAIN_NO_TC")) m->tg = tg_build(m, flat_off, bias_ptr, m->tg_why);
+        if (!getenv("LINNA_TRAIN_NO_TC")) m->tg = tg_build(m, flat_off, bias_ptr, blob_off, m->tg_why);
         else m->tg_why = "LINNA_TRAIN_NO_TC set";
         cudaGetLastError();
     }
@@ -827,6 +834,12 @@ int linna_debug_tc_counters(linna_model_t *m, int64_t *out, int32_t max_ctas)
 {
     if (!m || !out) return 0;
     return tc_debug_read(m->tc, reinterpret_cast<long long *>(out), max_ctas);
+}
+
+int linna_debug_tg_counters(linna_model_t *m, int64_t *out, int32_t max_steps)
+{
+    if (!m || !out) return 0;
+    return tg_debug_read(m->tg, reinterpret_cast<long long *>(out), max_steps);
 }
 
 int linna_model_set_fold(linna_model_t *m, int32_t on)

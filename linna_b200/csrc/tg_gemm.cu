@@ -12,10 +12,16 @@
 //     with exact bf16 x bf16 products and fp32 accumulation in tensor memory.
 //   * two-level accumulation as in tc_f16.cu: the tensor core truncates its fp32 accumulator on every instruction
 //     (~0.5 ulp of the accumulator, toward zero), so every k-chunk (64 values of K = 24 instructions) is drained from
-//     tensor memory and added with round-to-nearest into 64 register accumulators per epilogue thread -- and the three
-//     orders of magnitude of the split go to three SEPARATE tensor-memory accumulators (h.h | h.m + m.h | m.m + h.l +
-//     l.h), so that the 20 small-term instructions of a chunk truncate at THEIR magnitude (2^-8, 2^-16 of the sum) and
-//     only 4 instructions per chunk touch the leading accumulator (two buffers of 3 x 64 columns).
+//     tensor memory and added with round-to-nearest into 64 register accumulators per epilogue thread -- and the leading
+//     term goes to its OWN tensor-memory accumulator (h.h | everything else), so that the 20 small-term instructions of
+//     a chunk truncate at THEIR magnitude (2^-8 of the sum and below) and only 4 instructions per chunk touch the leading
+//     accumulator.  A segment is two k-chunks (8 leading instructions; two ring buffers of 2 x 64 columns): with three
+//     accumulators drained every chunk the tcgen05.ld traffic, not the tensor core, set the pace.
+//   * split-K: a layer of few tiles and a long contraction is cut into up to 4 k-ranges per tile, one CTA each; the
+//     partial tiles go through an L2-resident workspace and the LAST CTA to arrive (atomic ticket) adds them in the
+//     fixed order of the k-ranges and runs the epilogue -- deterministic, no floating-point atomics.
+//   * every launch is a programmatic dependent launch: barrier set-up and tensor-memory allocation of layer l+1
+//     overlap the tail of layer l (griddepcontrol.wait before the first dependent access).
 //   * operands are 128-byte-swizzled tiles filled by TMA (3 stages x 72 KB): forward / backward-data read
 //     activations [batch][features] and weights [out][in] (or the transposed copy) K-major; the weight-gradient GEMM
 //     dW[n][k] = sum_b gz[b][n] x[b][k] contracts over the BATCH and reads the very same activation planes as
@@ -59,6 +65,7 @@ struct TgStep {
     int32_t n_tiles;              // column tiles of 64
     int64_t out_off;              // element offset of the output's plane 0 inside the activation blob
     int32_t out_ld, out_rows;     // row pitch (elements) and rows per plane of the output
+    int32_t mapOut, pad0_;        // tensor map of the output (box 64 x 128 rows, 128-byte swizzle): TMA store of the tile
     int32_t write_ones;           // column N of the output is the bias column of the next layer's input
     int32_t relu, save_mask, apply_mask;
     int64_t mask_off;             // word offset of this layer's relu bits (save) / of the producer's bits (apply)
@@ -74,6 +81,9 @@ struct TgWLayer {
     float gscale, pack_scale;     // alpha of a res-block's second layer (gradient and packed copies), else 1
     int64_t wf_off, wb_off;       // plane 0 of the packed forward [N][K] / backward [K][N] copy (elements of the weight blob)
     int32_t wf_ld, wf_rows, wb_ld, wb_rows;
+    // the FP32 kernels' packed copies inside the model blob (float offsets): Wt[k][ldf] + n, W[n][ldb] + k, bias[n]
+    int64_t blob_f, blob_b, blob_bias;
+    int32_t blob_ldf, blob_ldb;
 };
 struct TgWTile {
     int32_t layer, m0, n0, pad_;
@@ -103,6 +113,11 @@ struct TgArgs {
     __nv_bfloat16 *wblob;         // packed weight planes
     AdamArgs adam;
     int *err;
+    float *ws;                    // split-K workspace: [tile][k-range][128][64] partial tiles
+    int32_t *sem;                 // [tile] arrival tickets
+    int32_t splitk;               // k-ranges per tile (CTAs per tile) of this launch: 1, 2 or 4
+    long long *dbg;               // LINNA_TG_DEBUG: [launch slot][8] cycle stamps of CTA 0 (profiling aid), or nullptr
+    int32_t dbg_slot;
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -237,6 +252,7 @@ struct TgTileDesc {
     const CUtensorMap *mapA[2], *mapB[2];
     int32_t rowsA[2], rowsB[2], K[2];
     int32_t nphase, m0, n0;
+    int32_t i0, i1;               // this CTA's range of the flattened (phase, k-chunk) list (split-K), [i0, i1)
     bool mn_major;
 };
 
@@ -245,33 +261,44 @@ struct TgPipe {
     uint32_t tmem_slot;
 };
 
-__device__ __forceinline__ void tg_gemm_tile(const TgTileDesc &t, uint8_t *smem, TgPipe &pp, float (&racc)[TG_BN], int *err)
+__device__ __forceinline__ void tg_gemm_tile(const TgTileDesc &t, uint8_t *smem, TgPipe &pp, float (&racc)[TG_BN], int *err,
+                                             long long *dbg = nullptr)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (dbg && threadIdx.x == 64) dbg[0] = clock64();
     if (threadIdx.x == 0) {
         for (int s = 0; s < TG_STAGES; ++s) tg_mbar_init(&pp.full_bar[s], 1), tg_mbar_init(&pp.empty_bar[s], 1);
         for (int b = 0; b < 2; ++b) tg_mbar_init(&pp.tfull_bar[b], 1), tg_mbar_init(&pp.tempty_bar[b], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (warp == 0 && lane < 2 * t.nphase) {   // descriptor fetch overlaps the predecessor's tail
+        const CUtensorMap *mp = (lane & 1) ? t.mapB[lane >> 1] : t.mapA[lane >> 1];
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(mp)) : "memory");
+    }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tg_smem_u32(&pp.tmem_slot)), "r"(512)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tg_smem_u32(&pp.tmem_slot)), "r"(256)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tg_fence_before();
     __syncthreads();
     tg_fence_after();
+    // everything above overlapped the previous kernel's tail (programmatic dependent launch); from here on its
+    // results are read
+    if (dbg && threadIdx.x == 64) dbg[1] = clock64();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (dbg && threadIdx.x == 64) dbg[2] = clock64();
     const uint32_t tmem_base = pp.tmem_slot;
-    int nk[2];
-    nk[0] = (t.K[0] + TG_KC - 1) / TG_KC, nk[1] = t.nphase > 1 ? (t.K[1] + TG_KC - 1) / TG_KC : 0;
-    const int total = nk[0] + nk[1];
+    const int nk0 = (t.K[0] + TG_KC - 1) / TG_KC;
+    const int total = t.i1 - t.i0;
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
         int stage = 0;
         uint32_t ph = 0;
-        for (int p = 0; p < t.nphase; ++p)
-            for (int kc = 0; kc < nk[p]; ++kc) {
+        for (int i = t.i0; i < t.i1; ++i) {
+            {
+                const int p = i < nk0 ? 0 : 1, kc = i < nk0 ? i : i - nk0;
                 tg_mbar_wait(&pp.empty_bar[stage], ph ^ 1, err, 21);
                 if (tg_elect_one()) {
                     uint8_t *sa = smem + stage * TG_STAGE_BYTES, *sb = sa + 3 * TG_A_PLANE;
@@ -292,6 +319,7 @@ __device__ __forceinline__ void tg_gemm_tile(const TgTileDesc &t, uint8_t *smem,
                 __syncwarp();
                 if (++stage == TG_STAGES) stage = 0, ph ^= 1;
             }
+        }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
         int stage = 0;
@@ -299,8 +327,9 @@ __device__ __forceinline__ void tg_gemm_tile(const TgTileDesc &t, uint8_t *smem,
         const uint32_t idesc = tg_idesc(t.mn_major);
         const uint32_t kstep = t.mn_major ? (2048u >> 4) : (32u >> 4);   // descriptor start-address step of a K = 16 slice
         for (int it = 0; it < total; ++it) {
-            const int buf = it & 1;
-            tg_mbar_wait(&pp.tempty_bar[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u, err, 23);
+            const int seg = it >> 1, buf = seg & 1;
+            const bool seg_first = (it & 1) == 0, seg_last = (it & 1) == 1 || it + 1 == total;
+            if (seg_first) tg_mbar_wait(&pp.tempty_bar[buf], ((uint32_t)(seg >> 1) & 1u) ^ 1u, err, 23);
             tg_mbar_wait(&pp.full_bar[stage], ph, err, 22);
             tg_fence_after();
             if (tg_elect_one()) {
@@ -309,20 +338,20 @@ __device__ __forceinline__ void tg_gemm_tile(const TgTileDesc &t, uint8_t *smem,
                                al = tg_sdesc(sa + 2 * TG_A_PLANE, TG_A_PLANE / 2);
                 const uint64_t bh = tg_sdesc(sb, TG_B_PLANE), bm = tg_sdesc(sb + TG_B_PLANE, TG_B_PLANE),
                                bl = tg_sdesc(sb + 2 * TG_B_PLANE, TG_B_PLANE);
-                const uint32_t d0 = tmem_base + buf * (3 * TG_BN), d1 = d0 + TG_BN, d2 = d1 + TG_BN;   // h.h | 2^-8 | 2^-16 terms
+                const uint32_t d0 = tmem_base + buf * (2 * TG_BN), d1 = d0 + TG_BN;   // h.h | all smaller terms
 #pragma unroll
                 for (int ks = 0; ks < TG_KC / 16; ++ks) {
                     const uint64_t o = (uint64_t)(ks * kstep);
-                    const uint32_t acc = ks > 0 ? 1u : 0u;
-                    tg_mma(d2, am + o, bm + o, idesc, acc);
-                    tg_mma(d2, ah + o, bl + o, idesc, 1u);
-                    tg_mma(d2, al + o, bh + o, idesc, 1u);
-                    tg_mma(d1, ah + o, bm + o, idesc, acc);
+                    const uint32_t acc = (ks > 0 || !seg_first) ? 1u : 0u;
+                    tg_mma(d1, am + o, bm + o, idesc, acc);
+                    tg_mma(d1, ah + o, bl + o, idesc, 1u);
+                    tg_mma(d1, al + o, bh + o, idesc, 1u);
+                    tg_mma(d1, ah + o, bm + o, idesc, 1u);
                     tg_mma(d1, am + o, bh + o, idesc, 1u);
                     tg_mma(d0, ah + o, bh + o, idesc, acc);
                 }
-                tg_commit(&pp.empty_bar[stage]);    // the operand stage is free when these MMAs retire
-                tg_commit(&pp.tfull_bar[buf]);      // and the partial tile can be drained
+                tg_commit(&pp.empty_bar[stage]);                  // the operand stage is free when these MMAs retire
+                if (seg_last) tg_commit(&pp.tfull_bar[buf]);      // and the partial tile can be drained
             }
             __syncwarp();
             if (++stage == TG_STAGES) stage = 0, ph ^= 1;
@@ -332,24 +361,25 @@ __device__ __forceinline__ void tg_gemm_tile(const TgTileDesc &t, uint8_t *smem,
         const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll
         for (int j = 0; j < TG_BN; ++j) racc[j] = 0.f;
-        for (int it = 0; it < total; ++it) {
-            const int buf = it & 1;
-            tg_mbar_wait(&pp.tfull_bar[buf], (uint32_t)(it >> 1) & 1u, err, 24);
+        const int nseg = (total + 1) >> 1;
+        for (int seg = 0; seg < nseg; ++seg) {
+            const int buf = seg & 1;
+            tg_mbar_wait(&pp.tfull_bar[buf], (uint32_t)(seg >> 1) & 1u, err, 24);
             tg_fence_after();
 #pragma unroll
             for (int cb = 0; cb < TG_BN; cb += 32) {
-                uint32_t r0[32], r1[32], r2[32];
-                tg_tmem_ld32(tmem_lane + buf * (3 * TG_BN) + cb, r0);
-                tg_tmem_ld32(tmem_lane + buf * (3 * TG_BN) + TG_BN + cb, r1);
-                tg_tmem_ld32(tmem_lane + buf * (3 * TG_BN) + 2 * TG_BN + cb, r2);
+                uint32_t r0[32], r1[32];
+                tg_tmem_ld32(tmem_lane + buf * (2 * TG_BN) + cb, r0);
+                tg_tmem_ld32(tmem_lane + buf * (2 * TG_BN) + TG_BN + cb, r1);
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    racc[cb + j] += (__uint_as_float(r2[j]) + __uint_as_float(r1[j])) + __uint_as_float(r0[j]);
+                for (int j = 0; j < 32; ++j) racc[cb + j] += __uint_as_float(r1[j]) + __uint_as_float(r0[j]);
             }
             tg_fence_before();
             __syncwarp();
             if (lane == 0) tg_mbar_arrive(&pp.tempty_bar[buf]);
+            if (dbg && threadIdx.x == 64 && seg == 0) dbg[3] = clock64();
         }
+        if (dbg && threadIdx.x == 64) dbg[4] = clock64();
     }
 }
 
@@ -359,21 +389,70 @@ __device__ __forceinline__ void tg_gemm_finish(TgPipe &pp)
     __syncthreads();
     if ((threadIdx.x >> 5) == 1) {
         tg_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(pp.tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(pp.tmem_slot), "r"(256) : "memory");
     }
 }
 
-// 64 output values of one row -> the three bf16 planes of a row-major matrix (128 contiguous bytes per plane)
-__device__ __forceinline__ void tg_store_planes(__nv_bfloat16 *base, int64_t plane_stride, int64_t elem_off, const float (&v)[TG_BN])
+__device__ __forceinline__ void tg_tma_store_2d(const void *smem_src, const CUtensorMap *map, int c0, int c1)
 {
-#pragma unroll
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(map)), "r"(tg_smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// 64 output values of tile row `row` -> the three bf16 planes of the staging tile in shared memory (3 x [128 rows x
+// 128 B], 128-byte swizzle: 16-byte chunk c of a row sits at chunk c ^ (row & 7)), which one thread then hands to TMA.
+__device__ __forceinline__ void tg_stage_planes(uint8_t *stg, int row, const float *v)
+{
+    const uint32_t base = tg_smem_u32(stg) + (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+#pragma unroll 1
     for (int j = 0; j < TG_BN; j += 8) {
         uint32_t h[4], m[4], l[4];
 #pragma unroll
         for (int e = 0; e < 8; e += 2) tg_split3(v[j + e], v[j + e + 1], h[e >> 1], m[e >> 1], l[e >> 1]);
-        *reinterpret_cast<uint4 *>(base + elem_off + j) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4 *>(base + plane_stride + elem_off + j) = make_uint4(m[0], m[1], m[2], m[3]);
-        *reinterpret_cast<uint4 *>(base + 2 * plane_stride + elem_off + j) = make_uint4(l[0], l[1], l[2], l[3]);
+        const uint32_t o = base + ((((uint32_t)j >> 3) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + TG_A_PLANE), "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + 2 * TG_A_PLANE), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+    }
+}
+// the 128 epilogue threads have staged their rows: one of them sends the three planes of the tile to global memory
+__device__ __forceinline__ void tg_store_tile(uint8_t *stg, const CUtensorMap *map, int col0, int row0, int plane_rows)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) {
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) tg_tma_store_2d(stg + pl * TG_A_PLANE, map, col0, pl * plane_rows + row0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+// [128 rows][64 floats] tile between global memory (row pitch `ld`) and shared memory (row pitch 65), coalesced: a warp
+// moves one row per instruction (lane = column).  Rows >= nrows / columns >= ncols are read as 0 and not written.
+constexpr int TG_FT_LD = TG_BN + 1;
+__device__ __forceinline__ void tg_ftile_load(float *tile, const float *g, int64_t ld, int nrows, int ncols)
+{
+    const int wq = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
+    for (int rr = 0; rr < 32; ++rr) {
+        const int r = wq * 32 + rr;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = 32 * h + lane;
+            tile[r * TG_FT_LD + j] = (r < nrows && j < ncols) ? __ldg(g + (int64_t)r * ld + j) : 0.f;
+        }
+    }
+}
+__device__ __forceinline__ void tg_ftile_store(const float *tile, float *g, int64_t ld, int nrows, int ncols)
+{
+    const int wq = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
+    for (int rr = 0; rr < 32; ++rr) {
+        const int r = wq * 32 + rr;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = 32 * h + lane;
+            if (r < nrows && j < ncols) g[(int64_t)r * ld + j] = tile[r * TG_FT_LD + j];
+        }
     }
 }
 
@@ -387,134 +466,221 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_layer_kernel(const TgArgs ar
     for (int i = threadIdx.x; i < (int)(sizeof(TgStep) / 4); i += TG_THREADS)
         reinterpret_cast<uint32_t *>(&st)[i] = reinterpret_cast<const uint32_t *>(args.step)[i];
     __syncthreads();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next layer may set itself up while this one runs
     TgTileDesc t;
     t.nphase = st.nphase, t.mn_major = false;
     for (int p = 0; p < 2; ++p) {
         t.mapA[p] = args.maps + st.mapA[p], t.mapB[p] = args.maps + st.mapB[p];
         t.rowsA[p] = st.rowsA[p], t.rowsB[p] = st.rowsB[p], t.K[p] = st.K[p];
     }
-    const int nt = blockIdx.x % st.n_tiles, mt = blockIdx.x / st.n_tiles;
+    const int S = args.splitk;
+    const int tile = blockIdx.x / S, kr = blockIdx.x - tile * S;
+    const int nt = tile % st.n_tiles, mt = tile / st.n_tiles;
     t.m0 = mt * TG_BM, t.n0 = nt * TG_BN;
+    {
+        const int T = (st.K[0] + TG_KC - 1) / TG_KC + (st.nphase > 1 ? (st.K[1] + TG_KC - 1) / TG_KC : 0);
+        t.i0 = (int)((int64_t)T * kr / S), t.i1 = (int)((int64_t)T * (kr + 1) / S);
+    }
     float racc[TG_BN];
-    tg_gemm_tile(t, smem, pp, racc, args.err);
+    long long *dbg = (args.dbg && blockIdx.x == 0) ? args.dbg + 8 * args.dbg_slot : nullptr;
+    tg_gemm_tile(t, smem, pp, racc, args.err, dbg);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp >= 2) {
+    __shared__ int s_last;
+    bool do_epilogue = true;
+    if (S > 1) {
+        // split-K: park the partial tile in the workspace; the last k-range to arrive adds all of them in k-range order
+        if (warp >= 2) {
+            const int row = (warp & 3) * 32 + lane;
+            // [tile][k-range][float4 column][row]: a warp instruction writes 32 consecutive rows = 512 contiguous bytes
+            float4 *wsp = reinterpret_cast<float4 *>(args.ws) + (size_t)(tile * S + kr) * (TG_BN / 4) * TG_BM + row;
+#pragma unroll
+            for (int j = 0; j < TG_BN; j += 4) wsp[(size_t)(j >> 2) * TG_BM] = make_float4(racc[j], racc[j + 1], racc[j + 2], racc[j + 3]);
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) {
+                const int ticket = atomicAdd(args.sem + tile, 1);
+                s_last = ticket == S - 1 ? 1 : 0;
+                if (ticket == S - 1) args.sem[tile] = 0;   // ready for the next launch
+                __threadfence();
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            do_epilogue = s_last != 0;
+            if (do_epilogue) {
+#pragma unroll
+                for (int j = 0; j < TG_BN; ++j) racc[j] = 0.f;
+                for (int r = 0; r < S; ++r) {
+                    const float4 *src = reinterpret_cast<const float4 *>(args.ws) + (size_t)(tile * S + r) * (TG_BN / 4) * TG_BM + row;
+#pragma unroll
+                    for (int j = 0; j < TG_BN; j += 4) {
+                        const float4 v4 = __ldcg(src + (size_t)(j >> 2) * TG_BM);
+                        racc[j] += v4.x, racc[j + 1] += v4.y, racc[j + 2] += v4.z, racc[j + 3] += v4.w;
+                    }
+                }
+            }
+        }
+    }
+    if (warp >= 2 && do_epilogue) {
+        // The operand stages are free (every MMA of this CTA has retired): stage 0 becomes the bf16x3 staging tile of the
+        // output (48 KB, sent by TMA), stage 1 a [128][65] fp32 tile for the loss steps' coalesced global traffic.
+        uint8_t *stg = smem;
+        float *ftile = reinterpret_cast<float *>(smem + TG_STAGE_BYTES);
         const int row = (warp & 3) * 32 + lane;
         const int grow = t.m0 + row;
         const bool valid = grow < args.B;
         const int N = st.N, n0 = t.n0;
+        const int nrows = args.B - t.m0 < TG_BM ? (args.B - t.m0 < 0 ? 0 : args.B - t.m0) : TG_BM;
+        const int ncols = N - n0 < TG_BN ? (N - n0 < 0 ? 0 : N - n0) : TG_BN;
         const Consts &c = args.c;
-        float v[TG_BN];
-        if (st.epi == TG_ACT || st.epi == TG_BWD) {
-            uint32_t mw[2] = {0u, 0u};
+        // The accumulators go to this thread's own row of a [128][65] fp32 tile in shared memory and every epilogue is a
+        // ROLLED loop over that row: fully unrolled over 64 register accumulators the three epilogues were ~100 KB of
+        // straight-line code executed once per CTA, i.e. bound by instruction fetch (measured: 8 - 12 us per tile).
+        float *vrow = ftile + row * TG_FT_LD;
+        float *yrow = reinterpret_cast<float *>(smem + TG_STAGE_BYTES + 36 * 1024) + row * TG_FT_LD;   // second tile (targets / residual)
+#pragma unroll
+        for (int j = 0; j < TG_BN; ++j) vrow[j] = racc[j];
+        const int epi = st.epi;
+        if (epi == TG_ACT || epi == TG_BWD) {
+            uint32_t mw[2] = {0xffffffffu, 0xffffffffu};
             if (st.apply_mask) {
                 const uint2 m2 = *reinterpret_cast<const uint2 *>(args.masks + st.mask_off + (size_t)grow * st.mask_ld + (n0 >> 5));
                 mw[0] = m2.x, mw[1] = m2.y;
             }
+            const float *bias = st.bias;
+            const float bscale = st.bias_scale;
+            const bool relu = st.relu != 0, ones = st.write_ones != 0;
             uint32_t sw[2] = {0u, 0u};
-#pragma unroll
-            for (int j = 0; j < TG_BN; ++j) {
-                const int col = n0 + j;
-                float y = racc[j];
-                if (st.bias && col < N) y += st.bias_scale * __ldg(st.bias + col);
-                if (st.relu) y = fmaxf(y, 0.f);
-                if (st.apply_mask) y = ((mw[j >> 5] >> (j & 31)) & 1u) ? y : 0.f;
-                if (st.save_mask) sw[j >> 5] |= (y > 0.f ? 1u : 0u) << (j & 31);
-                if (!(valid && col < N)) y = (valid && col == N && st.write_ones) ? 1.f : 0.f;
-                v[j] = y;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                uint32_t bits = 0u;
+                const uint32_t mwh = mw[h];
+#pragma unroll 4
+                for (int jj = 0; jj < 32; ++jj) {
+                    const int j = 32 * h + jj, col = n0 + j;
+                    float y = vrow[j];
+                    if (bias && col < N) y += bscale * __ldg(bias + col);
+                    if (relu) y = fmaxf(y, 0.f);
+                    y = ((mwh >> jj) & 1u) ? y : 0.f;
+                    bits |= (y > 0.f ? 1u : 0u) << jj;
+                    if (!(valid && col < N)) y = (valid && col == N && ones) ? 1.f : 0.f;
+                    vrow[j] = y;
+                }
+                sw[h] = bits;
             }
             if (st.save_mask)
                 *reinterpret_cast<uint2 *>(args.masks + st.mask_off + (size_t)grow * st.mask_ld + (n0 >> 5)) = make_uint2(sw[0], sw[1]);
-            tg_store_planes(args.act + st.out_off, (int64_t)st.out_rows * st.out_ld, (int64_t)grow * st.out_ld + n0, v);
-        } else if (st.epi == TG_HEAD) {
-            // v = yhat; residual in normalised space (Auxilleryfunc, linna/util.py:1070-1088)
+            tg_stage_planes(stg, row, vrow);
+            tg_store_tile(stg, args.maps + st.mapOut, n0, t.m0, st.out_rows);
+        } else if (epi == TG_HEAD) {
+            // vrow = yhat - bias; residual in normalised space (Auxilleryfunc, linna/util.py:1070-1088)
+            float *ytile = reinterpret_cast<float *>(smem + TG_STAGE_BYTES + 36 * 1024);
+            tg_ftile_load(ytile, args.target + (size_t)t.m0 * N + n0, N, nrows, ncols);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             uint32_t okw[2] = {0u, 0u};
-#pragma unroll
-            for (int j = 0; j < TG_BN; ++j) {
-                const int col = n0 + j;
-                float dv = 0.f;
-                if (valid && col < N) {
-                    const float yh = racc[j] + (st.bias ? st.bias_scale * __ldg(st.bias + col) : 0.f);
-                    const float ys = __ldg(c.y_std + col), ym = __ldg(c.y_mean + col);
-                    const float sg = c.sigma ? __ldg(c.sigma + col) : 1.f;
-                    const float dh = __ldg(c.data_hat + col);
-                    const float Y = __ldg(args.target + (size_t)grow * N + col);
-                    float tt = Y / sg;                                              // util.py:432
-                    if (c.ypositive) tt = logf(tt);                                 // util.py:567-568
-                    tt = (tt - ym) / ys;                                            // util.py:570
-                    const bool ok = !(Y == 1e-30f || Y == 1e10f || dh == 1e-30f);    // util.py:1072
-                    dv = args.delta_kind == 0 ? tt - yh : args.delta_kind == 1 ? tt - dh : yh - dh;
-                    if (!ok) dv = 0.f;
-                    okw[j >> 5] |= (ok ? 1u : 0u) << (j & 31);
+            const float *bias = st.bias;
+            const float bscale = st.bias_scale;
+            const int kind = args.delta_kind;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                uint32_t bits = 0u;
+#pragma unroll 2
+                for (int jj = 0; jj < 32; ++jj) {
+                    const int j = 32 * h + jj, col = n0 + j;
+                    float dv = 0.f;
+                    if (valid && col < N) {
+                        const float yh = vrow[j] + (bias ? bscale * __ldg(bias + col) : 0.f);
+                        const float ys = __ldg(c.y_std + col), ym = __ldg(c.y_mean + col);
+                        const float sg = c.sigma ? __ldg(c.sigma + col) : 1.f;
+                        const float dh = __ldg(c.data_hat + col);
+                        const float Y = yrow[j];
+                        float tt = Y / sg;                                              // util.py:432
+                        if (c.ypositive) tt = logf(tt);                                 // util.py:567-568
+                        tt = (tt - ym) / ys;                                            // util.py:570
+                        const bool ok = !(Y == 1e-30f || Y == 1e10f || dh == 1e-30f);    // util.py:1072
+                        dv = kind == 0 ? tt - yh : kind == 1 ? tt - dh : yh - dh;
+                        if (!ok) dv = 0.f;
+                        bits |= (ok ? 1u : 0u) << jj;
+                    }
+                    vrow[j] = dv;
                 }
-                v[j] = dv;
+                okw[h] = bits;
             }
             *reinterpret_cast<uint2 *>(args.masks + st.mask_off + (size_t)grow * st.mask_ld + (n0 >> 5)) = make_uint2(okw[0], okw[1]);
-#pragma unroll
-            for (int j = 0; j < TG_BN; j += 4)
-                *reinterpret_cast<float4 *>(args.delta32 + (size_t)grow * args.dld + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            tg_store_planes(args.act + st.out_off, (int64_t)st.out_rows * st.out_ld, (int64_t)grow * st.out_ld + n0, v);
+            tg_stage_planes(stg, row, vrow);
+            tg_store_tile(stg, args.maps + st.mapOut, n0, t.m0, st.out_rows);     // (its barrier also publishes the fp32 rows)
+            tg_ftile_store(ftile, args.delta32 + (size_t)t.m0 * args.dld + n0, args.dld, TG_BM, TG_BN);
         } else {   // TG_LOSSQ: q = delta @ Chat^-1 ; chi2 += q . delta ; g_yhat = -2 q ok / (cmd B)
+            float *dtile = reinterpret_cast<float *>(smem + TG_STAGE_BYTES + 36 * 1024);
+            tg_ftile_load(dtile, args.delta32 + (size_t)t.m0 * args.dld + n0, args.dld, TG_BM, TG_BN);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             const uint2 ok2 = *reinterpret_cast<const uint2 *>(args.masks + st.mask_off + (size_t)grow * st.mask_ld + (n0 >> 5));
             const uint32_t okw[2] = {ok2.x, ok2.y};
             const float rs = (valid && args.cmd) ? -2.0f * args.loss_inv_B / __ldg(args.cmd + grow) : 0.f;
             float part = 0.f;
-#pragma unroll
-            for (int j = 0; j < TG_BN; j += 4) {
-                const float4 d4 = *reinterpret_cast<const float4 *>(args.delta32 + (size_t)grow * args.dld + n0 + j);
-                const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int col = n0 + j + e;
-                    const float q = (valid && col < N) ? racc[j + e] : 0.f;
-                    part = fmaf(q, dd[e], part);
-                    v[j + e] = ((okw[(j + e) >> 5] >> ((j + e) & 31)) & 1u) ? q * rs : 0.f;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t okh = okw[h];
+#pragma unroll 4
+                for (int jj = 0; jj < 32; ++jj) {
+                    const int j = 32 * h + jj, col = n0 + j;
+                    const float q = (valid && col < N) ? vrow[j] : 0.f;
+                    part = fmaf(q, yrow[j], part);
+                    vrow[j] = ((okh >> jj) & 1u) ? q * rs : 0.f;
                 }
             }
             args.chi_part[(size_t)grow * args.chi_ld + (n0 / TG_BN)] = part;
-            if (args.want_grad)
-                tg_store_planes(args.act + st.out_off, (int64_t)st.out_rows * st.out_ld, (int64_t)grow * st.out_ld + n0, v);
+            if (args.want_grad) {
+                tg_stage_planes(stg, row, vrow);
+                tg_store_tile(stg, args.maps + st.mapOut, n0, t.m0, st.out_rows);
+            }
         }
     }
+    if (dbg && threadIdx.x == 64) dbg[5] = clock64();
     tg_gemm_finish(pp);
+    if (dbg && threadIdx.x == 64) dbg[6] = clock64();
 }
 
 // ------------------------------------------------------------------------------------------ weight gradients + AdamW
+// torch.optim.AdamW (linna/predictor_gpu.py:267): decoupled weight decay, bias-corrected moments
 __device__ __forceinline__ float tg_adamw(const AdamArgs &a, int idx, float g)
 {
     float p = a.params[idx], m = a.m[idx], v = a.v[idx];
-    p *= 1.0f - a.lr * a.wd;                       // decoupled weight decay (torch.optim.AdamW, predictor_gpu.py:267)
+    p *= 1.0f - a.lr * a.wd;
     m = m + (1.0f - a.beta1) * (g - m);
     v = v * a.beta2 + (1.0f - a.beta2) * g * g;
     const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
     p = p - (a.lr / a.bc1) * (m / denom);
     a.params[idx] = p, a.m[idx] = m, a.v[idx] = v;
-    a.blob[a.map_fwd[idx]] = p;                    // the FP32 kernel's packed copies (predict / chi^2 calls between steps)
-    const int mb = a.map_bwd[idx];
-    if (mb >= 0) a.blob[mb] = p;
     return p;
 }
 
-// bf16x3 planes of one weight into the packed forward [n][k] and backward [k][n] copies
+__device__ __forceinline__ void tg_split3_1(float x, __nv_bfloat16 &h, __nv_bfloat16 &m, __nv_bfloat16 &l)
+{
+    h = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h);
+    m = __float2bfloat16_rn(r1);
+    l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+}
+
+// bf16x3 planes of one weight into the packed forward [n][k] and backward [k][n] copies (set-up / repack path)
 __device__ __forceinline__ void tg_pack_weight(__nv_bfloat16 *wblob, const TgWLayer &L, int n, int k, float p)
 {
-    const float x = p * L.pack_scale;
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    const float r1 = x - __bfloat162float(h);
-    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
-    const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+    __nv_bfloat16 h, m, l;
+    tg_split3_1(p * L.pack_scale, h, m, l);
     const int64_t pf = (int64_t)L.wf_rows * L.wf_ld, of = L.wf_off + (int64_t)n * L.wf_ld + k;
     wblob[of] = h, wblob[of + pf] = m, wblob[of + 2 * pf] = l;
     const int64_t pb = (int64_t)L.wb_rows * L.wb_ld, ob = L.wb_off + (int64_t)k * L.wb_ld + n;
     wblob[ob] = h, wblob[ob + pb] = m, wblob[ob + 2 * pb] = l;
 }
 
+constexpr int TG_WT_LD = TG_BN + 1;   // padded row pitch of the gradient tile in shared memory
+
 __global__ void __launch_bounds__(TG_THREADS, 1) tg_wgrad_kernel(const TgArgs args)
 {
     extern __shared__ uint8_t tg_smem_raw[];
     __shared__ TgPipe pp;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tg_smem_raw) + 1023) & ~(uintptr_t)1023);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const TgWTile wt = args.wtiles[blockIdx.x];
     const TgWLayer L = args.wlayers[wt.layer];
     TgTileDesc t;
@@ -523,29 +689,87 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_wgrad_kernel(const TgArgs ar
     t.rowsA[0] = t.rowsA[1] = t.rowsB[0] = t.rowsB[1] = args.B_pad;
     t.K[0] = args.B_eff, t.K[1] = 0;
     t.m0 = wt.m0, t.n0 = wt.n0;
+    t.i0 = 0, t.i1 = args.B_eff / TG_KC;
     float racc[TG_BN];
-    tg_gemm_tile(t, smem, pp, racc, args.err);
+    long long *dbg = (args.dbg && blockIdx.x == 0) ? args.dbg + 8 * 40 : nullptr;
+    tg_gemm_tile(t, smem, pp, racc, args.err, dbg);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp >= 2) {
-        const int n = wt.m0 + (warp & 3) * 32 + lane;
-        if (n < L.N) {
+        // The GEMM leaves thread = row n with 64 k-values; parameters, moments and the forward copies are contiguous in
+        // k.  The tile goes through shared memory (the operand stages are free: every MMA has retired) so that pass 1
+        // runs with lane = k (coalesced AdamW state, forward planes, backward FP32 copy) and pass 2 with lane = n
+        // (backward planes, forward FP32 copy).
+        float *tile = reinterpret_cast<float *>(smem);
+        const int wq = warp & 3, row = wq * 32 + lane;
 #pragma unroll
-            for (int j = 0; j < TG_BN; ++j) {
-                const int k = wt.n0 + j;
-                const float g = L.gscale * racc[j];
+        for (int j = 0; j < TG_BN; ++j) tile[row * TG_WT_LD + j] = L.gscale * racc[j];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const AdamArgs &ad = args.adam;
+        const int64_t pf = (int64_t)L.wf_rows * L.wf_ld;
+        // four rows (eight coalesced 128-byte lines of each of p, m, v) in flight per batch
+        for (int r0 = 0; r0 < 32; r0 += 4) {
+            int idx[8];
+            float g[8], pp_[8], mm_[8], vv_[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r = wq * 32 + r0 + (q >> 1), n = wt.m0 + r, j = 32 * (q & 1) + lane, k = wt.n0 + j;
+                idx[q] = -1;
+                if (n < L.N) {
+                    if (k < L.K) idx[q] = L.w_flat + n * L.K + k;
+                    else if (k == L.K && L.b_flat >= 0) idx[q] = L.b_flat + n;
+                }
+                g[q] = tile[r * TG_WT_LD + j];
+            }
+            if (ad.fuse) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (idx[q] >= 0) pp_[q] = ad.params[idx[q]], mm_[q] = ad.m[idx[q]], vv_[q] = ad.v[idx[q]];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (idx[q] < 0) continue;
+                const int r = wq * 32 + r0 + (q >> 1), n = wt.m0 + r, j = 32 * (q & 1) + lane, k = wt.n0 + j;
+                if (!ad.fuse) { ad.grads[idx[q]] = g[q]; continue; }
+                float p = pp_[q], m = mm_[q], v = vv_[q];
+                p *= 1.0f - ad.lr * ad.wd;                       // torch.optim.AdamW (predictor_gpu.py:267)
+                m = m + (1.0f - ad.beta1) * (g[q] - m);
+                v = v * ad.beta2 + (1.0f - ad.beta2) * g[q] * g[q];
+                const float denom = sqrtf(v) / ad.bc2_sqrt + ad.eps;
+                p = p - (ad.lr / ad.bc1) * (m / denom);
+                ad.params[idx[q]] = p, ad.m[idx[q]] = m, ad.v[idx[q]] = v;
                 if (k < L.K) {
-                    const int idx = L.w_flat + n * L.K + k;
-                    if (args.adam.fuse) tg_pack_weight(args.wblob, L, n, k, tg_adamw(args.adam, idx, g));
-                    else args.adam.grads[idx] = g;
-                } else if (k == L.K && L.b_flat >= 0) {
-                    const int idx = L.b_flat + n;
-                    if (args.adam.fuse) tg_adamw(args.adam, idx, g);
-                    else args.adam.grads[idx] = g;
+                    tile[r * TG_WT_LD + j] = p;
+                    __nv_bfloat16 b0, b1, b2;
+                    tg_split3_1(p * L.pack_scale, b0, b1, b2);
+                    const int64_t of = L.wf_off + (int64_t)n * L.wf_ld + k;
+                    args.wblob[of] = b0, args.wblob[of + pf] = b1, args.wblob[of + 2 * pf] = b2;
+                    ad.blob[L.blob_b + (int64_t)n * L.blob_ldb + k] = p;
+                } else
+                    ad.blob[L.blob_bias + n] = p;
+            }
+        }
+        if (ad.fuse) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int n = wt.m0 + row;
+            if (n < L.N) {
+                const int64_t pb = (int64_t)L.wb_rows * L.wb_ld;
+#pragma unroll 8
+                for (int j = 0; j < TG_BN; ++j) {
+                    const int k = wt.n0 + j;
+                    if (k >= L.K) break;
+                    const float p = tile[row * TG_WT_LD + j];
+                    __nv_bfloat16 b0, b1, b2;
+                    tg_split3_1(p * L.pack_scale, b0, b1, b2);
+                    const int64_t ob = L.wb_off + (int64_t)k * L.wb_ld + n;
+                    args.wblob[ob] = b0, args.wblob[ob + pb] = b1, args.wblob[ob + 2 * pb] = b2;
+                    ad.blob[L.blob_f + (int64_t)k * L.blob_ldf + n] = p;
                 }
             }
         }
     }
+    if (dbg && threadIdx.x == 64) dbg[5] = clock64();
     tg_gemm_finish(pp);
+    if (dbg && threadIdx.x == 64) dbg[6] = clock64();
 }
 
 // params -> packed bf16x3 planes of every weight matrix (set-up, load_state_dict, after the stand-alone AdamW)
@@ -626,6 +850,10 @@ struct TgContext {
     int in_ld = 0;
     int lossq_tiles = 0;
     int64_t max_wn = 0;
+    float *ws = nullptr;
+    int32_t *sem = nullptr;
+    int max_tiles = 0, num_sms = 148;
+    long long *dbg = nullptr;     // LINNA_TG_DEBUG
 };
 
 cudaError_t tg_repack(TgContext *t, const float *params, cudaStream_t stream);
@@ -635,6 +863,7 @@ void tg_destroy(TgContext *t)
     if (!t) return;
     cudaFree(t->act), cudaFree(t->wblob), cudaFree(t->masks), cudaFree(t->delta32), cudaFree(t->chi_part);
     cudaFree(t->maps_dev), cudaFree(t->steps_dev), cudaFree(t->wlayers_dev), cudaFree(t->wtiles_dev), cudaFree(t->err_dev);
+    cudaFree(t->ws), cudaFree(t->sem), cudaFree(t->dbg);
     delete t;
 }
 
@@ -644,7 +873,8 @@ static inline int tg_pad(int n, int q) { return (n + q - 1) / q * q; }
 // tile table.  `flat_off` gives, per op, the offsets of (w, b, w2, b2, ws) in the flat parameter vector.  Returns
 // nullptr and fills `why` when the network shape is not covered (identity skips, extra linear branch).
 TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> &flat_off,
-                    const std::vector<std::array<const float *, 2>> &bias_ptr, std::string &why)
+                    const std::vector<std::array<const float *, 2>> &bias_ptr, const std::vector<std::array<int64_t, 8>> &blob_off,
+                    std::string &why)
 {
     if (m->has_extra) { why = "extra linear branch"; return nullptr; }
     for (const OpHost &op : m->ops)
@@ -768,7 +998,7 @@ TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> 
         TgStep s;
         memset(&s, 0, sizeof s);
         s.epi = epi, s.nphase = 1, s.N = N, s.bias = nullptr, s.bias_scale = 1.f;
-        s.out_off = mats[out_mat].off, s.out_ld = mats[out_mat].ld, s.out_rows = B_pad;
+        s.out_off = mats[out_mat].off, s.out_ld = mats[out_mat].ld, s.out_rows = B_pad, s.mapOut = mats[out_mat].mapA;
         s.n_tiles = mats[out_mat].ld / 64;
         return s;
     };
@@ -852,9 +1082,12 @@ TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> 
 
     // ---- weight-gradient layers and tiles
     std::vector<TgWLayer> wl;
-    auto add_wl = [&](int gz_mat, int x_mat, int N, int K, int wf, int bf, float gs, const WMat &f, const WMat &b) {
+    auto pad4i = [](int n) { return (n + 3) & ~3; };
+    auto add_wl = [&](int gz_mat, int x_mat, int N, int K, int wf, int bf, float gs, const WMat &f, const WMat &b, int64_t bl_f,
+                      int64_t bl_b, int64_t bl_bias) {
         TgWLayer L;
         memset(&L, 0, sizeof L);
+        L.blob_f = bl_f, L.blob_b = bl_b, L.blob_bias = bl_bias, L.blob_ldf = pad4i(N), L.blob_ldb = pad4i(K);
         L.mapA = mats[gz_mat].mapMN, L.mapB = mats[x_mat].mapMN, L.N = N, L.K = K, L.w_flat = wf, L.b_flat = bf;
         L.gscale = gs, L.pack_scale = gs;
         L.wf_off = f.off, L.wf_ld = f.ld, L.wf_rows = f.rows, L.wb_off = b.off, L.wb_ld = b.ld, L.wb_rows = b.rows;
@@ -864,11 +1097,14 @@ TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> 
         const OpHost &op = m->ops[i];
         const int xin = i == 0 ? mX : mAct[i - 1];
         if (op.kind == LINNA_OP_LINEAR) {
-            add_wl(mGz[i], xin, op.out, op.in, flat_off[i][0], flat_off[i][1], 1.f, ow[i].f, ow[i].b);
+            add_wl(mGz[i], xin, op.out, op.in, flat_off[i][0], flat_off[i][1], 1.f, ow[i].f, ow[i].b, blob_off[i][0], blob_off[i][1],
+                   blob_off[i][2]);
         } else {
-            add_wl(mGzh[i], xin, op.mid, op.in, flat_off[i][0], flat_off[i][1], 1.f, ow[i].f, ow[i].b);
-            add_wl(mGz[i], mHid[i], op.out, op.mid, flat_off[i][2], flat_off[i][3], op.alpha, ow[i].f2, ow[i].b2);
-            add_wl(mGz[i], xin, op.out, op.in, flat_off[i][4], -1, 1.f, ow[i].fs, ow[i].bs);
+            add_wl(mGzh[i], xin, op.mid, op.in, flat_off[i][0], flat_off[i][1], 1.f, ow[i].f, ow[i].b, blob_off[i][0], blob_off[i][1],
+                   blob_off[i][2]);
+            add_wl(mGz[i], mHid[i], op.out, op.mid, flat_off[i][2], flat_off[i][3], op.alpha, ow[i].f2, ow[i].b2, blob_off[i][3],
+                   blob_off[i][4], blob_off[i][5]);
+            add_wl(mGz[i], xin, op.out, op.in, flat_off[i][4], -1, 1.f, ow[i].fs, ow[i].bs, blob_off[i][6], blob_off[i][7], -1);
         }
     }
     std::vector<TgWTile> tiles;
@@ -909,6 +1145,15 @@ TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> 
     cudaMemcpy(t->wtiles_dev, tiles.data(), tiles.size() * sizeof(TgWTile), cudaMemcpyHostToDevice);
     if (cudaMalloc(&t->err_dev, sizeof(int)) != cudaSuccess) return bail("cudaMalloc err");
     cudaMemset(t->err_dev, 0, sizeof(int));
+    t->num_sms = m->num_sms;
+    if (getenv("LINNA_TG_DEBUG")) {
+        if (cudaMalloc(&t->dbg, 64 * 8 * sizeof(long long)) != cudaSuccess) return bail("cudaMalloc dbg");
+        cudaMemset(t->dbg, 0, 64 * 8 * sizeof(long long));
+    }
+    for (const TgStep &s : t->steps) t->max_tiles = std::max(t->max_tiles, (B_pad / TG_BM) * s.n_tiles);
+    if (cudaMalloc(&t->ws, (size_t)t->max_tiles * 4 * TG_BM * TG_BN * sizeof(float)) != cudaSuccess) return bail("cudaMalloc split-K workspace");
+    if (cudaMalloc(&t->sem, (size_t)t->max_tiles * sizeof(int32_t)) != cudaSuccess) return bail("cudaMalloc split-K tickets");
+    cudaMemset(t->sem, 0, (size_t)t->max_tiles * sizeof(int32_t));
     if (cudaFuncSetAttribute(tg_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(tg_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES) != cudaSuccess)
         return bail("cudaFuncSetAttribute(tg kernels)");
@@ -952,7 +1197,37 @@ static TgArgs tg_args(const linna_model *m, TgContext *t, int64_t B)
     a.B_eff = (int)((B + TG_BM - 1) / TG_BM) * TG_BM;
     a.delta32 = t->delta32, a.dld = t->dld, a.chi_part = t->chi_part, a.chi_ld = t->chi_ld, a.c = m->consts;
     a.wlayers = t->wlayers_dev, a.wtiles = t->wtiles_dev, a.wblob = t->wblob, a.err = t->err_dev;
+    a.ws = t->ws, a.sem = t->sem, a.splitk = 1;
     return a;
+}
+
+// Programmatic dependent launch: the kernel may start (barrier set-up, tensor-memory allocation) while its predecessor
+// in the stream is still running; it executes griddepcontrol.wait before touching anything the predecessor wrote.
+template <typename Kern>
+static cudaError_t tg_launch_pdl(Kern kern, int grid, cudaStream_t stream, const TgArgs &a)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(TG_THREADS), cfg.dynamicSmemBytes = TG_SMEM_BYTES, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+// one layer step over `m_tiles` row tiles: up to 4 k-ranges per tile when the layer has few tiles and a long contraction
+static cudaError_t tg_launch_layer(TgContext *t, TgArgs &a, int si, int m_tiles, cudaStream_t stream)
+{
+    const TgStep &s = t->steps[si];
+    const int tiles = m_tiles * s.n_tiles;
+    const int T = (s.K[0] + TG_KC - 1) / TG_KC + (s.nphase > 1 ? (s.K[1] + TG_KC - 1) / TG_KC : 0);
+    int S = 1;
+    while (S < 4 && tiles * (2 * S) <= t->num_sms && T >= 4 * S) S *= 2;
+    if (getenv("LINNA_TG_NO_SPLITK")) S = 1;
+    a.step = t->steps_dev + si, a.splitk = S;
+    a.dbg = t->dbg, a.dbg_slot = si;
+    return tg_launch_pdl(tg_layer_kernel, tiles * S, stream, a);
 }
 
 // forward + loss head + quadratic form over B <= max_batch rows; `want_grad` also leaves d loss / d yhat for the
@@ -971,8 +1246,7 @@ static int tg_forward_loss(const linna_model *m, TgContext *t, const float *X, c
     }
     // delta_kind 1 (target vs data) does not need the network at all, but the chi^2 calls are not hot: same path
     for (int si = 0; si <= t->i_lossq; ++si) {
-        a.step = t->steps_dev + si;
-        tg_layer_kernel<<<m_tiles * t->steps[si].n_tiles, TG_THREADS, TG_SMEM_BYTES, stream>>>(a);
+        if (tg_launch_layer(t, a, si, m_tiles, stream) != cudaSuccess) return -1;
         ++launches;
     }
     tg_loss_kernel<<<1, 256, 0, stream>>>(t->chi_part, t->chi_ld, t->lossq_tiles, cmd, (int)B, rows, mean);
@@ -988,12 +1262,11 @@ int tg_train_step(const linna_model *m, TgContext *t, const float *X, const floa
     TgArgs a = tg_args(m, t, B);
     const int m_tiles = (int)((B + TG_BM - 1) / TG_BM);
     for (int si = t->i_lossq + 1; si < t->n_steps; ++si) {
-        a.step = t->steps_dev + si;
-        tg_layer_kernel<<<m_tiles * t->steps[si].n_tiles, TG_THREADS, TG_SMEM_BYTES, stream>>>(a);
+        if (tg_launch_layer(t, a, si, m_tiles, stream) != cudaSuccess) return -1;
         ++launches;
     }
-    a.adam = ad;
-    tg_wgrad_kernel<<<t->n_wtiles, TG_THREADS, TG_SMEM_BYTES, stream>>>(a);
+    a.adam = ad, a.dbg = t->dbg;
+    if (tg_launch_pdl(tg_wgrad_kernel, t->n_wtiles, stream, a) != cudaSuccess) return -1;
     ++launches;
     return cudaGetLastError() == cudaSuccess ? launches : -1;
 }
@@ -1010,6 +1283,16 @@ int tg_chisq(const linna_model *m, TgContext *t, const float *X, const float *Y,
         launches += l;
     }
     return launches;
+}
+
+// LINNA_TG_DEBUG: cycle stamps of CTA 0 of every layer launch of the last step: [step][8]
+int tg_debug_read(TgContext *t, long long *out, int max_steps)
+{
+    if (!t || !t->dbg) return 0;
+    const int n = std::min(max_steps, 41);   // slots 0 .. n_steps-1: layer launches; slot 40: the weight-gradient launch
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, t->dbg, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+    return n;
 }
 
 int tg_check(TgContext *t)

@@ -86,6 +86,7 @@ def load_library():
     lib.linna_model_set_fold.argtypes = [vp, i32]
     lib.linna_debug_tc_counters.argtypes = [vp, vp, i32]
     lib.linna_model_last_kernel.argtypes = [vp]
+    lib.linna_debug_tg_counters.argtypes = [vp, vp, i32]
     u64 = ctypes.c_uint64
     lib.linna_stretch_propose.argtypes = [vp, i32, vp, vp, i64, i64, ctypes.c_float, u64, u64, vp, vp, vp]
     lib.linna_stretch_accept.argtypes = [vp, vp, vp, i32, vp, i64, vp, vp, vp, u64, u64, vp]
@@ -258,6 +259,12 @@ class Engine:
         """Per-CTA cycle counters of the last tensor-core launch (needs LINNA_TC_DEBUG=1 in the environment)."""
         buf = np.zeros((max_ctas, 128), np.int64)
         n = self.lib.linna_debug_tc_counters(self.handle, buf.ctypes.data_as(ctypes.c_void_p), max_ctas)
+        return buf[:n]
+
+    def tg_counters(self, max_steps=64):
+        """clock64 stamps of CTA 0 of every layer launch of the last training step (needs LINNA_TG_DEBUG=1)."""
+        buf = np.zeros((max_steps, 8), np.int64)
+        n = self.lib.linna_debug_tg_counters(self.handle, buf.ctypes.data_as(ctypes.c_void_p), max_steps)
         return buf[:n]
 
     def set_fold(self, on):

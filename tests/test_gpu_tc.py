@@ -169,16 +169,21 @@ def test_tc_fp16_overflow_rows_are_fixed_up():
     agree with the float64 oracle like any other row, and the neighbours are untouched."""
     p = synthetic.make_problem(12, 40, seed=21)
     p.X_std = p.X_std.copy()
-    p.X_std[3] = 2e-5                                   # theta_3 in [-5, 5]  ->  |xhat_3| up to 2.5e5
+    p.X_std[3] = 2e-5
+    # a unit Gaussian prior centred on 0 keeps theta_3 = u_3 exact: xhat_3 = u_3 / 2e-5 is well conditioned in float32
+    # (a flat prior would compute theta = 10 Phi(u) - 5 with float32 cancellation and make the TEST ill-conditioned)
+    p.priors[3] = dict(param="p3", dist="gauss", arg1=0.0, arg2=1.0)
+    p.theta0 = p.theta0.copy()
+    p.theta0[3] = 0.0
     e = engine.engine_from_problem(p, with_likelihood=False)
     m0 = e.predict(np.asarray(p.theta0, np.float32)[None, :], engine.LINNA_OUT_M)[0]
     p.set_data_from_prediction(m0)
     e.set_likelihood(p.priors, np.asarray(p.data, np.float32), p.inv_cov, 1.0)
     n = 3000
     u = synthetic.walkers(n, 12, scale=0.3, seed=2)
-    u[:, 3] *= 1e-4                                     # most walkers: |xhat_3| <~ 4e3, inside the fp16 range
+    u[:, 3] *= 1e-4                                     # most walkers: |xhat_3| <~ 5, inside the fp16 range
     hot = np.arange(5, n, 97)
-    u[hot, 3] = np.linspace(0.4, 1.2, hot.size) * np.where(np.arange(hot.size) % 2, 1, -1)   # |xhat_3| ~ 0.8e5 .. 2e5
+    u[hot, 3] = np.linspace(1.6, 4.0, hot.size) * np.where(np.arange(hot.size) % 2, 1, -1)   # |xhat_3| = 0.8e5 .. 2e5
     o = Oracle(p, arch)
     ref = o.lnp(u, np.float64, grad=True)
     assert np.all(np.isfinite(ref["lnp"]))
@@ -194,11 +199,16 @@ def test_tc_fp16_overflow_rows_are_fixed_up():
     # the fixed-up rows sit at chi^2 ~ 1e8 .. 1e10: the FP32 kernel's own accuracy there (a few 1e-6 relative)
     assert np.all(np.abs(lnp[hot] - ref["lnp"][hot]) <= 5e-6 * np.abs(ref["lnp"][hot])), np.abs(lnp[hot] / ref["lnp"][hot] - 1).max()
     e.set_path("ffma")
-    ff = e.lnp(_dev(u)).cpu().numpy()[hot].astype(np.float64)     # they ARE FP32-kernel rows (8-row tiles in the fix-up)
+    ffl, ffg = e.lnp_grad(_dev(u))                                # they ARE FP32-kernel rows (8-row tiles in the fix-up)
+    ff, ffg = ffl.cpu().numpy()[hot].astype(np.float64), ffg.cpu().numpy()[hot].astype(np.float64)
     assert np.all(np.abs(ff - lnp[hot]) <= 2e-6 * np.abs(ff))
+    assert np.max(np.max(np.abs(ffg - grad[hot]), axis=1) / np.max(np.abs(ffg), axis=1)) < 1e-4
     e.set_path("tc")
     rel = np.max(np.abs(grad - ref["grad"]), axis=1) / np.max(np.abs(ref["grad"]), axis=1)
-    assert np.median(rel) < 1e-5 and rel[cold].max() < 2e-4 and rel[hot].max() < 1e-3, (np.median(rel), rel[cold].max(), rel[hot].max())
+    # (the fixed-up rows carry float32's own error at |xhat| ~ 1e5: a few per cent of a gradient dominated by 1/X_std)
+    # 1 / X_std = 5e4 amplifies the relu kinks of the gradient along u_3 (two correct float32 evaluations can put a unit
+    # whose pre-activation is within rounding of 0 on either side, cf. test_tc_full_size_c3): a few rows may differ more
+    assert np.median(rel) < 1e-5 and np.mean(rel[cold] > 2e-4) < 3e-3 and rel[hot].max() < 5e-2, (np.median(rel), rel[cold].max(), rel[hot].max())
     assert np.array_equal(e.lnp(_dev(u)).cpu().numpy(), lnp.astype(np.float32))
     # a NaN input is still -inf (util.py:1015-1016) after the fix-up
     u2 = u.copy()

@@ -107,18 +107,25 @@ def test_adamw_steps_match_reference(name, full, fused, path):
     # correct float32 evaluations can differ by ~lr in single weights.  The goldens record how far the reference's own
     # float32 result is from its float64 run per tensor (`f32_final_err`: up to 1.4e-3 at the C3 shape, lr = 2e-3); the
     # CUDA result may be as far from the float32 reference as that, and no further.
-    spread = dict(zip(keys, g["f32_final_err"]))
+    # Which weights sit on such a knife edge differs between two float32 evaluations, so the cap for a single weight is
+    # the largest spread seen in ANY tensor of the case (at least the tight bar), and only a few weights may use it.
+    spread = float(np.max(g["f32_final_err"]))
     if full:
         for k in keys:
             ref = g["final_" + k]
-            assert np.max(np.abs(wd[k] - ref)) <= max(1e-4 * max(np.max(np.abs(ref)), 1e-3) + 3e-5, 1.5 * spread[k]), k
-            assert np.max(np.abs(wd[k] - g["f64_final_" + k])) <= max(1e-4 * max(np.max(np.abs(ref)), 1e-3) + 3e-5, 1.5 * spread[k]), k
+            tight = 1e-4 * max(np.max(np.abs(ref)), 1e-3) + 3e-5
+            for which, rr in (("f32", ref), ("f64", g["f64_final_" + k])):
+                d = np.abs(wd[k] - rr)
+                assert np.max(d) <= max(tight, 1.5 * spread), (k, which)
+                if which == "f32":     # against the float32 reference only a few weights may use the wide cap
+                    assert np.mean(d > tight) <= 2e-3 + 1.0 / d.size, k
     else:
         ref = g["final_layer1"]
-        bar = max(1e-4 * np.max(np.abs(ref)) + 3e-5, 1.5 * spread["layer1.weight"])
-        assert np.max(np.abs(wd["layer1.weight"] - ref)) <= bar
-        assert np.max(np.abs(wd["layer1.weight"] - g["f64_final_layer1"])) <= bar
-        assert np.mean(np.abs(wd["layer1.weight"] - ref) > 1e-4 * np.max(np.abs(ref)) + 3e-5) < 2e-3     # and only in a few weights
+        tight = 1e-4 * np.max(np.abs(ref)) + 3e-5
+        for rr in (ref, g["f64_final_layer1"]):
+            d = np.abs(wd["layer1.weight"] - rr)
+            assert np.max(d) <= max(tight, 1.5 * spread)
+            assert np.mean(d > tight) < 2e-3     # and only in a few weights
         np.testing.assert_allclose([float(np.linalg.norm(wd[k].astype(np.float64))) for k in keys], g["final_norm"], rtol=1e-4)
     # the packed weights inside the engine follow the flat vector: predictions use the updated weights
     th = g["theta"][:4].astype(np.float32)
