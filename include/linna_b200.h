@@ -216,6 +216,27 @@ int linna_stretch_propose(const float *x, int32_t d, const int64_t *first, const
 int linna_stretch_accept(float *x, float *lnp, float *naccepted, int32_t d, const int64_t *first, int64_t ns, const float *y,
                          const float *lnp_y, const float *z, uint64_t seed, uint64_t offset, void *stream);
 
+
+/* ---- batched Hamiltonian Monte Carlo step (linna/HMCSampler.py:23-66; every chain has its own Metropolis test) -----------
+ * One sample of every chain = linna_hmc_begin, then per leapfrog step linna_lnp_grad(xn) followed by linna_hmc_step
+ * (all but the last step), then linna_hmc_end.  x, lnp, grad: current state of the chains [nc][d] / [nc] / [nc][d]; mass [d].
+ * begin: p ~ N(0, m) (Philox keyed by (seed, chain, offset)), H0 = sum p^2/2m - lnP, p += eps/2 grad, xn = x + eps p/m.
+ * step : p += eps grad_n, xn += eps p/m.
+ * end  : p += eps/2 grad_n, H1 = sum p^2/2m - lnP(xn); accept iff U < exp(min(H0 - H1, 0)) and lnP(xn) is finite; accepted
+ *        chains get x = xn, lnp = lnp_n, grad = grad_n, naccepted += 1. */
+int linna_hmc_begin(const float *x, const float *lnp, const float *grad, const float *mass, int32_t d, int64_t nc, float eps,
+                    uint64_t seed, uint64_t offset, float *p, float *xn, float *H0, void *stream);
+int linna_hmc_step(float *p, float *xn, const float *grad_n, const float *mass, int32_t d, int64_t nc, float eps, void *stream);
+int linna_hmc_end(float *x, float *lnp, float *grad, const float *xn, const float *lnp_n, const float *grad_n, const float *p,
+                  const float *mass, const float *H0, int32_t d, int64_t nc, float eps, uint64_t seed, uint64_t offset,
+                  float *naccepted, void *stream);
+
+/* ---- convergence statistics (checkmeanstd, linna/sampler.py:370-387) -----------------------------------------------------
+ * Mean and population standard deviation per column of rows [r0, r1) of a DEVICE matrix x[rows][d] (float32, or float64
+ * when is_double != 0), two-pass reduction in float64; mean_host / std_host are HOST arrays [d]. */
+int linna_column_moments(const void *x, int32_t is_double, int64_t r0, int64_t r1, int32_t d, double *mean_host,
+                         double *std_host, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

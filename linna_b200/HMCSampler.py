@@ -11,7 +11,9 @@ Two things are different:
   * ``x0`` may be ``[C, n]``: C independent chains advanced together, each with its own
     accept/reject (the reference sums the Hamiltonian over everything, so a batched ``x0`` there
     would be accepted or rejected jointly -- SURVEY 3.2).  ``sample_chains`` is the fully
-    device-resident form used for the LSST-shaped HMC config (C4).
+    device-resident form used for the LSST-shaped HMC config (C4): hand-written leapfrog /
+    Metropolis kernels around the fused lnP+gradient launch, chains sharded over the GPUs of a
+    ``torchrun`` job.
 """
 import numpy as np
 import torch
@@ -85,38 +87,59 @@ class HMCSampler:
         return chain
 
     @torch.no_grad()
-    def sample_chains(self, num_samps, num_steps, step_size, generator=None, thin=1):
-        """All chains resident on the GPU: positions, momenta, Metropolis test and RNG stay on the
-        device; per sample only ``num_steps + 1`` fused lnP+grad launches and a handful of
-        elementwise updates are issued.  Returns (samples [num_samps/thin, C, n] latent positions,
-        lnP [.., C], acceptance fraction)."""
+    def sample_chains(self, num_samps, num_steps, step_size, generator=None, thin=1, seed=None, distributed=None):
+        """All chains resident on the GPU: positions, momenta, Metropolis test and RNG stay on the device.  One sample of
+        every chain is ``num_steps`` fused lnP+gradient launches (``linna_lnp_grad``) plus ONE sampler kernel per leapfrog
+        step (``csrc/sampler_kernels.cu``: momentum draw + Hamiltonian + half kick + drift; kick + drift; half kick +
+        Hamiltonian + per-chain Metropolis select) -- the reference's leapfrog (linna/HMCSampler.py:23-66) batched over
+        chains, each chain with its own accept / reject.
+
+        Under ``torch.distributed`` (one process per GPU, world > 1; ``distributed=False`` switches it off) the chains are
+        sharded over the ranks -- they are independent, no collective touches the sampling loop -- and the returned
+        samples are the chains of ALL ranks, gathered once at the end.
+
+        Returns (samples [num_samps/thin, C, n] latent positions, lnP [.., C], acceptance fraction)."""
+        from . import engine as _engine
+        from . import parallel
         dev = torch.device("cuda", torch.cuda.current_device())
-        x = self.x.detach().to(dev, torch.float32).reshape(-1, self.x.shape[-1]).contiguous()
-        m = self.m.to(dev)
+        x_all = self.x.detach().to(dev, torch.float32).reshape(-1, self.x.shape[-1]).contiguous()
+        rank, world = parallel.world()
+        if distributed is False:
+            rank, world = 0, 1
+        lo, hi = parallel.shard_rows(x_all.shape[0], rank, world)
+        x = x_all[lo:hi].contiguous()
+        m = self.m.to(dev, torch.float32).reshape(-1).contiguous()
+        if m.numel() == 1:
+            m = m.expand(x.shape[1]).contiguous()
         vg = self.lnP.value_and_grad
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 31 - 1, (1,), generator=generator, device=generator.device if generator is not None else "cpu").item())
+        seed = int(seed) + 7919 * rank                                  # every rank its own Philox streams
         lnP, grad = vg(x)
-        keep_x, keep_l, nacc = [], [], torch.zeros((), device=dev)
+        lnP, grad = lnP.contiguous(), grad.contiguous()
+        nacc = torch.zeros(x.shape[0], dtype=torch.float32, device=dev)
+        keep_x, keep_l = [], []
         for s in range(num_samps):
-            p = torch.randn(x.shape, device=dev, generator=generator) * torch.sqrt(m)
-            H0 = (0.5 * p.square() / m).sum(-1) - lnP
-            xn, g, l = x, grad, lnP
-            p = p + 0.5 * step_size * g
+            p, xn, H0 = _engine.hmc_begin(x, lnP, grad, m, step_size, seed, 8 * s)
             for i in range(num_steps):
-                xn = xn + step_size * (p / m)
                 l, g = vg(xn)
-                p = p + (step_size if i + 1 < num_steps else 0.5 * step_size) * g
-            H1 = (0.5 * p.square() / m).sum(-1) - l
-            acc = torch.rand(x.shape[0], device=dev, generator=generator) < torch.exp(torch.clamp(H0 - H1, max=0.0))
-            acc = acc & torch.isfinite(l)
-            x = torch.where(acc[:, None], xn, x)
-            grad = torch.where(acc[:, None], g, grad)
-            lnP = torch.where(acc, l, lnP)
-            nacc += acc.float().mean()
+                if i + 1 < num_steps:
+                    _engine.hmc_step(p, xn, g, m, step_size)
+            _engine.hmc_end(x, lnP, grad, xn, l.contiguous(), g.contiguous(), p, m, H0, step_size, seed, 8 * s + 4, nacc)
             if (s + 1) % thin == 0:
                 keep_x.append(x.clone())
                 keep_l.append(lnP.clone())
-        self.x = x
-        return torch.stack(keep_x), torch.stack(keep_l), float(nacc / max(num_samps, 1))
+        xs, ls = torch.stack(keep_x), torch.stack(keep_l)
+        accfrac = nacc / max(num_samps, 1)
+        if world > 1:      # final chain assembly: the only collective of the run
+            xs = parallel.gather_rows(xs.permute(1, 0, 2).contiguous()).permute(1, 0, 2).contiguous()
+            ls = parallel.gather_rows(ls.permute(1, 0).contiguous()).permute(1, 0).contiguous()
+            accfrac = parallel.gather_rows(accfrac)
+            x_all = parallel.gather_rows(x)
+        else:
+            x_all = x
+        self.x = x_all
+        return xs, ls, float(accfrac.mean())
 
 
 HMCSampler.__module__ = "linna.HMCSampler"

@@ -754,7 +754,9 @@ void linna_model_destroy(linna_model_t *m)
     if (m->cstream) cudaStreamDestroy(m->cstream);
     if (m->dstream) cudaStreamDestroy(m->dstream);
     for (cudaEvent_t e : m->pipe_events) cudaEventDestroy(e);
+    if (m->pool) { delete m->pool; m->pool = nullptr; }
     if (m->h_stage) cudaFreeHost(m->h_stage);
+    if (m->h_in_stage) cudaFreeHost(m->h_in_stage);
     if (m->last_done) cudaEventDestroy(m->last_done);
     if (m->tc) tc_destroy(m->tc);
     if (m->d_in) cudaFree(m->d_in);
@@ -1008,6 +1010,17 @@ static bool is_pinned_host(const void *p)
     return at.type == cudaMemoryTypeHost;
 }
 
+static int ensure_pinned(float **p, size_t *cap, size_t need)
+{
+    if (*cap >= need) return LINNA_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr, *cap = 0;
+    if (cudaHostAlloc(p, (need + need / 4) * sizeof(float), cudaHostAllocDefault) != cudaSuccess)
+        return fail(LINNA_ENOMEM, "cudaHostAlloc of %zu floats failed", need);
+    *cap = need + need / 4;
+    return LINNA_OK;
+}
+
 static int lnp_host_pipelined(linna_model *m, const float *u, int64_t n, float *lnp, float *grad)
 {
     CUDA_TRY(cudaSetDevice(m->device));
@@ -1016,22 +1029,29 @@ static int lnp_host_pipelined(linna_model *m, const float *u, int64_t n, float *
     if ((rc = ensure(&m->d_in, &m->d_in_cap, (size_t)n * n_in))) return rc;
     if ((rc = ensure(&m->d_lnp, &m->d_lnp_cap, (size_t)n))) return rc;
     if (grad && (rc = ensure(&m->d_grad, &m->d_grad_cap, (size_t)n * n_in))) return rc;
-    // A device->host copy into pageable memory blocks the calling thread until the kernel before it has finished,
-    // which would serialise the pipeline: results for pageable user buffers land in a pinned staging area first
-    // and are copied out by the host while the GPU works on the next chunk.
-    const bool stage = !is_pinned_host(lnp) || (grad && !is_pinned_host(grad));
+    // Pageable caller buffers (what an emcee / zeus caller holds: plain numpy arrays) go through pinned staging on both
+    // sides.  cudaMemcpyAsync on pageable memory stages inside the driver on the CALLING thread (one memcpy stream of
+    // ~10 GB/s: 1.2 ms for the 12 MB of 10^5 C3 walkers, more than the kernel), and a device->host copy into pageable
+    // memory blocks until the kernel before it has finished.  Here a few pool threads fill the input staging chunk by
+    // chunk ahead of the GPU and drain the result staging behind it.
+    const bool stage_in = !is_pinned_host(u);
+    const bool stage_out = !is_pinned_host(lnp) || (grad && !is_pinned_host(grad));
     float *s_lnp = lnp, *s_grad = grad;
-    if (stage) {
-        const size_t need = (size_t)n * (1 + (grad ? n_in : 0));
-        if (m->h_stage_cap < need) {
-            if (m->h_stage) cudaFreeHost(m->h_stage);
-            m->h_stage = nullptr, m->h_stage_cap = 0;
-            if (cudaHostAlloc(&m->h_stage, (need + need / 4) * sizeof(float), cudaHostAllocDefault) != cudaSuccess)
-                return fail(LINNA_ENOMEM, "cudaHostAlloc of %zu floats failed", need);
-            m->h_stage_cap = need + need / 4;
-        }
+    const float *s_in = u;
+    if (stage_out) {
+        if ((rc = ensure_pinned(&m->h_stage, &m->h_stage_cap, (size_t)n * (1 + (grad ? n_in : 0))))) return rc;
         s_lnp = m->h_stage, s_grad = m->h_stage + n;
     }
+    if (stage_in) {
+        if ((rc = ensure_pinned(&m->h_in_stage, &m->h_in_stage_cap, (size_t)n * n_in))) return rc;
+        s_in = m->h_in_stage;
+    }
+    const bool big = (size_t)n * n_in * sizeof(float) >= ((size_t)1 << 20);
+    if ((stage_in || stage_out) && big && !m->pool) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        m->pool = new StagePool((int)std::max(1u, std::min(4u, hw > 1 ? hw - 1 : 1u)));
+    }
+    StagePool *pool = big ? m->pool : nullptr;
     const int64_t wave = (int64_t)(m->num_sms / 2) * 2 * 256;
     int64_t chunk = n;
     if (n >= 2 * wave) chunk = wave * ((n / wave + 15) / 16);          // at most 16 chunks
@@ -1041,33 +1061,88 @@ static int lnp_host_pipelined(linna_model *m, const float *u, int64_t n, float *
         CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         m->pipe_events.push_back(e);
     }
+    // input staging: every chunk in `parts` pieces, all submitted up front; in_left[k] counts the pieces still to copy
+    const int parts = 2;
+    std::vector<std::atomic<int>> in_left(nchunks);
+    std::atomic<int> out_left{0};
+    if (stage_in) {
+        float *dst = m->h_in_stage;
+        for (int k = 0; k < nchunks; ++k) {
+            const int64_t r0 = (int64_t)k * chunk, rows = std::min(chunk, n - r0);
+            if (!pool) {
+                in_left[k].store(0);
+                continue;
+            }
+            in_left[k].store(parts);
+            for (int q = 0; q < parts; ++q) {
+                const int64_t a0 = r0 + rows * q / parts, a1 = r0 + rows * (q + 1) / parts;
+                std::atomic<int> *cnt = &in_left[k];
+                pool->submit([=] {
+                    memcpy(dst + a0 * n_in, u + a0 * n_in, (size_t)(a1 - a0) * n_in * sizeof(float));
+                    cnt->fetch_sub(1, std::memory_order_release);
+                });
+            }
+        }
+    }
     auto copy_out = [&](int k) -> int {   // host side of chunk k: wait for its device->host copy, hand it to the caller
         const int64_t r0 = (int64_t)k * chunk, rows = std::min(chunk, n - r0);
         CUDA_TRY(cudaEventSynchronize(m->pipe_events[3 * k + 2]));
         memcpy(lnp + r0, s_lnp + r0, (size_t)rows * sizeof(float));
-        if (grad) memcpy(grad + r0 * n_in, s_grad + r0 * n_in, (size_t)rows * n_in * sizeof(float));
+        if (grad) {
+            if (pool) {   // n_in times the bytes of lnP: behind the GPU, on the pool
+                out_left.fetch_add(parts);
+                for (int q = 0; q < parts; ++q) {
+                    const int64_t a0 = r0 + rows * q / parts, a1 = r0 + rows * (q + 1) / parts;
+                    const float *src = s_grad;
+                    std::atomic<int> *cnt = &out_left;
+                    pool->submit([=] {
+                        memcpy(grad + a0 * n_in, src + a0 * n_in, (size_t)(a1 - a0) * n_in * sizeof(float));
+                        cnt->fetch_sub(1, std::memory_order_release);
+                    });
+                }
+            } else
+                memcpy(grad + r0 * n_in, s_grad + r0 * n_in, (size_t)rows * n_in * sizeof(float));
+        }
         return LINNA_OK;
     };
-    for (int k = 0; k < nchunks; ++k) {
+    auto drain_pool = [&]() {   // nothing of this call may still be running on the pool when it returns (or fails)
+        if (!pool) return;
+        for (int k = 0; k < nchunks; ++k)
+            while (stage_in && in_left[k].load(std::memory_order_acquire) > 0) std::this_thread::yield();
+        while (out_left.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+    };
+    rc = LINNA_OK;
+    for (int k = 0; k < nchunks && rc == LINNA_OK; ++k) {
         const int64_t r0 = (int64_t)k * chunk, rows = std::min(chunk, n - r0);
         cudaEvent_t landed = m->pipe_events[3 * k], done = m->pipe_events[3 * k + 1], home = m->pipe_events[3 * k + 2];
-        CUDA_TRY(cudaMemcpyAsync(m->d_in + r0 * n_in, u + r0 * n_in, (size_t)rows * n_in * sizeof(float), cudaMemcpyHostToDevice,
-                                 m->cstream));
-        CUDA_TRY(cudaEventRecord(landed, m->cstream));
-        CUDA_TRY(cudaStreamWaitEvent(m->hstream, landed, 0));
+        if (stage_in) {
+            if (pool)
+                while (in_left[k].load(std::memory_order_acquire) > 0) std::this_thread::yield();
+            else
+                memcpy(m->h_in_stage + r0 * n_in, u + r0 * n_in, (size_t)rows * n_in * sizeof(float));
+        }
+        cudaError_t ce = cudaMemcpyAsync(m->d_in + r0 * n_in, s_in + r0 * n_in, (size_t)rows * n_in * sizeof(float),
+                                         cudaMemcpyHostToDevice, m->cstream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(landed, m->cstream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->hstream, landed, 0);
+        if (ce != cudaSuccess) { rc = fail(LINNA_ECUDA, "host->device stage: %s", cudaGetErrorString(ce)); break; }
         rc = grad ? linna_lnp_grad(m, m->d_in + r0 * n_in, rows, m->d_lnp + r0, m->d_grad + r0 * n_in, m->hstream)
                   : linna_lnp(m, m->d_in + r0 * n_in, rows, m->d_lnp + r0, m->hstream);
-        if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(done, m->hstream));
-        CUDA_TRY(cudaStreamWaitEvent(m->dstream, done, 0));
-        CUDA_TRY(cudaMemcpyAsync(s_lnp + r0, m->d_lnp + r0, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost, m->dstream));
-        if (grad)
-            CUDA_TRY(cudaMemcpyAsync(s_grad + r0 * n_in, m->d_grad + r0 * n_in, (size_t)rows * n_in * sizeof(float),
-                                     cudaMemcpyDeviceToHost, m->dstream));
-        CUDA_TRY(cudaEventRecord(home, m->dstream));
-        if (stage && k > 0 && (rc = copy_out(k - 1))) return rc;
+        if (rc) break;
+        ce = cudaEventRecord(done, m->hstream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->dstream, done, 0);
+        if (ce == cudaSuccess)
+            ce = cudaMemcpyAsync(s_lnp + r0, m->d_lnp + r0, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost, m->dstream);
+        if (ce == cudaSuccess && grad)
+            ce = cudaMemcpyAsync(s_grad + r0 * n_in, m->d_grad + r0 * n_in, (size_t)rows * n_in * sizeof(float),
+                                 cudaMemcpyDeviceToHost, m->dstream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(home, m->dstream);
+        if (ce != cudaSuccess) { rc = fail(LINNA_ECUDA, "device->host stage: %s", cudaGetErrorString(ce)); break; }
+        if (stage_out && k > 0) rc = copy_out(k - 1);
     }
-    if (stage && (rc = copy_out(nchunks - 1))) return rc;
+    if (rc == LINNA_OK && stage_out) rc = copy_out(nchunks - 1);
+    drain_pool();
+    if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(m->dstream));
     CUDA_TRY(cudaStreamSynchronize(m->hstream));
     return LINNA_OK;

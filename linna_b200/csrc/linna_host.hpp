@@ -1,7 +1,14 @@
 // Host-side model state shared by the C-ABI translation units (cabi.cu, tc_f16.cu).
 #pragma once
+#include <atomic>
+#include <condition_variable>
 #include <cstdint>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/linna_b200.h"
@@ -24,6 +31,50 @@ struct OpHost {
 };
 
 enum ProgKind { PROG_PREDICT = 0, PROG_LNP = 1, PROG_GRAD = 2, PROG_LOSS = 3, PROG_TRAIN = 4, PROG_COUNT = 5 };
+
+// A few host threads that move pageable caller buffers to / from pinned staging memory while the GPU works: one
+// thread copies ~10 GB/s, and a 12 MB walker block staged by one thread costs more than the kernel that consumes it.
+struct StagePool {
+    std::vector<std::thread> workers;
+    std::deque<std::function<void()>> jobs;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool stop = false;
+    explicit StagePool(int n)
+    {
+        for (int i = 0; i < n; ++i)
+            workers.emplace_back([this] {
+                for (;;) {
+                    std::function<void()> job;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [this] { return stop || !jobs.empty(); });
+                        if (stop && jobs.empty()) return;
+                        job = std::move(jobs.front());
+                        jobs.pop_front();
+                    }
+                    job();
+                }
+            });
+    }
+    void submit(std::function<void()> f)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            jobs.push_back(std::move(f));
+        }
+        cv.notify_one();
+    }
+    ~StagePool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (std::thread &t : workers) t.join();
+    }
+};
 
 struct linna_model {
     int device = 0, num_sms = 0;
@@ -87,6 +138,9 @@ struct linna_model {
     std::vector<cudaEvent_t> pipe_events;            // 3 per chunk: input landed, kernel finished, results on the host
     float *h_stage = nullptr;                        // pinned staging for results that go to pageable user buffers
     size_t h_stage_cap = 0;
+    float *h_in_stage = nullptr;                     // pinned staging for pageable input buffers
+    size_t h_in_stage_cap = 0;
+    StagePool *pool = nullptr;                       // host threads that fill / drain the staging buffers
     float *d_in = nullptr, *d_out = nullptr, *d_lnp = nullptr, *d_grad = nullptr;
     size_t d_in_cap = 0, d_out_cap = 0, d_lnp_cap = 0, d_grad_cap = 0;
 };

@@ -91,6 +91,10 @@ def load_library():
     lib.linna_stretch_propose.argtypes = [vp, i32, vp, vp, i64, i64, ctypes.c_float, u64, u64, vp, vp, vp]
     lib.linna_stretch_accept.argtypes = [vp, vp, vp, i32, vp, i64, vp, vp, vp, u64, u64, vp]
     f32 = ctypes.c_float
+    lib.linna_hmc_begin.argtypes = [vp, vp, vp, vp, i32, i64, f32, u64, u64, vp, vp, vp, vp]
+    lib.linna_hmc_step.argtypes = [vp, vp, vp, vp, i32, i64, f32, vp]
+    lib.linna_hmc_end.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, f32, u64, u64, vp, vp]
+    lib.linna_column_moments.argtypes = [vp, i32, i64, i64, i32, vp, vp, vp]
     lib.linna_train_setup.argtypes = [vp, ctypes.POINTER(TrainDesc)]
     lib.linna_train_num_params.argtypes = [vp]
     lib.linna_train_num_params.restype = ctypes.c_int64
@@ -134,6 +138,65 @@ def stretch_accept(x, lnp, naccepted, first, y, lnp_y, z, seed, offset):
                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc != 0:
         raise LinnaError("linna_stretch_accept failed (%d)" % rc)
+
+
+def _cur_stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def hmc_begin(x, lnp, grad, mass, eps, seed, offset):
+    """Momentum draw, initial Hamiltonian, first half kick and drift of every chain (linna/HMCSampler.py:25-36).
+    Returns (p, xn, H0) device tensors."""
+    import torch
+    lib = load_library()
+    nc, d = int(x.shape[0]), int(x.shape[1])
+    p, xn = torch.empty_like(x), torch.empty_like(x)
+    H0 = torch.empty(nc, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.linna_hmc_begin(x.data_ptr(), lnp.data_ptr(), grad.data_ptr(), mass.data_ptr(), d, nc, float(eps), int(seed),
+                                 int(offset), p.data_ptr(), xn.data_ptr(), H0.data_ptr(), _cur_stream())
+    if rc != 0:
+        raise LinnaError("linna_hmc_begin failed (%d)" % rc)
+    return p, xn, H0
+
+
+def hmc_step(p, xn, grad_n, mass, eps):
+    """Inner leapfrog step in place: p += eps grad(xn); xn += eps p / m (linna/HMCSampler.py:43-46)."""
+    import torch
+    lib = load_library()
+    with torch.cuda.device(p.device):
+        rc = lib.linna_hmc_step(p.data_ptr(), xn.data_ptr(), grad_n.data_ptr(), mass.data_ptr(), int(p.shape[1]), int(p.shape[0]),
+                                float(eps), _cur_stream())
+    if rc != 0:
+        raise LinnaError("linna_hmc_step failed (%d)" % rc)
+
+
+def hmc_end(x, lnp, grad, xn, lnp_n, grad_n, p, mass, H0, eps, seed, offset, naccepted):
+    """Last half kick, Hamiltonian and the per-chain Metropolis select, in place (linna/HMCSampler.py:51-59)."""
+    import torch
+    lib = load_library()
+    with torch.cuda.device(x.device):
+        rc = lib.linna_hmc_end(x.data_ptr(), lnp.data_ptr(), grad.data_ptr(), xn.data_ptr(), lnp_n.data_ptr(), grad_n.data_ptr(),
+                               p.data_ptr(), mass.data_ptr(), H0.data_ptr(), int(x.shape[1]), int(x.shape[0]), float(eps), int(seed),
+                               int(offset), naccepted.data_ptr(), _cur_stream())
+    if rc != 0:
+        raise LinnaError("linna_hmc_end failed (%d)" % rc)
+
+
+def column_moments(x2d, r0, r1):
+    """(mean, std) per column of rows [r0, r1) of a CUDA matrix (float32 / float64), float64 numpy arrays."""
+    import torch
+    lib = load_library()
+    assert x2d.is_cuda and x2d.dim() == 2 and x2d.is_contiguous() and x2d.dtype in (torch.float32, torch.float64)
+    d = int(x2d.shape[1])
+    mean, std = np.empty(d, np.float64), np.empty(d, np.float64)
+    with torch.cuda.device(x2d.device):
+        rc = lib.linna_column_moments(x2d.data_ptr(), int(x2d.dtype == torch.float64), int(r0), int(r1), d, mean.ctypes.data,
+                                      std.ctypes.data, _cur_stream())
+    if rc != 0:
+        raise LinnaError("linna_column_moments failed (%d)" % rc)
+    return mean, std
 
 
 def launch_count():

@@ -76,7 +76,7 @@ def integrated_time(chain, c=5.0):
         if chain.ndim == 2:
             chain = chain[:, :, None]
         if chain.size >= (1 << 20) and torch.cuda.is_available():
-            chain, on_gpu = torch.from_numpy(chain).cuda(), True
+            chain, on_gpu = torch.from_numpy(np.ascontiguousarray(chain).copy() if not chain.flags.writeable else chain).cuda(), True
     elif chain.dim() == 2:
         chain = chain[:, :, None]
     nstep, nwalk, ndim = chain.shape
@@ -93,23 +93,20 @@ def integrated_time(chain, c=5.0):
     return tau
 
 
-def _halves_shift_torch(x):
-    """(median |mean_a - mean_b| / std_b, median (std_a - std_b) / std_b) of the two halves of x [steps, walkers, ndim],
-    reductions in float64 on the tensor's device; two scalars come back."""
+def _halves_shift_device(x):
+    """(median |mean_a - mean_b| / std_b, median (std_a - std_b) / std_b) of the two halves of x [steps, walkers, ndim]
+    on the GPU: per-parameter mean and std of each half by the two-pass float64 reduction kernel
+    (``linna_column_moments``, csrc/sampler_kernels.cu); 4 x ndim numbers come back."""
+    nd = x.shape[-1]
     half = x.shape[0] // 2
-    a = x[:half].reshape(-1, x.shape[-1]).to(torch.float64)
-    b = x[half:].reshape(-1, x.shape[-1]).to(torch.float64)
-    sa, sb = a.std(dim=0, unbiased=False), b.std(dim=0, unbiased=False)
-    dm = _median_np(torch.abs(a.mean(dim=0) - b.mean(dim=0)) / sb)
-    ds = _median_np((sa - sb) / sb)
-    return float(dm), float(ds)
-
-
-def _median_np(v):
-    """numpy's median (mean of the two middle values for an even count) of a 1-D tensor."""
-    s, _ = torch.sort(v)
-    n = s.numel()
-    return (s[(n - 1) // 2] + s[n // 2]) / 2
+    rows_per_step = int(np.prod(x.shape[1:-1])) if x.dim() > 2 else 1
+    flat = x.reshape(-1, nd)
+    if flat.dtype not in (torch.float32, torch.float64):
+        flat = flat.to(torch.float32)
+    flat = flat.contiguous()
+    ma, sa = _engine.column_moments(flat, 0, half * rows_per_step)
+    mb, sb = _engine.column_moments(flat, half * rows_per_step, flat.shape[0])
+    return float(np.median(np.abs(ma - mb) / sb)), float(np.median((sa - sb) / sb))
 
 
 def checkmeanstd(samples, meanshift, stdshift):
@@ -120,10 +117,11 @@ def checkmeanstd(samples, meanshift, stdshift):
     on_gpu = torch.is_tensor(samples) and samples.is_cuda
     if not on_gpu and not torch.is_tensor(samples) and np.size(samples) >= (1 << 22) and torch.cuda.is_available():
         samples, on_gpu = torch.from_numpy(np.ascontiguousarray(samples)).cuda(), True
-    if torch.is_tensor(samples):
-        dm, ds = _halves_shift_torch(samples)
+    if on_gpu:
+        dm, ds = _halves_shift_device(samples)
         print(dm, ds, flush=True)
         return bool((dm < meanshift) & (ds < stdshift))
+    samples = samples.detach().cpu().numpy() if torch.is_tensor(samples) else np.asarray(samples)
     half = int(len(samples) / 2)
     a = samples[:half].reshape(-1, samples.shape[-1])
     b = samples[half:].reshape(-1, samples.shape[-1])
@@ -136,61 +134,136 @@ def checkmeanstd(samples, meanshift, stdshift):
 
 # ---------------------------------------------------------------------------------------- storage
 class ChainStore:
-    """Chain file with the reference's dataset names (linna/sampler.py:330-339, :572-578)."""
+    """Chain file with the reference's dataset names (linna/sampler.py:330-339, :572-578).
 
-    def __init__(self, filename, transform=None):
+    The chain is APPENDED, never rewritten: every flush adds its block to three raw float64 files
+    (``<name>.chain.f64`` / ``.chain_transformed.f64`` / ``.log_prob.f64`` + ``<name>.meta.json``) -- what the reference's
+    HDF5 back-end does with resizable datasets -- and the arrays are read back as memory maps, so neither the host memory
+    nor the I/O per convergence check grows with the length of the run.  ``finalize()`` writes the ``<name>.npz`` (and,
+    when h5py is importable, ``<name>.h5`` with group ``mcmc``) once, at the end.  A finished ``.npz`` is what is read on
+    resume; an unfinished run resumes from the raw files."""
+    NAMES = ("chain", "chain_transformed", "log_prob")
+
+    def __init__(self, filename, transform=None, fresh=False):
         self.base = filename[:-3] if filename.endswith(".h5") else filename[:-4] if filename.endswith(".npz") else filename
         self.transform = transform
-        self.chain = None           # [steps, walkers, ndim] latent positions
-        self.chain_transformed = None
-        self.log_prob = None
-        if os.path.isfile(self.base + ".npz"):
+        self.nsteps, self.nwalkers, self.ndim = 0, 0, 0
+        self._frozen = None          # arrays of a finished .npz
+        self._maps = {}
+        if fresh:
+            self._remove_files()
+        elif os.path.isfile(self.base + ".npz"):
             z = np.load(self.base + ".npz")
-            self.chain, self.chain_transformed, self.log_prob = z["chain"], z["chain_transformed"], z["log_prob"]
+            self._frozen = {k: z[k] for k in self.NAMES}
+            self.nsteps, self.nwalkers, self.ndim = self._frozen["chain"].shape
+        elif os.path.isfile(self.base + ".meta.json"):
+            import json
+            with open(self.base + ".meta.json") as f:
+                meta = json.load(f)
+            self.nsteps, self.nwalkers, self.ndim = int(meta["nsteps"]), int(meta["nwalkers"]), int(meta["ndim"])
+
+    def _remove_files(self):
+        for ext in (".npz", ".h5", ".meta.json") + tuple("." + n + ".f64" for n in self.NAMES):
+            if os.path.isfile(self.base + ext):
+                os.remove(self.base + ext)
+
+    def _path(self, name):
+        return self.base + "." + name + ".f64"
+
+    def _shape(self, name):
+        return (self.nsteps, self.nwalkers) if name == "log_prob" else (self.nsteps, self.nwalkers, self.ndim)
+
+    def _array(self, name):
+        if self._frozen is not None:
+            return self._frozen[name]
+        if self.nsteps == 0:
+            return None
+        mm = self._maps.get(name)
+        if mm is None or mm.shape[0] != self.nsteps:
+            mm = np.memmap(self._path(name), dtype=np.float64, mode="r", shape=self._shape(name))
+            self._maps[name] = mm
+        return mm
+
+    chain = property(lambda self: self._array("chain"))
+    chain_transformed = property(lambda self: self._array("chain_transformed"))
+    log_prob = property(lambda self: self._array("log_prob"))
 
     @property
     def iteration(self):
-        return 0 if self.chain is None else len(self.chain)
+        return self.nsteps
 
     def exists(self):
-        return self.chain is not None
+        return self.nsteps > 0
 
     def extend(self, coords, log_prob):
         coords = np.asarray(coords, np.float64)
+        if coords.shape[0] == 0:
+            return
+        if self._frozen is not None:     # continuing a finished chain: back to the appendable form first
+            frozen, self._frozen, self.nsteps = self._frozen, None, 0
+            for n in self.NAMES:
+                with open(self._path(n), "wb") as f:
+                    np.ascontiguousarray(frozen[n], np.float64).tofile(f)
+            self.nsteps = frozen["chain"].shape[0]
         tr = coords if self.transform is None else np.stack(
             [np.atleast_2d(self.transform(c.astype(np.float32))) for c in coords]).astype(np.float64)
-        if self.chain is None:
-            self.chain, self.chain_transformed, self.log_prob = coords, tr, np.asarray(log_prob, np.float64)
-        else:
-            self.chain = np.concatenate([self.chain, coords])
-            self.chain_transformed = np.concatenate([self.chain_transformed, tr])
-            self.log_prob = np.concatenate([self.log_prob, np.asarray(log_prob, np.float64)])
+        if self.nsteps == 0:
+            self.nwalkers, self.ndim = coords.shape[1], coords.shape[2]
+        for n, block in (("chain", coords), ("chain_transformed", tr), ("log_prob", np.asarray(log_prob, np.float64))):
+            with open(self._path(n), "ab") as f:
+                np.ascontiguousarray(block, np.float64).tofile(f)
+        self.nsteps += coords.shape[0]
+        self._maps = {}
 
     def save(self):
+        """Make the appended blocks durable: a few bytes of metadata (the blocks themselves are already on disk)."""
+        import json
+        with open(self.base + ".meta.json", "w") as f:
+            json.dump({"nsteps": self.nsteps, "nwalkers": self.nwalkers, "ndim": self.ndim}, f)
+
+    def finalize(self, max_bytes=2 << 30):
+        """End of the run: the portable single-file forms with the reference's dataset names."""
+        self.save()
+        if self.nsteps == 0 or self._frozen is not None:
+            return
+        if self.nsteps * self.nwalkers * (2 * self.ndim + 1) * 8 > max_bytes:
+            return                       # a chain this large stays in its raw appendable form
         np.savez(self.base + ".npz", chain=self.chain, chain_transformed=self.chain_transformed, log_prob=self.log_prob)
         try:
             import h5py
             with h5py.File(self.base + ".h5", "w") as f:
                 g = f.create_group("mcmc")
-                g.create_dataset("chain", data=self.chain)
-                g.create_dataset("chain_transformed", data=self.chain_transformed)
-                g.create_dataset("log_prob", data=self.log_prob)
+                for n in self.NAMES:
+                    g.create_dataset(n, data=self._array(n))
         except ImportError:
             pass
 
     def get_last_sample(self):
-        return self.chain[-1]
+        return np.asarray(self.chain[-1])
 
     def get_value(self, name, discard=0, flat=False, thin=1):
         v = {"chain": self.chain, "chain_transformed": self.chain_transformed, "samples": self.chain_transformed,
              "log_prob": self.log_prob}[name][discard::thin]
+        v = np.asarray(v)
         return v.reshape((-1,) + v.shape[2:]) if flat else v
 
     def get_log_prob(self, discard=0, flat=False, thin=1):
         return self.get_value("log_prob", discard, flat, thin)
 
     def get_autocorr_time(self, quiet=True, **kw):
-        return integrated_time(self.chain)
+        return integrated_time(thin_for_tau(self.chain))
+
+
+def thin_for_tau(chain, max_walkers=2048, max_bytes=1 << 30):
+    """The part of a stored chain [steps, walkers, ndim] that feeds the autocorrelation estimate: the walker-averaged
+    autocorrelation function of a few thousand walkers is as good as that of 10^5, and the FFT buffers are several
+    times the size of what goes in -- so the walkers are sub-sampled (evenly) until the block fits ``max_bytes``."""
+    steps, nw, nd = chain.shape
+    keep = min(nw, max_walkers, max(1, int(max_bytes // max(steps * nd * 8, 1))))
+    if keep >= nw:
+        return np.asarray(chain)
+    idx = np.linspace(0, nw - 1, keep).astype(np.int64)
+    return np.asarray(chain[:, idx, :])
 
 
 def read_chain_and_cut(chainname, nk, ntimes=20, walkercut=False, method="emcee", flat=False):
@@ -232,7 +305,15 @@ class EnsembleSampler:
     def reset(self):
         self.iteration = 0
         self._chain, self._lnp = [], []
+        self._first = 0               # iteration index of self._chain[0] (earlier snapshots were dropped after a flush)
         self.naccepted = torch.zeros(self.nwalkers, device=self.device)
+
+    def drop_before(self, iteration):
+        """Forget the device snapshots of iterations < ``iteration`` (they have been flushed to the chain store): the
+        sampler then holds ``check_every`` iterations on the GPU, not the whole run."""
+        k = max(0, min(int(iteration) - self._first, len(self._chain)))
+        del self._chain[:k], self._lnp[:k]
+        self._first += k
 
     def _eval(self, x):
         lp = self._lp
@@ -273,15 +354,21 @@ class EnsembleSampler:
             pass
         return x, lnp
 
+    def device_block(self, start=0):
+        """(positions [steps, walkers, ndim], lnP [steps, walkers]) of the iterations >= ``start`` still held, on the GPU."""
+        k = max(0, int(start) - self._first)
+        if len(self._chain) <= k:
+            return (torch.zeros((0, self.nwalkers, self.ndim), device=self.device),
+                    torch.zeros((0, self.nwalkers), device=self.device))
+        return torch.stack(self._chain[k:]), torch.stack(self._lnp[k:])
+
     def get_chain(self, flat=False, start=0):
         """Stored positions [steps, walkers, ndim] on the host, from iteration ``start`` on."""
-        part = self._chain[start:]
-        c = (torch.stack(part).cpu().numpy().astype(np.float64) if part else np.zeros((0, self.nwalkers, self.ndim)))
+        c = self.device_block(start)[0].cpu().numpy().astype(np.float64)
         return c.reshape(-1, self.ndim) if flat else c
 
     def get_log_prob(self, flat=False, start=0):
-        part = self._lnp[start:]
-        l = torch.stack(part).cpu().numpy().astype(np.float64) if part else np.zeros((0, self.nwalkers))
+        l = self.device_block(start)[1].cpu().numpy().astype(np.float64)
         return l.reshape(-1) if flat else l
 
     def get_autocorr_time(self, tol=0, **kw):
@@ -293,9 +380,18 @@ class EnsembleSampler:
 
 
 class HMCSampler:
-    """The reference's sampler wrapper (linna/sampler.py:389-554), ``method="emcee"`` branch: burn-in
-    with re-selection of the best positions, then sampling until  tau*ntimes < n,  |d tau|/tau < tautol
-    and the half-chain mean/std test pass (checked every 100 iterations)."""
+    """The reference's sampler wrapper (linna/sampler.py:389-554).
+
+    ``method="emcee"`` / ``"zeus"``: burn-in with re-selection of the best positions, then ensemble sampling until
+    tau*ntimes < n,  |d tau|/tau < tautol  and the half-chain mean/std test pass (checked every 100 iterations).
+    ``method="hmc"``: ``nwalkers`` independent HMC chains advanced together on the GPU
+    (``linna.HMCSampler.HMCSampler.sample_chains``: ``samp_steps`` leapfrog steps of size ``samp_eps`` per sample), same
+    storage and convergence logic.
+
+    Under ``torch.distributed`` (one process per GPU, world > 1) the walkers / chains are sharded over the ranks: every
+    rank runs its own sub-ensemble of nwalkers/world walkers (independent units: no collective inside an iteration), the
+    blocks of all ranks are gathered at every convergence check, rank 0 stores the chain and takes the decision, which is
+    broadcast.  This is the GPU form of the reference's one-walker-per-MPI-rank farm (linna/util.py:100-256)."""
     FILENAME = "chemcee_256.h5"
 
     def __init__(self, lnp, dlnp, ddlnp, ndim, nwalkers, x0=None, m=None, transform=None, torchspeed=False):
@@ -308,61 +404,146 @@ class HMCSampler:
     def sample(self, pool, nsamp, samp_steps=0, samp_eps=0, Madapt=1000, outdir="./", progress=False, overwrite=False,
                ntimes=10, tautol=0.01, method="emcee", incremental=True, meanshift=0.1, stdshift=0.1, nk=2,
                check_every=100, burnin=100):
-        if method not in ("emcee", "zeus"):
-            raise NotImplementedError("method %r: only the ensemble samplers are implemented here; for HMC use "
-                                      "linna.HMCSampler.HMCSampler.sample_chains" % (method,))
-        filename = os.path.join(outdir, self.FILENAME)
-        store = ChainStore(filename, self.transform)
-        x0 = self.x0
-        resume = False
-        if store.exists():
-            if overwrite:
-                store = ChainStore.__new__(ChainStore)
-                store.base, store.transform = filename[:-3], self.transform
-                store.chain = store.chain_transformed = store.log_prob = None
-            else:
-                print("init from previous")
-                x0, resume = store.get_last_sample(), True
-        self.sampler = EnsembleSampler(self.nwalkers, self.nparams, self.lnp)
+        from . import parallel
+        if method not in ("emcee", "zeus", "hmc"):
+            raise NotImplementedError("method %r: 'emcee' / 'zeus' (ensemble stretch move) and 'hmc' (batched chains) are "
+                                      "implemented; NUTS is a stub in the reference too (linna/sampler.py:14-21)" % (method,))
+        rank, world = parallel.world()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        filename = os.path.join(outdir, "chhmc.h5" if method == "hmc" else self.FILENAME)     # linna/sampler.py:466-471
+        store = ChainStore(filename, self.transform, fresh=bool(overwrite) and rank == 0)
+        if world > 1:
+            torch.distributed.barrier()
+            if rank != 0:
+                store = ChainStore(filename, self.transform)
+        x0 = np.asarray(self.x0, np.float64)
+        resume = store.exists()
+        if resume:
+            print("init from previous")
+            x0 = store.get_last_sample()
+        lo, hi = parallel.shard_rows(self.nwalkers, rank, world)
+        nloc = hi - lo
+        if method != "hmc" and nloc < 2 * self.nparams and world > 1:
+            raise ValueError("%d walkers over %d ranks leaves %d per rank: the stretch move needs >= 2 x ndim = %d walkers "
+                             "in every sub-ensemble" % (self.nwalkers, world, nloc, 2 * self.nparams))
+
+        def gathered(xb, lb):
+            """[steps, local walkers, ...] blocks of every rank -> [steps, all walkers, ...] (the same on all ranks)."""
+            if world == 1:
+                return xb, lb
+            xg = parallel.gather_rows(xb.permute(1, 0, 2).contiguous()).permute(1, 0, 2).contiguous()
+            lg = parallel.gather_rows(lb.permute(1, 0).contiguous()).permute(1, 0).contiguous()
+            return xg, lg
+
         print("start", flush=True)
+        if method == "hmc":
+            return self._sample_hmc(store, x0, lo, hi, rank, world, nsamp, samp_steps, samp_eps, ntimes, tautol, meanshift, stdshift,
+                                    nk, check_every, gathered, dev)
+        self.sampler = EnsembleSampler(nloc, self.nparams, self.lnp, seed=None if world == 1 else 1000003 * (rank + 1) + 17)
         if not incremental:
-            self.sampler.run_mcmc(x0, nsamp)
-            chain = self.sampler.get_chain(flat=True)
+            self.sampler.run_mcmc(x0[lo:hi], nsamp)
+            xb, _ = gathered(*self.sampler.device_block(0))
+            chain = xb.reshape(-1, self.nparams).cpu().numpy().astype(np.float64)
             return chain if self.transform is None else np.array([self.transform(c.astype(np.float32)) for c in chain])
         if not resume:
             print("burnin...", flush=True)
-            burn = EnsembleSampler(self.nwalkers, self.nparams, self.lnp)
-            burn.run_mcmc(x0, burnin)
+            burn = EnsembleSampler(nloc, self.nparams, self.lnp, seed=None if world == 1 else 7 * (rank + 1) + 1)
+            burn.run_mcmc(x0[lo:hi], burnin)
             flat, lp = burn.get_chain(flat=True), burn.get_log_prob(flat=True)
-            pos = flat[np.argsort(lp)[::-1][:int(50 * self.nwalkers)]]
-            x0 = pos[np.random.randint(0, len(pos), self.nwalkers), :]
+            pos = flat[np.argsort(lp)[::-1][:int(50 * nloc)]]
+            x0_loc = pos[np.random.randint(0, len(pos), nloc), :]
             print("burnin done...", flush=True)
+        else:
+            x0_loc = x0[lo:hi]
         old_tau = np.inf
         saved = 0
-        for _ in self.sampler.sample(x0, int(nsamp)):
-            it = self.sampler.iteration
-            if it % check_every:
+
+        def flush_and_check(final=False):
+            nonlocal old_tau, saved
+            xb, lb = gathered(*self.sampler.device_block(saved))
+            saved = self.sampler.iteration
+            self.sampler.drop_before(saved)       # the flushed snapshots leave the GPU
+            stop = False
+            if rank == 0:
+                store.extend(xb.cpu().numpy(), lb.cpu().numpy())   # only the new steps are appended to the files
+                store.save()
+                if not final:
+                    tau = integrated_time(thin_for_tau(store.chain))
+                    if np.isnan(np.sum(tau)) and saved > 10:
+                        stop = True
+                    else:
+                        converged = np.all(tau * ntimes < store.iteration)
+                        converged &= np.all(np.abs(old_tau - tau) / tau < tautol)
+                        keep = max(int(nk * np.mean(tau)), 2)
+                        converged &= checkmeanstd(np.asarray(store.chain[-keep:]), meanshift=meanshift, stdshift=stdshift)
+                        print("max, min tau diff, max tau, ninter: {0}, {1}, {2}, {3}\n".format(
+                            np.max(np.abs(old_tau - tau) / tau), np.min(np.abs(old_tau - tau) / tau), np.max(tau), store.iteration),
+                            flush=True)
+                        stop = bool(converged)
+                        old_tau = tau
+            if world > 1:
+                box = [stop]
+                torch.distributed.broadcast_object_list(box, src=0)
+                stop = bool(box[0])
+            return stop
+
+        for _ in self.sampler.sample(x0_loc, int(nsamp)):
+            if self.sampler.iteration % check_every:
                 continue
-            store.extend(self.sampler.get_chain(start=saved), self.sampler.get_log_prob(start=saved))   # only the new steps
-            saved = it
-            store.save()
-            tau = integrated_time(store.chain)
-            if np.isnan(np.sum(tau)) and it > 10:
+            if flush_and_check():
                 break
-            converged = np.all(tau * ntimes < store.iteration)
-            converged &= np.all(np.abs(old_tau - tau) / tau < tautol)
-            keep = max(int(nk * np.mean(tau)), 2)
-            converged &= checkmeanstd(store.chain[-keep:], meanshift=meanshift, stdshift=stdshift)
-            print("max, min tau diff, max tau, ninter: {0}, {1}, {2}, {3}\n".format(
-                np.max(np.abs(old_tau - tau) / tau), np.min(np.abs(old_tau - tau) / tau), np.max(tau), store.iteration),
-                flush=True)
-            if converged:
-                break
-            old_tau = tau
         if self.sampler.iteration > saved:
-            store.extend(self.sampler.get_chain(start=saved), self.sampler.get_log_prob(start=saved))
-            store.save()
+            flush_and_check(final=True)
+        if rank == 0:
+            store.finalize()
+        if world > 1:
+            torch.distributed.barrier()
+            if rank != 0:
+                store = ChainStore(filename, self.transform)
         self.sampler = None
+        return store
+
+    def _sample_hmc(self, store, x0, lo, hi, rank, world, nsamp, samp_steps, samp_eps, ntimes, tautol, meanshift, stdshift, nk,
+                    check_every, gathered, dev):
+        """``method="hmc"``: batched device HMC in blocks of ``check_every`` samples with the ensemble branch's storage
+        and convergence logic (the reference's hmc branch calls private helpers with mismatched signatures)."""
+        from .HMCSampler import HMCSampler as _TorchHMC
+        if not getattr(self.lnp, "fused", False):
+            raise NotImplementedError("method='hmc' needs the built-in Gaussian likelihood (fused lnP + gradient kernel)")
+        steps = int(samp_steps) if samp_steps else 5
+        eps = float(samp_eps) if samp_eps else 0.1
+        mass = torch.ones(self.nparams) if self.m is None else torch.as_tensor(np.asarray(self.m, np.float32)).reshape(-1)
+        hmc = _TorchHMC(self.lnp, torch.as_tensor(x0[lo:hi], dtype=torch.float32), mass, device="cuda")
+        old_tau, done = np.inf, 0
+        while done < int(nsamp):
+            nblk = int(min(check_every, int(nsamp) - done))
+            xs, ls, _ = hmc.sample_chains(nblk, steps, eps, seed=12345 + 104729 * (done // max(check_every, 1)), distributed=False)
+            done += nblk
+            xb, lb = gathered(xs, ls)
+            stop = False
+            if rank == 0:
+                store.extend(xb.cpu().numpy(), lb.cpu().numpy())
+                store.save()
+                tau = integrated_time(thin_for_tau(store.chain))
+                if not (np.isnan(np.sum(tau)) and done > 10):
+                    converged = np.all(tau * ntimes < store.iteration) and np.all(np.abs(old_tau - tau) / tau < tautol)
+                    keep = max(int(nk * np.mean(tau)), 2)
+                    converged = converged and checkmeanstd(np.asarray(store.chain[-keep:]), meanshift=meanshift, stdshift=stdshift)
+                    stop, old_tau = bool(converged), tau
+                else:
+                    stop = True
+            if world > 1:
+                box = [stop]
+                torch.distributed.broadcast_object_list(box, src=0)
+                stop = bool(box[0])
+            if stop:
+                break
+        if rank == 0:
+            store.finalize()
+        if world > 1:
+            torch.distributed.barrier()
+            if rank != 0:
+                store = ChainStore(os.path.join(os.path.dirname(store.base), os.path.basename(store.base)), self.transform)
         return store
 
 

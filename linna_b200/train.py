@@ -98,9 +98,14 @@ class FusedTrainer:
         return torch.stack([torch.median(loss), torch.max(frac), torch.median(frac)])
 
     # -- state exchange with the torch module / optimizer ----------------------------------
-    def reset_optimizer(self):
+    def reset_optimizer(self, weight_decay=1e-4):
+        """A fresh optimiser, as the reference's `AdamW(lr, weight_decay=1E-4)` after a re-initialisation or a roll-back
+        (predictor_gpu.py:329, :358): zero moments, step 0, and the weight decay back at its default (EarlyStopping may
+        have halved or doubled it)."""
         self.m.zero_(), self.v.zero_()
         self.t = 0
+        if weight_decay is not None:
+            self.weight_decay = float(weight_decay)
 
     def load_from_module(self):
         """Adopt the module's current parameters (after init_weight / load_checkpoint)."""

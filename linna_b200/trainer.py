@@ -72,6 +72,10 @@ def run_training(pred, dataset, num_epochs, loss_fn, val_dataset=None, val_metri
     dist_on = size > 1 and torch.distributed.is_available() and torch.distributed.is_initialized()
     world = torch.distributed.get_world_size() if dist_on else 1
     wrank = torch.distributed.get_rank() if dist_on else 0
+    # Data-parallel training (one process per GPU under torchrun): every rank runs this function with the same data set
+    # and the same seeds.  The rank that writes files / prints is the torch.distributed rank -- the reference's `rank`
+    # argument is never forwarded by train_NN / train_nn (linna/util.py:1287), so it cannot be trusted here.
+    rank = wrank if dist_on else rank
 
     outdir = pred.outdir
     lr_path = os.path.join(outdir, "lr.npy") if outdir is not None else None
@@ -88,16 +92,23 @@ def run_training(pred, dataset, num_epochs, loss_fn, val_dataset=None, val_metri
                 lr = box[0]
             if lr_path is not None and rank == 0:
                 np.save(lr_path, lr)
+            if dist_on:
+                torch.distributed.barrier()
     elif isinstance(pred.optim, torch.optim.Optimizer):
         lr = float(pred.optim.param_groups[0]["lr"])
     else:
         lr = 1e-3
-    lr = lr * size                                                       # predictor_gpu.py:246
+    # predictor_gpu.py:246 scales lr by `size` because every DDP rank of the reference would take a FULL batch (an
+    # effective batch of size x batch).  Here the rows of each batch are sharded over the ranks and the gradients
+    # averaged: the effective batch -- and therefore the learning rate -- is that of the single-GPU run.
+    if not dist_on:
+        lr = lr * size
     tr = probe
     tr.lr, tr.weight_decay = lr, 1e-4                                    # AdamW(lr, weight_decay=1E-4), :267
     tr.pg, tr.world = None, world
     if initfrombest:
-        if not _load_best(pred, tr):
+        # weights only: the reference builds a fresh AdamW(lr, weight_decay=1e-4) after loading them (predictor_gpu.py:247-267)
+        if not _load_best(pred, tr, with_optimizer=False):
             print("best.pth.tar does not exsit")
 
     have_val = val_dataset is not None
@@ -123,6 +134,8 @@ def run_training(pred, dataset, num_epochs, loss_fn, val_dataset=None, val_metri
             if world > 1:                                                # data-parallel: this rank's rows of the batch
                 idx = idx[wrank::world]
             tr.step(X[idx], Y[idx], cmd[idx], loss_out=losses_dev[b:b + 1])
+        if world > 1:     # the heuristics below must see the SAME numbers on every rank: the global batch means
+            torch.distributed.all_reduce(losses_dev, op=torch.distributed.ReduceOp.AVG)
         ep_losses = losses_dev.cpu().numpy().astype(np.float64)          # ONE device->host read per epoch
         train_losses.extend(ep_losses.tolist())
         loss = float(ep_losses[-1])
@@ -169,18 +182,24 @@ def run_training(pred, dataset, num_epochs, loss_fn, val_dataset=None, val_metri
                     else:
                         es.cooling = 0
                 elif crit == 2:
-                    print("early stop", flush=True)
-                    print("learning rate", tr.lr, flush=True)
+                    # every rank sees the same losses and validation metrics (all-reduced gradients, identical val set),
+                    # so every rank takes this branch in the same epoch: all of them leave the loop together and none is
+                    # left waiting in the next all-reduce
                     if rank == 0:
+                        print("early stop", flush=True)
+                        print("learning rate", tr.lr, flush=True)
                         _checkpoint(pred, tr, i, is_best, force=True)
-                        break
+                    break
                 elif crit == 3:
                     print("\n weight decay too small: {0}\n".format(tr.weight_decay), flush=True)
                     if tr.weight_decay < 1e0:
                         tr.weight_decay *= 2
             old, told = val_metrics[-1][0], loss
+        force = (i % ckpt_every == 0 or i == num_epochs - 1)
         if outdir is not None and rank == 0:
-            _checkpoint(pred, tr, i, is_best, force=(i % ckpt_every == 0 or i == num_epochs - 1))
+            _checkpoint(pred, tr, i, is_best, force=force)
+        if world > 1 and outdir is not None and (is_best or force):
+            torch.distributed.barrier()      # best.pth.tar is complete before any rank may roll back to it
     tr.commit()
     pred._engine = None
     tr.engine.close()
@@ -200,16 +219,20 @@ def _checkpoint(pred, tr, epoch, is_best, force):
                              "optim_dict": tr.optim_state_dict()}, is_best=is_best, checkpoint=pred.outdir)
 
 
-def _load_best(pred, tr):
+def _load_best(pred, tr, with_optimizer=False):
+    """Weights of best.pth.tar into the module and the device trainer.  The reference's re-initialisations all build a
+    NEW AdamW(lr, weight_decay=1e-4) afterwards (predictor_gpu.py:267, :329, :358): the moments are not restored unless
+    asked for."""
     path = os.path.join(pred.outdir, "best.pth.tar") if pred.outdir is not None else None
     if path is None or not os.path.isfile(path):
         return False
     ckpt = nnutils.load_checkpoint(path, pred.model, None, device="cpu")
     tr.load_from_module()
-    try:
-        tr.load_optim_state_dict(ckpt.get("optim_dict", {}))
-    except Exception:
-        tr.reset_optimizer()
+    if with_optimizer:
+        try:
+            tr.load_optim_state_dict(ckpt.get("optim_dict", {}))
+        except Exception:
+            tr.reset_optimizer()
     return True
 
 
@@ -257,12 +280,29 @@ def train_NN(nnsampler, cov, inv_cov, sigma, outdir_in, outdir_list, data, dolog
     on the GPU here."""
     from . import util as U
     device = "cpu"                      # where the pickled transform tensors live; compute is on the GPU
+    # under torchrun (tsize > 1, one process per GPU) every rank computes the same statistics; one of them writes the files
+    dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+    writer = (not dist_on) or torch.distributed.get_rank() == 0
+
+    class _NoWrite:
+        def __init__(self, obj):
+            self._o = obj
+
+        def __getattr__(self, name):
+            return getattr(self._o, name)
+
+        def __call__(self, *a, **k):
+            return self._o(*a, **k)
+
+        def pickle(self, path):
+            if writer:
+                self._o.pickle(path)
     inv_cov_tensor = torch.tensor(inv_cov, dtype=torch.float64)
     cov_tensor = torch.tensor(cov, dtype=torch.float64)
     y_transform_data = U.Y_transform_data(sigma, device=device)
-    y_transform_data.pickle(os.path.join(outdir_in, "y_transform_data.pkl"))
+    _NoWrite(y_transform_data).pickle(os.path.join(outdir_in, "y_transform_data.pkl"))
     y_invtransform_data = U.Y_invtransform_data(sigma, device=device)
-    y_invtransform_data.pickle(os.path.join(outdir_in, "y_invtransform_data.pkl"))
+    _NoWrite(y_invtransform_data).pickle(os.path.join(outdir_in, "y_invtransform_data.pkl"))
     data_tensor = torch.from_numpy(data.astype(np.float32)).clone().requires_grad_()
 
     train_x, train_y, val_x, val_y, train_y_last = _load_sets(outdir_list)
@@ -307,7 +347,7 @@ def train_NN(nnsampler, cov, inv_cov, sigma, outdir_in, outdir_list, data, dolog
     X_mean = log10_cols(train_x).mean(axis=0)
     X_std = log10_cols(train_x).std(axis=0)
     X_transform = U.X_transform_class(X_mean, X_std, device, dolog10index)
-    X_transform.pickle(os.path.join(outdir_in, "X_transform.pkl"))
+    _NoWrite(X_transform).pickle(os.path.join(outdir_in, "X_transform.pkl"))
     f32 = lambda a: torch.tensor(a, dtype=torch.float32)
     if ypositive:
         logy = torch.log(y_transform_data(f32(train_y)).detach())
@@ -319,9 +359,11 @@ def train_NN(nnsampler, cov, inv_cov, sigma, outdir_in, outdir_list, data, dolog
         y_std = U.median_absolute_deviation(yn, y_mean, 0)
         y_std[y_std < 1e-10] = 1e0
     y_transform = U.Y_transform_class(y_mean, y_std, device, ypositive=ypositive)
-    y_transform.pickle(os.path.join(outdir_in, "y_transform.pkl"))
+    _NoWrite(y_transform).pickle(os.path.join(outdir_in, "y_transform.pkl"))
     y_inv_transform = U.Y_invtransform_class(y_mean, y_std, data_tensor, device, ypositive=ypositive)
-    y_inv_transform.pickle(os.path.join(outdir_in, "y_invtransform.pkl"))
+    _NoWrite(y_inv_transform).pickle(os.path.join(outdir_in, "y_invtransform.pkl"))
+    if dist_on:
+        torch.distributed.barrier()
 
     loss_fn = U.Loss_fn(data_tensor, cov_tensor, inv_cov_tensor, y_transform_data, y_inv_transform, device)
     val_metric_fn = U.Val_metric_fn(data_tensor, cov_tensor, inv_cov_tensor, y_transform_data, y_inv_transform, device)

@@ -137,3 +137,98 @@ def test_stretch_move_kernels_sample_a_gaussian():
     np.testing.assert_allclose(chain.mean(axis=0), mu.cpu().numpy(), atol=0.08)
     np.testing.assert_allclose(np.cov(chain, rowvar=False), cov, atol=0.15)
     assert 0.35 < es.acceptance_fraction.mean() < 0.75
+
+
+def test_checkmeanstd_device_reduction_matches_numpy():
+    """The half-chain mean / std shift test on the GPU (two-pass float64 reduction kernel, csrc/sampler_kernels.cu)
+    against numpy, float32 and float64 chains, ragged shapes."""
+    from linna_b200 import engine as E, sampler
+    rng = np.random.default_rng(2)
+    for shape, dt in (((400, 6, 3), np.float64), ((41, 5, 4), np.float32), ((301, 1000, 30), np.float32), ((64, 7, 300), np.float64)):
+        x = (rng.standard_normal(shape) * 1.7 + 3.0).astype(dt)
+        xd = torch.from_numpy(x).cuda()
+        flat = x.reshape(-1, shape[-1]).astype(np.float64)
+        r0, r1 = 5 * shape[1], flat.shape[0] - 3
+        m, sd = E.column_moments(xd.reshape(-1, shape[-1]), r0, r1)
+        np.testing.assert_allclose(m, flat[r0:r1].mean(0), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(sd, flat[r0:r1].std(0), rtol=1e-10)
+        half = shape[0] // 2
+        a, b = flat[:half * shape[1]], flat[half * shape[1]:]
+        ref = (np.median(np.abs(a.mean(0) - b.mean(0)) / b.std(0)), np.median((a.std(0) - b.std(0)) / b.std(0)))
+        np.testing.assert_allclose(sampler._halves_shift_device(xd), ref, rtol=1e-8, atol=1e-12)
+    good = rng.standard_normal((400, 64, 3))
+    drift = good + np.linspace(0, 3, 400)[:, None, None]
+    assert sampler.checkmeanstd(torch.from_numpy(good).cuda(), 0.2, 0.15) and not sampler.checkmeanstd(torch.from_numpy(drift).cuda(), 0.2, 0.15)
+
+
+def test_hmc_kernels_follow_the_reference_leapfrog():
+    """linna_hmc_begin / _step / _end against the reference's leapfrog written out in torch (linna/HMCSampler.py:25-59) on a
+    Gaussian target: same momenta (read back from the kernel), same trajectory, same Hamiltonians, and an accept decision
+    consistent with them for every chain."""
+    from linna_b200 import engine as E
+    C, d, eps, L = 300, 37, 0.07, 4
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((d, d))
+    icov = torch.from_numpy((np.linalg.inv(A @ A.T / d + np.eye(d))).astype(np.float32)).cuda()
+    mass = torch.from_numpy(rng.uniform(0.5, 2.0, d).astype(np.float32)).cuda()
+
+    def vg(x):
+        g = -(x @ icov)
+        return 0.5 * (x * g).sum(-1), g
+    x = torch.from_numpy(rng.standard_normal((C, d)).astype(np.float32)).cuda()
+    lnp, grad = vg(x)
+    x_k, lnp_k, grad_k = x.clone(), lnp.clone(), grad.clone()
+    p, xn, H0 = E.hmc_begin(x_k, lnp_k, grad_k, mass, eps, 99, 0)
+    p0 = p - 0.5 * eps * grad                                  # the momentum the kernel drew
+    assert abs(float((p0 / mass.sqrt()).mean())) < 0.05 and abs(float((p0 / mass.sqrt()).std()) - 1.0) < 0.05
+    np.testing.assert_allclose(H0.cpu().numpy(), ((0.5 * p0 * p0 / mass).sum(-1) - lnp).cpu().numpy(), rtol=2e-5, atol=1e-4)
+    # reference leapfrog from the same momentum
+    pr = p0 + 0.5 * eps * grad
+    xr = x + eps * pr / mass
+    np.testing.assert_allclose(xn.cpu().numpy(), xr.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    for i in range(L):
+        l, g = vg(xn)
+        lr_, gr = vg(xr)
+        if i + 1 < L:
+            E.hmc_step(p, xn, g, mass, eps)
+            pr = pr + eps * gr
+            xr = xr + eps * pr / mass
+    pr = pr + 0.5 * eps * gr
+    H1 = (0.5 * pr * pr / mass).sum(-1) - lr_
+    nacc = torch.zeros(C, device="cuda")
+    E.hmc_end(x_k, lnp_k, grad_k, xn, l.contiguous(), g.contiguous(), p, mass, H0, eps, 99, 4, nacc)
+    np.testing.assert_allclose(xn.cpu().numpy(), xr.cpu().numpy(), rtol=2e-4, atol=2e-5)
+    acc = nacc.cpu().numpy() > 0
+    dH = (H0 - H1).cpu().numpy()
+    assert np.all(acc[dH > 1e-3])                              # an energy decrease is always accepted
+    assert 0.5 < acc.mean() <= 1.0
+    moved = np.all(x_k.cpu().numpy() == xn.cpu().numpy(), axis=1)
+    stayed = np.all(x_k.cpu().numpy() == x.cpu().numpy(), axis=1)
+    assert np.array_equal(moved, acc) and np.array_equal(stayed, ~acc)           # position, lnP and gradient follow ONE decision
+    np.testing.assert_array_equal(lnp_k.cpu().numpy()[acc], l.cpu().numpy()[acc])
+    np.testing.assert_array_equal(lnp_k.cpu().numpy()[~acc], lnp.cpu().numpy()[~acc])
+    np.testing.assert_array_equal(grad_k.cpu().numpy()[acc], g.cpu().numpy()[acc])
+
+
+def test_run_mcmc_hmc_method(tmp_path):
+    """run_mcmc(method="hmc") (linna/util.py:1495; broken at HEAD) reaches the batched device HMC and stores
+    the chain under the reference's chhmc file name."""
+    import pickle
+    import shutil
+    import linna.util as U
+    from tests.helpers import GOLDEN
+    d = str(tmp_path / "iter_0")
+    shutil.copytree(os.path.join(GOLDEN, "ref_fixture_iter_0"), d)
+    pred, yinv = U.retrieve_model(d, 2, 2)
+    with open(os.path.join(d, "model_args.pkl"), "rb") as f:
+        args = pickle.load(f)
+    priors = [dict(param="x%d" % i, dist="flat", arg1=-2.0, arg2=2.0) for i in range(2)]
+    tr = U.Transform(priors)
+    lp = U.Log_prob(np.asarray(args[6]), np.asarray(args[2]), pred, yinv, tr, 1.0, U.gaussianlogliklihood, nograd=False)
+    dd = U.Ddlnp(np.asarray(args[6]), np.asarray(args[2]), pred, yinv, tr, 1.0)
+    ns = U.NN_samplerv1(d + "/", [[-2, 2], [-2, 2]])
+    np.random.seed(3)
+    store = U.run_mcmc(ns, d + "/", "hmc", 2, 256, np.zeros(2), lp, dlnp=None, ddlnp=dd, transform=tr, ntimes=5, tautol=0.2)
+    assert os.path.isfile(os.path.join(d, "chhmc.meta.json")) and store.iteration >= 100
+    ch = np.asarray(store.chain_transformed)
+    assert ch.shape[1:] == (256, 2) and np.all(np.abs(ch) <= 2.0) and np.all(np.isfinite(np.asarray(store.log_prob)))

@@ -208,7 +208,7 @@ def test_tc_fp16_overflow_rows_are_fixed_up():
     # (the fixed-up rows carry float32's own error at |xhat| ~ 1e5: a few per cent of a gradient dominated by 1/X_std)
     # 1 / X_std = 5e4 amplifies the relu kinks of the gradient along u_3 (two correct float32 evaluations can put a unit
     # whose pre-activation is within rounding of 0 on either side, cf. test_tc_full_size_c3): a few rows may differ more
-    assert np.median(rel) < 1e-5 and np.mean(rel[cold] > 2e-4) < 3e-3 and rel[hot].max() < 5e-2, (np.median(rel), rel[cold].max(), rel[hot].max())
+    assert np.median(rel) < 1e-5 and np.percentile(rel[cold], 99) < 2e-4 and rel[hot].max() < 5e-2, (np.median(rel), rel[cold].max(), rel[hot].max())
     assert np.array_equal(e.lnp(_dev(u)).cpu().numpy(), lnp.astype(np.float32))
     # a NaN input is still -inf (util.py:1015-1016) after the fix-up
     u2 = u.copy()

@@ -106,24 +106,41 @@ def test_checkmeanstd_and_chain_store(tmp_path):
     assert sampler.checkmeanstd(good, 0.2, 0.15)
     drift = good + np.linspace(0, 3, 400)[:, None, None]
     assert not sampler.checkmeanstd(drift, 0.2, 0.15)
-    # the tensor path (what runs on the GPU for large chains) computes the same two statistics
+    # a host tensor takes the same host path (the device path is the hand-written reduction kernel, tests/test_gpu_main.py)
     import torch
     for x in (good, drift, rng.standard_normal((41, 5, 4))):
-        half = len(x) // 2
-        a, b = x[:half].reshape(-1, x.shape[-1]), x[half:].reshape(-1, x.shape[-1])
-        sb = b.std(axis=0)
-        ref = (np.median(np.abs(a.mean(axis=0) - b.mean(axis=0)) / sb), np.median((a.std(axis=0) - sb) / sb))
-        np.testing.assert_allclose(sampler._halves_shift_torch(torch.from_numpy(x)), ref, rtol=1e-10, atol=1e-13)
         assert sampler.checkmeanstd(torch.from_numpy(x), 0.2, 0.15) == sampler.checkmeanstd(x, 0.2, 0.15)
+    # the chain store appends: blocks go to raw files as they come, nothing is rewritten, and an unfinished run can be
+    # picked up from them; finalize() writes the single-file .npz with the reference's dataset names
     name = str(tmp_path / "chemcee_256.h5")
     st = sampler.ChainStore(name, transform=lambda c: 2.0 * c)
     st.extend(good[:100], np.zeros((100, 6)))
+    size1 = os.path.getsize(str(tmp_path / "chemcee_256.chain.f64"))
     st.extend(good[100:250], np.ones((150, 6)))
     st.save()
-    st2 = sampler.ChainStore(name)
+    assert os.path.getsize(str(tmp_path / "chemcee_256.chain.f64")) == size1 * 250 // 100
+    assert not os.path.exists(str(tmp_path / "chemcee_256.npz"))
+    st2 = sampler.ChainStore(name)                       # resume of an unfinished run: from the raw files
     assert st2.exists() and st2.iteration == 250
     np.testing.assert_allclose(st2.get_value("chain_transformed"), 2.0 * good[:250])
+    np.testing.assert_allclose(st2.get_last_sample(), good[249])
+    st2.extend(good[250:300], np.ones((50, 6)))          # ... and continued
+    st2.finalize()
+    z = np.load(str(tmp_path / "chemcee_256.npz"))
+    assert set(z.files) == {"chain", "chain_transformed", "log_prob"} and z["chain"].shape == (300, 6, 3)
+    st3 = sampler.ChainStore(name)                       # a finished chain is read from the .npz
+    assert st3.iteration == 300
+    st3.extend(good[300:350], np.ones((50, 6)))          # continuing a finished chain converts it back
+    assert st3.iteration == 350 and np.allclose(st3.chain[299], good[299]) and np.allclose(st3.chain[349], good[349])
+    fresh = sampler.ChainStore(name, fresh=True)
+    assert not fresh.exists()
+    st = sampler.ChainStore(name, transform=lambda c: 2.0 * c)
+    st.extend(good[:250], np.concatenate([np.zeros((100, 6)), np.ones((150, 6))]))
+    st.finalize()
+    st2 = sampler.ChainStore(name)
     assert st2.get_log_prob(flat=True).shape == (1500,)
+    sub = sampler.thin_for_tau(rng.standard_normal((50, 5000, 3)), max_walkers=100)
+    assert sub.shape == (50, 100, 3)
     chain, lp, reader = sampler.read_chain_and_cut(name, nk=2, ntimes=20)
     assert chain.shape[1] == 3 and len(chain) % 6 == 0 and reader.iteration == 250
     with pytest.raises(FileNotFoundError):
