@@ -120,6 +120,17 @@ int linna_lnp(linna_model_t *m, const float *u, int64_t n, float *lnp, void *str
  * (linna/HMCSampler.py:29-48, linna/util.py:1023-1035 Dlnp).  grad: [n][n_in].  DEVICE pointers. */
 int linna_lnp_grad(linna_model_t *m, const float *u, int64_t n, float *lnp, float *grad, void *stream);
 
+/* Vector-Jacobian product of linna_predict -- what torch.autograd computes when the reference calls
+ * Predictor.predict(X, no_grad=False) (linna/predictor_gpu.py:495-496) or model(x) with parameters that require grad
+ * (linna/predictor_gpu.py:279-283): for a cotangent cot [n][n_out] of the requested output kind,
+ *   out    [n][n_out] (or NULL): the forward value itself,
+ *   gtheta [n][n_in]  (or NULL): sum_j cot[b][j] d out[b][j] / d theta[b][i],
+ *   gparams [n_params] (or NULL): sum_b,j cot[b][j] d out[b][j] / d p, flat state_dict order; needs linna_train_setup
+ *           (its row-major activation store) with max_batch >= n.
+ * One fused forward + backward-data launch (+ the weight-gradient launch).  DEVICE pointers. */
+int linna_predict_vjp(linna_model_t *m, const float *theta, int64_t n, const float *cot, int32_t out_kind, float *out, float *gtheta,
+                      float *gparams, void *stream);
+
 /* Host-buffer forms of the three calls above: the arrays are HOST memory (any pageable or pinned
  * buffer); the library stages them through pinned memory, runs the kernel and copies the result
  * back before returning.  These are what a per-call numpy caller (emcee/zeus with vectorize=True)
@@ -203,6 +214,15 @@ int linna_train_adamw(linna_model_t *m, float *params, float *adam_m, float *ada
 int linna_train_load_params(linna_model_t *m, const float *params, void *stream);
 /* Adopt a flat HOST parameter vector as the model's weights (end of training). */
 int linna_train_commit(linna_model_t *m, const float *params_host);
+
+/* Auxilleryfunc.__call__(y_pred, y_target) (linna/util.py:1070-1088) on free-standing DEVICE tensors: per row
+ * loss = chi2(target, pred) / chisqMd, chisqMd = max(chi2(target, data), n_out/2), chisqnnd = chi2(pred, data), all in the
+ * normalised space of the network output (y_pred [n][n_out] is the network output, y_target physical units), and, when
+ * dloss != NULL, d loss_b / d y_pred_b [n][n_out] for autograd.  Constants as for linna_train_setup; icov_hat symmetric.
+ * (Predictor.train does not come through here: the training kernels evaluate the loss in their epilogues.) */
+int linna_loss_terms(const float *y_pred, const float *y_target, int64_t n, int32_t n_out, const float *data_hat,
+                     const float *icov_hat, const float *sigma, const float *y_mean, const float *y_std, int32_t ypositive,
+                     float *loss, float *chisq_md, float *chisq_nnd, float *dloss, void *stream);
 
 /* ---- on-device ensemble-sampler step (emcee's stretch move, linna/sampler.py:493-503, 530) ---------------
  * One half-ensemble update is propose -> linna_lnp(y) -> accept, all on device pointers.

@@ -309,8 +309,11 @@ static int rebuild(linna_model *m)
         m->prog_valid[pk] = false;
         if ((pk == PROG_LNP || pk == PROG_GRAD) && !m->has_like) continue;
         if ((pk == PROG_LOSS || pk == PROG_TRAIN) && !m->has_train) continue;
-        const bool train = pk == PROG_TRAIN, lossprog = pk == PROG_LOSS || pk == PROG_TRAIN;
-        const bool grad = pk == PROG_GRAD || train;   // forward saves relu masks
+        const bool vjp = pk == PROG_VJP;
+        if (vjp && m->has_extra) continue;            // (ChtoModelv2_linear: no vector-Jacobian program)
+        // `train`: the forward and backward steps also leave row-major copies for the weight-gradient kernel
+        const bool train = pk == PROG_TRAIN || (vjp && m->has_train), lossprog = pk == PROG_LOSS || pk == PROG_TRAIN;
+        const bool grad = pk == PROG_GRAD || train || vjp;   // forward saves relu masks
         Program &pg = m->prog_host[pk];
         memset(&pg, 0, sizeof pg);
         pg.arena_features = arena_features;
@@ -351,6 +354,10 @@ static int rebuild(linna_model *m)
                 s.dst = other(cur);
                 if (train && !last) s.rm_off = rm_act[i + 1].off, s.rm_ld = rm_act[i + 1].ld;
                 if (last && lossprog && train) s.flags |= F_SAVE_MASK, s.mask_off = mask_loss;
+                if (last && vjp) {
+                    s.flags |= F_COT | F_OUT_VEC;
+                    if (train) s.rm_off = rm_gz[i].off, s.rm_ld = rm_gz[i].ld;
+                }
                 if (last && m->has_extra) {
                     s.src2 = bufX, s.K2 = n_in, s.wt2 = P(o_extra_f), s.ldw2 = pad4(n_out), s.bias = P(o_lastbias);
                 }
@@ -372,15 +379,60 @@ static int rebuild(linna_model *m)
                 y.epi = last ? EPI_HEAD : EPI_ACT;
                 y.dst = other(cur);
                 if (train && !last) y.rm_off = rm_act[i + 1].off, y.rm_ld = rm_act[i + 1].ld;
+                if (last && vjp) {
+                    y.flags |= F_COT | F_OUT_VEC;
+                    if (train) y.rm_off = rm_gz[i].off, y.rm_ld = rm_gz[i].ld;
+                }
                 cur = y.dst;
             }
             if (last) {
                 Step &s = pg.steps[ns - 1];
                 if (pk == PROG_PREDICT) s.flags |= F_OUT_VEC;
+                if (vjp && !(s.flags & F_COT)) s.flags |= F_COT | F_OUT_VEC;
                 if (pk == PROG_GRAD && m->ypositive) s.flags |= F_SAVE_Y, s.ybuf = bufY;
             }
         }
-        if (lossprog) {
+        if (vjp) {
+            // backward-data from the cotangent the head step left in `cur`, down to d out / d theta (EPI_GRAD with
+            // input_theta); with the training buffers present every d out / d z is also kept row-major for the
+            // weight-gradient kernel (parameter gradients of an arbitrary cotangent: autograd through model(x))
+            for (int i = (int)m->ops.size() - 1; i >= 0; --i) {
+                const OpHost &op = m->ops[i];
+                const OpOffsets &o = off[i];
+                int pmask = -1;
+                if (i > 0) {
+                    const OpHost &pv = m->ops[i - 1];
+                    if (pv.kind == LINNA_OP_RES || pv.act == LINNA_ACT_RELU) pmask = off[i - 1].mask_y;
+                }
+                if (op.kind == LINNA_OP_LINEAR) {
+                    Step &s2 = new_step();
+                    s2.src1 = cur, s2.K1 = op.out, s2.wt1 = P(o.w_b), s2.ldw1 = pad4(op.in), s2.N = op.in;
+                    s2.epi = i == 0 ? EPI_GRAD : EPI_BWD;
+                    if (pmask >= 0) s2.flags |= F_APPLY_MASK, s2.mask_off = pmask;
+                    if (train && i > 0) s2.rm_off = rm_gz[i - 1].off, s2.rm_ld = rm_gz[i - 1].ld;
+                    s2.dst = other(cur);
+                    cur = s2.dst;
+                } else {
+                    Step &h = new_step();
+                    h.src1 = cur, h.K1 = op.out, h.wt1 = P(o.w2_b), h.ldw1 = pad4(op.mid), h.N = op.mid;
+                    h.scale = op.alpha, h.epi = EPI_BWD, h.flags = F_APPLY_MASK, h.mask_off = o.mask_h, h.dst = bufH;
+                    if (train) h.rm_off = rm_gzh[i].off, h.rm_ld = rm_gzh[i].ld;
+                    Step &x = new_step();
+                    if (op.has_ws) {
+                        x.src1 = cur, x.K1 = op.out, x.wt1 = P(o.ws_b), x.ldw1 = pad4(op.in);
+                        x.src2 = bufH, x.K2 = op.mid, x.wt2 = P(o.w_b), x.ldw2 = pad4(op.in);
+                    } else {
+                        x.src1 = bufH, x.K1 = op.mid, x.wt1 = P(o.w_b), x.ldw1 = pad4(op.in);
+                        x.src2 = cur, x.flags |= F_ADD_SRC2;
+                    }
+                    x.N = op.in, x.epi = i == 0 ? EPI_GRAD : EPI_BWD;
+                    if (pmask >= 0) x.flags |= F_APPLY_MASK, x.mask_off = pmask;
+                    if (train && i > 0) x.rm_off = rm_gz[i - 1].off, x.rm_ld = rm_gz[i - 1].ld;
+                    x.dst = other(cur);
+                    cur = x.dst;
+                }
+            }
+        } else if (lossprog) {
             // q = delta @ Chat^-1 ; chi2 = q . delta ; (training) g_yhat = -2 q mask / (cmd B)
             const int dbuf = cur;
             Step &q = new_step();
@@ -971,6 +1023,41 @@ int linna_lnp_grad(linna_model_t *m, const float *u, int64_t n, float *lnp, floa
 {
     if (n > 0 && (!lnp || !grad)) return fail(LINNA_EINVAL, "null output");
     return run(m, PROG_GRAD, u, n, nullptr, 0, lnp, grad, 0, (cudaStream_t)stream);
+}
+
+static int ensure(float **p, size_t *cap, size_t need);
+
+int linna_predict_vjp(linna_model_t *m, const float *theta, int64_t n, const float *cot, int32_t out_kind, float *out, float *gtheta,
+                      float *gparams, void *stream)
+{
+    if (!m) return fail(LINNA_EINVAL, "null model");
+    if (out_kind < LINNA_OUT_YHAT || out_kind > LINNA_OUT_M) return fail(LINNA_EINVAL, "bad out_kind");
+    if (n < 0) return fail(LINNA_EINVAL, "negative n");
+    if (n == 0) return LINNA_OK;
+    if (!theta || !cot) return fail(LINNA_EINVAL, "null buffer");
+    if (!m->prog_valid[PROG_VJP]) return fail(LINNA_EINVAL, "vector-Jacobian program unavailable for this model (extra linear branch)");
+    if (gparams && (!m->has_train || n > m->max_batch))
+        return fail(LINNA_ESTATE, "parameter gradients need linna_train_setup with max_batch >= n (%lld)", (long long)n);
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (!gtheta) {
+        if ((rc = ensure(&m->d_grad, &m->d_grad_cap, (size_t)n * m->n_in))) return rc;
+        gtheta = m->d_grad;
+    }
+    KernelArgs p;
+    memset(&p, 0, sizeof p);
+    p.target = cot, p.rm_base = gparams ? m->rm : nullptr, p.loss_inv_B = 1.f;
+    if ((rc = run(m, PROG_VJP, theta, n, out, out_kind, nullptr, gtheta, 1, st, &p))) return rc;
+    if (gparams) {
+        AdamArgs a;
+        memset(&a, 0, sizeof a);
+        a.grads = gparams, a.fuse = 0;
+        CUDA_TRY(launch_wgrad(m->wg_layers_dev, m->wg_tiles_dev, m->n_wg_tiles, m->rm, (int)n, a, st));
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaEventRecord(m->last_done, st));
+    }
+    return LINNA_OK;
 }
 
 static int ensure(float **p, size_t *cap, size_t need)

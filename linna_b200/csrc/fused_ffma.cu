@@ -418,9 +418,25 @@ __global__ void __launch_bounds__(kThreads, RG == 1 ? 1 : 2) fused_ffma_kernel(c
                                 y[i] = yy;
                                 d[i] = yy * sg - dt;                                  // util.py:458, :954
                             }
-                            store8(arena + (size_t)(st.dst + cidx) * BM + row_base, d);
+                            if (st.flags & F_COT) {
+                                // vector-Jacobian product: the cotangent of the requested output (yhat | y | m) pulled back
+                                // to yhat: d y / d yhat = y_std (x y with the exp), d m / d y = sigma
+                                float ct[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const int r = row_base + i;
+                                    float g = r < nrows ? __ldg(args.target + (row0 + r) * n_out + cidx) : 0.f;
+                                    if ((st.flags & F_RELU) && !(v[i] > 0.f)) g = 0.f;
+                                    if (args.out_kind != LINNA_OUT_YHAT) g *= c.ypositive ? ys * y[i] : ys;
+                                    if (args.out_kind == LINNA_OUT_M) g *= sg;
+                                    ct[i] = g;
+                                }
+                                store8(arena + (size_t)(st.dst + cidx) * BM + row_base, ct);
+                                if (st.rm_off >= 0) store_rm(args.rm_base, st, row0 + args.rm_row0, row_base, nrows, cidx, ct);
+                            } else
+                                store8(arena + (size_t)(st.dst + cidx) * BM + row_base, d);
                             if (st.flags & F_SAVE_Y) store8(arena + (size_t)(st.ybuf + cidx) * BM + row_base, y);
-                            if (st.flags & F_OUT_VEC) {
+                            if ((st.flags & F_OUT_VEC) && args.out_vec) {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     int r = row_base + i;
@@ -464,8 +480,8 @@ __global__ void __launch_bounds__(kThreads, RG == 1 ? 1 : 2) fused_ffma_kernel(c
                             if (st.rm_off >= 0) store_rm(args.rm_base, st, row0 + args.rm_row0, row_base, nrows, cidx, v);
                         } else if (st.epi == EPI_GRAD) {
                             // chain through xhat = (theta' - mean)/std, theta' = log10(theta), theta = prior(u)
-                            const int kind = c.prior_kind[cidx];
-                            const float ps = c.prior_scale[cidx], psh = c.prior_shift[cidx];
+                            const int kind = args.input_theta ? 0 : c.prior_kind[cidx];
+                            const float ps = args.input_theta ? 1.f : c.prior_scale[cidx], psh = args.input_theta ? 0.f : c.prior_shift[cidx];
                             const float inv_std = 1.0f / c.x_std[cidx];
                             const bool lg = c.log10_flag && c.log10_flag[cidx];
 #pragma unroll
@@ -475,6 +491,11 @@ __global__ void __launch_bounds__(kThreads, RG == 1 ? 1 : 2) fused_ffma_kernel(c
                                     const int64_t gr = grow(r);
                                     float u = args.in[gr * n_in + cidx];
                                     float gx = v[i] * inv_std;
+                                    if (args.input_theta) {   // input is the physical parameter itself: no prior map, no prior term
+                                        if (lg) gx /= (u * 2.30258509299404568f);
+                                        args.grad[gr * n_in + cidx] = gx;
+                                        continue;
+                                    }
                                     if (lg) gx /= (prior_map(u, kind, ps, psh) * 2.30258509299404568f);
                                     float jac = ps;
                                     if (kind == LINNA_PRIOR_FLAT) jac *= 0.398942280401432678f * expf(-0.5f * u * u);

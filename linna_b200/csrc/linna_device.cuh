@@ -38,7 +38,8 @@ enum StepFlags : int32_t {
     F_MUL_YSAVE = 32,   // BWD: multiply by saved y (ypositive: d exp)
     F_SAVE_Y = 64,      // HEAD: save y into ybuf (ypositive + backward)
     F_OUT_VEC = 128,    // HEAD: write the selected vector (yhat / y / m) to the global output
-    F_LOSS_GRAD = 256   // LOSSQ: also emit d loss / d yhat (training); otherwise chi^2 only
+    F_LOSS_GRAD = 256,  // LOSSQ: also emit d loss / d yhat (training); otherwise chi^2 only
+    F_COT = 512         // HEAD: vector-Jacobian product -- dst receives cot[row][c] * d out / d yhat (cot = args.target) instead of d
 };
 
 struct Step {

@@ -30,7 +30,7 @@ struct OpHost {
     bool has_ws;
 };
 
-enum ProgKind { PROG_PREDICT = 0, PROG_LNP = 1, PROG_GRAD = 2, PROG_LOSS = 3, PROG_TRAIN = 4, PROG_COUNT = 5 };
+enum ProgKind { PROG_PREDICT = 0, PROG_LNP = 1, PROG_GRAD = 2, PROG_LOSS = 3, PROG_TRAIN = 4, PROG_VJP = 5, PROG_COUNT = 6 };
 
 // A few host threads that move pageable caller buffers to / from pinned staging memory while the GPU works: one
 // thread copies ~10 GB/s, and a 12 MB walker block staged by one thread costs more than the kernel that consumes it.
@@ -112,7 +112,7 @@ struct linna_model {
     size_t blob_floats = 0;
     Program *prog_dev = nullptr;  // [PROG_COUNT]
     Program prog_host[PROG_COUNT];
-    bool prog_valid[PROG_COUNT] = {false, false, false, false, false};
+    bool prog_valid[PROG_COUNT] = {false, false, false, false, false, false};
     Consts consts;
     float *arena = nullptr;
     uint8_t *masks = nullptr;

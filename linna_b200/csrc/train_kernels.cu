@@ -179,3 +179,126 @@ cudaError_t launch_fill_col(float *base, int ld, int col, int rows, float value,
 }
 
 }  // namespace linna
+
+// ------------------------------------------------------------------------------------------------------------------
+// Free-standing loss terms: Auxilleryfunc.__call__(y_pred, y_target) (linna/util.py:1070-1088) for tensors the caller
+// already holds -- the three quadratic forms of the training loss in normalised space for rows of network output
+// `y_pred` and physical targets `y_target`, plus d loss_b / d y_pred_b for autograd.  Eight rows per CTA: the three
+// residual vectors of every row sit in shared memory, a thread owns output columns j = tid, tid + 256, ... and walks
+// the (symmetrised) C_hat^-1 column-wise with coalesced loads.  Not a hot path (Predictor.train never calls it: the
+// training kernels evaluate the loss in their own epilogues) -- it exists so that Loss_fn / Val_metric_fn work on
+// free-standing tensors exactly like the reference's.
+namespace linna {
+
+constexpr int LT_ROWS = 8;
+
+__global__ void __launch_bounds__(256) loss_terms_kernel(const float *__restrict__ y_pred, const float *__restrict__ y_target, int64_t n,
+                                                         int n_out, const float *__restrict__ data_hat, const float *__restrict__ icov,
+                                                         const float *__restrict__ sigma, const float *__restrict__ y_mean,
+                                                         const float *__restrict__ y_std, int ypositive, float *__restrict__ loss,
+                                                         float *__restrict__ chisq_md, float *__restrict__ chisq_nnd,
+                                                         float *__restrict__ dloss)
+{
+    extern __shared__ float lt_smem[];                 // [3][LT_ROWS][n_out] residuals, then [3][LT_ROWS] reductions
+    float *delta = lt_smem;
+    double *red = reinterpret_cast<double *>(lt_smem + 3 * LT_ROWS * n_out);     // 96 n_out bytes in: 8-byte aligned
+    __shared__ double chi[3][LT_ROWS];
+    const int64_t row0 = (int64_t)blockIdx.x * LT_ROWS;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < LT_ROWS * n_out; e += 256) {
+        const int r = e / n_out, j = e - r * n_out;
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        if (row0 + r < n) {
+            const float Y = y_target[(row0 + r) * n_out + j], yp = y_pred[(row0 + r) * n_out + j], dh = data_hat[j];
+            float t = Y / (sigma ? sigma[j] : 1.f);                                  // util.py:432
+            if (ypositive) t = logf(t);                                              // util.py:567-568
+            t = (t - y_mean[j]) / y_std[j];                                          // util.py:570
+            if (!(Y == 1e-30f || Y == 1e10f || dh == 1e-30f)) d0 = t - yp, d1 = t - dh, d2 = yp - dh;   // util.py:1072
+        }
+        delta[(0 * LT_ROWS + r) * n_out + j] = d0, delta[(1 * LT_ROWS + r) * n_out + j] = d1, delta[(2 * LT_ROWS + r) * n_out + j] = d2;
+    }
+    if (tid < 3 * LT_ROWS) chi[tid / LT_ROWS][tid % LT_ROWS] = 0.0;
+    __syncthreads();
+    double part[3][LT_ROWS];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int r = 0; r < LT_ROWS; ++r) part[k][r] = 0.0;
+    for (int j = tid; j < n_out; j += 256) {
+        float q[3][LT_ROWS];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int r = 0; r < LT_ROWS; ++r) q[k][r] = 0.f;
+        for (int i = 0; i < n_out; ++i) {
+            const float c = icov[(size_t)i * n_out + j];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int r = 0; r < LT_ROWS; ++r) q[k][r] = fmaf(delta[(k * LT_ROWS + r) * n_out + i], c, q[k][r]);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int r = 0; r < LT_ROWS; ++r) part[k][r] += (double)(q[k][r] * delta[(k * LT_ROWS + r) * n_out + j]);
+        if (dloss)   // raw q of the target-vs-prediction form; scaled by -2 / chi2_Md below, once that is known
+#pragma unroll
+            for (int r = 0; r < LT_ROWS; ++r)
+                if (row0 + r < n) dloss[(row0 + r) * n_out + j] = q[0][r];
+    }
+    // block reduction of the 24 partial sums
+    for (int k = 0; k < 3; ++k)
+        for (int r = 0; r < LT_ROWS; ++r) {
+            double v = part[k][r];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((tid & 31) == 0) red[tid >> 5] = v;
+            __syncthreads();
+            if (tid == 0) {
+                double s = 0.0;
+                for (int w = 0; w < 8; ++w) s += red[w];
+                chi[k][r] = s;
+            }
+            __syncthreads();
+        }
+    if (tid < LT_ROWS && row0 + tid < n) {
+        const float mnn = (float)chi[0][tid], nnd = (float)chi[2][tid];
+        float md = (float)chi[1][tid];
+        if (md < 0.5f * (float)n_out) md = 0.5f * (float)n_out;                      // util.py:1086
+        loss[row0 + tid] = mnn / md, chisq_md[row0 + tid] = md, chisq_nnd[row0 + tid] = nnd;   // util.py:1087
+        chi[1][tid] = (double)md;
+    }
+    __syncthreads();
+    if (dloss) {
+        for (int e = tid; e < LT_ROWS * n_out; e += 256) {
+            const int r = e / n_out, j = e - r * n_out;
+            if (row0 + r >= n) continue;
+            // d (delta^T A delta / md) / d y_pred = -2 A delta / md where the entry is not masked (delta = t - y_pred)
+            const float Y = y_target[(row0 + r) * n_out + j];
+            const bool masked = Y == 1e-30f || Y == 1e10f || data_hat[j] == 1e-30f;
+            const float g = dloss[(row0 + r) * n_out + j] * (float)(-2.0 / chi[1][r]);
+            dloss[(row0 + r) * n_out + j] = masked ? 0.f : g;
+        }
+    }
+}
+
+}  // namespace linna
+
+extern "C" int linna_loss_terms(const float *y_pred, const float *y_target, int64_t n, int32_t n_out, const float *data_hat,
+                                const float *icov_hat, const float *sigma, const float *y_mean, const float *y_std, int32_t ypositive,
+                                float *loss, float *chisq_md, float *chisq_nnd, float *dloss, void *stream)
+{
+    if (!y_pred || !y_target || !data_hat || !icov_hat || !y_mean || !y_std || !loss || !chisq_md || !chisq_nnd || n < 0 || n_out <= 0)
+        return -1;
+    if (n == 0) return 0;
+    const size_t smem = ((size_t)3 * linna::LT_ROWS * n_out + 2) * sizeof(float) + 8 * sizeof(double);
+    if (smem > 200 * 1024) return -1;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(linna::loss_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -3;
+        attr = true;
+    }
+    const int grid = (int)((n + linna::LT_ROWS - 1) / linna::LT_ROWS);
+    linna::loss_terms_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(y_pred, y_target, n, n_out, data_hat, icov_hat, sigma, y_mean, y_std,
+                                                                        ypositive, loss, chisq_md, chisq_nnd, dloss);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}

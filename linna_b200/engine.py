@@ -77,6 +77,7 @@ def load_library():
     lib.linna_predict.argtypes = [vp, vp, i64, vp, i32, vp]
     lib.linna_lnp.argtypes = [vp, vp, i64, vp, vp]
     lib.linna_lnp_grad.argtypes = [vp, vp, i64, vp, vp, vp]
+    lib.linna_predict_vjp.argtypes = [vp, vp, i64, vp, i32, vp, vp, vp, vp]
     lib.linna_predict_host.argtypes = [vp, vp, i64, vp, i32]
     lib.linna_lnp_host.argtypes = [vp, vp, i64, vp]
     lib.linna_lnp_grad_host.argtypes = [vp, vp, i64, vp, vp]
@@ -103,6 +104,7 @@ def load_library():
     lib.linna_train_adamw.argtypes = [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp]
     lib.linna_train_load_params.argtypes = [vp, vp, vp]
     lib.linna_train_commit.argtypes = [vp, vp]
+    lib.linna_loss_terms.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.linna_train_set_path.argtypes = [vp, i32]
     lib.linna_train_last_kernel.argtypes = [vp]
     if lib.linna_abi_version() != 1:
@@ -197,6 +199,26 @@ def column_moments(x2d, r0, r1):
     if rc != 0:
         raise LinnaError("linna_column_moments failed (%d)" % rc)
     return mean, std
+
+
+def loss_terms(y_pred, y_target, data_hat, icov_hat, sigma, y_mean, y_std, ypositive, want_grad=False):
+    """(loss, chisqMd, chisqnnd[, d loss/d y_pred]) per row: Auxilleryfunc.__call__ (linna/util.py:1070-1088) on CUDA
+    tensors, one kernel launch."""
+    import torch
+    lib = load_library()
+    n, n_out = int(y_pred.shape[0]), int(y_pred.shape[1])
+    dev = y_pred.device
+    loss = torch.empty(n, dtype=torch.float32, device=dev)
+    md, nnd = torch.empty_like(loss), torch.empty_like(loss)
+    g = torch.empty_like(y_pred) if want_grad else None
+    with torch.cuda.device(dev):
+        rc = lib.linna_loss_terms(y_pred.data_ptr(), y_target.data_ptr(), n, n_out, data_hat.data_ptr(), icov_hat.data_ptr(),
+                                  sigma.data_ptr() if sigma is not None else None, y_mean.data_ptr(), y_std.data_ptr(),
+                                  int(bool(ypositive)), loss.data_ptr(), md.data_ptr(), nnd.data_ptr(),
+                                  g.data_ptr() if g is not None else None, _cur_stream())
+    if rc != 0:
+        raise LinnaError("linna_loss_terms failed (%d)" % rc)
+    return loss, md, nnd, g
 
 
 def launch_count():
@@ -408,6 +430,19 @@ class Engine:
             self._check(self.lib.linna_predict(self.handle, th.data_ptr(), th.shape[0], out.data_ptr(), out_kind,
                                                self._stream()))
         return out
+
+    def predict_vjp(self, theta, cot, out_kind=LINNA_OUT_Y, want_params=False):
+        """Vector-Jacobian product of ``predict`` for CUDA tensors: returns (d/d theta [n, n_in], flat parameter gradient
+        or None).  ``want_params`` needs ``train_setup`` (max_batch >= n)."""
+        import torch
+        th = self._prep_dev(theta, self.n_in)
+        ct = self._prep_dev(cot, self.n_out)
+        gth = torch.empty_like(th)
+        gp = torch.zeros(self.n_params, dtype=torch.float32, device=th.device) if want_params else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.linna_predict_vjp(self.handle, th.data_ptr(), th.shape[0], ct.data_ptr(), int(out_kind), None,
+                                                   gth.data_ptr(), gp.data_ptr() if gp is not None else None, self._stream()))
+        return gth, gp
 
     @staticmethod
     def _host_out(out, shape):

@@ -148,18 +148,99 @@ class FusedTrainer:
         self.engine.train_commit(self.p.detach().cpu().numpy())
 
 
+class _LossTerms(torch.autograd.Function):
+    """loss rows with d loss / d y_pred attached (the other two outputs carry no gradient to y_pred that the reference's
+    Loss_fn uses: chisqMd depends on the targets only, chisqnnd is a diagnostic)."""
+
+    @staticmethod
+    def forward(ctx, y_pred, y_target, consts):
+        data_hat, icov, sigma, y_mean, y_std, ypos = consts
+        want = y_pred.requires_grad
+        loss, md, nnd, g = _engine.loss_terms(y_pred.detach().contiguous(), y_target.detach().contiguous(), data_hat, icov, sigma,
+                                              y_mean, y_std, ypos, want_grad=want)
+        if want:
+            ctx.save_for_backward(g)
+        ctx.mark_non_differentiable(md, nnd)
+        return loss, md, nnd
+
+    @staticmethod
+    def backward(ctx, gl, gmd, gnnd):
+        (g,) = ctx.saved_tensors
+        return gl.unsqueeze(-1) * g, None, None
+
+
 def loss_terms(aux, y_pred, y_target):
-    raise NotImplementedError(
-        "Auxilleryfunc/Loss_fn on free-standing tensors is not part of the fused path: the loss is evaluated "
-        "inside the training kernels (Predictor.train, train.FusedTrainer.step / val_metric)")
+    """``Auxilleryfunc.__call__`` on free-standing tensors (linna/util.py:1070-1088): (loss, chisqMd, chisqnnd) per row,
+    differentiable with respect to ``y_pred`` -- one kernel launch (``linna_loss_terms``).  CUDA tensors stay on their
+    device; host tensors are evaluated on the current GPU and the results returned on the host, like every other
+    evaluation in this package (there is no CPU arithmetic path)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("Loss_fn / Val_metric_fn: no CUDA device -- linna_b200 has no CPU fallback")
+    src = y_pred.device
+    dev = src if src.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+    key = str(dev)
+    cache = aux.__dict__.setdefault("_dev_consts", {})
+    if key not in cache:
+        data_hat, icov, sigma, y_mean, y_std, ypos = aux.constants()
+        f = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(dev)
+        cache[key] = (f(data_hat), f(icov), f(sigma), f(y_mean), f(y_std), ypos)
+    yp = y_pred.to(dev, torch.float32)
+    yt = y_target.to(dev, torch.float32)
+    one = yp.dim() == 1
+    if one:
+        yp, yt = yp.reshape(1, -1), yt.reshape(1, -1)
+    loss, md, nnd = _LossTerms.apply(yp, yt, cache[key])
+    return loss.to(src), md.to(src), nnd.to(src)
+
+
+class _EmulatorFunction(torch.autograd.Function):
+    """y = emulator(x) with the kernel-computed vector-Jacobian products attached: what torch.autograd does for the
+    reference's ``model(X_transform(X))`` / ``Predictor.predict(X, no_grad=False)`` (linna/predictor_gpu.py:279-283,
+    :495-496).  Forward = ``linna_predict``; backward = ONE fused forward + backward-data launch (``linna_predict_vjp``)
+    plus, when parameters require grad, the weight-gradient launch."""
+
+    @staticmethod
+    def forward(ctx, x, eng, out_kind, params_owner, *params):
+        ctx.eng, ctx.out_kind, ctx.nparams = eng, out_kind, len(params)
+        ctx.want_params = any(p.requires_grad for p in params)
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.pdevs = [p.device for p in params]
+        ctx.x_dev = x.device
+        xd = x.detach().to(torch.device("cuda", eng.device), torch.float32).contiguous()
+        ctx.save_for_backward(xd)
+        ctx.need_x = x.requires_grad
+        return eng.predict(xd, out_kind).to(x.device)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (xd,) = ctx.saved_tensors
+        gth, gp = ctx.eng.predict_vjp(xd, gy.to(xd.device, torch.float32).contiguous(), ctx.out_kind, want_params=ctx.want_params)
+        grads = [None] * ctx.nparams
+        if gp is not None:
+            o = 0
+            for i, shp in enumerate(ctx.shapes):
+                n = int(np.prod(shp))
+                grads[i] = gp[o:o + n].reshape(shp).to(ctx.pdevs[i])
+                o += n
+        return (gth.to(ctx.x_dev) if ctx.need_x else None, None, None, None) + tuple(grads)
 
 
 def emulator_forward_autograd(model, x):
-    raise NotImplementedError(
-        "autograd through model(x) is not wired up: gradients of lnP come from Log_prob (fused kernel) and "
-        "training gradients from train.FusedTrainer")
+    """``model(x)`` under autograd (x [B, n_in] on the GPU; input and / or parameters may require grad)."""
+    eng = model.bare_engine(x.device.index)
+    params = [p for _, p in model.named_parameters()]
+    if any(p.requires_grad for p in params):
+        if getattr(eng, "_vjp_batch", 0) < x.shape[0]:       # row-major activation store for the weight-gradient kernel
+            eng.train_setup(np.zeros(model.out_size, np.float32), np.eye(model.out_size, dtype=np.float32), int(x.shape[0]))
+            eng._vjp_batch = int(x.shape[0])
+    return _EmulatorFunction.apply(x, eng, _engine.LINNA_OUT_YHAT, model, *params)
 
 
 def predict_with_grad(pred, X):
-    raise NotImplementedError("Predictor.predict(no_grad=False) on a tensor that requires grad: use Log_prob(..., "
-                              "nograd=False) / Log_prob.value_and_grad for d lnP/du")
+    """``Predictor.predict(X, no_grad=False)`` for a tensor that requires grad: d predict / d X through the kernel
+    (the emulator weights are constants here, as in the reference's sampling-time use, linna/util.py:1012)."""
+    eng = pred._get_engine()
+    one = X.dim() == 1
+    X2 = X.reshape(1, -1) if one else X
+    y = _EmulatorFunction.apply(X2, eng, _engine.LINNA_OUT_Y, None)
+    return y.view(-1) if one else y

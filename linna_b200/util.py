@@ -475,6 +475,11 @@ class Auxilleryfunc:
         from .train import loss_terms
         return loss_terms(self, y_pred, y_target)
 
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d.pop("_dev_consts", None)
+        return d
+
 
 class Loss_fn:
     """mean over the batch of chi2(target, pred)/max(chi2(target, data), n_out/2) in normalised
