@@ -7,6 +7,11 @@
  * linna_last_error() gives the message.  There is no CPU fallback: creating a model
  * without a CUDA device fails with LINNA_ENODEV.
  *
+ * Threading: a model owns scratch state (activation arenas, relu masks, staging buffers, the training planes) that every
+ * launch on it uses, so calls on ONE model must not overlap in time from several host threads; launches issued on different
+ * streams are serialised on the device by the library itself (an event chain).  Different models are independent.  Every
+ * entry point runs on the model's device and restores the caller's current device before it returns.
+ *
  * Each entry point names the reference interface it replaces (paths relative to the
  * reference checkout, chto/linna).  INTEGRATION.md shows the reference-side ctypes
  * binding.

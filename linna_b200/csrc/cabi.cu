@@ -55,6 +55,25 @@ static int fail(int code, const char *fmt, ...)
     g_err = buf;
     return code;
 }
+// The entry points work on the model's device and leave the caller's current device as they found it.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+        if (prev == dev) prev = -1;   // nothing to restore
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define LINNA_ON_DEVICE(m)                                                                         \
+    DeviceGuard dev_guard_((m)->device);                                                           \
+    if (!dev_guard_.ok) return fail(LINNA_ECUDA, "cudaSetDevice(%d) failed", (m)->device)
+
 #define CUDA_TRY(x)                                                                                   \
     do {                                                                                              \
         cudaError_t e_ = (x);                                                                         \
@@ -105,7 +124,7 @@ struct OpOffsets {
 
 static void free_device(linna_model *m)
 {
-    cudaSetDevice(m->device);
+    DeviceGuard guard(m->device);
     if (m->blob) cudaFree(m->blob);
     if (m->prog_dev) cudaFree(m->prog_dev);
     if (m->arena) cudaFree(m->arena);
@@ -123,7 +142,7 @@ static void free_device(linna_model *m)
 // (Re)build the device blob and the three step programs from the host copies.
 static int rebuild(linna_model *m)
 {
-    CUDA_TRY(cudaSetDevice(m->device));
+    LINNA_ON_DEVICE(m);
     CUDA_TRY(cudaDeviceSynchronize());  // no launch may still be reading the blob we are about to replace
     if (m->tc) { tc_destroy(m->tc); m->tc = nullptr; }
     if (m->tg) { tg_destroy(m->tg); m->tg = nullptr; }
@@ -691,6 +710,9 @@ static int rebuild(linna_model *m)
         m->tg_why.clear();
         if (!getenv("LINNA_TRAIN_NO_TC")) m->tg = tg_build(m, flat_off, bias_ptr, blob_off, m->tg_why);
         else m->tg_why = "LINNA_TRAIN_NO_TC set";
+        if (!m->tg)
+            fprintf(stderr, "linna_b200: tensor-core training kernels unavailable for this model (%s); training runs on the FP32 "
+                            "FFMA kernels\n", m->tg_why.c_str());
         cudaGetLastError();
     }
     return LINNA_OK;
@@ -783,7 +805,7 @@ int linna_model_create(const linna_model_desc_t *d, int device, linna_model_t **
         m->extra_scale = d->extra_linear_scale;
         m->n_params += (int64_t)d->n_out * d->n_in + d->n_out;
     }
-    cudaSetDevice(device);
+    DeviceGuard guard(device);
     rc = rebuild(m);
     if (rc) { free_device(m); delete m; return rc; }
     if (cudaStreamCreateWithFlags(&m->hstream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -800,7 +822,7 @@ int linna_model_create(const linna_model_desc_t *d, int device, linna_model_t **
 void linna_model_destroy(linna_model_t *m)
 {
     if (!m) return;
-    cudaSetDevice(m->device);
+    DeviceGuard guard(m->device);
     cudaDeviceSynchronize();
     if (m->hstream) cudaStreamDestroy(m->hstream);
     if (m->cstream) cudaStreamDestroy(m->cstream);
@@ -918,7 +940,7 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
     if (n == 0) return LINNA_OK;
     if (!in) return fail(LINNA_EINVAL, "null input");
     if (!m->prog_valid[pk]) return fail(LINNA_ESTATE, "likelihood constants not set (linna_model_set_likelihood)");
-    CUDA_TRY(cudaSetDevice(m->device));
+    LINNA_ON_DEVICE(m);
     if (m->have_last && m->last_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, m->last_done, 0));
     // Large lnP / lnP+gradient batches go to the tensor-core (tcgen05) kernel; everything else stays on the
     // FP32 FFMA kernel.
@@ -934,6 +956,9 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
                 m->tc_failed = true;
                 m->tc_why = why;
                 if (m->path == 2) return fail(LINNA_EINVAL, "tensor-core path unavailable: %s", why.c_str());
+                // automatic selection: say (once per model build) that this model runs ~9x slower than it could
+                fprintf(stderr, "linna_b200: tensor-core likelihood kernel unavailable for this model (%s); large batches run on the "
+                                "FP32 FFMA kernel\n", why.c_str());
             }
         }
         if (m->tc && pk == PROG_GRAD && !tc_has_grad(m->tc)) {
@@ -1038,7 +1063,7 @@ int linna_predict_vjp(linna_model_t *m, const float *theta, int64_t n, const flo
     if (!m->prog_valid[PROG_VJP]) return fail(LINNA_EINVAL, "vector-Jacobian program unavailable for this model (extra linear branch)");
     if (gparams && (!m->has_train || n > m->max_batch))
         return fail(LINNA_ESTATE, "parameter gradients need linna_train_setup with max_batch >= n (%lld)", (long long)n);
-    CUDA_TRY(cudaSetDevice(m->device));
+    LINNA_ON_DEVICE(m);
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (!gtheta) {
@@ -1076,7 +1101,7 @@ int linna_predict_host(linna_model_t *m, const float *theta, int64_t n, float *o
     if (!m) return fail(LINNA_EINVAL, "null model");
     if (n <= 0) return n == 0 ? LINNA_OK : fail(LINNA_EINVAL, "negative n");
     if (!theta || !out) return fail(LINNA_EINVAL, "null buffer");
-    CUDA_TRY(cudaSetDevice(m->device));
+    LINNA_ON_DEVICE(m);
     int rc;
     if ((rc = ensure(&m->d_in, &m->d_in_cap, (size_t)n * m->n_in))) return rc;
     if ((rc = ensure(&m->d_out, &m->d_out_cap, (size_t)n * m->n_out))) return rc;
@@ -1110,7 +1135,7 @@ static int ensure_pinned(float **p, size_t *cap, size_t need)
 
 static int lnp_host_pipelined(linna_model *m, const float *u, int64_t n, float *lnp, float *grad)
 {
-    CUDA_TRY(cudaSetDevice(m->device));
+    LINNA_ON_DEVICE(m);
     int rc;
     const int n_in = m->n_in;
     if ((rc = ensure(&m->d_in, &m->d_in_cap, (size_t)n * n_in))) return rc;
@@ -1283,7 +1308,7 @@ int linna_train_chisq(linna_model_t *m, const float *X, const float *Y, int64_t 
     if (m->train_path == 2 && !m->tg) return fail(LINNA_EINVAL, "tensor-core training path unavailable: %s", m->tg_why.c_str());
     if (m->tg && m->train_path != 1 && n > 0) {
         if (!X) return fail(LINNA_EINVAL, "null input");
-        CUDA_TRY(cudaSetDevice(m->device));
+        LINNA_ON_DEVICE(m);
         cudaStream_t st = (cudaStream_t)stream;
         if (m->have_last && m->last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, m->last_done, 0));
         const int l = tg_chisq(m, m->tg, X, Y, n, kind, chi2, st);
@@ -1328,7 +1353,7 @@ int linna_train_step(linna_model_t *m, const float *X, const float *Y, const flo
     if (m->train_path == 2 && !m->tg) return fail(LINNA_EINVAL, "tensor-core training path unavailable: %s", m->tg_why.c_str());
     if (m->tg && m->train_path != 1) {
         // tensor-core path: one launch per layer (forward, loss, backward-data), one for every weight gradient + AdamW
-        CUDA_TRY(cudaSetDevice(m->device));
+        LINNA_ON_DEVICE(m);
         if (m->have_last && m->last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, m->last_done, 0));
         AdamArgs a = adam_args(m, params, adam_m, adam_v, grads, step, lr, beta1, beta2, eps, weight_decay, fuse_adam ? 1 : 0);
         const int l = tg_train_step(m, m->tg, X, Y, cmd, B, a, loss_rows, loss_mean, st);
@@ -1372,7 +1397,7 @@ int linna_train_adamw(linna_model_t *m, float *params, float *adam_m, float *ada
 {
     if (!m || !m->has_train) return fail(LINNA_ESTATE, "linna_train_setup has not been called");
     if (!params || !adam_m || !adam_v || !grads) return fail(LINNA_EINVAL, "null buffer");
-    CUDA_TRY(cudaSetDevice(m->device));
+    LINNA_ON_DEVICE(m);
     cudaStream_t st = (cudaStream_t)stream;
     if (m->have_last && m->last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, m->last_done, 0));
     AdamArgs a = adam_args(m, params, adam_m, adam_v, const_cast<float *>(grads), step, lr, beta1, beta2, eps, weight_decay, 1);
@@ -1391,7 +1416,7 @@ int linna_train_load_params(linna_model_t *m, const float *params, void *stream)
 {
     if (!m || !m->has_train) return fail(LINNA_ESTATE, "linna_train_setup has not been called");
     if (!params) return fail(LINNA_EINVAL, "null buffer");
-    CUDA_TRY(cudaSetDevice(m->device));
+    LINNA_ON_DEVICE(m);
     cudaStream_t st = (cudaStream_t)stream;
     if (m->have_last && m->last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, m->last_done, 0));
     CUDA_TRY(launch_scatter_params(params, m->blob, m->map_fwd_dev, m->map_bwd_dev, (int)m->n_params, st));

@@ -320,7 +320,7 @@ class Log_prob:
         if not torch.cuda.is_available():
             raise RuntimeError("Log_prob: no CUDA device -- linna_b200 has no CPU fallback")
         dev = torch.cuda.current_device()
-        key = (dev, self.model.param_key(), float(self.T))
+        key = (dev, self.model.param_key(), float(self.T), self._constants_key())
         if self._engine is None or self._engine_key != key:
             eng = self.model.make_engine(dev, sigma=self.y_invtransform_data.sigma)
             inv = self.invcov_new.detach().cpu().numpy().astype(np.float64)
@@ -329,6 +329,21 @@ class Log_prob:
                 self._engine.close()
             self._engine, self._engine_key = eng, key
         return self._engine
+
+    def _constants_key(self):
+        """Identity + version of everything else the packed likelihood holds: replacing (or writing in place to) the data
+        vector, the inverse covariance, sigma or the priors of an existing Log_prob rebuilds the engine."""
+        def tk(t):
+            return (t.data_ptr(), t._version, tuple(t.shape)) if torch.is_tensor(t) else id(t)
+        sg = getattr(self.y_invtransform_data, "sigma", None)
+        pri = tuple((p.get("dist"), float(p.get("arg1")), float(p.get("arg2"))) for p in self.transform.priors)
+        return (tk(self.data_new), tk(self.invcov_new), tk(sg), pri)
+
+    def invalidate(self):
+        """Drop the packed engine (for changes `_constants_key` cannot see, e.g. writes through ``tensor.data``)."""
+        if self._engine is not None:
+            self._engine.close()
+        self._engine, self._engine_key = None, None
 
     def __getstate__(self):   # instances are pickled to pool workers in the reference (util.py:149-152)
         d = self.__dict__.copy()
@@ -401,24 +416,78 @@ class Dlnp:
 
 
 class Ddlnp:
-    """Hessian of lnP by central differences of the kernel gradient: 2*n_in batched gradient rows
-    in ONE launch (reference: n_in extra autograd passes, linna/util.py:1037-1051).  Used once for
-    the HMC mass matrix (linna/sampler.py:430-433)."""
+    """Hessian of lnP at one point -- what the reference obtains by double backward (n_in extra autograd passes,
+    linna/util.py:1043-1051; used once for the HMC mass matrix, linna/sampler.py:430-433), here EXACTLY from one kernel
+    launch instead of finite differences.
 
-    def __init__(self, data_new, invcov_new, model, y_invtransform_data, transform, temperature, eps=1e-3):
+    The emulator is piecewise linear in xhat (relu network: its second derivative vanishes almost everywhere, which is also
+    what autograd's double backward returns), so with J = d yhat / d xhat at the point -- n_out vector-Jacobian rows with
+    the identity as cotangent, ONE fused forward + backward launch (``linna_predict_vjp``) -- everything else is analytic
+    and done in float64 on the host:
+
+        m_j   = sigma_j f(y_std_j yhat_j + y_mean_j)              f = id (or exp: ypositive)
+        lnL   = -1/(2T) d^T C^-1 d,  d = m - data
+        H_xx  = -1/T [ J^T diag(m') C^-1 diag(m') J + J^T diag(m'' . C^-1 d) J ]
+        H_uu  = D H_xx D + diag(grad_xhat lnL . xhat''(u)) - I,   D = diag(d xhat / d u)
+
+    with xhat(u) = (log10?(theta(u)) - X_mean) / X_std and theta(u) the prior map (Gaussian: affine; flat: the normal CDF)."""
+
+    def __init__(self, data_new, invcov_new, model, y_invtransform_data, transform, temperature, eps=None):
         self.log_prob = Log_prob(data_new, invcov_new, model, y_invtransform_data, transform, temperature,
                                  gaussianlogliklihood)
-        self.eps = eps
 
     def __call__(self, x):
-        u = np.asarray(x, np.float64).reshape(-1)
-        n = u.size
-        pts = np.repeat(u[None, :], 2 * n, axis=0)
-        pts[np.arange(n), np.arange(n)] += self.eps
-        pts[n + np.arange(n), np.arange(n)] -= self.eps
-        _, g = self.log_prob.engine().lnp_grad(pts.astype(np.float32))
-        hess = (g[:n].astype(np.float64) - g[n:].astype(np.float64)) / (2 * self.eps)
-        return 0.5 * (hess + hess.T)
+        from . import engine as _e
+        from .predictor_gpu import _transform_constants
+        lp = self.log_prob
+        eng = lp.engine()
+        u = np.asarray(x.detach().cpu().numpy() if torch.is_tensor(x) else x, np.float64).reshape(-1)
+        n_in, n_out = eng.n_in, eng.n_out
+        pred = lp.model
+        x_mean, x_std, log10, y_mean, y_std, ypos = _transform_constants(pred.X_transform, pred.y_transform, n_in, n_out)
+        x_mean, x_std, y_mean, y_std = (a.astype(np.float64) for a in (x_mean, x_std, y_mean, y_std))
+        sigma = lp.y_invtransform_data.sigma.detach().cpu().numpy().astype(np.float64).reshape(-1)
+        data = lp.data_new.detach().cpu().numpy().astype(np.float64).reshape(-1)
+        icov = lp.invcov_new.detach().cpu().numpy().astype(np.float64)
+        icov = 0.5 * (icov + icov.T)
+        T = float(lp.T)
+        # prior map and input transform, with first and second derivatives (linna/util.py:339-343, :483-497)
+        th, th1, th2 = np.empty(n_in), np.empty(n_in), np.empty(n_in)
+        from math import erf, exp, pi, sqrt
+        for i, p in enumerate(lp.transform.priors):
+            if p["dist"] == "gauss":
+                th[i], th1[i], th2[i] = u[i] * p["arg2"] + p["arg1"], p["arg2"], 0.0
+            else:
+                w = p["arg2"] - p["arg1"]
+                phi = exp(-0.5 * u[i] * u[i]) / sqrt(2 * pi)
+                th[i], th1[i], th2[i] = 0.5 * (1 + erf(u[i] / sqrt(2))) * w + p["arg1"], w * phi, -u[i] * w * phi
+        xh1, xh2 = th1 / x_std, th2 / x_std
+        dxh_dth = 1.0 / x_std
+        if log10 is not None:
+            ln10 = np.log(10.0)
+            for i in log10:
+                dxh_dth[i] = 1.0 / (th[i] * ln10 * x_std[i])
+                xh1[i] = th1[i] / (th[i] * ln10 * x_std[i])
+                xh2[i] = (th2[i] * th[i] - th1[i] ** 2) / (th[i] ** 2 * ln10 * x_std[i])
+        # yhat and J = d yhat / d xhat from the kernel: n_out rows of the same point, identity cotangent
+        dev = torch.device("cuda", eng.device)
+        theta_rep = torch.from_numpy(np.repeat(th[None, :].astype(np.float32), n_out, axis=0)).to(dev)
+        yhat = eng.predict(theta_rep[:1], _e.LINNA_OUT_YHAT).cpu().numpy().astype(np.float64).reshape(-1)
+        gth, _ = eng.predict_vjp(theta_rep, torch.eye(n_out, dtype=torch.float32, device=dev), _e.LINNA_OUT_YHAT)
+        J = gth.cpu().numpy().astype(np.float64) / dxh_dth[None, :]           # d yhat_j / d xhat_i
+        z = y_std * yhat + y_mean
+        if ypos:
+            m = sigma * np.exp(z)
+            m1, m2 = m * y_std, m * y_std ** 2
+        else:
+            m = sigma * z
+            m1, m2 = sigma * y_std, np.zeros(n_out)
+        c = icov @ (m - data)
+        A = J * m1[:, None]
+        Hxx = -(A.T @ icov @ A + J.T @ (J * (m2 * c)[:, None])) / T
+        gx = -(A.T @ c) / T
+        H = xh1[:, None] * Hxx * xh1[None, :] + np.diag(gx * xh2) - np.eye(n_in)
+        return 0.5 * (H + H.T)
 
 
 class LogPrior:
