@@ -146,15 +146,17 @@ int linna_lnp_grad_host(linna_model_t *m, const float *u, int64_t n, float *lnp,
 
 /* Introspection used by bench.py / tests. */
 int linna_model_info(const linna_model_t *m, int32_t *n_in, int32_t *n_out, int64_t *n_params, int32_t *num_sms);
-/* Kernel selection for linna_lnp / linna_lnp_grad: 0 = automatic (the default: tensor-core kernel for
- * n >= tc_min_rows, default 256, FP32 FFMA kernel below and wherever the tensor-core program does not apply),
- * 1 = FP32 FFMA kernel only, 2 = tensor-core (tcgen05, split-fp16) kernel only.  tc_min_rows <= 0 keeps the
- * current threshold. */
+/* Kernel selection for linna_lnp / linna_lnp_grad / linna_predict: 0 = automatic (the default: tensor-core kernel
+ * for n >= tc_min_rows, default 256; below that the small-batch cluster kernel, which splits every layer over the
+ * CTAs of a thread-block cluster and keeps the activations in distributed shared memory; the FP32 FFMA kernel
+ * wherever neither applies), 1 = FP32 FFMA kernel only, 2 = tensor-core (tcgen05, split-fp16) kernel only,
+ * 3 = cluster kernel only.  tc_min_rows <= 0 keeps the current threshold. */
 int linna_model_set_path(linna_model_t *m, int32_t path, int64_t tc_min_rows);
 /* lnP evaluates the last linear layer, the inverse output transform and the Cholesky product as ONE folded
  * affine map (formed in float64 at pack time); 0 switches the folding off (unfolded reference order). */
 int linna_model_set_fold(linna_model_t *m, int32_t on);
-/* Which kernel served the last launch on this model: 0 none yet, 1 FP32 FFMA kernel, 2 tensor-core kernel. */
+/* Which kernel served the last launch on this model: 0 none yet, 1 FP32 FFMA kernel, 2 tensor-core kernel,
+ * 3 small-batch cluster kernel. */
 int linna_model_last_kernel(const linna_model_t *m);
 /* Profiling hook (environment LINNA_TC_DEBUG set when the tensor-core context is built): copies the per-CTA
  * cycle counters of the last tensor-core launch into out[max_ctas][128] and returns the number of CTAs
@@ -165,6 +167,10 @@ int linna_model_last_kernel(const linna_model_t *m);
  * issuer, [40..] of epilogue group 0, [64..] of which waiting for accumulators, [88..] of which chunk
  * epilogues. */
 int linna_debug_tc_counters(linna_model_t *m, int64_t *out, int32_t max_ctas);
+/* Profiling hook (environment LINNA_CLUSTER_DEBUG set): per program step, the cycles thread 0 of the first cluster spent
+ * in the k-loop, the k-lane reduction, the epilogue + broadcast and the cluster barrier, summed over the launches since
+ * the last read; out[max_values] receives up to 64 x 4 values. */
+int linna_debug_cluster_counters(int64_t *out, int32_t max_values);
 /* Profiling hook of the tensor-core training kernels (environment LINNA_TG_DEBUG set at linna_train_setup): clock64 stamps
  * of CTA 0 of every layer launch of the last step, out[step][8] = {kernel entry, set-up done, predecessor complete
  * (griddepcontrol.wait), first segment drained, contraction done, epilogue done, tensor memory freed, 0}; returns the

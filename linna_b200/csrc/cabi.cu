@@ -15,6 +15,10 @@
 namespace linna {
 cudaError_t launch_fused_ffma(const KernelArgs &args, int rg, int grid, cudaStream_t stream);
 int fused_ffma_max_ctas_per_sm(int rg);
+size_t cluster_ffma_smem_bytes(const Program &pg, int n_out, int cs, int depth, int *chi_q_out);
+int cluster_ffma_max_clusters(int cs, int depth, size_t smem);
+cudaError_t launch_cluster_ffma(const KernelArgs &args, int chi_q, int cs, int depth, int clusters, size_t smem, cudaStream_t stream);
+int cluster_ffma_debug_read(long long *out, int max_values);
 cudaError_t launch_wgrad(const WgradLayer *layers, const WgradTile *tiles, int n_tiles, const float *rm_base, int B,
                          const AdamArgs &ad, cudaStream_t stream);
 cudaError_t launch_adamw(const AdamArgs &ad, int n_params, int num_sms, cudaStream_t stream);
@@ -147,6 +151,7 @@ static int rebuild(linna_model *m)
     if (m->tc) { tc_destroy(m->tc); m->tc = nullptr; }
     if (m->tg) { tg_destroy(m->tg); m->tg = nullptr; }
     m->tc_failed = false;
+    for (int i = 0; i < PROG_COUNT; ++i) m->cl_state[i] = 0;
     const int n_in = m->n_in, n_out = m->n_out;
     Builder B;
     std::vector<OpOffsets> off(m->ops.size());
@@ -898,7 +903,7 @@ int linna_model_info(const linna_model_t *m, int32_t *n_in, int32_t *n_out, int6
 
 int linna_model_set_path(linna_model_t *m, int32_t path, int64_t tc_min_rows)
 {
-    if (!m || path < 0 || path > 2) return fail(LINNA_EINVAL, "path must be 0 (auto), 1 (FFMA) or 2 (tensor core)");
+    if (!m || path < 0 || path > 3) return fail(LINNA_EINVAL, "path must be 0 (auto), 1 (FFMA), 2 (tensor core) or 3 (cluster)");
     m->path = path;
     if (tc_min_rows > 0) m->tc_min_rows = tc_min_rows;
     return LINNA_OK;
@@ -910,6 +915,12 @@ int linna_debug_tc_counters(linna_model_t *m, int64_t *out, int32_t max_ctas)
 {
     if (!m || !out) return 0;
     return tc_debug_read(m->tc, reinterpret_cast<long long *>(out), max_ctas);
+}
+
+int linna_debug_cluster_counters(int64_t *out, int32_t max_values)
+{
+    if (!out) return 0;
+    return cluster_ffma_debug_read(reinterpret_cast<long long *>(out), max_values);
 }
 
 int linna_debug_tg_counters(linna_model_t *m, int64_t *out, int32_t max_steps)
@@ -932,6 +943,54 @@ int linna_model_set_tile_rows(linna_model_t *m, int32_t rows)
     return LINNA_OK;
 }
 
+// Launch geometry of the small-batch cluster kernel for program pk: the largest cluster the device schedules (16 CTAs,
+// else 8) with the deepest weight ring that fits next to the shared-memory activation arena.
+static bool cluster_resolve(linna_model *m, int pk)
+{
+    if (m->cl_state[pk]) return m->cl_state[pk] > 0;
+    m->cl_state[pk] = -1;
+    const Program &pg = m->prog_host[pk];
+    int maxN = 0;
+    for (int i = 0; i < pg.n_steps; ++i) {
+        maxN = std::max(maxN, pg.steps[i].N);
+        if (pg.steps[i].rm_off >= 0 || (pg.steps[i].flags & F_COT)) { m->cl_why = "program keeps row-major copies"; return false; }
+    }
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device);
+    const char *ecs = getenv("LINNA_CLUSTER_SIZE");
+    const int want = ecs ? atoi(ecs) : 16;
+    for (int cs : {16, 8}) {
+        if (cs > want) continue;
+        if (maxN > 256 * cs) continue;
+        for (int depth : {16, 8}) {
+            int chi_q = 0;
+            const size_t smem = cluster_ffma_smem_bytes(pg, m->n_out, cs, depth, &chi_q);
+            if (smem + 8192 > (size_t)max_smem) continue;   // the kernel's static shared memory (step table) comes on top
+            const int nc = cluster_ffma_max_clusters(cs, depth, smem);
+            if (nc < 1) continue;
+            m->cl_cs[pk] = cs, m->cl_depth[pk] = depth, m->cl_clusters[pk] = nc, m->cl_chi_q[pk] = chi_q, m->cl_smem[pk] = smem;
+            m->cl_state[pk] = 1;
+            return true;
+        }
+    }
+    m->cl_why = "activation arena does not fit in shared memory / no cluster can be scheduled";
+    return false;
+}
+
+// lnP must not depend on whether the gradient was asked for: the likelihood and the gradient program take the cluster
+// kernel together or not at all (the gradient program carries the relu masks and may not fit where the other does).
+static bool cluster_usable(linna_model *m, int pk)
+{
+    if (pk == PROG_LNP || pk == PROG_GRAD) {
+        for (int q : {PROG_LNP, PROG_GRAD})
+            if (m->prog_valid[q] && !cluster_resolve(m, q)) {
+                m->cl_state[pk] = -1;
+                return false;
+            }
+    }
+    return cluster_resolve(m, pk);
+}
+
 static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_vec, int out_kind, float *lnp, float *grad,
                int input_theta, cudaStream_t stream, const KernelArgs *proto = nullptr)
 {
@@ -942,6 +1001,27 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
     if (!m->prog_valid[pk]) return fail(LINNA_ESTATE, "likelihood constants not set (linna_model_set_likelihood)");
     LINNA_ON_DEVICE(m);
     if (m->have_last && m->last_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, m->last_done, 0));
+    // Small batches (an emcee ensemble of a few walkers, a handful of HMC chains, one predict call): the cluster kernel,
+    // which spreads every layer over the CTAs of a thread-block cluster instead of streaming all weights through one SM.
+    if ((pk == PROG_PREDICT || pk == PROG_LNP || pk == PROG_GRAD) && !proto &&
+        (m->path == 3 || (m->path == 0 && !m->force_rows && n <= m->cl_max_rows && n < m->tc_min_rows))) {
+        // auto mode: up to two tiles of 8 walkers per schedulable cluster (beyond that the tiled kernel, which puts one
+        // tile on every SM, is faster: scratch/cluster_time.py)
+        if (cluster_usable(m, pk) && (m->path == 3 || n <= 16 * (int64_t)m->cl_clusters[pk])) {
+            KernelArgs a;
+            memset(&a, 0, sizeof a);
+            a.prog = m->prog_dev + pk, a.c = m->consts, a.in = in, a.out_vec = out_vec, a.lnp = lnp, a.grad = grad;
+            a.n = n, a.input_theta = input_theta, a.out_kind = out_kind;
+            const int clusters = (int)std::min<int64_t>((n + 7) / 8, m->cl_clusters[pk]);
+            CUDA_TRY(launch_cluster_ffma(a, m->cl_chi_q[pk], m->cl_cs[pk], m->cl_depth[pk], clusters, m->cl_smem[pk], stream));
+            g_launches.fetch_add(1);
+            m->last_kernel = 3;
+            CUDA_TRY(cudaEventRecord(m->last_done, stream));
+            m->last_stream = stream, m->have_last = true;
+            return LINNA_OK;
+        }
+        if (m->path == 3 && m->cl_state[pk] < 0) return fail(LINNA_EINVAL, "cluster kernel unavailable: %s", m->cl_why.c_str());
+    }
     // Large lnP / lnP+gradient batches go to the tensor-core (tcgen05) kernel; everything else stays on the
     // FP32 FFMA kernel.
     if ((pk == PROG_LNP || pk == PROG_GRAD) && !proto && m->path == 2 && (m->tc_failed || m->has_extra))

@@ -129,8 +129,15 @@ struct linna_model {
     linna::TcContext *tc = nullptr;
     bool tc_failed = false;
     std::string tc_why;           // why the tensor-core program could not be built for this model
-    int path = 0;                 // 0 auto (tensor core from tc_min_rows rows on), 1 FFMA only, 2 tensor core only
-    int last_kernel = 0;          // kernel that served the last launch: 1 FFMA, 2 tensor core
+    int path = 0;                 // 0 auto (cluster kernel below tc_min_rows rows, tensor core from there on), 1 FFMA only,
+                                  // 2 tensor core only, 3 cluster kernel only
+    int last_kernel = 0;          // kernel that served the last launch: 1 FFMA, 2 tensor core, 3 cluster (small batch)
+    // small-batch cluster kernel (cluster_ffma.cu): launch geometry per program, resolved at first use
+    int cl_state[PROG_COUNT] = {0, 0, 0, 0, 0, 0};   // 0 not resolved yet, 1 available, -1 unavailable (cl_why)
+    int cl_cs[PROG_COUNT] = {0}, cl_depth[PROG_COUNT] = {0}, cl_clusters[PROG_COUNT] = {0}, cl_chi_q[PROG_COUNT] = {0};
+    size_t cl_smem[PROG_COUNT] = {0};
+    std::string cl_why;
+    int64_t cl_max_rows = 255;    // auto mode: batches up to this many rows (and below tc_min_rows) take the cluster kernel
     int64_t tc_min_rows = 256;    // one full walker pair; one tensor-core pass (0.14 ms at C3) beats the FFMA kernel (0.20 ms) at every size (scratch/crossover.py)
     // host-buffer API staging
     cudaStream_t hstream = nullptr;                  // compute stream of the host-buffer entry points

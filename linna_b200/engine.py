@@ -88,6 +88,7 @@ def load_library():
     lib.linna_debug_tc_counters.argtypes = [vp, vp, i32]
     lib.linna_model_last_kernel.argtypes = [vp]
     lib.linna_debug_tg_counters.argtypes = [vp, vp, i32]
+    lib.linna_debug_cluster_counters.argtypes = [vp, i32]
     u64 = ctypes.c_uint64
     lib.linna_stretch_propose.argtypes = [vp, i32, vp, vp, i64, i64, ctypes.c_float, u64, u64, vp, vp, vp]
     lib.linna_stretch_accept.argtypes = [vp, vp, vp, i32, vp, i64, vp, vp, vp, u64, u64, vp]
@@ -221,6 +222,14 @@ def loss_terms(y_pred, y_target, data_hat, icov_hat, sigma, y_mean, y_std, yposi
     return loss, md, nnd, g
 
 
+def cluster_counters():
+    """Per-step cycle counters of the small-batch cluster kernel since the last read (needs LINNA_CLUSTER_DEBUG=1):
+    array [64, 4] = k-loop, k-lane reduction, epilogue + broadcast, cluster barrier."""
+    buf = np.zeros((128, 4), np.int64)
+    load_library().linna_debug_cluster_counters(buf.ctypes.data_as(ctypes.c_void_p), 512)
+    return buf
+
+
 def launch_count():
     return int(load_library().linna_launch_count())
 
@@ -332,13 +341,13 @@ class Engine:
         self._check(self.lib.linna_model_set_tile_rows(self.handle, int(rows)))
 
     def set_path(self, path, tc_min_rows=0):
-        """'auto' | 'ffma' | 'tc' -- which kernel serves lnp()."""
-        code = {"auto": 0, "ffma": 1, "tc": 2}[path]
+        """'auto' | 'ffma' | 'tc' | 'cluster' -- which kernel serves lnp() / lnp_grad() / predict()."""
+        code = {"auto": 0, "ffma": 1, "tc": 2, "cluster": 3}[path]
         self._check(self.lib.linna_model_set_path(self.handle, code, int(tc_min_rows)))
 
     def last_kernel(self):
-        """'ffma' | 'tc' | None -- the kernel that served the last launch."""
-        return {0: None, 1: "ffma", 2: "tc"}[int(self.lib.linna_model_last_kernel(self.handle))]
+        """'ffma' | 'tc' | 'cluster' | None -- the kernel that served the last launch."""
+        return {0: None, 1: "ffma", 2: "tc", 3: "cluster"}[int(self.lib.linna_model_last_kernel(self.handle))]
 
     def tc_counters(self, max_ctas=256):
         """Per-CTA cycle counters of the last tensor-core launch (needs LINNA_TC_DEBUG=1 in the environment)."""

@@ -18,9 +18,10 @@ def _dev(a):
     return torch.from_numpy(np.ascontiguousarray(a, np.float32)).cuda()
 
 
-def _check_case(g, p, quad, rows):
+def _check_case(g, p, quad, rows, path="auto"):
     e = engine.engine_from_problem(p, quad=quad)
     e.set_tile_rows(rows)
+    e.set_path(path)
     u = g["u"] if "u" in g else None
     lnp, grad = e.lnp_grad(_dev(u))
     lnp_only = e.lnp(_dev(u))
@@ -48,12 +49,21 @@ def test_fixture(quad, rows):
     np.testing.assert_allclose(y[0], [0.10346876, -0.31955421], atol=1e-6)
 
 
+@pytest.mark.parametrize("path", ["ffma", "cluster"])
 @pytest.mark.parametrize("name", SYNTH)
 @pytest.mark.parametrize("quad", ["chol", "dense"])
-def test_synthetic_vs_reference_golden(name, quad):
+def test_synthetic_vs_reference_golden(name, quad, path):
+    """Both FP32 kernels -- the tiled FFMA kernel and the small-batch cluster kernel (columns of every layer split over
+    a thread-block cluster, activations in distributed shared memory) -- against the reference's own outputs."""
     g = load_golden(name)
     p = problem_from_golden(g)
-    e, lnp, grad, lnp_only = _check_case(g, p, quad, 0)
+    try:
+        e, lnp, grad, lnp_only = _check_case(g, p, quad, 0, path)
+    except engine.LinnaError as ex:
+        if path == "cluster" and "cluster kernel unavailable" in str(ex) and p.n_out >= 1000:
+            pytest.skip("the activation arena of this shape does not fit in shared memory: auto mode serves it with the FFMA kernel")
+        raise
+    assert e.last_kernel() == path
     k = g["f32_m"].shape[0]
     theta = g["f32_theta"]
     m = e.predict(_dev(theta), engine.LINNA_OUT_M).cpu().numpy()
@@ -97,10 +107,12 @@ def test_host_buffer_entry_points_match_device():
     assert np.array_equal(e.predict(th), e.predict(_dev(th)).cpu().numpy())
 
 
-def test_ragged_empty_and_nan():
+@pytest.mark.parametrize("path", ["auto", "ffma", "cluster"])
+def test_ragged_empty_and_nan(path):
     g = load_golden("tiny")
     p = problem_from_golden(g)
     e = engine.engine_from_problem(p)
+    e.set_path(path)
     assert e.lnp(np.zeros((0, p.n_in), np.float32)).shape == (0,)
     o = Oracle(p, arch)
     for n in (1, 7, 8, 9, 33, 257):
@@ -113,6 +125,38 @@ def test_ragged_empty_and_nan():
     u[2, 1] = np.nan
     got = e.lnp(u)
     assert np.isneginf(got[2]) and np.all(np.isfinite(np.delete(got, 2))), "NaN -> -inf (util.py:1015-1016)"
+
+
+def test_cluster_kernel_is_the_small_batch_default_and_deterministic():
+    """Auto mode: batches below one tensor-core walker pair run on the cluster kernel; a row's value does not depend on
+    its position in the batch, on the batch size or on the launch (fixed summation order), and the three kernels agree."""
+    g = load_golden("c3s")
+    p = problem_from_golden(g)
+    e = engine.engine_from_problem(p)
+    u = synthetic.walkers(60, p.n_in, scale=0.5, seed=4)
+    a = e.lnp(_dev(u)).cpu().numpy()
+    assert e.last_kernel() == "cluster"
+    assert np.array_equal(a, e.lnp(_dev(u)).cpu().numpy())
+    perm = np.random.default_rng(1).permutation(60)
+    assert np.array_equal(e.lnp(_dev(u[perm])).cpu().numpy(), a[perm])
+    assert np.array_equal(e.lnp(_dev(u[:5])).cpu().numpy(), a[:5])
+    l2, g2 = e.lnp_grad(_dev(u))
+    assert e.last_kernel() == "cluster" and np.array_equal(l2.cpu().numpy(), a)
+    e.set_path("ffma")
+    lf, gf = e.lnp_grad(_dev(u))
+    assert e.last_kernel() == "ffma"
+    assert np.all(np.abs(lf.cpu().numpy() - a) <= lnp_tol(a))
+    assert rel_inf(g2.cpu().numpy(), gf.cpu().numpy()) < 2e-5
+    ref = Oracle(p, arch).lnp(u, np.float64, grad=True)
+    assert np.all(np.abs(a - ref["lnp"]) <= lnp_tol(ref["lnp"]))
+    assert rel_inf(g2.cpu().numpy(), ref["grad"]) < 2e-4
+    e.set_path("cluster")   # forced: any batch size walks the tiles with the clusters the device schedules
+    ub = synthetic.walkers(3001, p.n_in, scale=0.5, seed=5)
+    refb = Oracle(p, arch).lnp(ub[::50], np.float64)
+    got = e.lnp(_dev(ub)).cpu().numpy()
+    assert e.last_kernel() == "cluster" and np.all(np.abs(got[::50] - refb["lnp"]) <= lnp_tol(refb["lnp"]))
+    th = g["f32_theta"]
+    assert rel_inf(e.predict(_dev(th), engine.LINNA_OUT_M).cpu().numpy(), g["f32_m"]) < 1e-5 and e.last_kernel() == "cluster"
 
 
 def test_full_size_c3_properties():
