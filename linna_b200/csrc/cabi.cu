@@ -1226,6 +1226,24 @@ static int lnp_host_pipelined(linna_model *m, const float *u, int64_t n, float *
     // ~10 GB/s: 1.2 ms for the 12 MB of 10^5 C3 walkers, more than the kernel), and a device->host copy into pageable
     // memory blocks until the kernel before it has finished.  Here a few pool threads fill the input staging chunk by
     // chunk ahead of the GPU and drain the result staging behind it.
+    if ((size_t)n * n_in * sizeof(float) <= ((size_t)64 << 10)) {
+        // Latency path (an emcee ensemble of a few walkers per call): nothing to pipeline -- one stream, pinned staging on
+        // both sides, one synchronisation.
+        const size_t out_floats = (size_t)n * (1 + (grad ? n_in : 0));
+        if ((rc = ensure_pinned(&m->h_in_stage, &m->h_in_stage_cap, (size_t)n * n_in))) return rc;
+        if ((rc = ensure_pinned(&m->h_stage, &m->h_stage_cap, out_floats))) return rc;
+        memcpy(m->h_in_stage, u, (size_t)n * n_in * sizeof(float));
+        CUDA_TRY(cudaMemcpyAsync(m->d_in, m->h_in_stage, (size_t)n * n_in * sizeof(float), cudaMemcpyHostToDevice, m->hstream));
+        rc = grad ? linna_lnp_grad(m, m->d_in, n, m->d_lnp, m->d_grad, m->hstream) : linna_lnp(m, m->d_in, n, m->d_lnp, m->hstream);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(m->h_stage, m->d_lnp, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, m->hstream));
+        if (grad)
+            CUDA_TRY(cudaMemcpyAsync(m->h_stage + n, m->d_grad, (size_t)n * n_in * sizeof(float), cudaMemcpyDeviceToHost, m->hstream));
+        CUDA_TRY(cudaStreamSynchronize(m->hstream));
+        memcpy(lnp, m->h_stage, (size_t)n * sizeof(float));
+        if (grad) memcpy(grad, m->h_stage + n, (size_t)n * n_in * sizeof(float));
+        return LINNA_OK;
+    }
     const bool stage_in = !is_pinned_host(u);
     const bool stage_out = !is_pinned_host(lnp) || (grad && !is_pinned_host(grad));
     float *s_lnp = lnp, *s_grad = grad;
@@ -1241,7 +1259,10 @@ static int lnp_host_pipelined(linna_model *m, const float *u, int64_t n, float *
     const bool big = (size_t)n * n_in * sizeof(float) >= ((size_t)1 << 20);
     if ((stage_in || stage_out) && big && !m->pool) {
         const unsigned hw = std::thread::hardware_concurrency();
-        m->pool = new StagePool((int)std::max(1u, std::min(4u, hw > 1 ? hw - 1 : 1u)));
+        // enough threads that the FIRST chunk (nothing overlaps its staging) is copied at several times one core's rate
+        const char *ep = getenv("LINNA_STAGE_THREADS");
+        const unsigned want = ep ? (unsigned)std::max(1, atoi(ep)) : 8u;
+        m->pool = new StagePool((int)std::max(1u, std::min(want, hw > 1 ? hw - 1 : 1u)));
     }
     StagePool *pool = big ? m->pool : nullptr;
     const int64_t wave = (int64_t)(m->num_sms / 2) * 2 * 256;
@@ -1254,7 +1275,7 @@ static int lnp_host_pipelined(linna_model *m, const float *u, int64_t n, float *
         m->pipe_events.push_back(e);
     }
     // input staging: every chunk in `parts` pieces, all submitted up front; in_left[k] counts the pieces still to copy
-    const int parts = 2;
+    const int parts = pool ? (int)std::min<size_t>(8, std::max<size_t>(2, pool->workers.size())) : 2;
     std::vector<std::atomic<int>> in_left(nchunks);
     std::atomic<int> out_left{0};
     if (stage_in) {
