@@ -123,7 +123,11 @@ def ml_sampler_core(ntrainArr, nvalArr, nkeepArr, ntimesArr, ntautolArr, meanshi
             if not os.path.isfile(os.path.join(outdir_in, "finish.pkl")):
                 train_gpu.main(outdir_in)
         model, y_invtransform_data = retrieve_model(outdir_in, len(init), len(data), nnmodel_in)
-        if _chain_file(outdir_in, filename) is not None and os.path.isfile(os.path.join(outdir_in, "mcmc_done.pkl")):
+        cf = _chain_file(outdir_in, filename)
+        if cf is not None and (os.path.isfile(os.path.join(outdir_in, "mcmc_done.pkl")) or
+                               (cf.endswith(".h5") and not os.path.isfile(cf[:-3] + ".meta.json"))):
+            # a finished chain of this package, or a chain file written by the reference itself (an HDF5 file with none of
+            # this package's bookkeeping beside it): linna/main.py:273-274 skips the MCMC whenever the chain file exists
             continue
         invcov_new = torch.from_numpy(inv_cov.astype(np.float32))
         data_new = torch.from_numpy(data.astype(np.float32))

@@ -156,11 +156,31 @@ class ChainStore:
             z = np.load(self.base + ".npz")
             self._frozen = {k: z[k] for k in self.NAMES}
             self.nsteps, self.nwalkers, self.ndim = self._frozen["chain"].shape
+        elif os.path.isfile(self.base + ".h5") and not os.path.isfile(self.base + ".meta.json"):
+            self._frozen = self._load_h5(self.base + ".h5")    # a chain written by the reference (emcee HDFBackend)
+            self.nsteps, self.nwalkers, self.ndim = self._frozen["chain"].shape
         elif os.path.isfile(self.base + ".meta.json"):
             import json
             with open(self.base + ".meta.json") as f:
                 meta = json.load(f)
             self.nsteps, self.nwalkers, self.ndim = int(meta["nsteps"]), int(meta["nwalkers"]), int(meta["ndim"])
+
+    @staticmethod
+    def _load_h5(path, group="mcmc"):
+        """The datasets of an emcee-style HDF5 chain (linna/sampler.py:330-368), cut at the attribute ``iteration``
+        (emcee grows its datasets ahead of the samples it has written)."""
+        from .h5read import H5File
+        f = H5File(path)
+        names = f.keys("/" + group)
+        it = f.attrs("/" + group).get("iteration")
+        out = {}
+        for n in ("chain", "chain_transformed", "log_prob"):
+            src = n if n in names else ("chain" if n == "chain_transformed" else None)   # linna/util.py:81-84
+            if src is None:
+                raise KeyError("%s: no dataset %r in group %r" % (path, n, group))
+            v = f.dataset("/%s/%s" % (group, src))
+            out[n] = np.ascontiguousarray(v[:int(it)] if it is not None else v, np.float64)
+        return out
 
     def _remove_files(self):
         for ext in (".npz", ".h5", ".meta.json") + tuple("." + n + ".f64" for n in self.NAMES):

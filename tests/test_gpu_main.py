@@ -232,3 +232,87 @@ def test_run_mcmc_hmc_method(tmp_path):
     assert os.path.isfile(os.path.join(d, "chhmc.meta.json")) and store.iteration >= 100
     ch = np.asarray(store.chain_transformed)
     assert ch.shape[1:] == (256, 2) and np.all(np.abs(ch) <= 2.0) and np.all(np.isfinite(np.asarray(store.log_prob)))
+
+
+def _ref_reading_args():
+    """The arguments of the reference's own tests/test_main.py (chto/linna)."""
+    ndim = 2
+    priors = [dict(param="test_%d" % i, dist="flat", arg1=-2.0, arg2=2.0) for i in range(ndim)]
+    return dict(ntrainArr=[20], nvalArr=[5], nkeepArr=[1], ntimesArr=[2], ntautolArr=[0.5], meanshiftArr=[100], stdshiftArr=[100],
+                priors=priors, data=np.array([0.1, 1.0]), cov=np.diag([0.5, 0.2]), init=np.array([0.3, 0.6]), nwalkers=4,
+                temperatureArr=[1.0], params=dict(trainingoption=1, num_epochs=10, batch_size=5))
+
+
+def test_reading_of_the_reference_output_directory(tmp_path):
+    """The reference's test_reading (tests/test_main.py:46-52): ml_sampler_core pointed at the output directory the
+    reference ships -- trained emulator, finish.pkl and the emcee chain file -- trains nothing, samples nothing, reads the
+    chain back and must return the moments the reference asserts."""
+    import shutil
+    from linna.main import ml_sampler_core
+    from linna.nn import ChtoModelv2
+    from tests.helpers import GOLDEN
+    out = tmp_path / "2dgaussian_Fulltconn"
+    shutil.copytree(os.path.join(GOLDEN, "ref_fixture_iter_0"), out / "iter_0")
+    shutil.copy(os.path.join(GOLDEN, "ref_chain", "chemcee_256.h5"), out / "iter_0" / "chemcee_256.h5")
+    a = _ref_reading_args()
+    import hashlib
+    digest = lambda n: hashlib.sha1(open(out / "iter_0" / n, "rb").read()).hexdigest()
+    before = {n: digest(n) for n in ("best.pth.tar", "last.pth.tar", "chemcee_256.h5", "train_samples_y.npy")}
+
+    def theory(x, outdirs):
+        raise AssertionError("the finished directory must not evaluate the theory again")
+    chain, logprob = ml_sampler_core(a["ntrainArr"], a["nvalArr"], a["nkeepArr"], a["ntimesArr"], a["ntautolArr"], a["meanshiftArr"],
+                                     a["stdshiftArr"], str(out) + "/", theory, a["priors"], a["data"], a["cov"], a["init"], None,
+                                     a["nwalkers"], "cuda", None, False, a["temperatureArr"], omegab2cut=None, docuda=False, tsize=1,
+                                     gpunode=None, nnmodel_in=ChtoModelv2, params=a["params"], method="emcee")
+    np.testing.assert_almost_equal(np.mean(chain), 0.15151080063411168, decimal=5)
+    np.testing.assert_almost_equal(np.std(chain), 0.9633211647095377, decimal=5)
+    assert chain.shape == (56, 2) and np.asarray(logprob).shape == (800,)
+    assert {n: digest(n) for n in before} == before, "nothing may be retrained or resampled in a finished reference directory"
+    assert not any(f.startswith("chemcee_256.") and f != "chemcee_256.h5" for f in os.listdir(out / "iter_0"))
+
+
+def test_posterior_moments_match_the_reference_chain(tmp_path):
+    """Posterior moments against the chain the reference sampled with ITS emulator path (emcee + per-walker
+    Log_prob.__call__ on the CPU, tests/golden/ref_chain): the same emulator files, likelihood and priors, sampled here
+    by the GPU ensemble sampler over the fused kernel.  The shipped chain is short (200 iterations of 4 walkers,
+    tau ~ 14: about 50 independent samples after burn-in), so the bar is its own standard error -- 4 sigma on the mean,
+    4 sigma on the standard deviation -- and the stored log-probabilities of its walkers must be reproduced by the kernel
+    to the likelihood tolerance."""
+    import pickle
+    import shutil
+    import linna.util as U
+    from linna_b200.sampler import ChainStore, EnsembleSampler, integrated_time
+    from tests.helpers import GOLDEN, lnp_tol
+    d = str(tmp_path / "iter_0")
+    shutil.copytree(os.path.join(GOLDEN, "ref_fixture_iter_0"), d)
+    ref = ChainStore(os.path.join(GOLDEN, "ref_chain", "chemcee_256.h5"))
+    pred, yinv = U.retrieve_model(d, 2, 2)
+    with open(os.path.join(d, "model_args.pkl"), "rb") as f:
+        args = pickle.load(f)
+    priors = [dict(param="test_%d" % i, dist="flat", arg1=-2.0, arg2=2.0) for i in range(2)]
+    tr = U.Transform(priors)
+    lp = U.Log_prob(np.asarray(args[6]), np.asarray(args[2]), pred, yinv, tr, 1.0, U.gaussianlogliklihood, nograd=True)
+    # (1) every log-probability the reference stored for its own walkers, re-evaluated by the kernel on the stored positions
+    u_ref = np.asarray(ref.chain).reshape(-1, 2)
+    got = lp(u_ref.astype(np.float32)).numpy().astype(np.float64)
+    want = np.asarray(ref.log_prob).reshape(-1)
+    assert np.all(np.abs(got - want) <= np.maximum(lnp_tol(want), 2e-5)), np.abs(got - want).max()
+    # (2) moments of a long GPU chain against the reference chain after its burn-in
+    tau = integrated_time(ref.chain)
+    burn = int(3 * tau.max())
+    tail = np.asarray(ref.chain_transformed)[burn:].reshape(-1, 2)
+    n_eff = tail.shape[0] / tau.max()                       # walkers of one ensemble are correlated: a generous count
+    torch.manual_seed(0)
+    np.random.seed(0)
+    samp = EnsembleSampler(512, 2, lp, seed=5)
+    x0 = 0.5 * np.random.standard_normal((512, 2))
+    samp.run_mcmc(x0, 400)
+    u = samp.get_chain()[150:].reshape(-1, 2)
+    th = np.asarray(tr(u.astype(np.float64)))
+    mean, std = th.mean(0), th.std(0)
+    se_mean = tail.std(0) / np.sqrt(n_eff)
+    se_std = tail.std(0) / np.sqrt(2 * n_eff)
+    assert np.all(np.abs(tail.mean(0) - mean) < 4 * se_mean), (tail.mean(0), mean, se_mean)
+    assert np.all(np.abs(tail.std(0) - std) < 4 * se_std), (tail.std(0), std, se_std)
+    assert np.all(np.abs(th) <= 2.0)
