@@ -235,6 +235,14 @@ int linna_loss_terms(const float *y_pred, const float *y_target, int64_t n, int3
                      const float *icov_hat, const float *sigma, const float *y_mean, const float *y_std, int32_t ypositive,
                      float *loss, float *chisq_md, float *chisq_nnd, float *dloss, void *stream);
 
+/* Normalisation statistics of the training set on the device (device pointers): per column c of the row-major matrix
+ * Y [n][d], median[c] = LOWER median (torch.median's convention) of v = f(Y[r][c] / sigma[c]) with f = log when take_log
+ * (ypositive) else the identity, and, when mad != NULL, mad[c] = lower median of |v - median[c]| -- y_mean and y_std of
+ * Y_transform_class as train_NN takes them (linna/util.py:1440-1450, median_absolute_deviation :1308-1313; two CPU sorts
+ * of the whole set there).  Radix selection, exact: bit-identical to the reference for take_log == 0.  sigma may be NULL. */
+int linna_column_median_mad(const float *Y, int64_t n, int32_t d, const float *sigma, int32_t take_log, float *median,
+                            float *mad, void *stream);
+
 /* ---- on-device ensemble-sampler step (emcee's stretch move, linna/sampler.py:493-503, 530) ---------------
  * One half-ensemble update is propose -> linna_lnp(y) -> accept, all on device pointers.
  * propose: for i < ns: partner = second[randint(n_second)], z ~ g(z) on [1/a, a],

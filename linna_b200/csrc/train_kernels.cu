@@ -9,6 +9,7 @@
 //   adamw_kernel  : the stand-alone update used after an NCCL all-reduce of the flat gradient.
 //   mean_kernel   : deterministic mean of the per-row losses (Loss_fn, linna/util.py:1114-1115).
 #include "linna_device.cuh"
+#include "../../include/linna_b200.h"
 
 namespace linna {
 
@@ -301,4 +302,69 @@ extern "C" int linna_loss_terms(const float *y_pred, const float *y_target, int6
     linna::loss_terms_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(y_pred, y_target, n, n_out, data_hat, icov_hat, sigma, y_mean, y_std,
                                                                         ypositive, loss, chisq_md, chisq_nnd, dloss);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+// ------------------------------------------------------------------------------------------ training-set statistics
+// Per-column LOWER median (what torch.median returns) of f(Y[r][c]) over the rows of a row-major [n][d] matrix, by radix
+// selection on order-preserving 32-bit keys: four passes of a 256-bin histogram, one CTA per column, no sort and no
+// shared-memory capacity limit.  f(v) = v / sigma_c, optionally log(.), optionally |. - centre_c|: the reference's
+// normalisation statistics y_mean = median(y / sigma) and y_std = median |y / sigma - y_mean| (linna/util.py:1440-1450,
+// :1308-1313), which it takes with two CPU sorts of the whole training set.  The matrix (21 MB at 10^4 x 500) is read
+// from L2.
+namespace linna {
+__device__ __forceinline__ uint32_t stat_key(float v)
+{
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float stat_unkey(uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__global__ void __launch_bounds__(256) column_select_kernel(const float *__restrict__ Y, int64_t n, int d, const float *__restrict__ sigma,
+                                                           int take_log, const float *__restrict__ centre, float *__restrict__ out)
+{
+    __shared__ unsigned hist[256];
+    __shared__ uint32_t s_prefix, s_mask;
+    __shared__ long long s_k;
+    const int c = blockIdx.x;
+    const float sg = sigma ? sigma[c] : 1.f, ctr = centre ? centre[c] : 0.f;
+    if (threadIdx.x == 0) s_prefix = 0u, s_mask = 0u, s_k = (n - 1) / 2;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[threadIdx.x] = 0u;
+        __syncthreads();
+        const uint32_t prefix = s_prefix, mask = s_mask;
+        for (int64_t r = threadIdx.x; r < n; r += 256) {
+            float v = Y[r * d + c] / sg;                 // Y_transform_data, linna/util.py:432
+            if (take_log) v = logf(v);
+            if (centre) v = fabsf(v - ctr);
+            const uint32_t key = stat_key(v);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long k = s_k, cum = 0;
+            int b = 0;
+            for (; b < 255; ++b) {
+                if (cum + (long long)hist[b] > k) break;
+                cum += hist[b];
+            }
+            s_k = k - cum;
+            s_prefix = prefix | ((uint32_t)b << shift);
+            s_mask = mask | (255u << shift);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[c] = stat_unkey(s_prefix);
+}
+}  // namespace linna
+
+extern "C" int linna_column_median_mad(const float *Y, int64_t n, int32_t d, const float *sigma, int32_t take_log, float *median,
+                                       float *mad, void *stream)
+{
+    if (!Y || !median || n <= 0 || d <= 0) return LINNA_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    linna::column_select_kernel<<<d, 256, 0, st>>>(Y, n, d, sigma, take_log, nullptr, median);
+    if (mad) linna::column_select_kernel<<<d, 256, 0, st>>>(Y, n, d, sigma, take_log, median, mad);
+    return cudaGetLastError() == cudaSuccess ? LINNA_OK : LINNA_ECUDA;
 }

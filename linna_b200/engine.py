@@ -89,6 +89,7 @@ def load_library():
     lib.linna_model_last_kernel.argtypes = [vp]
     lib.linna_debug_tg_counters.argtypes = [vp, vp, i32]
     lib.linna_debug_cluster_counters.argtypes = [vp, i32]
+    lib.linna_column_median_mad.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
     u64 = ctypes.c_uint64
     lib.linna_stretch_propose.argtypes = [vp, i32, vp, vp, i64, i64, ctypes.c_float, u64, u64, vp, vp, vp]
     lib.linna_stretch_accept.argtypes = [vp, vp, vp, i32, vp, i64, vp, vp, vp, u64, u64, vp]
@@ -220,6 +221,24 @@ def loss_terms(y_pred, y_target, data_hat, icov_hat, sigma, y_mean, y_std, yposi
     if rc != 0:
         raise LinnaError("linna_loss_terms failed (%d)" % rc)
     return loss, md, nnd, g
+
+
+def column_median_mad(Y, sigma=None, take_log=False):
+    """(median, MAD) per column of the CUDA tensor Y [n, d] after v = Y / sigma (log(v) when take_log): the training-set
+    statistics of train_NN (linna/util.py:1440-1450) by radix selection on the device; lower medians, as torch.median."""
+    import torch
+    lib = load_library()
+    Y = Y.contiguous()
+    n, d = int(Y.shape[0]), int(Y.shape[1])
+    med = torch.empty(d, dtype=torch.float32, device=Y.device)
+    mad = torch.empty_like(med)
+    sg = None if sigma is None else torch.as_tensor(sigma, dtype=torch.float32, device=Y.device).contiguous()
+    with torch.cuda.device(Y.device):
+        rc = lib.linna_column_median_mad(Y.data_ptr(), n, d, sg.data_ptr() if sg is not None else None, int(bool(take_log)),
+                                         med.data_ptr(), mad.data_ptr(), _cur_stream())
+    if rc != 0:
+        raise LinnaError("linna_column_median_mad failed (%d)" % rc)
+    return med, mad
 
 
 def cluster_counters():

@@ -136,8 +136,9 @@ def checkmeanstd(samples, meanshift, stdshift):
 class ChainStore:
     """Chain file with the reference's dataset names (linna/sampler.py:330-339, :572-578).
 
-    The chain is APPENDED, never rewritten: every flush adds its block to three raw float64 files
-    (``<name>.chain.f64`` / ``.chain_transformed.f64`` / ``.log_prob.f64`` + ``<name>.meta.json``) -- what the reference's
+    The chain is APPENDED, never rewritten: every flush adds its block to three raw files
+    (``<name>.chain.f32`` / ``.chain_transformed.f32`` / ``.log_prob.f32`` + ``<name>.meta.json``; float32 is what the GPU
+    sampler produces -- runs started by an older build keep their ``.f64`` files) -- what the reference's
     HDF5 back-end does with resizable datasets -- and the arrays are read back as memory maps, so neither the host memory
     nor the I/O per convergence check grows with the length of the run.  ``finalize()`` writes the ``<name>.npz`` (and,
     when h5py is importable, ``<name>.h5`` with group ``mcmc``) once, at the end.  A finished ``.npz`` is what is read on
@@ -150,6 +151,7 @@ class ChainStore:
         self.nsteps, self.nwalkers, self.ndim = 0, 0, 0
         self._frozen = None          # arrays of a finished .npz
         self._maps = {}
+        self._raw = "f32"            # element type of the raw append files
         if fresh:
             self._remove_files()
         elif os.path.isfile(self.base + ".npz"):
@@ -164,6 +166,7 @@ class ChainStore:
             with open(self.base + ".meta.json") as f:
                 meta = json.load(f)
             self.nsteps, self.nwalkers, self.ndim = int(meta["nsteps"]), int(meta["nwalkers"]), int(meta["ndim"])
+            self._raw = meta.get("dtype", "f64")
 
     @staticmethod
     def _load_h5(path, group="mcmc"):
@@ -183,12 +186,16 @@ class ChainStore:
         return out
 
     def _remove_files(self):
-        for ext in (".npz", ".h5", ".meta.json") + tuple("." + n + ".f64" for n in self.NAMES):
+        for ext in (".npz", ".h5", ".meta.json") + tuple("." + n + e for n in self.NAMES for e in (".f64", ".f32")):
             if os.path.isfile(self.base + ext):
                 os.remove(self.base + ext)
 
     def _path(self, name):
-        return self.base + "." + name + ".f64"
+        return self.base + "." + name + "." + self._raw
+
+    @property
+    def _dtype(self):
+        return np.float32 if self._raw == "f32" else np.float64
 
     def _shape(self, name):
         return (self.nsteps, self.nwalkers) if name == "log_prob" else (self.nsteps, self.nwalkers, self.ndim)
@@ -200,7 +207,7 @@ class ChainStore:
             return None
         mm = self._maps.get(name)
         if mm is None or mm.shape[0] != self.nsteps:
-            mm = np.memmap(self._path(name), dtype=np.float64, mode="r", shape=self._shape(name))
+            mm = np.memmap(self._path(name), dtype=self._dtype, mode="r", shape=self._shape(name))
             self._maps[name] = mm
         return mm
 
@@ -215,23 +222,29 @@ class ChainStore:
     def exists(self):
         return self.nsteps > 0
 
-    def extend(self, coords, log_prob):
-        coords = np.asarray(coords, np.float64)
+    def extend(self, coords, log_prob, transformed=None):
+        """Append a block [steps, walkers, ndim].  ``transformed``: the block already mapped to physical parameters (the
+        samplers do that on the GPU, one elementwise pass over the device block, instead of one host call per step)."""
+        coords = np.asarray(coords)
         if coords.shape[0] == 0:
             return
         if self._frozen is not None:     # continuing a finished chain: back to the appendable form first
             frozen, self._frozen, self.nsteps = self._frozen, None, 0
             for n in self.NAMES:
                 with open(self._path(n), "wb") as f:
-                    np.ascontiguousarray(frozen[n], np.float64).tofile(f)
+                    np.ascontiguousarray(frozen[n], self._dtype).tofile(f)
             self.nsteps = frozen["chain"].shape[0]
-        tr = coords if self.transform is None else np.stack(
-            [np.atleast_2d(self.transform(c.astype(np.float32))) for c in coords]).astype(np.float64)
+        if transformed is not None:
+            tr = np.asarray(transformed).reshape(coords.shape)
+        else:
+            tr = coords if self.transform is None else np.stack(
+                [np.atleast_2d(self.transform(c.astype(np.float32))) for c in coords])
         if self.nsteps == 0:
             self.nwalkers, self.ndim = coords.shape[1], coords.shape[2]
-        for n, block in (("chain", coords), ("chain_transformed", tr), ("log_prob", np.asarray(log_prob, np.float64))):
+        for n, block in (("chain", coords), ("chain_transformed", tr), ("log_prob", np.asarray(log_prob))):
             with open(self._path(n), "ab") as f:
-                np.ascontiguousarray(block, np.float64).tofile(f)
+                for step in block:       # step by step: no second copy of a GB-sized block when the element type differs
+                    np.ascontiguousarray(step, self._dtype).tofile(f)
         self.nsteps += coords.shape[0]
         self._maps = {}
 
@@ -239,7 +252,7 @@ class ChainStore:
         """Make the appended blocks durable: a few bytes of metadata (the blocks themselves are already on disk)."""
         import json
         with open(self.base + ".meta.json", "w") as f:
-            json.dump({"nsteps": self.nsteps, "nwalkers": self.nwalkers, "ndim": self.ndim}, f)
+            json.dump({"nsteps": self.nsteps, "nwalkers": self.nwalkers, "ndim": self.ndim, "dtype": self._raw}, f)
 
     def finalize(self, max_bytes=2 << 30):
         """End of the run: the portable single-file forms with the reference's dataset names."""
@@ -248,13 +261,14 @@ class ChainStore:
             return
         if self.nsteps * self.nwalkers * (2 * self.ndim + 1) * 8 > max_bytes:
             return                       # a chain this large stays in its raw appendable form
-        np.savez(self.base + ".npz", chain=self.chain, chain_transformed=self.chain_transformed, log_prob=self.log_prob)
+        f64 = lambda a: np.asarray(a, np.float64)        # the reference's chain files hold float64 (emcee's default dtype)
+        np.savez(self.base + ".npz", chain=f64(self.chain), chain_transformed=f64(self.chain_transformed), log_prob=f64(self.log_prob))
         try:
             import h5py
             with h5py.File(self.base + ".h5", "w") as f:
                 g = f.create_group("mcmc")
                 for n in self.NAMES:
-                    g.create_dataset(n, data=self._array(n))
+                    g.create_dataset(n, data=f64(self._array(n)))
         except ImportError:
             pass
 
@@ -272,6 +286,36 @@ class ChainStore:
 
     def get_autocorr_time(self, quiet=True, **kw):
         return integrated_time(thin_for_tau(self.chain))
+
+
+def transform_block_device(transform, xb):
+    """chain_transformed of a device block [steps, walkers, ndim]: the prior map (linna/util.py:323-347) applied on the
+    GPU in one elementwise pass, or None when ``transform`` is not one of this package's prior maps (then ChainStore
+    falls back to one host call per step, as the reference's back-end does, linna/sampler.py:356)."""
+    if transform is None or not hasattr(transform, "priors") or not hasattr(transform, "_col") or not xb.is_cuda:
+        return None
+    nd = xb.shape[-1]
+    flat = xb.reshape(-1, nd).to(torch.float32)
+    cols = [transform._col(flat[:, i], p) for i, p in enumerate(transform.priors)]
+    return torch.stack(cols, dim=1).reshape(xb.shape)
+
+
+_PINNED = {}
+
+
+def to_host_pinned(name, t):
+    """Device block -> numpy through a cached pinned staging tensor (a fresh pageable ``.cpu()`` of a 1.2 GB block moves
+    at ~2 GB/s; the pinned copy at PCIe rate).  The returned array aliases the staging buffer: it is valid until the next
+    call with the same ``name``."""
+    key = (name, t.device.index)
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
+        buf = torch.empty(int(t.numel() * 1.25) + 16, dtype=t.dtype, pin_memory=True)
+        _PINNED[key] = buf
+    dst = buf[:t.numel()].view(t.shape)
+    dst.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return dst.numpy()
 
 
 def thin_for_tau(chain, max_walkers=2048, max_bytes=1 << 30):
@@ -485,7 +529,9 @@ class HMCSampler:
             self.sampler.drop_before(saved)       # the flushed snapshots leave the GPU
             stop = False
             if rank == 0:
-                store.extend(xb.cpu().numpy(), lb.cpu().numpy())   # only the new steps are appended to the files
+                tb = transform_block_device(self.transform, xb)
+                store.extend(to_host_pinned("x", xb), to_host_pinned("lnp", lb),   # only the new steps are appended to the files
+                             transformed=None if tb is None else to_host_pinned("theta", tb))
                 store.save()
                 if not final:
                     tau = integrated_time(thin_for_tau(store.chain))
@@ -542,7 +588,9 @@ class HMCSampler:
             xb, lb = gathered(xs, ls)
             stop = False
             if rank == 0:
-                store.extend(xb.cpu().numpy(), lb.cpu().numpy())
+                tb = transform_block_device(self.transform, xb)
+                store.extend(to_host_pinned("x", xb), to_host_pinned("lnp", lb),
+                             transformed=None if tb is None else to_host_pinned("theta", tb))
                 store.save()
                 tau = integrated_time(thin_for_tau(store.chain))
                 if not (np.isnan(np.sum(tau)) and done > 10):

@@ -348,15 +348,15 @@ def train_NN(nnsampler, cov, inv_cov, sigma, outdir_in, outdir_list, data, dolog
     X_std = log10_cols(train_x).std(axis=0)
     X_transform = U.X_transform_class(X_mean, X_std, device, dolog10index)
     _NoWrite(X_transform).pickle(os.path.join(outdir_in, "X_transform.pkl"))
-    f32 = lambda a: torch.tensor(a, dtype=torch.float32)
-    if ypositive:
-        logy = torch.log(y_transform_data(f32(train_y)).detach())
-        y_mean = logy.median(axis=0).values
-        y_std = U.median_absolute_deviation(logy, y_mean, 0)
-    else:
-        yn = y_transform_data(f32(train_y_last)).detach()
-        y_mean = yn.median(axis=0).values
-        y_std = U.median_absolute_deviation(yn, y_mean, 0)
+    # y_mean = median(y / sigma), y_std = median |y / sigma - y_mean| (linna/util.py:1440-1450): radix selection on the
+    # GPU (engine.column_median_mad) instead of two CPU sorts of the whole training set; same lower-median convention
+    from . import engine as _eng
+    ysrc = train_y if ypositive else train_y_last
+    y_dev = torch.as_tensor(np.ascontiguousarray(ysrc, np.float32)).cuda()
+    y_mean, y_std = _eng.column_median_mad(y_dev, np.asarray(sigma, np.float32), take_log=bool(ypositive))
+    y_mean, y_std = y_mean.cpu(), y_std.cpu()
+    del y_dev
+    if not ypositive:
         y_std[y_std < 1e-10] = 1e0
     y_transform = U.Y_transform_class(y_mean, y_std, device, ypositive=ypositive)
     _NoWrite(y_transform).pickle(os.path.join(outdir_in, "y_transform.pkl"))

@@ -220,3 +220,31 @@ def test_training_converges_and_dp_path_equals_fused():
         assert vm.shape == (3,) and vm[0] < 0.1 * hist[0]
         tr.commit()
     np.testing.assert_allclose(runs[0][:50], runs[1][:50], rtol=2e-3)
+
+
+@pytest.mark.parametrize("take_log", [False, True])
+def test_training_set_statistics_on_device(take_log):
+    """y_mean / y_std of Y_transform_class (median and median absolute deviation of y / sigma, linna/util.py:1440-1450,
+    :1308-1313) by radix selection on the GPU against the reference's own torch expressions on the CPU: bit-identical
+    without the log, to float32 rounding of logf with it."""
+    from linna_b200 import engine
+    rng = np.random.default_rng(3)
+    for n, d in ((10000, 500), (4097, 33), (2, 5), (1, 3)):
+        Y = rng.standard_normal((n, d)).astype(np.float32) * 3 + (5 if take_log else 0)
+        if take_log:
+            Y = np.abs(Y) + 1e-3
+        Y[rng.integers(0, n, 7), rng.integers(0, d, 7)] = 1e10 if not take_log else 1e-30     # clipped outliers (util.py:1432)
+        Y[:, 0] = 2.5                                                                          # a constant column: MAD = 0
+        sigma = (0.5 + rng.random(d)).astype(np.float32)
+        v = torch.from_numpy(Y) / torch.from_numpy(sigma)          # Y_transform_data, linna/util.py:432
+        if take_log:
+            v = torch.log(v)
+        want_med = v.median(axis=0).values
+        want_mad = torch.abs(v - want_med).median(axis=0).values   # median_absolute_deviation, linna/util.py:1308-1313
+        med, mad = engine.column_median_mad(torch.from_numpy(Y).cuda(), sigma, take_log=take_log)
+        med, mad = med.cpu(), mad.cpu()
+        if take_log:
+            assert torch.allclose(med, want_med, rtol=1e-6, atol=1e-6) and torch.allclose(mad, want_mad, rtol=1e-5, atol=2e-6)
+        else:
+            assert torch.equal(med, want_med) and torch.equal(mad, want_mad), (n, d)
+        assert float(mad[0]) == 0.0

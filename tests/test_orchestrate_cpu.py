@@ -115,10 +115,10 @@ def test_checkmeanstd_and_chain_store(tmp_path):
     name = str(tmp_path / "chemcee_256.h5")
     st = sampler.ChainStore(name, transform=lambda c: 2.0 * c)
     st.extend(good[:100], np.zeros((100, 6)))
-    size1 = os.path.getsize(str(tmp_path / "chemcee_256.chain.f64"))
+    size1 = os.path.getsize(str(tmp_path / "chemcee_256.chain.f32"))
     st.extend(good[100:250], np.ones((150, 6)))
     st.save()
-    assert os.path.getsize(str(tmp_path / "chemcee_256.chain.f64")) == size1 * 250 // 100
+    assert os.path.getsize(str(tmp_path / "chemcee_256.chain.f32")) == size1 * 250 // 100
     assert not os.path.exists(str(tmp_path / "chemcee_256.npz"))
     st2 = sampler.ChainStore(name)                       # resume of an unfinished run: from the raw files
     assert st2.exists() and st2.iteration == 250
