@@ -248,6 +248,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cluster_ffma_kernel(const ClArg
 
     const int n_in = c.n_in, n_out = c.n_out;
     const int n_steps = prog->n_steps;
+    const bool ktiming = cargs.dbg && tid == 0 && rank == 0 && cid == 0;   // LINNA_CLUSTER_DEBUG: phases outside the step loop
+    const long long k_t0 = ktiming ? clock64() : 0;
     {
         const int nwords = n_steps * (int)(sizeof(Step) / 4);
         const uint32_t *src = reinterpret_cast<const uint32_t *>(prog->steps);
@@ -260,6 +262,21 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cluster_ffma_kernel(const ClArg
     const int64_t ntiles = (n_rows + CL_ROWS - 1) / CL_ROWS;
     const int64_t my_tiles = (int64_t)cid < ntiles ? (ntiles - cid + ncl - 1) / ncl : 0;
 
+    const unsigned arena_s = cl_opaque(cl_smem_u32(arena));
+    const unsigned chi_all_s = cl_opaque(cl_smem_u32(chi_all));
+
+    const unsigned bar_s = cl_opaque(cl_smem_u32(full_bar));
+    if (tid == 0) {
+        cl_mbar_init(bar_s, 1), cl_mbar_init(bar_s + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned gstep = 0, phase_bits = 0;   // steps executed so far (over all tiles): a step uses barrier gstep & 1; bit b of
+                                          // phase_bits is the parity of the phases barrier b has completed on THIS CTA
+    // The cluster barrier comes BEFORE the first weight loads: its release fence would otherwise wait for every one of
+    // them (a full DRAM / L2 round trip on top of the time the slowest CTA needs to start).
+    const long long k_t1 = ktiming ? clock64() : 0;
+    cl_cluster_sync();    // every CTA of the cluster is running, with its barriers initialised, before anything is written across it
+    const long long k_t2 = ktiming ? clock64() : 0;
     // ---- weight stream: D loads in flight per thread, across step and tile boundaries
     ClStream ws;
     ws.init(s_steps, n_steps, (int)rank, (int)cs, tid, my_tiles);
@@ -275,17 +292,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cluster_ffma_kernel(const ClArg
         }
         cl_commit();
     }
-    const unsigned arena_s = cl_opaque(cl_smem_u32(arena));
-    const unsigned chi_all_s = cl_opaque(cl_smem_u32(chi_all));
-
-    const unsigned bar_s = cl_opaque(cl_smem_u32(full_bar));
-    if (tid == 0) {
-        cl_mbar_init(bar_s, 1), cl_mbar_init(bar_s + 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    unsigned gstep = 0, phase_bits = 0;   // steps executed so far (over all tiles): a step uses barrier gstep & 1; bit b of
-                                          // phase_bits is the parity of the phases barrier b has completed on THIS CTA
-    cl_cluster_sync();    // every CTA of the cluster is running, with its barriers initialised, before anything is written across it
 
     for (int64_t tl = 0; tl < my_tiles; ++tl) {
         const int64_t row0 = ((int64_t)cid + tl * ncl) * CL_ROWS;
@@ -306,14 +312,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cluster_ffma_kernel(const ClArg
                 }
                 xb[(size_t)i * CL_ROWS + r] = th;
             }
-            if (tid < CL_ROWS) {
+            {   // lnprior = -|u|^2 / 2 (util.py:1165): warp w sums row w (lanes stride over the parameters, fixed shuffle tree)
                 float s = 0.f;
-                if (tid < nrows && !args.input_theta) {
-                    const float *ur = in + (row0 + tid) * n_in;
-                    for (int i = 0; i < n_in; ++i) { const float u = ur[i]; s = fmaf(u, u, s); }
+                if (warp < nrows && !args.input_theta) {
+                    const float *ur = in + (row0 + warp) * n_in;
+                    for (int i = lane; i < n_in; i += 32) { const float u = ur[i]; s = fmaf(u, u, s); }
                 }
-                lnprior[tid] = -0.5f * s;                                             // util.py:1165
-                chi_acc[tid] = 0.0;
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) lnprior[warp] = -0.5f * s, chi_acc[warp] = 0.0;
             }
         }
         __syncthreads();
@@ -453,6 +459,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cluster_ffma_kernel(const ClArg
                     for (int p = 0; p < P; ++p) {
                         const float4 t = *reinterpret_cast<const float4 *>(red + (size_t)(p * g.Q + q) * 32 + cc * 8 + rh * 4);
                         v[0] += t.x, v[1] += t.y, v[2] += t.z, v[3] += t.w;
+                        if (timing && p == 0) cargs.dbg[4 * kMaxSteps + 4 * si + 2] += (v[0] != 12345.f ? clock64() : 0) - t2;
                     }
                     if (timing) cargs.dbg[4 * kMaxSteps + 4 * si + 0] += clock64() - t2;
                     const float b = st.bias ? st.scale * (item == tid ? bpre : __ldg(st.bias + cidx)) : 0.f;
@@ -601,8 +608,13 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cluster_ffma_kernel(const ClArg
         }
         __syncthreads();
     }
+    const long long k_t3 = ktiming ? clock64() : 0;
     cl_wait<0>();
     cl_cluster_sync();   // no CTA exits while a peer may still write into its shared memory
+    if (ktiming) {
+        long long *d = cargs.dbg + 4 * kMaxSteps + 4 * 60;   // [set-up + ring prefill, first cluster barrier, tiles, last barrier]
+        d[0] += k_t1 - k_t0, d[1] += k_t2 - k_t1, d[2] += k_t3 - k_t2, d[3] += clock64() - k_t3;
+    }
 }
 
 size_t cluster_ffma_smem_bytes(const Program &pg, int n_out, int cs, int depth, int *chi_q_out)

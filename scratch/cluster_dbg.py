@@ -21,5 +21,6 @@ torch.cuda.synchronize()
 c = engine.cluster_counters() / iters
 print("step  kloop  reduce  epilogue  barrier")
 for i in range(16):
-    if c[i].sum() > 0: print(i, c[i].round(0), "epilogue: after partial sums / after bias", c[64 + i][:2].round(0))
-print("total cycles", c.sum(), "per column", c.sum(0))
+    if c[i].sum() > 0: print(i, c[i].round(0), "epilogue: after partial sums / after bias / after first LDS", c[64 + i][:3].round(0))
+print("steps total cycles", c[:64].sum(), "per column", c[:64].sum(0))
+print("outside the step loop: set-up + ring prefill, first cluster barrier, all tiles, last barrier:", c[64 + 60].round(0))
