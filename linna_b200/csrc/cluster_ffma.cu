@@ -152,23 +152,41 @@ __device__ __forceinline__ void cl_reduce_scatter(float (&v)[32], int lane, floa
 
 // Work split of one step inside the cluster: CTA `rank` owns Q quads of columns starting at col0; thread `tid` owns
 // quad q and k-lane s of S (threads beyond Q*S idle).  `pow2`: the k-lanes of a warp can be combined by shuffles.
+// The CTA-level part (Q, col0) is worked out once per kernel for every step (ClStepGeo, shared memory): the weight
+// stream crosses a phase boundary at every second or third load, and with the integer divisions of this split inside it
+// the stream bookkeeping, not the FFMAs, set the pace of the k-loop (ncu: the division sequences were executed for every
+// third refill).
+struct ClStepGeo {
+    int Q, col0, qshift;   // qshift = log2(Q) when Q is a power of two, else -1
+};
 struct ClGeo {
     int Q, S, q, s, col0;
     bool active, pow2;
 };
-__device__ __forceinline__ ClGeo cl_geo(int N, int rank, int cs, int tid)
+__device__ __forceinline__ ClStepGeo cl_step_geo(int N, int rank, int cs)
 {
-    ClGeo g;
+    ClStepGeo g;
     const int cpc = (((N + cs - 1) / cs) + 3) & ~3;
     g.col0 = rank * cpc;
     int nc = N - g.col0;
     nc = nc < 0 ? 0 : (nc > cpc ? cpc : nc);
     g.Q = (nc + 3) >> 2;
-    g.pow2 = g.Q > 0 && g.Q <= 32 && (g.Q & (g.Q - 1)) == 0;
-    g.S = g.Q > 0 ? CL_THREADS / g.Q : 1;
-    g.q = g.Q > 0 ? tid % g.Q : 0;
-    g.s = g.Q > 0 ? tid / g.Q : 0;
-    g.active = g.Q > 0 && g.s < g.S;
+    g.qshift = (g.Q > 0 && (g.Q & (g.Q - 1)) == 0) ? 31 - __clz(g.Q) : -1;
+    return g;
+}
+__device__ __forceinline__ ClGeo cl_geo(const ClStepGeo &sg, int tid)
+{
+    ClGeo g;
+    g.Q = sg.Q, g.col0 = sg.col0;
+    g.pow2 = sg.qshift >= 0 && sg.Q <= 32;
+    if (sg.qshift >= 0) {
+        g.q = tid & (sg.Q - 1), g.s = tid >> sg.qshift, g.S = CL_THREADS >> sg.qshift;
+    } else if (sg.Q > 0) {
+        g.s = tid / sg.Q, g.q = tid - g.s * sg.Q, g.S = CL_THREADS / sg.Q;
+    } else {
+        g.q = 0, g.s = 0, g.S = 1;
+    }
+    g.active = sg.Q > 0 && g.s < g.S;
     return g;
 }
 
@@ -176,7 +194,8 @@ __device__ __forceinline__ ClGeo cl_geo(int N, int rank, int cs, int tid)
 // step of every tile of the cluster, in program order.
 struct ClStream {
     const Step *steps;
-    int n_steps, rank, cs, tid;
+    const ClStepGeo *geo;
+    int n_steps, tid;
     long long tiles_left;
     int si, ph;
     int k, K, S;
@@ -195,7 +214,7 @@ struct ClStream {
             const float *w = ph == 0 ? st.wt1 : st.wt2;
             if (ph > 1) { ++si, ph = 0; continue; }
             if (Kp > 0 && w) {
-                const ClGeo g = cl_geo(st.N, rank, cs, tid);
+                const ClGeo g = cl_geo(geo[si], tid);
                 if (g.active && g.s < Kp) {
                     const int ldw = ph == 0 ? st.ldw1 : st.ldw2;
                     k = g.s, K = Kp, S = g.S;
@@ -207,9 +226,9 @@ struct ClStream {
             ++ph;
         }
     }
-    __device__ __forceinline__ void init(const Step *steps_, int n_steps_, int rank_, int cs_, int tid_, long long tiles)
+    __device__ __forceinline__ void init(const Step *steps_, const ClStepGeo *geo_, int n_steps_, int tid_, long long tiles)
     {
-        steps = steps_, n_steps = n_steps_, rank = rank_, cs = cs_, tid = tid_, tiles_left = tiles;
+        steps = steps_, geo = geo_, n_steps = n_steps_, tid = tid_, tiles_left = tiles;
         si = 0, ph = 0, done = false, k = 0, K = 0, S = 1, p = nullptr, stride = 0;
         open_phase();
     }
@@ -225,6 +244,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cluster_ffma_kernel(const ClArg
 {
     extern __shared__ float4 cl_smem4[];
     __shared__ Step s_steps[kMaxSteps];
+    __shared__ ClStepGeo s_geo[kMaxSteps];
     __shared__ __align__(8) uint64_t full_bar[2];   // "the outputs of step s have landed in this CTA's arena", by step parity
     const KernelArgs &args = cargs.a;
     const Program *__restrict__ prog = args.prog;
@@ -257,6 +277,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cluster_ffma_kernel(const ClArg
         for (int i = tid; i < nwords; i += CL_THREADS) dst[i] = src[i];
     }
     __syncthreads();
+    if (tid < n_steps) s_geo[tid] = cl_step_geo(s_steps[tid].N, (int)rank, (int)cs);
+    __syncthreads();
 
     const int64_t n_rows = args.n;
     const int64_t ntiles = (n_rows + CL_ROWS - 1) / CL_ROWS;
@@ -279,7 +301,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cluster_ffma_kernel(const ClArg
     const long long k_t2 = ktiming ? clock64() : 0;
     // ---- weight stream: D loads in flight per thread, across step and tile boundaries
     ClStream ws;
-    ws.init(s_steps, n_steps, (int)rank, (int)cs, tid, my_tiles);
+    ws.init(s_steps, s_geo, n_steps, tid, my_tiles);
     // shared-space addresses are taken once and laundered through an opaque move: ptxas otherwise rebuilds the shared
     // window base (S2UR SR_CgaCtaId + LEA) in front of every use, inside the k-loop
     const unsigned ring_s = cl_opaque(cl_smem_u32(ring) + (unsigned)tid * 16u);
@@ -329,7 +351,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cluster_ffma_kernel(const ClArg
         for (int si = 0; si < n_steps; ++si) {
             const Step &st = s_steps[si];
             const int N = st.N;
-            const ClGeo g = cl_geo(N, (int)rank, (int)cs, tid);
+            const ClGeo g = cl_geo(s_geo[si], tid);
             const bool timing = cargs.dbg && tid == 0 && rank == 0 && cid == 0;
             const long long t0 = timing ? clock64() : 0;
             // Hand-over of the step's outputs.  Every CTA sends each of its columns to all arenas with st.async, which
