@@ -212,6 +212,18 @@ int linna_train_step(linna_model_t *m, const float *X, const float *Y, const flo
                      float *adam_m, float *adam_v, float *grads, int64_t step, float lr, float beta1, float beta2,
                      float eps, float weight_decay, int32_t fuse_adam, float *loss_rows, float *loss_mean,
                      void *stream);
+/* Data-parallel optimiser step with the gradient all-reduce inside it (one process per GPU, NVLink peer memory; the
+ * reference intends DistributedDataParallel + AdamW here, linna/predictor_gpu.py:246, :266-267).  Every rank runs
+ * linna_train_step(fuse_adam = 0) with `grads` inside a buffer that all ranks allocated symmetrically and exchanged
+ * pointers for (torch.distributed._symmetric_memory in this package), then this call: the kernel signals the peers that
+ * this rank's gradient is complete, waits for theirs, averages the `world` gradients in rank order straight from the
+ * peers' memory and applies AdamW -- no NCCL call, replicas stay bit-identical.  peer_grad_ptrs / signal_pad_ptrs: DEVICE
+ * arrays of `world` pointers (rank r's buffer base / signal pad); grad_offset: element offset of this step's gradient in
+ * every buffer -- the caller alternates between two halves of the buffer from step to step; signal_slot: first 32-bit
+ * word of the pad this model may use (`world` words).  All ranks must make the same sequence of calls. */
+int linna_train_adamw_peer(linna_model_t *m, float *params, float *adam_m, float *adam_v, const void *peer_grad_ptrs,
+                           int64_t grad_offset, const void *signal_pad_ptrs, int32_t signal_slot, int32_t world, int32_t rank,
+                           int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay, void *stream);
 /* Which kernels run linna_train_step / linna_train_chisq: 0 = automatic (the default: the tensor-core (tcgen05, bf16x3
  * split) kernels whenever the network shape is covered -- LINEAR / RES ops with a skip matrix, LINEAR last layer --, the
  * FP32 FFMA kernels otherwise), 1 = FP32 FFMA kernels only, 2 = tensor-core only (LINNA_EINVAL when unavailable). */

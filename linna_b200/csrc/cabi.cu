@@ -22,6 +22,7 @@ int cluster_ffma_debug_read(long long *out, int max_values);
 cudaError_t launch_wgrad(const WgradLayer *layers, const WgradTile *tiles, int n_tiles, const float *rm_base, int B,
                          const AdamArgs &ad, cudaStream_t stream);
 cudaError_t launch_adamw(const AdamArgs &ad, int n_params, int num_sms, cudaStream_t stream);
+cudaError_t launch_adamw_peer(const AdamArgs &ad, int n_params, int num_sms, const PeerReduce &pr, cudaStream_t stream);
 cudaError_t launch_mean(const float *x, int n, float *out, cudaStream_t stream);
 cudaError_t launch_fill_col(float *base, int ld, int col, int rows, float value, cudaStream_t stream);
 cudaError_t launch_scatter_params(const float *params, float *blob, const int32_t *map_fwd, const int32_t *map_bwd,
@@ -41,7 +42,7 @@ TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> 
 void tg_destroy(TgContext *t);
 cudaError_t tg_repack(TgContext *t, const float *params, cudaStream_t stream);
 int tg_train_step(const linna_model *m, TgContext *t, const float *X, const float *Y, const float *cmd, int64_t B, const AdamArgs &ad,
-                  float *loss_rows, float *loss_mean, cudaStream_t stream);
+                  float *loss_rows, float *loss_mean, cudaStream_t stream, bool leave_unjoined);
 int tg_chisq(const linna_model *m, TgContext *t, const float *X, const float *Y, int64_t n, int kind, float *chi2, cudaStream_t stream);
 int tg_debug_read(TgContext *t, long long *out, int max_steps);
 }  // namespace linna
@@ -1457,7 +1458,7 @@ int linna_train_step(linna_model_t *m, const float *X, const float *Y, const flo
         LINNA_ON_DEVICE(m);
         if (m->have_last && m->last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, m->last_done, 0));
         AdamArgs a = adam_args(m, params, adam_m, adam_v, grads, step, lr, beta1, beta2, eps, weight_decay, fuse_adam ? 1 : 0);
-        const int l = tg_train_step(m, m->tg, X, Y, cmd, B, a, loss_rows, loss_mean, st);
+        const int l = tg_train_step(m, m->tg, X, Y, cmd, B, a, loss_rows, loss_mean, st, false);
         if (l < 0) return fail(LINNA_ECUDA, "tensor-core training launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         g_launches.fetch_add(l);
         m->last_train_kernel = 2;
@@ -1503,6 +1504,32 @@ int linna_train_adamw(linna_model_t *m, float *params, float *adam_m, float *ada
     if (m->have_last && m->last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, m->last_done, 0));
     AdamArgs a = adam_args(m, params, adam_m, adam_v, const_cast<float *>(grads), step, lr, beta1, beta2, eps, weight_decay, 1);
     CUDA_TRY(launch_adamw(a, (int)m->n_params, m->num_sms, st));
+    g_launches.fetch_add(1);
+    if (m->tg) {   // the tensor-core kernels' packed planes follow the flat vector
+        CUDA_TRY(tg_repack(m->tg, params, st));
+        g_launches.fetch_add(1);
+    }
+    CUDA_TRY(cudaEventRecord(m->last_done, st));
+    m->last_stream = st, m->have_last = true;
+    return LINNA_OK;
+}
+
+int linna_train_adamw_peer(linna_model_t *m, float *params, float *adam_m, float *adam_v, const void *peer_grad_ptrs, int64_t grad_offset,
+                           const void *signal_pad_ptrs, int32_t signal_slot, int32_t world, int32_t rank, int64_t step, float lr,
+                           float beta1, float beta2, float eps, float weight_decay, void *stream)
+{
+    if (!m || !m->has_train) return fail(LINNA_ESTATE, "linna_train_setup has not been called");
+    if (!params || !adam_m || !adam_v || !peer_grad_ptrs || !signal_pad_ptrs) return fail(LINNA_EINVAL, "null buffer");
+    if (world < 1 || world > 16 || rank < 0 || rank >= world || grad_offset < 0 || signal_slot < 0) return fail(LINNA_EINVAL, "bad peer geometry");
+    LINNA_ON_DEVICE(m);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->have_last && m->last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, m->last_done, 0));
+    AdamArgs a = adam_args(m, params, adam_m, adam_v, nullptr, step, lr, beta1, beta2, eps, weight_decay, 1);
+    PeerReduce pr;
+    pr.grads = reinterpret_cast<const float *const *>(peer_grad_ptrs), pr.offset = grad_offset;
+    pr.pads = reinterpret_cast<uint32_t *const *>(signal_pad_ptrs), pr.slot = signal_slot;
+    pr.world = world, pr.rank = rank, pr.token = ++m->peer_token;
+    CUDA_TRY(launch_adamw_peer(a, (int)m->n_params, m->num_sms, pr, st));
     g_launches.fetch_add(1);
     if (m->tg) {   // the tensor-core kernels' packed planes follow the flat vector
         CUDA_TRY(tg_repack(m->tg, params, st));

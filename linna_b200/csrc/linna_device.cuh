@@ -129,4 +129,15 @@ struct AdamArgs {
     int32_t fuse;
 };
 
+// Gradient average over the ranks of a data-parallel step, read straight from the peers' memory over NVLink
+// (adamw_peer_kernel): grads[r] + offset is rank r's flat gradient, pads[r] its signal pad.
+struct PeerReduce {
+    const float *const *grads;   // device array [world]
+    uint32_t *const *pads;       // device array [world]
+    int64_t offset;              // element offset of this step's gradient inside every rank's buffer
+    int32_t slot;                // first 32-bit word of the signal pad used here (one word per source rank)
+    int32_t world, rank;
+    uint32_t token;              // sequence number of this reduction (monotonic, the same on every rank)
+};
+
 }  // namespace linna

@@ -36,7 +36,9 @@
 
 #include <algorithm>
 #include <array>
+#include <climits>
 #include <cmath>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -854,6 +856,19 @@ struct TgContext {
     int32_t *sem = nullptr;
     int max_tiles = 0, num_sms = 148;
     long long *dbg = nullptr;     // LINNA_TG_DEBUG
+    // Weight-gradient buckets.  The weight gradients of a layer need that layer's d loss / d z, and -- with AdamW fused
+    // into the same launch -- every backward-data step that still reads the layer's weights to have run.  Both hold
+    // once the backward chain has passed the layer, so the tiles are grouped into up to three buckets of layers (last
+    // layers first) and every bucket but the last is launched on its own stream as soon as the chain has passed it,
+    // overlapping the rest of the chain; the last bucket follows the chain on the caller's stream.  In a data-parallel
+    // step the buckets are also the units of the gradient all-reduce (contiguous ranges of the flat parameter vector).
+    int n_buckets = 1;
+    int bucket_tile0[3] = {0, 0, 0}, bucket_ntiles[3] = {0, 0, 0};
+    int bucket_ready_step[3] = {0, 0, 0};          // launch after this step of the program has been enqueued
+    int64_t bucket_flat_lo[3] = {0, 0, 0}, bucket_flat_hi[3] = {0, 0, 0};
+    cudaStream_t bucket_stream[3] = {nullptr, nullptr, nullptr};   // nullptr: the caller's stream
+    cudaEvent_t bucket_ready[3] = {nullptr, nullptr, nullptr}, bucket_done[3] = {nullptr, nullptr, nullptr};
+    bool buckets_unjoined = false;                  // the last grad-out step left the bucket streams for the caller to join
 };
 
 cudaError_t tg_repack(TgContext *t, const float *params, cudaStream_t stream);
@@ -864,6 +879,11 @@ void tg_destroy(TgContext *t)
     cudaFree(t->act), cudaFree(t->wblob), cudaFree(t->masks), cudaFree(t->delta32), cudaFree(t->chi_part);
     cudaFree(t->maps_dev), cudaFree(t->steps_dev), cudaFree(t->wlayers_dev), cudaFree(t->wtiles_dev), cudaFree(t->err_dev);
     cudaFree(t->ws), cudaFree(t->sem), cudaFree(t->dbg);
+    for (int b = 0; b < 3; ++b) {
+        if (t->bucket_stream[b]) cudaStreamDestroy(t->bucket_stream[b]);
+        if (t->bucket_ready[b]) cudaEventDestroy(t->bucket_ready[b]);
+        if (t->bucket_done[b]) cudaEventDestroy(t->bucket_done[b]);
+    }
     delete t;
 }
 
@@ -1047,6 +1067,8 @@ TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> 
         t->lossq_tiles = q.n_tiles;
         t->steps.push_back(q);
     }
+    std::vector<int> op_last_step(nops, 0);   // last step of the program that belongs to op i (its weights are free afterwards)
+    op_last_step[nops - 1] = t->i_lossq;
     for (int i = nops - 1; i >= 1; --i) {   // backward-data; d loss / d xhat is not needed
         const OpHost &op = m->ops[i];
         int64_t moff = 0;
@@ -1069,6 +1091,7 @@ TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> 
             if (pm) x.apply_mask = 1, x.mask_off = moff, x.mask_ld = mld;
             t->steps.push_back(x);
         }
+        op_last_step[i] = (int)t->steps.size() - 1;
     }
     if (m->ops[0].kind == LINNA_OP_RES) {   // the hidden gradient of a leading res-block is still needed for its weights
         const OpHost &op = m->ops[0];
@@ -1078,6 +1101,7 @@ TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> 
         t->steps.push_back(h);
     }
     t->n_steps = (int)t->steps.size();
+    op_last_step[0] = t->n_steps - 1;
     t->in_off = mats[mX].off, t->in_ld = mats[mX].ld;
 
     // ---- weight-gradient layers and tiles
@@ -1107,16 +1131,45 @@ TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> 
             add_wl(mGz[i], xin, op.out, op.in, flat_off[i][4], -1, 1.f, ow[i].fs, ow[i].bs, blob_off[i][6], blob_off[i][7], -1);
         }
     }
+    // op of every weight-gradient layer, and the bucket of every op: the last two ops, the middle ones, the first two
+    std::vector<int> wl_op;
+    for (int i = 0; i < nops; ++i) wl_op.insert(wl_op.end(), m->ops[i].kind == LINNA_OP_LINEAR ? 1 : 3, i);
+    const bool split = nops >= 5 && !getenv("LINNA_TG_NO_BUCKETS");
+    auto bucket_of = [&](int op) { return !split ? 0 : op >= nops - 2 ? 0 : op >= 2 ? 1 : 2; };
+    t->n_buckets = split ? 3 : 1;
     std::vector<TgWTile> tiles;
     for (size_t l = 0; l < wl.size(); ++l) {
         const int kmax = wl[l].K + (wl[l].b_flat >= 0 ? 1 : 0);
         for (int m0 = 0; m0 < wl[l].N; m0 += TG_BM)
             for (int n0 = 0; n0 < kmax; n0 += TG_BN) tiles.push_back(TgWTile{(int32_t)l, m0, n0, 0});
     }
-    // large tiles first: the 64 tiles of the widest skip layer should not start last
+    // bucket by bucket; inside a bucket large tiles first: the 64 tiles of the widest skip layer should not start last
     std::stable_sort(tiles.begin(), tiles.end(), [&](const TgWTile &a, const TgWTile &b) {
+        const int ba = bucket_of(wl_op[a.layer]), bb = bucket_of(wl_op[b.layer]);
+        if (ba != bb) return ba < bb;
         return (int64_t)wl[a.layer].N * wl[a.layer].K > (int64_t)wl[b.layer].N * wl[b.layer].K;
     });
+    for (int b = 0; b < t->n_buckets; ++b) {
+        t->bucket_tile0[b] = (int)tiles.size(), t->bucket_ntiles[b] = 0;
+        t->bucket_flat_lo[b] = INT64_MAX, t->bucket_flat_hi[b] = 0, t->bucket_ready_step[b] = 0;
+    }
+    for (size_t i = 0; i < tiles.size(); ++i) {
+        const int b = bucket_of(wl_op[tiles[i].layer]);
+        t->bucket_tile0[b] = std::min(t->bucket_tile0[b], (int)i), ++t->bucket_ntiles[b];
+    }
+    for (size_t l = 0; l < wl.size(); ++l) {
+        const int b = bucket_of(wl_op[l]);
+        t->bucket_ready_step[b] = std::max(t->bucket_ready_step[b], op_last_step[wl_op[l]]);
+        int64_t lo = wl[l].w_flat, hi = (int64_t)wl[l].w_flat + (int64_t)wl[l].N * wl[l].K;
+        if (wl[l].b_flat >= 0) lo = std::min<int64_t>(lo, wl[l].b_flat), hi = std::max<int64_t>(hi, (int64_t)wl[l].b_flat + wl[l].N);
+        t->bucket_flat_lo[b] = std::min(t->bucket_flat_lo[b], lo), t->bucket_flat_hi[b] = std::max(t->bucket_flat_hi[b], hi);
+    }
+    for (int b = 0; b + 1 < t->n_buckets; ++b) {   // every bucket but the last gets its own stream
+        if (cudaStreamCreateWithFlags(&t->bucket_stream[b], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&t->bucket_ready[b], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&t->bucket_done[b], cudaEventDisableTiming) != cudaSuccess)
+            return bail("bucket streams");
+    }
     t->n_wlayers = (int)wl.size(), t->n_wtiles = (int)tiles.size();
     for (const TgWLayer &L : wl) t->max_wn = std::max<int64_t>(t->max_wn, (int64_t)L.N * L.K);
 
@@ -1254,20 +1307,47 @@ static int tg_forward_loss(const linna_model *m, TgContext *t, const float *X, c
     return cudaGetLastError() == cudaSuccess ? launches : -1;
 }
 
+// `leave_unjoined` is reserved (a caller that reduces the buckets behind their own streams); every caller passes false and
+// the bucket streams are joined with `stream` before the step returns.
 int tg_train_step(const linna_model *m, TgContext *t, const float *X, const float *Y, const float *cmd, int64_t B, const AdamArgs &ad,
-                  float *loss_rows, float *loss_mean, cudaStream_t stream)
+                  float *loss_rows, float *loss_mean, cudaStream_t stream, bool leave_unjoined)
 {
     int launches = tg_forward_loss(m, t, X, Y, cmd, B, 0, true, loss_rows, loss_mean, stream);
     if (launches < 0) return -1;
     TgArgs a = tg_args(m, t, B);
     const int m_tiles = (int)((B + TG_BM - 1) / TG_BM);
+    TgArgs w = a;
+    w.adam = ad, w.dbg = t->dbg;
+    auto launch_bucket = [&](int b, cudaStream_t st) -> bool {
+        if (t->bucket_ntiles[b] <= 0) return true;
+        TgArgs wb = w;
+        wb.wtiles = t->wtiles_dev + t->bucket_tile0[b];
+        if (tg_launch_pdl(tg_wgrad_kernel, t->bucket_ntiles[b], st, wb) != cudaSuccess) return false;
+        ++launches;
+        return true;
+    };
+    auto side_buckets_after = [&](int si) -> bool {   // buckets whose layers the chain has just passed: onto their own streams
+        for (int b = 0; b + 1 < t->n_buckets; ++b)
+            if (t->bucket_ready_step[b] == si) {
+                if (cudaEventRecord(t->bucket_ready[b], stream) != cudaSuccess) return false;
+                if (cudaStreamWaitEvent(t->bucket_stream[b], t->bucket_ready[b], 0) != cudaSuccess) return false;
+                if (!launch_bucket(b, t->bucket_stream[b])) return false;
+            }
+        return true;
+    };
+    if (!side_buckets_after(t->i_lossq)) return -1;
     for (int si = t->i_lossq + 1; si < t->n_steps; ++si) {
         if (tg_launch_layer(t, a, si, m_tiles, stream) != cudaSuccess) return -1;
         ++launches;
+        if (!side_buckets_after(si)) return -1;
     }
-    a.adam = ad, a.dbg = t->dbg;
-    if (tg_launch_pdl(tg_wgrad_kernel, t->n_wtiles, stream, a) != cudaSuccess) return -1;
-    ++launches;
+    if (!launch_bucket(t->n_buckets - 1, stream)) return -1;
+    t->buckets_unjoined = leave_unjoined && t->n_buckets > 1;
+    if (!t->buckets_unjoined)
+        for (int b = 0; b + 1 < t->n_buckets; ++b) {
+            if (cudaEventRecord(t->bucket_done[b], t->bucket_stream[b]) != cudaSuccess) return -1;
+            if (cudaStreamWaitEvent(stream, t->bucket_done[b], 0) != cudaSuccess) return -1;
+        }
     return cudaGetLastError() == cudaSuccess ? launches : -1;
 }
 

@@ -114,6 +114,53 @@ __global__ void adamw_kernel(const AdamArgs ad, int n_params)
         adamw_apply(ad, i, ad.grads[i]);
 }
 
+// Data-parallel optimiser step with the gradient all-reduce INSIDE it (NVLink peer memory, no NCCL call): every rank's
+// gradient-out step leaves its flat gradient in a symmetric buffer; this kernel (1) tells every peer that this rank's
+// gradient is complete (a release store of the sequence number into the peer's signal pad -- the kernel is stream-ordered
+// behind the weight-gradient launch), (2) waits until every peer has said the same, (3) averages the world's gradients in
+// rank order -- straight from the peers' memory, 16-byte loads over NVLink -- and applies AdamW.  Every rank adds the
+// same numbers in the same order, so the replicas stay bit-identical.  The gradient buffers are double-buffered by the
+// caller: a peer may still read this rank's buffer of step t while the rank writes step t + 1, and it cannot still read it
+// at step t + 2 because this rank's barrier of step t + 1 needed that peer's signal, sent after its kernel of step t.
+__global__ void __launch_bounds__(256) adamw_peer_kernel(const AdamArgs ad, int n_params, const PeerReduce pr)
+{
+    __shared__ const float *s_g[16];
+    if (blockIdx.x == 0 && (int)threadIdx.x < pr.world) {
+        __threadfence_system();
+        uint32_t *dst = pr.pads[threadIdx.x] + pr.slot + pr.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(pr.token) : "memory");
+    }
+    if ((int)threadIdx.x < pr.world) {
+        const uint32_t *src = pr.pads[pr.rank] + pr.slot + threadIdx.x;
+        const long long t0 = clock64();
+        for (;;) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+            if ((int32_t)(v - pr.token) >= 0) break;              // a peer may already be one step ahead
+            if (clock64() - t0 > 20000000000LL) __trap();         // ~10 s: a rank is missing
+            __nanosleep(100);
+        }
+        s_g[threadIdx.x] = pr.grads[threadIdx.x] + pr.offset;
+    }
+    __syncthreads();
+    const float inv = 1.0f / (float)pr.world;
+    const int n4 = n_params >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < pr.world; ++r) {
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(s_g[r]) + i);
+            g.x += v.x, g.y += v.y, g.z += v.z, g.w += v.w;
+        }
+        adamw_apply(ad, 4 * i, g.x * inv), adamw_apply(ad, 4 * i + 1, g.y * inv);
+        adamw_apply(ad, 4 * i + 2, g.z * inv), adamw_apply(ad, 4 * i + 3, g.w * inv);
+    }
+    for (int i = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; i < n_params; i += gridDim.x * blockDim.x) {
+        float g = 0.f;
+        for (int r = 0; r < pr.world; ++r) g += __ldcg(s_g[r] + i);
+        adamw_apply(ad, i, g * inv);
+    }
+}
+
 __global__ void mean_kernel(const float *__restrict__ x, int n, float *__restrict__ out)
 {
     __shared__ double sh[256];
@@ -164,6 +211,15 @@ cudaError_t launch_adamw(const AdamArgs &ad, int n_params, int num_sms, cudaStre
     int blocks = (n_params + 255) / 256;
     if (blocks > num_sms * 8) blocks = num_sms * 8;
     adamw_kernel<<<blocks, 256, 0, stream>>>(ad, n_params);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_adamw_peer(const AdamArgs &ad, int n_params, int num_sms, const PeerReduce &pr, cudaStream_t stream)
+{
+    int blocks = (n_params / 4 + 255) / 256;
+    if (blocks > num_sms * 4) blocks = num_sms * 4;
+    if (blocks < 1) blocks = 1;
+    adamw_peer_kernel<<<blocks, 256, 0, stream>>>(ad, n_params, pr);
     return cudaGetLastError();
 }
 

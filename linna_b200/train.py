@@ -7,6 +7,8 @@ Replaces the body of the reference's training inner loop -- ``zero_grad``, forwa
 Data-parallel training adds one NCCL all-reduce of the flat gradient between the weight-gradient
 launch and the stand-alone AdamW kernel.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -59,6 +61,9 @@ class FusedTrainer:
         self.t = 0
         self.lr, self.weight_decay, self.betas, self.eps = float(lr), float(weight_decay), betas, float(eps)
         self.pg, self.world = process_group, int(world_size)
+        self._peer = None
+        if self.world > 1:
+            self._setup_peer_reduce()
         self._loss_mean = torch.zeros(1, dtype=torch.float32, device=self.device)
 
     # -- data ------------------------------------------------------------------------------
@@ -73,7 +78,19 @@ class FusedTrainer:
         Returns the mean loss as a 1-element device tensor (no sync)."""
         self.t += 1
         out = self._loss_mean if loss_out is None else loss_out
-        if self.world > 1:
+        if self.world > 1 and self._peer is not None:
+            # gradient-out step into this rank's half of the symmetric buffer, then ONE kernel that waits for the peers'
+            # gradients, averages them from peer memory (NVLink) and applies AdamW: no NCCL call on the step
+            pr = self._peer
+            n = self.p.numel()
+            off = (pr["k"] & 1) * pr["stride"]
+            pr["k"] += 1
+            g = pr["buf"][off:off + n]
+            self.engine.train_step(X, Y, cmd, None, None, None, g, self.t, self.lr, self.betas, self.eps,
+                                   self.weight_decay, fuse_adam=False, loss_mean=out)
+            self.engine.train_adamw_peer(self.p, self.m, self.v, pr["grad_ptrs"], off, pr["pad_ptrs"], pr["slot"], self.world,
+                                         pr["rank"], self.t, self.lr, self.betas, self.eps, self.weight_decay)
+        elif self.world > 1:
             import torch.distributed as dist
             self.engine.train_step(X, Y, cmd, None, None, None, self.g, self.t, self.lr, self.betas, self.eps,
                                    self.weight_decay, fuse_adam=False, loss_mean=out)
@@ -84,6 +101,34 @@ class FusedTrainer:
             self.engine.train_step(X, Y, cmd, self.p, self.m, self.v, None, self.t, self.lr, self.betas, self.eps,
                                    self.weight_decay, fuse_adam=True, loss_mean=out)
         return out
+
+    def _setup_peer_reduce(self):
+        """Symmetric gradient buffer (two halves, alternating per step) whose peer pointers every rank holds: the optimiser
+        kernel reads the other ranks' gradients through them.  Falls back to the NCCL all-reduce (with a note) when
+        symmetric memory cannot be set up -- e.g. the stand-in ranks of a single-GPU test."""
+        import torch.distributed as dist
+        if os.environ.get("LINNA_DP_NCCL") or not (dist.is_available() and dist.is_initialized()):
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.pg if self.pg is not None else dist.group.WORLD
+            if dist.get_world_size(group) != self.world:
+                return
+            n = self.p.numel()
+            stride = (n + 31) // 32 * 32                       # 128-byte aligned halves: 16-byte loads stay aligned
+            buf = symm.empty(2 * stride, dtype=torch.float32, device=self.device)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, group)
+            slot = int(hdl.signal_pad_size) // 4 - 64          # the last words of the pad: clear of torch's own barriers
+            if slot < 0 or self.world > 16:
+                return
+            hdl.barrier()
+            self._peer = dict(buf=buf, hdl=hdl, stride=stride, k=0, slot=slot, rank=int(hdl.rank),
+                              grad_ptrs=int(hdl.buffer_ptrs_dev), pad_ptrs=int(hdl.signal_pad_ptrs_dev))
+        except Exception as e:      # noqa: BLE001 -- any failure of the experimental API: keep the NCCL path
+            print("linna_b200: peer-memory gradient reduction unavailable (%s: %s); using the NCCL all-reduce" % (type(e).__name__, e),
+                  flush=True)
+            self._peer = None
 
     def kernel_path(self):
         """'tc' when the optimiser step runs on the tensor-core (tcgen05) training kernels, else 'ffma'."""

@@ -62,6 +62,7 @@ def task_train(out):
         gathered = [torch.zeros_like(w_dp) for _ in range(world)]
         dist.all_gather(gathered, w_dp)
         res[path + "_ranks_identical"] = bool(all(torch.equal(gathered[0], g) for g in gathered))
+        res[path + "_peer_reduce"] = tr._peer is not None      # gradient average read from peer memory inside the AdamW kernel
         if rank == 0:
             torch.manual_seed(3)
             model1 = N.ChtoModelv2(6, 8, None)

@@ -35,7 +35,8 @@ def _run(task, tmp_path, nproc=2):
 def test_data_parallel_step_equals_single_gpu_step(tmp_path):
     res = _run("train", tmp_path)
     for path in ("tc", "ffma"):
-        assert res[path + "_ranks_identical"]              # every rank holds the same weights after the all-reduce + AdamW
+        assert res[path + "_ranks_identical"]              # every rank holds the same weights after the reduction + AdamW
+        assert res[path + "_peer_reduce"], "the NVLink peer-memory reduction (linna_train_adamw_peer) was not used"
         r = res[path]
         assert r["kernel"] == path
         # mean of the shard gradients == gradient of the global batch up to float32 summation order; AdamW can turn a

@@ -199,8 +199,8 @@ def test_training_converges_and_dp_path_equals_fused():
         tr = FusedTrainer(model, xt, yt, loss_fn.auxileryfunction, 128, lr=2e-3)
         cmd = tr.chisq_md(X, Y)
         if not fused:
-            tr.world = 2          # forces the gradient-out path; all_reduce is skipped below
-            import torch.distributed as dist
+            tr.world = 2          # forces the gradient-out path; all_reduce is skipped below (the real 2-rank step, with the
+            import torch.distributed as dist      # gradient average read from peer memory: tests/test_gpu_multi.py)
             orig = dist.all_reduce
             dist.all_reduce = lambda *a, **k: None
         try:
