@@ -564,8 +564,7 @@ class HMCSampler:
             store.finalize()
         if world > 1:
             torch.distributed.barrier()
-            if rank != 0:
-                store = ChainStore(filename, self.transform)
+            store = ChainStore(filename, self.transform)     # every rank (rank 0 too) reads the finished chain the same way
         self.sampler = None
         return store
 
@@ -610,8 +609,7 @@ class HMCSampler:
             store.finalize()
         if world > 1:
             torch.distributed.barrier()
-            if rank != 0:
-                store = ChainStore(os.path.join(os.path.dirname(store.base), os.path.basename(store.base)), self.transform)
+            store = ChainStore(os.path.join(os.path.dirname(store.base), os.path.basename(store.base)), self.transform)
         return store
 
 
