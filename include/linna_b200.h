@@ -219,10 +219,13 @@ int linna_train_step(linna_model_t *m, const float *X, const float *Y, const flo
  * this rank's gradient is complete, waits for theirs, averages the `world` gradients in rank order straight from the
  * peers' memory and applies AdamW -- no NCCL call, replicas stay bit-identical.  peer_grad_ptrs / signal_pad_ptrs: DEVICE
  * arrays of `world` pointers (rank r's buffer base / signal pad); grad_offset: element offset of this step's gradient in
- * every buffer -- the caller alternates between two halves of the buffer from step to step; signal_slot: first 32-bit
- * word of the pad this model may use (`world` words).  All ranks must make the same sequence of calls. */
+ * every buffer -- the caller alternates between two halves of the buffer from step to step; avg_offset < 0: every
+ * rank reads all the peers' gradients itself (world <= 2), avg_offset >= 0: two-phase form -- element offset of a third
+ * region of every buffer in which each rank leaves the average of ITS slice of the vector, fetched by the others after a
+ * second barrier (remote reads ~2 x the vector whatever the world size); signal_slot: first 32-bit word of the pad this
+ * model may use (32 words).  All ranks must make the same sequence of calls. */
 int linna_train_adamw_peer(linna_model_t *m, float *params, float *adam_m, float *adam_v, const void *peer_grad_ptrs,
-                           int64_t grad_offset, const void *signal_pad_ptrs, int32_t signal_slot, int32_t world, int32_t rank,
+                           int64_t grad_offset, int64_t avg_offset, const void *signal_pad_ptrs, int32_t signal_slot, int32_t world, int32_t rank,
                            int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay, void *stream);
 /* Which kernels run linna_train_step / linna_train_chisq: 0 = automatic (the default: the tensor-core (tcgen05, bf16x3
  * split) kernels whenever the network shape is covered -- LINEAR / RES ops with a skip matrix, LINEAR last layer --, the

@@ -134,6 +134,7 @@ static void free_device(linna_model *m)
     if (m->prog_dev) cudaFree(m->prog_dev);
     if (m->arena) cudaFree(m->arena);
     if (m->masks) cudaFree(m->masks);
+    if (m->peer_ticket) { cudaFree(m->peer_ticket); m->peer_ticket = nullptr; }
     if (m->rm) cudaFree(m->rm);
     if (m->wg_layers_dev) cudaFree(m->wg_layers_dev);
     if (m->wg_tiles_dev) cudaFree(m->wg_tiles_dev);
@@ -1515,7 +1516,7 @@ int linna_train_adamw(linna_model_t *m, float *params, float *adam_m, float *ada
 }
 
 int linna_train_adamw_peer(linna_model_t *m, float *params, float *adam_m, float *adam_v, const void *peer_grad_ptrs, int64_t grad_offset,
-                           const void *signal_pad_ptrs, int32_t signal_slot, int32_t world, int32_t rank, int64_t step, float lr,
+                           int64_t avg_offset, const void *signal_pad_ptrs, int32_t signal_slot, int32_t world, int32_t rank, int64_t step, float lr,
                            float beta1, float beta2, float eps, float weight_decay, void *stream)
 {
     if (!m || !m->has_train) return fail(LINNA_ESTATE, "linna_train_setup has not been called");
@@ -1526,7 +1527,12 @@ int linna_train_adamw_peer(linna_model_t *m, float *params, float *adam_m, float
     if (m->have_last && m->last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, m->last_done, 0));
     AdamArgs a = adam_args(m, params, adam_m, adam_v, nullptr, step, lr, beta1, beta2, eps, weight_decay, 1);
     PeerReduce pr;
+    if (avg_offset >= 0 && !m->peer_ticket) {
+        CUDA_TRY(cudaMalloc(&m->peer_ticket, sizeof(int32_t)));
+        CUDA_TRY(cudaMemset(m->peer_ticket, 0, sizeof(int32_t)));
+    }
     pr.grads = reinterpret_cast<const float *const *>(peer_grad_ptrs), pr.offset = grad_offset;
+    pr.avg_offset = avg_offset, pr.ticket = m->peer_ticket;
     pr.pads = reinterpret_cast<uint32_t *const *>(signal_pad_ptrs), pr.slot = signal_slot;
     pr.world = world, pr.rank = rank, pr.token = ++m->peer_token;
     CUDA_TRY(launch_adamw_peer(a, (int)m->n_params, m->num_sms, pr, st));

@@ -135,6 +135,8 @@ struct PeerReduce {
     const float *const *grads;   // device array [world]
     uint32_t *const *pads;       // device array [world]
     int64_t offset;              // element offset of this step's gradient inside every rank's buffer
+    int64_t avg_offset;          // >= 0: two-phase reduction, element offset of the averaged-gradient region of every buffer
+    int32_t *ticket;             // device-local arrival counter of the two-phase form (zero between launches)
     int32_t slot;                // first 32-bit word of the signal pad used here (one word per source rank)
     int32_t world, rank;
     uint32_t token;              // sequence number of this reduction (monotonic, the same on every rank)

@@ -108,6 +108,7 @@ struct linna_model {
     int train_path = 0;            // 0 auto (tensor core when available), 1 FP32 FFMA kernels, 2 tensor core only
     int last_train_kernel = 0;     // 1 FFMA, 2 tensor core
     uint32_t peer_token = 0;       // sequence number of the peer-memory gradient reductions (linna_train_adamw_peer)
+    int32_t *peer_ticket = nullptr;   // arrival counter of the two-phase reduction
     // device state
     float *blob = nullptr;
     size_t blob_floats = 0;

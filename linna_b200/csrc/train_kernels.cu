@@ -119,45 +119,100 @@ __global__ void adamw_kernel(const AdamArgs ad, int n_params)
 // gradient is complete (a release store of the sequence number into the peer's signal pad -- the kernel is stream-ordered
 // behind the weight-gradient launch), (2) waits until every peer has said the same, (3) averages the world's gradients in
 // rank order -- straight from the peers' memory, 16-byte loads over NVLink -- and applies AdamW.  Every rank adds the
-// same numbers in the same order, so the replicas stay bit-identical.  The gradient buffers are double-buffered by the
-// caller: a peer may still read this rank's buffer of step t while the rank writes step t + 1, and it cannot still read it
-// at step t + 2 because this rank's barrier of step t + 1 needed that peer's signal, sent after its kernel of step t.
+// same numbers in the same order, so the replicas stay bit-identical.
+//   one phase (world <= 2): every rank reads all the peers' gradients itself.
+//   two phases (avg_offset >= 0): rank r averages only ITS slice of the vector (reduce-scatter by pull) into the `avg`
+//     region of its buffer; when the whole grid has done so (arrival counter) the last CTA tells the peers, and after that
+//     second barrier every rank applies AdamW to the full vector, fetching each slice's average from its owner: ~2 x the
+//     vector in remote reads whatever the world size, instead of (world - 1) x.
+// The gradient buffers are double-buffered by the caller: a peer may still read this rank's buffer of step t while the
+// rank writes step t + 1, and it cannot still read it at step t + 2 because this rank's barrier of step t + 1 needed that
+// peer's signal, sent after its kernel of step t; the same argument covers the `avg` region.
+__device__ __forceinline__ void peer_signal(const PeerReduce &pr, int slot)
+{
+    __threadfence_system();
+    uint32_t *dst = pr.pads[threadIdx.x] + slot + pr.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(pr.token) : "memory");
+}
+__device__ __forceinline__ void peer_wait(const PeerReduce &pr, int slot)
+{
+    const uint32_t *src = pr.pads[pr.rank] + slot + threadIdx.x;
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+        if ((int32_t)(v - pr.token) >= 0) break;              // a peer may already be one step ahead
+        if (clock64() - t0 > 20000000000LL) __trap();         // ~10 s: a rank is missing
+        __nanosleep(100);
+    }
+}
+
 __global__ void __launch_bounds__(256) adamw_peer_kernel(const AdamArgs ad, int n_params, const PeerReduce pr)
 {
     __shared__ const float *s_g[16];
-    if (blockIdx.x == 0 && (int)threadIdx.x < pr.world) {
-        __threadfence_system();
-        uint32_t *dst = pr.pads[threadIdx.x] + pr.slot + pr.rank;
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(pr.token) : "memory");
-    }
+    __shared__ int s_last;
+    if (blockIdx.x == 0 && (int)threadIdx.x < pr.world) peer_signal(pr, pr.slot);
     if ((int)threadIdx.x < pr.world) {
-        const uint32_t *src = pr.pads[pr.rank] + pr.slot + threadIdx.x;
-        const long long t0 = clock64();
-        for (;;) {
-            uint32_t v;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
-            if ((int32_t)(v - pr.token) >= 0) break;              // a peer may already be one step ahead
-            if (clock64() - t0 > 20000000000LL) __trap();         // ~10 s: a rank is missing
-            __nanosleep(100);
-        }
-        s_g[threadIdx.x] = pr.grads[threadIdx.x] + pr.offset;
+        peer_wait(pr, pr.slot);
+        s_g[threadIdx.x] = pr.grads[threadIdx.x];
     }
     __syncthreads();
     const float inv = 1.0f / (float)pr.world;
     const int n4 = n_params >> 2;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    if (pr.avg_offset < 0) {
+        for (int i = tid; i < n4; i += nthr) {
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < pr.world; ++r) {
+                const float4 v = __ldcg(reinterpret_cast<const float4 *>(s_g[r] + pr.offset) + i);
+                g.x += v.x, g.y += v.y, g.z += v.z, g.w += v.w;
+            }
+            adamw_apply(ad, 4 * i, g.x * inv), adamw_apply(ad, 4 * i + 1, g.y * inv);
+            adamw_apply(ad, 4 * i + 2, g.z * inv), adamw_apply(ad, 4 * i + 3, g.w * inv);
+        }
+        for (int i = 4 * n4 + tid; i < n_params; i += nthr) {
+            float g = 0.f;
+            for (int r = 0; r < pr.world; ++r) g += __ldcg(s_g[r] + pr.offset + i);
+            adamw_apply(ad, i, g * inv);
+        }
+        return;
+    }
+    // ---- phase 1: this rank's slice, averaged into its own `avg` region (quads of 4 floats; the tail quad is padded)
+    const int nq = (n_params + 3) >> 2;                               // quads of the (padded) vector
+    const int qchunk = (nq + pr.world - 1) / pr.world;                // quads per rank
+    const int q0 = pr.rank * qchunk, q1 = min(nq, q0 + qchunk);
+    float4 *avg_mine = reinterpret_cast<float4 *>(const_cast<float *>(s_g[pr.rank]) + pr.avg_offset);
+    for (int i = q0 + tid; i < q1; i += nthr) {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int r = 0; r < pr.world; ++r) {
-            const float4 v = __ldcg(reinterpret_cast<const float4 *>(s_g[r]) + i);
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(s_g[r] + pr.offset) + i);
             g.x += v.x, g.y += v.y, g.z += v.z, g.w += v.w;
         }
-        adamw_apply(ad, 4 * i, g.x * inv), adamw_apply(ad, 4 * i + 1, g.y * inv);
-        adamw_apply(ad, 4 * i + 2, g.z * inv), adamw_apply(ad, 4 * i + 3, g.w * inv);
+        avg_mine[i] = make_float4(g.x * inv, g.y * inv, g.z * inv, g.w * inv);
     }
-    for (int i = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; i < n_params; i += gridDim.x * blockDim.x) {
-        float g = 0.f;
-        for (int r = 0; r < pr.world; ++r) g += __ldcg(s_g[r] + i);
-        adamw_apply(ad, i, g * inv);
+    // ---- the whole grid has written its part -> tell the peers; then wait for theirs
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(pr.ticket, 1);
+        s_last = t == (int)gridDim.x - 1;
+        if (s_last) *pr.ticket = 0;      // ready for the next launch (stream-ordered)
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (s_last && (int)threadIdx.x < pr.world) peer_signal(pr, pr.slot + 16);
+    if ((int)threadIdx.x < pr.world) peer_wait(pr, pr.slot + 16);
+    __syncthreads();
+    // ---- phase 2: AdamW on the full vector, every slice's average from its owner
+    for (int i = tid; i < nq; i += nthr) {
+        const int owner = i / qchunk;
+        const float4 g = __ldcg(reinterpret_cast<const float4 *>(s_g[owner] + pr.avg_offset) + i);
+        if (4 * i + 3 < n_params) {
+            adamw_apply(ad, 4 * i, g.x), adamw_apply(ad, 4 * i + 1, g.y), adamw_apply(ad, 4 * i + 2, g.z), adamw_apply(ad, 4 * i + 3, g.w);
+        } else {
+            const float gv[4] = {g.x, g.y, g.z, g.w};
+            for (int e = 0; e < 4 && 4 * i + e < n_params; ++e) adamw_apply(ad, 4 * i + e, gv[e]);
+        }
     }
 }
 
@@ -217,7 +272,9 @@ cudaError_t launch_adamw(const AdamArgs &ad, int n_params, int num_sms, cudaStre
 cudaError_t launch_adamw_peer(const AdamArgs &ad, int n_params, int num_sms, const PeerReduce &pr, cudaStream_t stream)
 {
     int blocks = (n_params / 4 + 255) / 256;
-    if (blocks > num_sms * 4) blocks = num_sms * 4;
+    // the two-phase form holds a grid-wide barrier: every CTA must be resident (256 threads, few registers: 2 per SM is safe)
+    const int cap = pr.avg_offset >= 0 ? num_sms * 2 : num_sms * 4;
+    if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     adamw_peer_kernel<<<blocks, 256, 0, stream>>>(ad, n_params, pr);
     return cudaGetLastError();

@@ -108,7 +108,7 @@ def load_library():
     lib.linna_train_commit.argtypes = [vp, vp]
     lib.linna_loss_terms.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.linna_train_set_path.argtypes = [vp, i32]
-    lib.linna_train_adamw_peer.argtypes = [vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i64, f32, f32, f32, f32, f32, vp]
+    lib.linna_train_adamw_peer.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp, i32, i32, i32, i64, f32, f32, f32, f32, f32, vp]
     lib.linna_train_last_kernel.argtypes = [vp]
     if lib.linna_abi_version() != 1:
         raise LinnaError("linna_b200: ABI version mismatch")
@@ -557,13 +557,13 @@ class Engine:
                                                   self._stream()))
         return loss_mean, loss_rows
 
-    def train_adamw_peer(self, params, adam_m, adam_v, peer_grad_ptrs, grad_offset, signal_pad_ptrs, signal_slot, world, rank, step,
-                         lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4):
+    def train_adamw_peer(self, params, adam_m, adam_v, peer_grad_ptrs, grad_offset, avg_offset, signal_pad_ptrs, signal_slot, world,
+                         rank, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4):
         """AdamW on the average of the ranks' gradients, read from the peers' memory inside the kernel (linna_train_adamw_peer)."""
         import torch
         with torch.cuda.device(self.device):
             self._check(self.lib.linna_train_adamw_peer(self.handle, params.data_ptr(), adam_m.data_ptr(), adam_v.data_ptr(),
-                                                        int(peer_grad_ptrs), int(grad_offset), int(signal_pad_ptrs), int(signal_slot),
+                                                        int(peer_grad_ptrs), int(grad_offset), int(avg_offset), int(signal_pad_ptrs), int(signal_slot),
                                                         int(world), int(rank), int(step), float(lr), float(betas[0]), float(betas[1]),
                                                         float(eps), float(weight_decay), self._stream()))
 

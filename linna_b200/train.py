@@ -88,8 +88,8 @@ class FusedTrainer:
             g = pr["buf"][off:off + n]
             self.engine.train_step(X, Y, cmd, None, None, None, g, self.t, self.lr, self.betas, self.eps,
                                    self.weight_decay, fuse_adam=False, loss_mean=out)
-            self.engine.train_adamw_peer(self.p, self.m, self.v, pr["grad_ptrs"], off, pr["pad_ptrs"], pr["slot"], self.world,
-                                         pr["rank"], self.t, self.lr, self.betas, self.eps, self.weight_decay)
+            self.engine.train_adamw_peer(self.p, self.m, self.v, pr["grad_ptrs"], off, pr["avg"], pr["pad_ptrs"], pr["slot"],
+                                         self.world, pr["rank"], self.t, self.lr, self.betas, self.eps, self.weight_decay)
         elif self.world > 1:
             import torch.distributed as dist
             self.engine.train_step(X, Y, cmd, None, None, None, self.g, self.t, self.lr, self.betas, self.eps,
@@ -116,14 +116,15 @@ class FusedTrainer:
                 return
             n = self.p.numel()
             stride = (n + 31) // 32 * 32                       # 128-byte aligned halves: 16-byte loads stay aligned
-            buf = symm.empty(2 * stride, dtype=torch.float32, device=self.device)
+            buf = symm.empty(3 * stride, dtype=torch.float32, device=self.device)   # two gradient halves + the averaged slices
             buf.zero_()
             hdl = symm.rendezvous(buf, group)
             slot = int(hdl.signal_pad_size) // 4 - 64          # the last words of the pad: clear of torch's own barriers
             if slot < 0 or self.world > 16:
                 return
             hdl.barrier()
-            self._peer = dict(buf=buf, hdl=hdl, stride=stride, k=0, slot=slot, rank=int(hdl.rank),
+            two_phase = (self.world > 2 or bool(os.environ.get("LINNA_DP_TWO_PHASE"))) and not os.environ.get("LINNA_DP_ONE_PHASE")
+            self._peer = dict(buf=buf, hdl=hdl, stride=stride, k=0, slot=slot, rank=int(hdl.rank), avg=2 * stride if two_phase else -1,
                               grad_ptrs=int(hdl.buffer_ptrs_dev), pad_ptrs=int(hdl.signal_pad_ptrs_dev))
         except Exception as e:      # noqa: BLE001 -- any failure of the experimental API: keep the NCCL path
             print("linna_b200: peer-memory gradient reduction unavailable (%s: %s); using the NCCL all-reduce" % (type(e).__name__, e),
