@@ -147,7 +147,7 @@ int linna_lnp_grad_host(linna_model_t *m, const float *u, int64_t n, float *lnp,
 /* Introspection used by bench.py / tests. */
 int linna_model_info(const linna_model_t *m, int32_t *n_in, int32_t *n_out, int64_t *n_params, int32_t *num_sms);
 /* Kernel selection for linna_lnp / linna_lnp_grad / linna_predict: 0 = automatic (the default: tensor-core kernel
- * for n >= tc_min_rows, default 256; below that the small-batch cluster kernel, which splits every layer over the
+ * -- lnP, lnP + gradient and predict programs -- for n >= tc_min_rows, default 256; below that the small-batch cluster kernel, which splits every layer over the
  * CTAs of a thread-block cluster and keeps the activations in distributed shared memory; the FP32 FFMA kernel
  * wherever neither applies), 1 = FP32 FFMA kernel only, 2 = tensor-core (tcgen05, split-fp16) kernel only,
  * 3 = cluster kernel only.  tc_min_rows <= 0 keeps the current threshold. */

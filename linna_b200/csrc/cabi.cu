@@ -33,6 +33,10 @@ cudaError_t tc_launch_lnp(const linna_model *m, TcContext *t, const float *u, in
 cudaError_t tc_launch_grad(const linna_model *m, TcContext *t, const float *u, int64_t n, float *lnp, float *grad,
                            cudaStream_t stream);
 bool tc_has_grad(const TcContext *t);
+bool tc_has_lnp(const TcContext *t);
+bool tc_has_predict(const TcContext *t);
+cudaError_t tc_launch_predict(const linna_model *m, TcContext *t, const float *theta, int64_t n, float *out, int out_kind,
+                              cudaStream_t stream);
 void tc_fix_buffers(TcContext *t, const int32_t **rows, const int32_t **count, int32_t **next_count);
 void tc_launch_done(TcContext *t);
 int tc_debug_read(TcContext *t, long long *out, int max_ctas);
@@ -1026,11 +1030,11 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
     }
     // Large lnP / lnP+gradient batches go to the tensor-core (tcgen05) kernel; everything else stays on the
     // FP32 FFMA kernel.
-    if ((pk == PROG_LNP || pk == PROG_GRAD) && !proto && m->path == 2 && (m->tc_failed || m->has_extra))
+    const bool tc_prog = pk == PROG_LNP || pk == PROG_GRAD || pk == PROG_PREDICT;
+    if (tc_prog && !proto && m->path == 2 && (m->tc_failed || m->has_extra))
         return fail(LINNA_EINVAL, "tensor-core path unavailable: %s",
                     m->has_extra ? "extra linear branch not supported on the tensor-core path" : m->tc_why.c_str());
-    if ((pk == PROG_LNP || pk == PROG_GRAD) && !proto && m->path != 1 && !m->has_extra && !m->tc_failed &&
-        (m->path == 2 || n >= m->tc_min_rows)) {
+    if (tc_prog && !proto && m->path != 1 && m->path != 3 && !m->has_extra && !m->tc_failed && (m->path == 2 || n >= m->tc_min_rows)) {
         if (!m->tc) {
             std::string why;
             m->tc = tc_build(m, why);
@@ -1043,11 +1047,15 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
                                 "FP32 FFMA kernel\n", why.c_str());
             }
         }
-        if (m->tc && pk == PROG_GRAD && !tc_has_grad(m->tc)) {
-            if (m->path == 2) return fail(LINNA_EINVAL, "tensor-core gradient path needs the folded likelihood tail");
+        const bool have = m->tc && (pk == PROG_PREDICT ? tc_has_predict(m->tc) : pk == PROG_GRAD ? tc_has_grad(m->tc) : tc_has_lnp(m->tc));
+        if (m->tc && !have) {
+            if (m->path == 2)
+                return fail(LINNA_EINVAL, pk == PROG_GRAD ? "tensor-core gradient path needs the folded likelihood tail"
+                                                          : "tensor-core path needs the Cholesky form of the quadratic");
         } else if (m->tc) {
             if (pk == PROG_LNP) CUDA_TRY(tc_launch_lnp(m, m->tc, in, n, lnp, stream));
-            else CUDA_TRY(tc_launch_grad(m, m->tc, in, n, lnp, grad, stream));
+            else if (pk == PROG_GRAD) CUDA_TRY(tc_launch_grad(m, m->tc, in, n, lnp, grad, stream));
+            else CUDA_TRY(tc_launch_predict(m, m->tc, in, n, out_vec, out_kind, stream));
             g_launches.fetch_add(1);
             {
                 // Fix-up: rows that came out NaN on the tensor-core path (an activation beyond the fp16 range) are redone
@@ -1056,7 +1064,8 @@ static int run(linna_model *m, int pk, const float *in, int64_t n, float *out_ve
                 KernelArgs a;
                 memset(&a, 0, sizeof a);
                 a.prog = m->prog_dev + pk, a.c = m->consts, a.in = in, a.lnp = lnp, a.grad = grad;
-                a.arena = m->arena, a.masks = m->masks, a.n = n;
+                a.out_vec = out_vec, a.out_kind = out_kind, a.input_theta = input_theta;
+                a.arena = m->arena, a.masks = m->masks, a.n = pk == PROG_PREDICT ? 2 * n + 1024 : n;
                 tc_fix_buffers(m->tc, &a.row_index, &a.n_dev, &a.zero_me);
                 const int grid = (int)std::min<int64_t>((n + 7) / 8, std::min(m->num_sms, 32));
                 CUDA_TRY(launch_fused_ffma(a, 1, grid, stream));

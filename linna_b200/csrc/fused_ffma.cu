@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, RG == 1 ? 1 : 2) fused_ffma_kernel(c
                                         float o = args.out_kind == LINNA_OUT_YHAT ? v[i]
                                                   : args.out_kind == LINNA_OUT_Y  ? y[i]
                                                                                   : y[i] * sg;
-                                        args.out_vec[(row0 + r) * n_out + cidx] = o;
+                                        args.out_vec[grow(r) * n_out + cidx] = o;
                                     }
                                 }
                             }

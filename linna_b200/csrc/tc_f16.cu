@@ -78,11 +78,11 @@ constexpr int TF_MAX_STEPS = 48;
 // epilogue group 0 [40, 64), and of that group's waits for accumulators [64, 88) and chunk epilogues [88, 112)
 constexpr int TF_DBG_STRIDE = 128;
 
-enum TfEpi : int32_t { TF_ACT = 0, TF_HEAD = 1, TF_CHI2 = 2, TF_BWD = 3, TF_GRADOUT = 4 };
+enum TfEpi : int32_t { TF_ACT = 0, TF_HEAD = 1, TF_CHI2 = 2, TF_BWD = 3, TF_GRADOUT = 4, TF_PREDICT = 5 };
 enum TfFlags : int32_t { TFF_RELU = 1, TFF_SAVE_MASK = 2, TFF_APPLY_MASK = 4, TFF_TRI = 8,
                          TFF_LAST_USE0 = 16, TFF_LAST_USE1 = 32,     // phase 0 / 1 is the last reader of its activation slot
                          TFF_ROWSCALE = 64 };   // first backward step: apply the per-walker power-of-two gradient scale
-enum TfVariant : int32_t { TFV_ACT = 0, TFV_ACT_SAVE, TFV_CHI2, TFV_CHI2_STORE, TFV_BWD, TFV_HEAD, TFV_HEAD_EXP, TFV_GRADOUT };
+enum TfVariant : int32_t { TFV_ACT = 0, TFV_ACT_SAVE, TFV_CHI2, TFV_CHI2_STORE, TFV_BWD, TFV_HEAD, TFV_HEAD_EXP, TFV_GRADOUT, TFV_PREDICT };
 
 struct TfStep {
     int32_t nphase;
@@ -133,6 +133,10 @@ struct TfArgs {
     int32_t *fix_count;
     int32_t *fix_rows;
     int32_t fix_cap;
+    // Predictor.predict (PREDICT program): physical parameters in (no prior map), the selected vector out
+    float *out_vec;           // [n][n_out]
+    int32_t out_kind;         // LINNA_OUT_*
+    int32_t input_theta;
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -806,7 +810,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                             if (i < n_in && valid) {
                                 const float uu = __ldg(u + i);
                                 lnprior = fmaf(uu, uu, lnprior);
-                                float th = tf_prior_map(uu, c.prior_kind[i], c.prior_scale[i], c.prior_shift[i]);
+                                float th = args.input_theta ? uu : tf_prior_map(uu, c.prior_kind[i], c.prior_scale[i], c.prior_shift[i]);
                                 if (c.log10_flag && c.log10_flag[i]) th = log10f(th);
                                 xh = (th - c.x_mean[i]) / c.x_std[i];
                             }
@@ -896,6 +900,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) tc_f1
                     case TFV_BWD: tf_chunk_epilogue<false, false, false, false, true, false, true>(racc, st, c0, mword, bias_s, x); break;
                     case TFV_HEAD: tf_chunk_epilogue<true, true, false, false, false, false, true>(racc, st, c0, mword, bias_s, x); break;
                     case TFV_HEAD_EXP: tf_chunk_epilogue<true, true, true, false, false, false, true>(racc, st, c0, mword, bias_s, x); break;
+                    case TFV_PREDICT: {
+                        // yhat = W s + b ; y = yhat y_std + y_mean (exp) ; m = y sigma (linna/util.py:532-542, :457-458): the
+                        // selected vector goes straight to global memory, 128 contiguous floats of this walker's row.
+                        // (Static indices only: one dynamic index would move all 128 accumulators to local memory.)
+                        bool bad = false;
+                        if (valid) {
+                            float *orow = args.out_vec + grow * c.n_out + c0;
+                            const int nc = st.N - c0;   // columns of this group that exist (may exceed 128)
+                            const bool vec4 = (c.n_out & 3) == 0;
+                            const int okind = args.out_kind;
+#pragma unroll
+                            for (int g4 = 0; g4 < 32; ++g4) {
+                                if (4 * g4 < nc) {
+                                    float v[4];
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const int j = 4 * g4 + e;
+                                        float t = fmaf(racc[j], st.inv_scale, bias_s[j]);
+                                        t = max_nan(t, st.clampv);
+                                        if (okind != LINNA_OUT_YHAT && j < nc) {
+                                            t = fmaf(t, __ldg(c.y_std + c0 + j), __ldg(c.y_mean + c0 + j));   // util.py:542
+                                            if (c.ypositive) t = expf(t);                                     // util.py:540
+                                            if (okind == LINNA_OUT_M && c.sigma) t *= __ldg(c.sigma + c0 + j);  // util.py:458
+                                        }
+                                        bad |= (t != t) && j < nc;
+                                        v[e] = t;
+                                    }
+                                    if (vec4 && 4 * g4 + 3 < nc) {
+                                        *reinterpret_cast<float4 *>(orow + 4 * g4) = make_float4(v[0], v[1], v[2], v[3]);
+                                    } else {
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e)
+                                            if (4 * g4 + e < nc) orow[4 * g4 + e] = v[e];
+                                    }
+                                }
+                            }
+                        }
+                        if (bad && args.fix_rows) {   // an activation beyond the fp16 range: the FP32 kernel redoes this row
+                            const int k = atomicAdd(args.fix_count, 1);
+                            if (k < args.fix_cap) args.fix_rows[k] = (int32_t)grow;
+                        }
+                    } break;
                     default: {
                         // TFV_GRADOUT (n_in <= 64: group 0 only): chain through xhat = (theta' - mean)/std,
                         // theta' = log10(theta), theta = prior(u).  The accumulators go through this thread's own
@@ -1000,7 +1046,7 @@ struct TcContext {
     int32_t *fix_rows = nullptr;      // [fix_cap]
     int64_t fix_cap = 0;
     uint64_t launches = 0;
-    bool has_grad = false;
+    bool has_lnp = false, has_grad = false, has_predict = false;
     int grid = 0;
     std::string error;
 };
@@ -1096,8 +1142,8 @@ struct Packer {
 TcContext *tc_build(const linna_model *m, std::string &why)
 {
     if (m->has_extra) { why = "extra linear branch not supported on the tensor-core path"; return nullptr; }
-    if (!m->has_like) { why = "likelihood not set"; return nullptr; }
-    if (m->quad_kind != LINNA_QUAD_CHOL) { why = "tensor-core path needs the Cholesky form of the quadratic"; return nullptr; }
+    // the likelihood programs need the likelihood constants in Cholesky form; the predict program needs neither
+    const bool like_ok = m->has_like && m->quad_kind == LINNA_QUAD_CHOL;
     if (m->n_in > 64) { why = "tensor-core path supports at most 64 input parameters"; return nullptr; }
     EncodeTiledFn encode = nullptr;
     {
@@ -1112,7 +1158,7 @@ TcContext *tc_build(const linna_model *m, std::string &why)
     }
     const int n_out = m->n_out;
     const int nops = (int)m->ops.size();
-    const bool fold = linna_can_fold(m);
+    const bool fold = like_ok && linna_can_fold(m);
     std::vector<float> Af, cf;
     if (fold) linna_fold_tail(m, Af, cf);
     for (const OpHost &op : m->ops)
@@ -1129,21 +1175,23 @@ TcContext *tc_build(const linna_model *m, std::string &why)
     struct BiasRef { int prog, step, what; size_t off; };   // what: 0 bias, 1 vscale, 2 sub
     std::vector<BiasRef> bias_refs;
     std::vector<float> sigL;   // (diag(sigma) L) for the unfolded chi^2
-    if (!fold) {
+    if (!fold && like_ok) {
         sigL.resize((size_t)n_out * n_out);
         for (int k = 0; k < n_out; ++k)
             for (int n = 0; n < n_out; ++n) sigL[(size_t)k * n_out + n] = m->sigma[k] * m->quad[(size_t)k * n_out + n];
     }
 
-    TfProgram pgs[2];
+    TfProgram pgs[3];   // [0] lnP, [1] lnP + gradient, [2] predict
     const int seg_kc = tc_seg_kc();
     int mask_words_total = 0;
     bool has_grad = fold;   // the backward program is built on the folded tail only
-    for (int pk = 0; pk < 2; ++pk) {
+    for (int pk = 0; pk < 3; ++pk) {
         TfProgram &pg = pgs[pk];
         memset(&pg, 0, sizeof pg);
-        if (pk == 1 && !has_grad) break;
-        const bool grad = pk == 1;
+        if (pk == 1 && !has_grad) continue;
+        if (pk < 2 && !like_ok) continue;
+        const bool grad = pk == 1, predict = pk == 2;
+        const bool fold_here = fold && !predict;
         int ns = 0, pubs[2] = {1, 0};   // the prologue publishes one chunk of column group 0
         int slot_pub[NSLOT][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
         int mask_words = 0;
@@ -1197,7 +1245,7 @@ TcContext *tc_build(const linna_model *m, std::string &why)
         for (int i = 0; i < nops; ++i) {
             const OpHost &op = m->ops[i];
             const bool last = i + 1 == nops;
-            if (last && fold) break;
+            if (last && fold_here) break;
             if (op.kind == LINNA_OP_LINEAR) {
                 TfStep &s = new_step();
                 MatSrc ms{op.w.data(), op.out, op.in, false, 1.f};
@@ -1208,11 +1256,11 @@ TcContext *tc_build(const linna_model *m, std::string &why)
                     s.flags |= TFF_RELU;
                     if (grad) s.flags |= TFF_SAVE_MASK, s.mask_word = mask_y[i] = new_mask(op.out);
                 }
-                s.epi = last ? TF_HEAD : TF_ACT;
-                set_dst(s, other(cur));
-                if (last) set_head(op.b, 1.f, op.out, s.inv_scale);
+                s.epi = last ? (predict ? TF_PREDICT : TF_HEAD) : TF_ACT;
+                if (!(last && predict)) set_dst(s, other(cur));
+                if (last && !predict) set_head(op.b, 1.f, op.out, s.inv_scale);
                 else set_bias(op.b, 1.f, op.out);
-                cur = s.dst;
+                if (!(last && predict)) cur = s.dst;
             } else {
                 TfStep &hs = new_step();
                 MatSrc m1{op.w.data(), op.mid, op.in, false, 1.f};
@@ -1243,7 +1291,9 @@ TcContext *tc_build(const linna_model *m, std::string &why)
             const OpHost &pv = m->ops[i - 1];
             return (pv.kind == LINNA_OP_RES || pv.act == LINNA_ACT_RELU) ? mask_y[i - 1] : -1;
         };
-        if (fold) {
+        if (predict) {
+            // nothing after the last layer: its epilogue writes the selected vector
+        } else if (fold) {
             // r = Af s + cf ; chi^2 = |r|^2
             const int K = m->ops.back().in, sbuf = cur;
             TfStep &q = new_step();
@@ -1327,6 +1377,7 @@ TcContext *tc_build(const linna_model *m, std::string &why)
             case TF_HEAD: s.variant = m->ypositive ? TFV_HEAD_EXP : TFV_HEAD; break;
             case TF_CHI2: s.variant = s.dst >= 0 ? TFV_CHI2_STORE : TFV_CHI2; break;
             case TF_BWD: s.variant = TFV_BWD; break;
+            case TF_PREDICT: s.variant = TFV_PREDICT; break;
             default: s.variant = TFV_GRADOUT; break;
             }
         }
@@ -1337,7 +1388,7 @@ TcContext *tc_build(const linna_model *m, std::string &why)
     int slot_col[NSLOT], ncol = 0;
     for (int s = 0; s < NSLOT; ++s) slot_col[s] = ncol, ncol += slot_w[s];
     const int ld = 2 * ncol;   // halves per arena row: every activation column is a (hi, lo) pair
-    for (int pk = 0; pk < 2; ++pk) {
+    for (int pk = 0; pk < 3; ++pk) {
         TfProgram &pg = pgs[pk];
         pg.in_col = 2 * slot_col[SLOT_X], pg.mask_words = std::max(mask_words_total, 4);
         for (int i = 0; i < pg.n_steps; ++i) {
@@ -1351,7 +1402,8 @@ TcContext *tc_build(const linna_model *m, std::string &why)
     auto bail = [&](const std::string &msg) { why = msg; tc_destroy(t); return (TcContext *)nullptr; };
     t->grid = m->num_sms & ~1;   // whole CTA pairs
     t->ld = ld;
-    t->has_grad = has_grad;
+    t->has_lnp = like_ok, t->has_grad = like_ok && has_grad;
+    t->has_predict = m->ops.back().kind == LINNA_OP_LINEAR && pgs[2].n_steps > 0;
     if (cudaMalloc(&t->wblob, P.w.size() * sizeof(__half)) != cudaSuccess) return bail("cudaMalloc weights");
     if (cudaMemcpy(t->wblob, P.w.data(), P.w.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) return bail("upload");
     if (cudaMalloc(&t->fblob, std::max<size_t>(P.f.size(), 64) * sizeof(float)) != cudaSuccess) return bail("cudaMalloc biases");
@@ -1369,7 +1421,7 @@ TcContext *tc_build(const linna_model *m, std::string &why)
     // per weight matrix: a 128-row box for full chunks and a box as tall as one CTA's share of the last chunk
     auto tail_rows_of = [](int N) { const int last = N - (N - 1) / TF_NC * TF_NC; return ((last + 31) & ~31) / 2; };
     std::vector<CUtensorMap> maps(2 + 2 * P.mats.size());
-    for (int pk = 0; pk < 2; ++pk)
+    for (int pk = 0; pk < 3; ++pk)
         for (int i = 0; i < pgs[pk].n_steps; ++i) {
             TfStep &s = pgs[pk].steps[i];
             s.tail_rows = tail_rows_of(s.N);
@@ -1402,8 +1454,8 @@ TcContext *tc_build(const linna_model *m, std::string &why)
     }
     if (cudaMalloc(&t->maps_dev, maps.size() * sizeof(CUtensorMap)) != cudaSuccess) return bail("cudaMalloc maps");
     cudaMemcpy(t->maps_dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
-    if (cudaMalloc(&t->prog_dev, 2 * sizeof(TfProgram)) != cudaSuccess) return bail("cudaMalloc prog");
-    cudaMemcpy(t->prog_dev, pgs, 2 * sizeof(TfProgram), cudaMemcpyHostToDevice);
+    if (cudaMalloc(&t->prog_dev, 3 * sizeof(TfProgram)) != cudaSuccess) return bail("cudaMalloc prog");
+    cudaMemcpy(t->prog_dev, pgs, 3 * sizeof(TfProgram), cudaMemcpyHostToDevice);
     if (cudaMalloc(&t->err_dev, sizeof(int)) != cudaSuccess) return bail("cudaMalloc err");
     cudaMemset(t->err_dev, 0, sizeof(int));
     if (cudaMalloc(&t->fix_count, 2 * sizeof(int32_t)) != cudaSuccess) return bail("cudaMalloc fix_count");
@@ -1420,6 +1472,8 @@ TcContext *tc_build(const linna_model *m, std::string &why)
 }
 
 bool tc_has_grad(const TcContext *t) { return t && t->has_grad; }
+bool tc_has_lnp(const TcContext *t) { return t && t->has_lnp; }
+bool tc_has_predict(const TcContext *t) { return t && t->has_predict; }
 
 // LINNA_TC_DEBUG: per-CTA cycle counters of the last launch -> host ([grid][8]); returns the grid size
 int tc_debug_read(TcContext *t, long long *out, int max_ctas)
@@ -1439,12 +1493,12 @@ void tc_fix_buffers(TcContext *t, const int32_t **rows, const int32_t **count, i
 }
 
 static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const float *u, int64_t n, float *lnp, float *grad,
-                             cudaStream_t stream)
+                             cudaStream_t stream, float *out_vec = nullptr, int out_kind = 0)
 {
     if (t->fix_cap < n) {   // stream-ordered with every launch that used the old list (one model, chained launches)
         if (t->fix_rows) cudaFreeAsync(t->fix_rows, stream);
         t->fix_rows = nullptr, t->fix_cap = 0;
-        const int64_t want = n + n / 4 + 1024;
+        const int64_t want = 2 * n + 1024;   // the predict program may list a row once per column group
         cudaError_t e = cudaMallocAsync(&t->fix_rows, (size_t)want * sizeof(int32_t), stream);
         if (e != cudaSuccess) return e;
         t->fix_cap = want;
@@ -1455,6 +1509,7 @@ static cudaError_t tc_launch(const linna_model *m, TcContext *t, int pk, const f
     a.fix_cap = (int32_t)std::min<int64_t>(t->fix_cap, 0x7fffffff);
     a.prog = t->prog_dev + pk, a.maps = t->maps_dev, a.c = m->consts;
     a.in = u, a.lnp = lnp, a.grad = grad, a.masks = t->masks, a.n = n, a.err = t->err_dev, a.dbg = t->dbg_dev;
+    a.out_vec = out_vec, a.out_kind = out_kind, a.input_theta = pk == 2 ? 1 : 0;
     const int64_t pairs = (n + 2 * TF_M - 1) / (2 * TF_M);
     // One cluster of two CTAs per TWO walker pairs ("slots"), interleaved layer by layer: the layer-to-layer
     // dependency bubble of one pair is filled with the other pair's MMAs (measured +4% on lnP, +1% on lnP+grad at
@@ -1482,6 +1537,13 @@ cudaError_t tc_launch_grad(const linna_model *m, TcContext *t, const float *u, i
                            cudaStream_t stream)
 {
     return tc_launch(m, t, 1, u, n, lnp, grad, stream);
+}
+
+// Predictor.predict: physical parameters in, the selected vector (yhat | y | m) out
+cudaError_t tc_launch_predict(const linna_model *m, TcContext *t, const float *theta, int64_t n, float *out, int out_kind,
+                              cudaStream_t stream)
+{
+    return tc_launch(m, t, 2, theta, n, nullptr, nullptr, stream, out, out_kind);
 }
 
 }  // namespace linna

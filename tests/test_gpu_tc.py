@@ -23,7 +23,7 @@ torch = pytest.importorskip("torch")
 
 from linna_b200 import arch, engine, synthetic
 from oracle.oracle import Oracle
-from tests.helpers import fixture_problem, lnp_tol, load_golden, problem_from_golden
+from tests.helpers import fixture_problem, lnp_tol, load_golden, problem_from_golden, rel_inf
 
 pytestmark = pytest.mark.gpu
 
@@ -278,3 +278,53 @@ def test_tc_segment_lengths_and_slots(monkeypatch, seg_kc, slots):
         rel = np.max(np.abs(grad[sl] - g["f64_grad"]), axis=1) / np.max(np.abs(g["f64_grad"]), axis=1)
         assert rel.max() < 2e-4, rel.max()
     assert np.array_equal(lnp[:n], lnp[-n:])           # batch position does not matter
+
+
+@pytest.mark.parametrize("name", ["c3s", "c4s", "ypos", "c1", "simple"])
+def test_tc_predict_data_vectors(name):
+    """Predictor.predict on the tensor-core kernel (PREDICT program: the unfolded last layer, the inverse output transform
+    in its epilogue): north star's 1e-5 relative bar on the predicted data vectors, against the reference's own float32
+    outputs -- the bar the tensor-core path could not be held to while it only produced lnP."""
+    g = load_golden(name)
+    p = problem_from_golden(g)
+    e = engine.engine_from_problem(p)
+    theta = g["f32_theta"]
+    rep = int(np.ceil(600 / len(theta)))
+    big = np.ascontiguousarray(np.tile(theta, (rep, 1)), np.float32)        # >= 256 rows: the tensor-core path
+    for kind, want in ((engine.LINNA_OUT_M, g["f32_m"]), (engine.LINNA_OUT_Y, g["f32_y"]), (engine.LINNA_OUT_YHAT, g["f32_yhat"])):
+        e.set_path("tc")
+        got = e.predict(torch.from_numpy(big).cuda(), kind).cpu().numpy()
+        assert e.last_kernel() == "tc"
+        assert got.shape == (len(big), p.n_out)
+        assert np.array_equal(got[:len(theta)], got[len(theta):2 * len(theta)])      # a row does not depend on its position
+        assert rel_inf(got[:len(theta)], want) < 1e-5, (name, kind, rel_inf(got[:len(theta)], want))
+        e.set_path("ffma")
+        ref = e.predict(torch.from_numpy(big).cuda(), kind).cpu().numpy()
+        assert rel_inf(got, ref) < 1e-5
+    # auto mode: large predict batches take the tensor-core kernel, and a model without likelihood constants can use it too
+    e.set_path("auto")
+    e.predict(torch.from_numpy(big).cuda(), engine.LINNA_OUT_M)
+    assert e.last_kernel() == "tc"
+    e2 = engine.engine_from_problem(p, with_likelihood=False)
+    got2 = e2.predict(torch.from_numpy(big).cuda(), engine.LINNA_OUT_M).cpu().numpy()
+    assert e2.last_kernel() == "tc" and rel_inf(got2[:len(theta)], g["f32_m"]) < 1e-5
+
+
+def test_tc_predict_overflow_rows_are_fixed_up():
+    """A row whose activations leave the fp16 range comes out of the tensor-core predict program as NaN and is recomputed
+    by the FP32 kernel in the fix-up launch: the caller sees the reference's finite numbers."""
+    g = load_golden("c3s")
+    p = problem_from_golden(g)
+    e = engine.engine_from_problem(p)
+    theta = np.tile(g["f32_theta"], (40, 1)).astype(np.float32)[:300]
+    theta[7] *= 4e4          # |xhat| ~ 1e5: the first layer overflows fp16
+    theta[123] *= -3e4
+    e.set_path("ffma")
+    ref = e.predict(torch.from_numpy(theta).cuda(), engine.LINNA_OUT_M).cpu().numpy()
+    e.set_path("tc")
+    got = e.predict(torch.from_numpy(theta).cuda(), engine.LINNA_OUT_M).cpu().numpy()
+    assert e.last_kernel() == "tc"
+    assert np.all(np.isfinite(ref[7])) and np.array_equal(got[7], ref[7]) and np.array_equal(got[123], ref[123])
+    keep = np.ones(300, bool)
+    keep[[7, 123]] = False
+    assert rel_inf(got[keep], ref[keep]) < 1e-5
