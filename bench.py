@@ -605,6 +605,37 @@ def c1_record(D, args):
     return rec
 
 
+def sampler_record(D, args, p, eng, iters=10, warmup=3):
+    """f1: the ensemble sampler's own loop on the device -- per iteration one permutation, and per half-ensemble one
+    stretch-move proposal kernel, one likelihood launch over 10^5 proposals and one accept kernel
+    (linna_b200/sampler.py: EnsembleSampler.sample; the reference drives emcee / zeus with one Log_prob call per walker,
+    linna/sampler.py:495)."""
+    torch = D.torch
+    from linna_b200 import engine
+    from linna_b200.sampler import EnsembleSampler
+    W = 2 * WORKLOADS["c3"][2]
+    smp = EnsembleSampler(W, p.n_in, eng.lnp, seed=11 + D.rank, device="cuda:%d" % D.local)
+    x = torch.from_numpy(synthetic.walkers(W, p.n_in, scale=0.3, seed=900 + D.rank)).cuda()
+    x, lnp = smp.run_mcmc(x, warmup, store=False)
+    D.barrier()
+    l0 = engine.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for x, lnp in smp.sample(x, iters, store=False, lnp0=lnp):
+        pass
+    ev1.record()
+    D.barrier()
+    ms = D.max(ev0.elapsed_time(ev1))
+    acc = float(smp.acceptance_fraction.mean())
+    return {"name": "c3_ensemble_sampler", "metric": "ensemble-sampler walker updates/sec", "value": W * D.world * iters / (ms * 1e-3),
+            "unit": "walker updates/s", "n_gpus": D.world, "steps": iters, "warmup": warmup, "ms_per_step": ms / iters, "scaling": "weak",
+            "config": {"workload": "C3, Goodman-Weare stretch move, %d walkers per GPU (two half-ensemble updates of 1e5 proposals per "
+                                   "iteration), every array device-resident" % W,
+                       "kernel_path": eng.last_kernel()},
+            "gpu_launches": int(engine.launch_count() - l0), "acceptance_fraction": acc,
+            "lnp_share": "one iteration = 2 likelihood launches of 1e5 walkers + 2 proposal + 2 accept kernels + torch.randperm"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -661,6 +692,7 @@ def main():
         sg = measure_sustained(D, p, eng, n, "grad", seconds=2.0)
         extra[-1]["sustained"] = {"value": n * world / (sg["ms_per_step"] * 1e-3), "ms_per_step": sg["ms_per_step"], "seconds": sg["seconds"],
                                   "clocks": sg["clocks"]}
+        extra.append(sampler_record(D, args, p, eng))
 
     if rank == 0:
         # ---- roofline of the dominant (only) kernel: useful flops / measured kernel time

@@ -835,11 +835,11 @@ void linna_model_destroy(linna_model_t *m)
     if (!m) return;
     DeviceGuard guard(m->device);
     cudaDeviceSynchronize();
+    if (m->helper) { delete m->helper; m->helper = nullptr; }
     if (m->hstream) cudaStreamDestroy(m->hstream);
     if (m->cstream) cudaStreamDestroy(m->cstream);
     if (m->dstream) cudaStreamDestroy(m->dstream);
     for (cudaEvent_t e : m->pipe_events) cudaEventDestroy(e);
-    if (m->pool) { delete m->pool; m->pool = nullptr; }
     if (m->h_stage) cudaFreeHost(m->h_stage);
     if (m->h_in_stage) cudaFreeHost(m->h_in_stage);
     if (m->last_done) cudaEventDestroy(m->last_done);
@@ -1203,8 +1203,8 @@ int linna_predict_host(linna_model_t *m, const float *theta, int64_t n, float *o
     return LINNA_OK;
 }
 
-// Host-buffer lnP / lnP+gradient: the batch is cut into chunks of one full wave of the tensor-core kernel
-// (2 walker-pair slots x 256 rows on every CTA pair) and the three legs run on three streams, so that the
+// Host-buffer lnP / lnP+gradient: the batch is cut into chunks of one round of the tensor-core kernel
+// (one walker pair of 256 rows on every CTA pair) and the three legs run on three streams, so that the
 // host->device copy of chunk k+1 and the device->host copy of chunk k-1 hide behind the kernel of chunk k.
 static bool is_pinned_host(const void *p)
 {
@@ -1224,6 +1224,73 @@ static int ensure_pinned(float **p, size_t *cap, size_t need)
     return LINNA_OK;
 }
 
+static inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+}
+
+// One pipelined host-buffer call, shared by the calling thread and the model's helper thread.
+struct StageJob {
+    // input staging: `npieces` pieces of `piece_rows` rows, claimed front to back through `next_piece` by whichever
+    // thread is free; piece_done[q] is set (release) when piece q sits in the pinned staging buffer
+    const float *u = nullptr;
+    float *in_stage = nullptr;
+    int64_t n = 0, piece_rows = 0;
+    int n_in = 0, npieces = 0;
+    std::atomic<int> next_piece{0};
+    std::atomic<uint8_t> *piece_done = nullptr;
+    // results: chunk k = rows [cstart[k], cstart[k+1]); `issued` counts the chunks whose device->host copy has been
+    // enqueued (home[k] recorded); the helper hands them to the caller's arrays in order
+    int nchunks = 0;
+    const int64_t *cstart = nullptr;
+    cudaEvent_t *events = nullptr;   // 3 per chunk, [3k + 2] = results of chunk k on the host
+    std::atomic<int> issued{0};
+    bool stage_in = false, stage_out = false;
+    float *lnp = nullptr, *grad = nullptr;
+    const float *s_lnp = nullptr, *s_grad = nullptr;
+    std::atomic<int> abort{0}, helper_done{0}, helper_err{0};
+};
+
+static inline void stage_piece(StageJob *j, int q)
+{
+    const int64_t a0 = (int64_t)q * j->piece_rows, pr = std::min(j->piece_rows, j->n - a0);
+    memcpy(j->in_stage + a0 * j->n_in, j->u + a0 * j->n_in, (size_t)pr * j->n_in * sizeof(float));
+    j->piece_done[q].store(1, std::memory_order_release);
+}
+
+static inline void copy_out_chunk(StageJob *j, int k)
+{
+    const int64_t r0 = j->cstart[k], rows = j->cstart[k + 1] - r0;
+    if (j->s_lnp != j->lnp) memcpy(j->lnp + r0, j->s_lnp + r0, (size_t)rows * sizeof(float));
+    if (j->grad && j->s_grad != j->grad) memcpy(j->grad + r0 * j->n_in, j->s_grad + r0 * j->n_in, (size_t)rows * j->n_in * sizeof(float));
+}
+
+static void stage_helper_run(StageJob *j)
+{
+    if (j->stage_in)
+        for (;;) {
+            if (j->abort.load(std::memory_order_relaxed)) break;
+            const int q = j->next_piece.fetch_add(1, std::memory_order_relaxed);
+            if (q >= j->npieces) break;
+            stage_piece(j, q);
+        }
+    if (j->stage_out)
+        for (int k = 0; k < j->nchunks; ++k) {
+            while (j->issued.load(std::memory_order_acquire) <= k && !j->abort.load(std::memory_order_relaxed)) cpu_relax();
+            if (j->abort.load(std::memory_order_relaxed)) break;
+            if (cudaEventSynchronize(j->events[3 * k + 2]) != cudaSuccess) {
+                j->helper_err.store(1);
+                break;
+            }
+            copy_out_chunk(j, k);
+        }
+    j->helper_done.store(1, std::memory_order_release);
+}
+
 static int lnp_host_pipelined(linna_model *m, const float *u, int64_t n, float *lnp, float *grad)
 {
     LINNA_ON_DEVICE(m);
@@ -1233,120 +1300,106 @@ static int lnp_host_pipelined(linna_model *m, const float *u, int64_t n, float *
     if ((rc = ensure(&m->d_lnp, &m->d_lnp_cap, (size_t)n))) return rc;
     if (grad && (rc = ensure(&m->d_grad, &m->d_grad_cap, (size_t)n * n_in))) return rc;
     // Pageable caller buffers (what an emcee / zeus caller holds: plain numpy arrays) go through pinned staging on both
-    // sides.  cudaMemcpyAsync on pageable memory stages inside the driver on the CALLING thread (one memcpy stream of
-    // ~10 GB/s: 1.2 ms for the 12 MB of 10^5 C3 walkers, more than the kernel), and a device->host copy into pageable
-    // memory blocks until the kernel before it has finished.  Here a few pool threads fill the input staging chunk by
-    // chunk ahead of the GPU and drain the result staging behind it.
-    if ((size_t)n * n_in * sizeof(float) <= ((size_t)64 << 10)) {
+    // sides.  cudaMemcpyAsync on pageable memory stages inside the driver on the CALLING thread (measured 17-20 GB/s:
+    // 0.6-0.7 ms for the 12 MB of 10^5 C3 walkers, most of a kernel), and a device->host copy into pageable memory blocks
+    // until the kernel before it has finished.  Here the calling thread and ONE helper thread fill the input staging
+    // piece by piece ahead of the GPU, and the helper drains the result staging behind it.
+    const size_t row_bytes = (size_t)n_in * sizeof(float);
+    if ((size_t)n * row_bytes <= ((size_t)64 << 10)) {
         // Latency path (an emcee ensemble of a few walkers per call): nothing to pipeline -- one stream, pinned staging on
         // both sides, one synchronisation.
         const size_t out_floats = (size_t)n * (1 + (grad ? n_in : 0));
         if ((rc = ensure_pinned(&m->h_in_stage, &m->h_in_stage_cap, (size_t)n * n_in))) return rc;
         if ((rc = ensure_pinned(&m->h_stage, &m->h_stage_cap, out_floats))) return rc;
-        memcpy(m->h_in_stage, u, (size_t)n * n_in * sizeof(float));
-        CUDA_TRY(cudaMemcpyAsync(m->d_in, m->h_in_stage, (size_t)n * n_in * sizeof(float), cudaMemcpyHostToDevice, m->hstream));
+        memcpy(m->h_in_stage, u, (size_t)n * row_bytes);
+        CUDA_TRY(cudaMemcpyAsync(m->d_in, m->h_in_stage, (size_t)n * row_bytes, cudaMemcpyHostToDevice, m->hstream));
         rc = grad ? linna_lnp_grad(m, m->d_in, n, m->d_lnp, m->d_grad, m->hstream) : linna_lnp(m, m->d_in, n, m->d_lnp, m->hstream);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(m->h_stage, m->d_lnp, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, m->hstream));
         if (grad)
-            CUDA_TRY(cudaMemcpyAsync(m->h_stage + n, m->d_grad, (size_t)n * n_in * sizeof(float), cudaMemcpyDeviceToHost, m->hstream));
+            CUDA_TRY(cudaMemcpyAsync(m->h_stage + n, m->d_grad, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, m->hstream));
         CUDA_TRY(cudaStreamSynchronize(m->hstream));
         memcpy(lnp, m->h_stage, (size_t)n * sizeof(float));
-        if (grad) memcpy(grad, m->h_stage + n, (size_t)n * n_in * sizeof(float));
+        if (grad) memcpy(grad, m->h_stage + n, (size_t)n * row_bytes);
         return LINNA_OK;
     }
-    const bool stage_in = !is_pinned_host(u);
-    const bool stage_out = !is_pinned_host(lnp) || (grad && !is_pinned_host(grad));
-    float *s_lnp = lnp, *s_grad = grad;
+    StageJob job;
+    job.stage_in = !is_pinned_host(u);
+    job.stage_out = !is_pinned_host(lnp) || (grad && !is_pinned_host(grad));
+    job.u = u, job.n = n, job.n_in = n_in, job.lnp = lnp, job.grad = grad, job.s_lnp = lnp, job.s_grad = grad;
     const float *s_in = u;
-    if (stage_out) {
+    if (job.stage_out) {
         if ((rc = ensure_pinned(&m->h_stage, &m->h_stage_cap, (size_t)n * (1 + (grad ? n_in : 0))))) return rc;
-        s_lnp = m->h_stage, s_grad = m->h_stage + n;
+        job.s_lnp = m->h_stage, job.s_grad = m->h_stage + n;
     }
-    if (stage_in) {
+    if (job.stage_in) {
         if ((rc = ensure_pinned(&m->h_in_stage, &m->h_in_stage_cap, (size_t)n * n_in))) return rc;
-        s_in = m->h_in_stage;
+        s_in = job.in_stage = m->h_in_stage;
     }
-    const bool big = (size_t)n * n_in * sizeof(float) >= ((size_t)1 << 20);
-    if ((stage_in || stage_out) && big && !m->pool) {
-        const unsigned hw = std::thread::hardware_concurrency();
-        // enough threads that the FIRST chunk (nothing overlaps its staging) is copied at several times one core's rate
-        const char *ep = getenv("LINNA_STAGE_THREADS");
-        const unsigned want = ep ? (unsigned)std::max(1, atoi(ep)) : 8u;
-        m->pool = new StagePool((int)std::max(1u, std::min(want, hw > 1 ? hw - 1 : 1u)));
-    }
-    StagePool *pool = big ? m->pool : nullptr;
-    const int64_t wave = (int64_t)(m->num_sms / 2) * 2 * 256;
-    int64_t chunk = n;
-    if (n >= 2 * wave) chunk = wave * ((n / wave + 15) / 16);          // at most 16 chunks
-    const int nchunks = (int)((n + chunk - 1) / chunk);
+    float *const s_lnp = const_cast<float *>(job.s_lnp), *const s_grad = const_cast<float *>(job.s_grad);
+    // Chunks: the kernel's time is a staircase in ROUNDS (one walker pair of 256 rows on every CTA pair: 0.17 ms at C3;
+    // two interleaved pairs 0.32 ms), so chunks are cut at round boundaries and cost no extra rounds: the first chunk is
+    // one round (the GPU starts after 1/6 of a 10^5-walker block has been staged), the others two rounds (at most 32
+    // chunks).
+    const int64_t round = (int64_t)(m->num_sms / 2) * 256;
+    std::vector<int64_t> cstart{0};
+    if (n > round + round / 4) {
+        const int64_t big_chunk = round * std::max<int64_t>(2, (n / round + 30) / 31);
+        cstart.push_back(round);
+        while (cstart.back() < n) cstart.push_back(std::min(n, cstart.back() + big_chunk));
+    } else
+        cstart.push_back(n);
+    const int nchunks = (int)cstart.size() - 1;
+    job.nchunks = nchunks, job.cstart = cstart.data();
     while ((int)m->pipe_events.size() < 3 * nchunks) {
         cudaEvent_t e;
         CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         m->pipe_events.push_back(e);
     }
-    // input staging: every chunk in `parts` pieces, all submitted up front; in_left[k] counts the pieces still to copy
-    const int parts = pool ? (int)std::min<size_t>(8, std::max<size_t>(2, pool->workers.size())) : 2;
-    std::vector<std::atomic<int>> in_left(nchunks);
-    std::atomic<int> out_left{0};
-    if (stage_in) {
-        float *dst = m->h_in_stage;
-        for (int k = 0; k < nchunks; ++k) {
-            const int64_t r0 = (int64_t)k * chunk, rows = std::min(chunk, n - r0);
-            if (!pool) {
-                in_left[k].store(0);
-                continue;
-            }
-            in_left[k].store(parts);
-            for (int q = 0; q < parts; ++q) {
-                const int64_t a0 = r0 + rows * q / parts, a1 = r0 + rows * (q + 1) / parts;
-                std::atomic<int> *cnt = &in_left[k];
-                pool->submit([=] {
-                    memcpy(dst + a0 * n_in, u + a0 * n_in, (size_t)(a1 - a0) * n_in * sizeof(float));
-                    cnt->fetch_sub(1, std::memory_order_release);
-                });
-            }
-        }
+    job.events = m->pipe_events.data();
+    // Input pieces of 512 KB, claimed front to back by the calling thread and the helper (scratch/e2e_probe.py on the
+    // 16-thread GPU box: one core copies 16.5 GB/s -- 0.73 ms for 12 MB, as long as the kernel itself, so a second copier
+    // is needed for the copies to hide behind the kernel; the earlier pool of 4 / 8 / 15 threads fed through a job queue
+    // was SLOWER than one thread, 66 / 60 / 40 M against 71 M evals/s: wake-ups and spinning waiters cost more than the
+    // copies).
+    job.piece_rows = std::max<int64_t>(1, (int64_t)(((size_t)512 << 10) / row_bytes));
+    job.npieces = job.stage_in ? (int)((n + job.piece_rows - 1) / job.piece_rows) : 0;
+    std::vector<std::atomic<uint8_t>> piece_done(job.npieces);
+    for (auto &d : piece_done) d.store(0, std::memory_order_relaxed);
+    job.piece_done = piece_done.data();
+    const bool use_helper = (job.stage_in || job.stage_out) && (size_t)n * row_bytes >= ((size_t)1 << 20);
+    if (use_helper) {
+        if (!m->helper) m->helper = new StageHelper(m->device, stage_helper_run);
+        m->helper->post(&job);
     }
-    auto copy_out = [&](int k) -> int {   // host side of chunk k: wait for its device->host copy, hand it to the caller
-        const int64_t r0 = (int64_t)k * chunk, rows = std::min(chunk, n - r0);
-        CUDA_TRY(cudaEventSynchronize(m->pipe_events[3 * k + 2]));
-        memcpy(lnp + r0, s_lnp + r0, (size_t)rows * sizeof(float));
-        if (grad) {
-            if (pool) {   // n_in times the bytes of lnP: behind the GPU, on the pool
-                out_left.fetch_add(parts);
-                for (int q = 0; q < parts; ++q) {
-                    const int64_t a0 = r0 + rows * q / parts, a1 = r0 + rows * (q + 1) / parts;
-                    const float *src = s_grad;
-                    std::atomic<int> *cnt = &out_left;
-                    pool->submit([=] {
-                        memcpy(grad + a0 * n_in, src + a0 * n_in, (size_t)(a1 - a0) * n_in * sizeof(float));
-                        cnt->fetch_sub(1, std::memory_order_release);
-                    });
-                }
-            } else
-                memcpy(grad + r0 * n_in, s_grad + r0 * n_in, (size_t)rows * n_in * sizeof(float));
-        }
-        return LINNA_OK;
-    };
-    auto drain_pool = [&]() {   // nothing of this call may still be running on the pool when it returns (or fails)
-        if (!pool) return;
-        for (int k = 0; k < nchunks; ++k)
-            while (stage_in && in_left[k].load(std::memory_order_acquire) > 0) std::this_thread::yield();
-        while (out_left.load(std::memory_order_acquire) > 0) std::this_thread::yield();
-    };
     rc = LINNA_OK;
+    int next_h2d = 0;   // pieces [0, next_h2d) are on their way to the device
     for (int k = 0; k < nchunks && rc == LINNA_OK; ++k) {
-        const int64_t r0 = (int64_t)k * chunk, rows = std::min(chunk, n - r0);
+        const int64_t r0 = cstart[k], rows = cstart[k + 1] - r0;
         cudaEvent_t landed = m->pipe_events[3 * k], done = m->pipe_events[3 * k + 1], home = m->pipe_events[3 * k + 2];
-        if (stage_in) {
-            if (pool)
-                while (in_left[k].load(std::memory_order_acquire) > 0) std::this_thread::yield();
-            else
-                memcpy(m->h_in_stage + r0 * n_in, u + r0 * n_in, (size_t)rows * n_in * sizeof(float));
+        cudaError_t ce = cudaSuccess;
+        if (job.stage_in) {
+            // every piece that overlaps this chunk: stage what nobody has claimed yet, wait for the helper's pieces, and
+            // send runs of finished pieces to the device (pieces straddle chunk boundaries; a piece is sent once)
+            const int q_end = (int)((cstart[k + 1] + job.piece_rows - 1) / job.piece_rows);
+            while (next_h2d < q_end && ce == cudaSuccess) {
+                if (!piece_done[next_h2d].load(std::memory_order_acquire)) {
+                    const int q = job.next_piece.load(std::memory_order_relaxed) < job.npieces
+                                      ? job.next_piece.fetch_add(1, std::memory_order_relaxed) : job.npieces;
+                    if (q < job.npieces) stage_piece(&job, q);
+                    else cpu_relax();   // the helper is finishing it
+                    continue;
+                }
+                int q1 = next_h2d + 1;
+                while (q1 < q_end && piece_done[q1].load(std::memory_order_acquire)) ++q1;
+                const int64_t a0 = (int64_t)next_h2d * job.piece_rows, a1 = std::min(n, (int64_t)q1 * job.piece_rows);
+                ce = cudaMemcpyAsync(m->d_in + a0 * n_in, m->h_in_stage + a0 * n_in, (size_t)(a1 - a0) * row_bytes, cudaMemcpyHostToDevice,
+                                     m->cstream);
+                next_h2d = q1;
+            }
+        } else {
+            ce = cudaMemcpyAsync(m->d_in + r0 * n_in, s_in + r0 * n_in, (size_t)rows * row_bytes, cudaMemcpyHostToDevice, m->cstream);
         }
-        cudaError_t ce = cudaMemcpyAsync(m->d_in + r0 * n_in, s_in + r0 * n_in, (size_t)rows * n_in * sizeof(float),
-                                         cudaMemcpyHostToDevice, m->cstream);
         if (ce == cudaSuccess) ce = cudaEventRecord(landed, m->cstream);
         if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->hstream, landed, 0);
         if (ce != cudaSuccess) { rc = fail(LINNA_ECUDA, "host->device stage: %s", cudaGetErrorString(ce)); break; }
@@ -1358,17 +1411,27 @@ static int lnp_host_pipelined(linna_model *m, const float *u, int64_t n, float *
         if (ce == cudaSuccess)
             ce = cudaMemcpyAsync(s_lnp + r0, m->d_lnp + r0, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost, m->dstream);
         if (ce == cudaSuccess && grad)
-            ce = cudaMemcpyAsync(s_grad + r0 * n_in, m->d_grad + r0 * n_in, (size_t)rows * n_in * sizeof(float),
-                                 cudaMemcpyDeviceToHost, m->dstream);
+            ce = cudaMemcpyAsync(s_grad + r0 * n_in, m->d_grad + r0 * n_in, (size_t)rows * row_bytes, cudaMemcpyDeviceToHost, m->dstream);
         if (ce == cudaSuccess) ce = cudaEventRecord(home, m->dstream);
         if (ce != cudaSuccess) { rc = fail(LINNA_ECUDA, "device->host stage: %s", cudaGetErrorString(ce)); break; }
-        if (stage_out && k > 0) rc = copy_out(k - 1);
+        job.issued.store(k + 1, std::memory_order_release);
     }
-    if (rc == LINNA_OK && stage_out) rc = copy_out(nchunks - 1);
-    drain_pool();
+    if (rc != LINNA_OK) job.abort.store(1);
+    if (use_helper) {   // the job lives on this stack frame: the helper must be through with it
+        while (!job.helper_done.load(std::memory_order_acquire)) cpu_relax();
+        if (rc == LINNA_OK && job.helper_err.load()) rc = fail(LINNA_ECUDA, "device->host stage: helper thread");
+    } else if (rc == LINNA_OK && job.stage_out) {
+        for (int k = 0; k < nchunks; ++k) {
+            const cudaError_t ce = cudaEventSynchronize(m->pipe_events[3 * k + 2]);
+            if (ce != cudaSuccess) { rc = fail(LINNA_ECUDA, "device->host stage: %s", cudaGetErrorString(ce)); break; }
+            copy_out_chunk(&job, k);
+        }
+    }
+    // nothing of this call may still be in flight when it returns (or fails): the staging buffers belong to the model
+    const cudaError_t e1 = cudaStreamSynchronize(m->cstream), e2 = cudaStreamSynchronize(m->hstream), e3 = cudaStreamSynchronize(m->dstream);
     if (rc) return rc;
-    CUDA_TRY(cudaStreamSynchronize(m->dstream));
-    CUDA_TRY(cudaStreamSynchronize(m->hstream));
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return fail(LINNA_ECUDA, "host-buffer pipeline: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
     return LINNA_OK;
 }
 

@@ -2,13 +2,11 @@
 #pragma once
 #include <atomic>
 #include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdint>
 #include <cstring>
-#include <deque>
-#include <functional>
-#include <mutex>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "../../include/linna_b200.h"
@@ -32,47 +30,49 @@ struct OpHost {
 
 enum ProgKind { PROG_PREDICT = 0, PROG_LNP = 1, PROG_GRAD = 2, PROG_LOSS = 3, PROG_TRAIN = 4, PROG_VJP = 5, PROG_COUNT = 6 };
 
-// A few host threads that move pageable caller buffers to / from pinned staging memory while the GPU works: one
-// thread copies ~10 GB/s, and a 12 MB walker block staged by one thread costs more than the kernel that consumes it.
-struct StagePool {
-    std::vector<std::thread> workers;
-    std::deque<std::function<void()>> jobs;
+// One helper thread per model for the host-buffer entry points (cabi.cu: lnp_host_pipelined): it stages pieces of a
+// pageable input next to the calling thread and hands finished results back to the caller's arrays.  It sleeps on a
+// condition variable between calls; a call posts ONE job (a pointer to a structure on the caller's stack).
+struct StageJob;
+struct StageHelper {
+    std::thread th;
     std::mutex mu;
     std::condition_variable cv;
+    StageJob *job = nullptr;
     bool stop = false;
-    explicit StagePool(int n)
+    void (*run)(StageJob *) = nullptr;
+    StageHelper(int device, void (*fn)(StageJob *)) : run(fn)
     {
-        for (int i = 0; i < n; ++i)
-            workers.emplace_back([this] {
-                for (;;) {
-                    std::function<void()> job;
-                    {
-                        std::unique_lock<std::mutex> lk(mu);
-                        cv.wait(lk, [this] { return stop || !jobs.empty(); });
-                        if (stop && jobs.empty()) return;
-                        job = std::move(jobs.front());
-                        jobs.pop_front();
-                    }
-                    job();
+        th = std::thread([this, device] {
+            cudaSetDevice(device);
+            for (;;) {
+                StageJob *j;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [this] { return stop || job; });
+                    if (stop) return;
+                    j = job, job = nullptr;
                 }
-            });
+                run(j);
+            }
+        });
     }
-    void submit(std::function<void()> f)
+    void post(StageJob *j)
     {
         {
             std::lock_guard<std::mutex> lk(mu);
-            jobs.push_back(std::move(f));
+            job = j;
         }
         cv.notify_one();
     }
-    ~StagePool()
+    ~StageHelper()
     {
         {
             std::lock_guard<std::mutex> lk(mu);
             stop = true;
         }
-        cv.notify_all();
-        for (std::thread &t : workers) t.join();
+        cv.notify_one();
+        th.join();
     }
 };
 
@@ -149,7 +149,7 @@ struct linna_model {
     size_t h_stage_cap = 0;
     float *h_in_stage = nullptr;                     // pinned staging for pageable input buffers
     size_t h_in_stage_cap = 0;
-    StagePool *pool = nullptr;                       // host threads that fill / drain the staging buffers
+    StageHelper *helper = nullptr;                   // second host thread of the pipelined host-buffer calls
     float *d_in = nullptr, *d_out = nullptr, *d_lnp = nullptr, *d_grad = nullptr;
     size_t d_in_cap = 0, d_out_cap = 0, d_lnp_cap = 0, d_grad_cap = 0;
 };

@@ -27,10 +27,13 @@
 //     dW[n][k] = sum_b gz[b][n] x[b][k] contracts over the BATCH and reads the very same activation planes as
 //     MN-major operands (instruction-descriptor transpose bits), so no transposed activation copy exists.  The
 //     bias gradient is the extra column k == K of x, which every producer epilogue sets to 1.
-//   * epilogues (one thread = one output row, 64 columns): bias + relu + mask bits + bf16x3 split (forward), the
+//   * epilogues (one thread = one output row, 32 columns): bias + relu + mask bits + bf16x3 split (forward), the
 //     normalised-space residual (loss head), chi^2 partials and d loss / d yhat (loss), relu-mask backward, and
 //     AdamW with the refresh of every packed copy of the weight (weight gradients).
-//   * warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2-5 = epilogue.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2-9 = epilogue: a thread owns one output row
+//     (tensor-memory lane) and HALF of the tile's 64 columns (warps 2-5 columns [0,32), warps 6-9 columns [32,64)).  The
+//     epilogues are latency-bound chains run once per CTA (one warp per scheduler with four warps: 5-8 us per tile,
+//     26 us for the AdamW epilogue, more than the k-loops); eight warps halve them.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -54,7 +57,9 @@ constexpr int TG_A_PLANE = TG_BM * 128;                        // 16 KB: 128 row
 constexpr int TG_B_PLANE = TG_BN * 128;                        // 8 KB
 constexpr int TG_STAGE_BYTES = 3 * (TG_A_PLANE + TG_B_PLANE);  // 72 KB
 constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_BYTES + 1024;
-constexpr int TG_THREADS = 192;
+constexpr int TG_EPI_THREADS = 256;   // 8 epilogue warps: warps w and w + 4 share a tensor-memory lane quarter and split the 64 columns
+constexpr int TG_HN = TG_BN / 2;       // columns per epilogue thread
+constexpr int TG_THREADS = 64 + TG_EPI_THREADS;
 
 enum TgEpi : int32_t { TG_ACT = 0, TG_HEAD = 1, TG_LOSSQ = 2, TG_BWD = 3 };
 
@@ -229,8 +234,8 @@ __device__ __forceinline__ void tg_tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tg_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // x = h + m + l, three bf16 values; two numbers per call (packed bf16x2 words)
 __device__ __forceinline__ void tg_split3(float a, float b, uint32_t &h, uint32_t &m, uint32_t &l)
 {
@@ -263,14 +268,14 @@ struct TgPipe {
     uint32_t tmem_slot;
 };
 
-__device__ __forceinline__ void tg_gemm_tile(const TgTileDesc &t, uint8_t *smem, TgPipe &pp, float (&racc)[TG_BN], int *err,
+__device__ __forceinline__ void tg_gemm_tile(const TgTileDesc &t, uint8_t *smem, TgPipe &pp, float (&racc)[TG_HN], int *err,
                                              long long *dbg = nullptr)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (dbg && threadIdx.x == 64) dbg[0] = clock64();
     if (threadIdx.x == 0) {
         for (int s = 0; s < TG_STAGES; ++s) tg_mbar_init(&pp.full_bar[s], 1), tg_mbar_init(&pp.empty_bar[s], 1);
-        for (int b = 0; b < 2; ++b) tg_mbar_init(&pp.tfull_bar[b], 1), tg_mbar_init(&pp.tempty_bar[b], 4);
+        for (int b = 0; b < 2; ++b) tg_mbar_init(&pp.tfull_bar[b], 1), tg_mbar_init(&pp.tempty_bar[b], TG_EPI_THREADS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0 && lane < 2 * t.nphase) {   // descriptor fetch overlaps the predecessor's tail
@@ -360,21 +365,21 @@ __device__ __forceinline__ void tg_gemm_tile(const TgTileDesc &t, uint8_t *smem,
         }
     } else {
         // =============================== epilogue warps: drain every k-chunk ===============================
-        const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp - 2) >> 2) * TG_HN);
 #pragma unroll
-        for (int j = 0; j < TG_BN; ++j) racc[j] = 0.f;
+        for (int j = 0; j < TG_HN; ++j) racc[j] = 0.f;
         const int nseg = (total + 1) >> 1;
         for (int seg = 0; seg < nseg; ++seg) {
             const int buf = seg & 1;
             tg_mbar_wait(&pp.tfull_bar[buf], (uint32_t)(seg >> 1) & 1u, err, 24);
             tg_fence_after();
-#pragma unroll
-            for (int cb = 0; cb < TG_BN; cb += 32) {
+            {
                 uint32_t r0[32], r1[32];
-                tg_tmem_ld32(tmem_lane + buf * (2 * TG_BN) + cb, r0);
-                tg_tmem_ld32(tmem_lane + buf * (2 * TG_BN) + TG_BN + cb, r1);
+                tg_tmem_ld32(tmem_lane + buf * (2 * TG_BN), r0);            // leading term
+                tg_tmem_ld32(tmem_lane + buf * (2 * TG_BN) + TG_BN, r1);    // all smaller terms
+                tg_tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) racc[cb + j] += __uint_as_float(r1[j]) + __uint_as_float(r0[j]);
+                for (int j = 0; j < TG_HN; ++j) racc[j] += __uint_as_float(r1[j]) + __uint_as_float(r0[j]);
             }
             tg_fence_before();
             __syncwarp();
@@ -402,13 +407,14 @@ __device__ __forceinline__ void tg_tma_store_2d(const void *smem_src, const CUte
                  : "l"(reinterpret_cast<uint64_t>(map)), "r"(tg_smem_u32(smem_src)), "r"(c0), "r"(c1)
                  : "memory");
 }
-// 64 output values of tile row `row` -> the three bf16 planes of the staging tile in shared memory (3 x [128 rows x
-// 128 B], 128-byte swizzle: 16-byte chunk c of a row sits at chunk c ^ (row & 7)), which one thread then hands to TMA.
-__device__ __forceinline__ void tg_stage_planes(uint8_t *stg, int row, const float *v)
+// The output values [j0, j0 + 32) of tile row `row` -> the three bf16 planes of the staging tile in shared memory (3 x
+// [128 rows x 128 B], 128-byte swizzle: 16-byte chunk c of a row sits at chunk c ^ (row & 7)), which one thread then
+// hands to TMA.
+__device__ __forceinline__ void tg_stage_planes(uint8_t *stg, int row, const float *v, int j0)
 {
     const uint32_t base = tg_smem_u32(stg) + (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
 #pragma unroll 1
-    for (int j = 0; j < TG_BN; j += 8) {
+    for (int j = j0; j < j0 + TG_HN; j += 8) {
         uint32_t h[4], m[4], l[4];
 #pragma unroll
         for (int e = 0; e < 8; e += 2) tg_split3(v[j + e], v[j + e + 1], h[e >> 1], m[e >> 1], l[e >> 1]);
@@ -418,11 +424,13 @@ __device__ __forceinline__ void tg_stage_planes(uint8_t *stg, int row, const flo
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + 2 * TG_A_PLANE), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
     }
 }
-// the 128 epilogue threads have staged their rows: one of them sends the three planes of the tile to global memory
+// barrier of the epilogue warps (the two service warps never join it)
+__device__ __forceinline__ void tg_epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TG_EPI_THREADS) : "memory"); }
+// the epilogue threads have staged their half rows: one of them sends the three planes of the tile to global memory
 __device__ __forceinline__ void tg_store_tile(uint8_t *stg, const CUtensorMap *map, int col0, int row0, int plane_rows)
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    tg_epi_sync();
     if (threadIdx.x == 64) {
 #pragma unroll
         for (int pl = 0; pl < 3; ++pl) tg_tma_store_2d(stg + pl * TG_A_PLANE, map, col0, pl * plane_rows + row0);
@@ -430,31 +438,26 @@ __device__ __forceinline__ void tg_store_tile(uint8_t *stg, const CUtensorMap *m
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
-// [128 rows][64 floats] tile between global memory (row pitch `ld`) and shared memory (row pitch 65), coalesced: a warp
-// moves one row per instruction (lane = column).  Rows >= nrows / columns >= ncols are read as 0 and not written.
+// [128 rows][64 floats] tile between global memory (row pitch `ld`) and shared memory (row pitch 65), coalesced: an
+// epilogue warp moves half a row per instruction (lane = column; warps 2-5 the left half, warps 6-9 the right half of the
+// 32 rows of their quarter), four rows in flight.  Rows >= nrows / columns >= ncols are read as 0 and not written.
 constexpr int TG_FT_LD = TG_BN + 1;
 __device__ __forceinline__ void tg_ftile_load(float *tile, const float *g, int64_t ld, int nrows, int ncols)
 {
-    const int wq = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, wq = warp & 3, j = TG_HN * ((warp - 2) >> 2) + (threadIdx.x & 31);
+#pragma unroll 4
     for (int rr = 0; rr < 32; ++rr) {
         const int r = wq * 32 + rr;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int j = 32 * h + lane;
-            tile[r * TG_FT_LD + j] = (r < nrows && j < ncols) ? __ldg(g + (int64_t)r * ld + j) : 0.f;
-        }
+        tile[r * TG_FT_LD + j] = (r < nrows && j < ncols) ? __ldg(g + (int64_t)r * ld + j) : 0.f;
     }
 }
 __device__ __forceinline__ void tg_ftile_store(const float *tile, float *g, int64_t ld, int nrows, int ncols)
 {
-    const int wq = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, wq = warp & 3, j = TG_HN * ((warp - 2) >> 2) + (threadIdx.x & 31);
+#pragma unroll 4
     for (int rr = 0; rr < 32; ++rr) {
         const int r = wq * 32 + rr;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int j = 32 * h + lane;
-            if (r < nrows && j < ncols) g[(int64_t)r * ld + j] = tile[r * TG_FT_LD + j];
-        }
+        if (r < nrows && j < ncols) g[(int64_t)r * ld + j] = tile[r * TG_FT_LD + j];
     }
 }
 
@@ -483,12 +486,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_layer_kernel(const TgArgs ar
         const int T = (st.K[0] + TG_KC - 1) / TG_KC + (st.nphase > 1 ? (st.K[1] + TG_KC - 1) / TG_KC : 0);
         t.i0 = (int)((int64_t)T * kr / S), t.i1 = (int)((int64_t)T * (kr + 1) / S);
     }
-    float racc[TG_BN];
+    float racc[TG_HN];
     long long *dbg = (args.dbg && blockIdx.x == 0) ? args.dbg + 8 * args.dbg_slot : nullptr;
     tg_gemm_tile(t, smem, pp, racc, args.err, dbg);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hh = (warp - 2) >> 2, j0 = TG_HN * hh;   // epilogue warps: this thread's half of the tile's columns
     __shared__ int s_last;
+    __shared__ float s_part[TG_BM];
     bool do_epilogue = true;
     if (S > 1) {
         // split-K: park the partial tile in the workspace; the last k-range to arrive adds all of them in k-range order
@@ -497,25 +502,26 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_layer_kernel(const TgArgs ar
             // [tile][k-range][float4 column][row]: a warp instruction writes 32 consecutive rows = 512 contiguous bytes
             float4 *wsp = reinterpret_cast<float4 *>(args.ws) + (size_t)(tile * S + kr) * (TG_BN / 4) * TG_BM + row;
 #pragma unroll
-            for (int j = 0; j < TG_BN; j += 4) wsp[(size_t)(j >> 2) * TG_BM] = make_float4(racc[j], racc[j + 1], racc[j + 2], racc[j + 3]);
+            for (int j = 0; j < TG_HN; j += 4)
+                wsp[(size_t)((j0 + j) >> 2) * TG_BM] = make_float4(racc[j], racc[j + 1], racc[j + 2], racc[j + 3]);
             __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            tg_epi_sync();
             if (threadIdx.x == 64) {
                 const int ticket = atomicAdd(args.sem + tile, 1);
                 s_last = ticket == S - 1 ? 1 : 0;
                 if (ticket == S - 1) args.sem[tile] = 0;   // ready for the next launch
                 __threadfence();
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            tg_epi_sync();
             do_epilogue = s_last != 0;
             if (do_epilogue) {
 #pragma unroll
-                for (int j = 0; j < TG_BN; ++j) racc[j] = 0.f;
+                for (int j = 0; j < TG_HN; ++j) racc[j] = 0.f;
                 for (int r = 0; r < S; ++r) {
                     const float4 *src = reinterpret_cast<const float4 *>(args.ws) + (size_t)(tile * S + r) * (TG_BN / 4) * TG_BM + row;
 #pragma unroll
-                    for (int j = 0; j < TG_BN; j += 4) {
-                        const float4 v4 = __ldcg(src + (size_t)(j >> 2) * TG_BM);
+                    for (int j = 0; j < TG_HN; j += 4) {
+                        const float4 v4 = __ldcg(src + (size_t)((j0 + j) >> 2) * TG_BM);
                         racc[j] += v4.x, racc[j + 1] += v4.y, racc[j + 2] += v4.z, racc[j + 3] += v4.w;
                     }
                 }
@@ -534,105 +540,89 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_layer_kernel(const TgArgs ar
         const int nrows = args.B - t.m0 < TG_BM ? (args.B - t.m0 < 0 ? 0 : args.B - t.m0) : TG_BM;
         const int ncols = N - n0 < TG_BN ? (N - n0 < 0 ? 0 : N - n0) : TG_BN;
         const Consts &c = args.c;
-        // The accumulators go to this thread's own row of a [128][65] fp32 tile in shared memory and every epilogue is a
-        // ROLLED loop over that row: fully unrolled over 64 register accumulators the three epilogues were ~100 KB of
-        // straight-line code executed once per CTA, i.e. bound by instruction fetch (measured: 8 - 12 us per tile).
+        // The accumulators go to this thread's own half row of a [128][65] fp32 tile in shared memory and every epilogue is
+        // a ROLLED loop over that half row: fully unrolled over the register accumulators the three epilogues were ~100 KB
+        // of straight-line code executed once per CTA, i.e. bound by instruction fetch (measured: 8 - 12 us per tile).
         float *vrow = ftile + row * TG_FT_LD;
         float *yrow = reinterpret_cast<float *>(smem + TG_STAGE_BYTES + 36 * 1024) + row * TG_FT_LD;   // second tile (targets / residual)
 #pragma unroll
-        for (int j = 0; j < TG_BN; ++j) vrow[j] = racc[j];
+        for (int j = 0; j < TG_HN; ++j) vrow[j0 + j] = racc[j];
         const int epi = st.epi;
+        // this thread's word of the row's relu / validity bits: 32 columns = one word
+        uint32_t *mword = args.masks + st.mask_off + (size_t)grow * st.mask_ld + (n0 >> 5) + hh;
         if (epi == TG_ACT || epi == TG_BWD) {
-            uint32_t mw[2] = {0xffffffffu, 0xffffffffu};
-            if (st.apply_mask) {
-                const uint2 m2 = *reinterpret_cast<const uint2 *>(args.masks + st.mask_off + (size_t)grow * st.mask_ld + (n0 >> 5));
-                mw[0] = m2.x, mw[1] = m2.y;
-            }
+            const uint32_t mwh = st.apply_mask ? *mword : 0xffffffffu;
             const float *bias = st.bias;
             const float bscale = st.bias_scale;
             const bool relu = st.relu != 0, ones = st.write_ones != 0;
-            uint32_t sw[2] = {0u, 0u};
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                uint32_t bits = 0u;
-                const uint32_t mwh = mw[h];
+            uint32_t bits = 0u;
 #pragma unroll 4
-                for (int jj = 0; jj < 32; ++jj) {
-                    const int j = 32 * h + jj, col = n0 + j;
-                    float y = vrow[j];
-                    if (bias && col < N) y += bscale * __ldg(bias + col);
-                    if (relu) y = fmaxf(y, 0.f);
-                    y = ((mwh >> jj) & 1u) ? y : 0.f;
-                    bits |= (y > 0.f ? 1u : 0u) << jj;
-                    if (!(valid && col < N)) y = (valid && col == N && ones) ? 1.f : 0.f;
-                    vrow[j] = y;
-                }
-                sw[h] = bits;
+            for (int jj = 0; jj < TG_HN; ++jj) {
+                const int j = j0 + jj, col = n0 + j;
+                float y = vrow[j];
+                if (bias && col < N) y += bscale * __ldg(bias + col);
+                if (relu) y = fmaxf(y, 0.f);
+                y = ((mwh >> jj) & 1u) ? y : 0.f;
+                bits |= (y > 0.f ? 1u : 0u) << jj;
+                if (!(valid && col < N)) y = (valid && col == N && ones) ? 1.f : 0.f;
+                vrow[j] = y;
             }
-            if (st.save_mask)
-                *reinterpret_cast<uint2 *>(args.masks + st.mask_off + (size_t)grow * st.mask_ld + (n0 >> 5)) = make_uint2(sw[0], sw[1]);
-            tg_stage_planes(stg, row, vrow);
+            if (st.save_mask) *mword = bits;
+            tg_stage_planes(stg, row, vrow, j0);
             tg_store_tile(stg, args.maps + st.mapOut, n0, t.m0, st.out_rows);
         } else if (epi == TG_HEAD) {
             // vrow = yhat - bias; residual in normalised space (Auxilleryfunc, linna/util.py:1070-1088)
             float *ytile = reinterpret_cast<float *>(smem + TG_STAGE_BYTES + 36 * 1024);
             tg_ftile_load(ytile, args.target + (size_t)t.m0 * N + n0, N, nrows, ncols);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            uint32_t okw[2] = {0u, 0u};
+            tg_epi_sync();
             const float *bias = st.bias;
             const float bscale = st.bias_scale;
             const int kind = args.delta_kind;
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                uint32_t bits = 0u;
+            uint32_t bits = 0u;
 #pragma unroll 2
-                for (int jj = 0; jj < 32; ++jj) {
-                    const int j = 32 * h + jj, col = n0 + j;
-                    float dv = 0.f;
-                    if (valid && col < N) {
-                        const float yh = vrow[j] + (bias ? bscale * __ldg(bias + col) : 0.f);
-                        const float ys = __ldg(c.y_std + col), ym = __ldg(c.y_mean + col);
-                        const float sg = c.sigma ? __ldg(c.sigma + col) : 1.f;
-                        const float dh = __ldg(c.data_hat + col);
-                        const float Y = yrow[j];
-                        float tt = Y / sg;                                              // util.py:432
-                        if (c.ypositive) tt = logf(tt);                                 // util.py:567-568
-                        tt = (tt - ym) / ys;                                            // util.py:570
-                        const bool ok = !(Y == 1e-30f || Y == 1e10f || dh == 1e-30f);    // util.py:1072
-                        dv = kind == 0 ? tt - yh : kind == 1 ? tt - dh : yh - dh;
-                        if (!ok) dv = 0.f;
-                        bits |= (ok ? 1u : 0u) << jj;
-                    }
-                    vrow[j] = dv;
+            for (int jj = 0; jj < TG_HN; ++jj) {
+                const int j = j0 + jj, col = n0 + j;
+                float dv = 0.f;
+                if (valid && col < N) {
+                    const float yh = vrow[j] + (bias ? bscale * __ldg(bias + col) : 0.f);
+                    const float ys = __ldg(c.y_std + col), ym = __ldg(c.y_mean + col);
+                    const float sg = c.sigma ? __ldg(c.sigma + col) : 1.f;
+                    const float dh = __ldg(c.data_hat + col);
+                    const float Y = yrow[j];
+                    float tt = Y / sg;                                              // util.py:432
+                    if (c.ypositive) tt = logf(tt);                                 // util.py:567-568
+                    tt = (tt - ym) / ys;                                            // util.py:570
+                    const bool ok = !(Y == 1e-30f || Y == 1e10f || dh == 1e-30f);    // util.py:1072
+                    dv = kind == 0 ? tt - yh : kind == 1 ? tt - dh : yh - dh;
+                    if (!ok) dv = 0.f;
+                    bits |= (ok ? 1u : 0u) << jj;
                 }
-                okw[h] = bits;
+                vrow[j] = dv;
             }
-            *reinterpret_cast<uint2 *>(args.masks + st.mask_off + (size_t)grow * st.mask_ld + (n0 >> 5)) = make_uint2(okw[0], okw[1]);
-            tg_stage_planes(stg, row, vrow);
+            *mword = bits;
+            tg_stage_planes(stg, row, vrow, j0);
             tg_store_tile(stg, args.maps + st.mapOut, n0, t.m0, st.out_rows);     // (its barrier also publishes the fp32 rows)
             tg_ftile_store(ftile, args.delta32 + (size_t)t.m0 * args.dld + n0, args.dld, TG_BM, TG_BN);
         } else {   // TG_LOSSQ: q = delta @ Chat^-1 ; chi2 += q . delta ; g_yhat = -2 q ok / (cmd B)
             float *dtile = reinterpret_cast<float *>(smem + TG_STAGE_BYTES + 36 * 1024);
             tg_ftile_load(dtile, args.delta32 + (size_t)t.m0 * args.dld + n0, args.dld, TG_BM, TG_BN);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const uint2 ok2 = *reinterpret_cast<const uint2 *>(args.masks + st.mask_off + (size_t)grow * st.mask_ld + (n0 >> 5));
-            const uint32_t okw[2] = {ok2.x, ok2.y};
+            tg_epi_sync();
+            const uint32_t okh = *mword;
             const float rs = (valid && args.cmd) ? -2.0f * args.loss_inv_B / __ldg(args.cmd + grow) : 0.f;
             float part = 0.f;
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t okh = okw[h];
 #pragma unroll 4
-                for (int jj = 0; jj < 32; ++jj) {
-                    const int j = 32 * h + jj, col = n0 + j;
-                    const float q = (valid && col < N) ? vrow[j] : 0.f;
-                    part = fmaf(q, yrow[j], part);
-                    vrow[j] = ((okh >> jj) & 1u) ? q * rs : 0.f;
-                }
+            for (int jj = 0; jj < TG_HN; ++jj) {
+                const int j = j0 + jj, col = n0 + j;
+                const float q = (valid && col < N) ? vrow[j] : 0.f;
+                part = fmaf(q, yrow[j], part);
+                vrow[j] = ((okh >> jj) & 1u) ? q * rs : 0.f;
             }
-            args.chi_part[(size_t)grow * args.chi_ld + (n0 / TG_BN)] = part;
+            // the row's chi^2 partial of this tile: left half + right half, in that order
+            if (hh) s_part[row] = part;
+            tg_epi_sync();
+            if (!hh) args.chi_part[(size_t)grow * args.chi_ld + (n0 / TG_BN)] = part + s_part[row];
             if (args.want_grad) {
-                tg_stage_planes(stg, row, vrow);
+                tg_stage_planes(stg, row, vrow, j0);
                 tg_store_tile(stg, args.maps + st.mapOut, n0, t.m0, st.out_rows);
             }
         }
@@ -692,24 +682,25 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_wgrad_kernel(const TgArgs ar
     t.K[0] = args.B_eff, t.K[1] = 0;
     t.m0 = wt.m0, t.n0 = wt.n0;
     t.i0 = 0, t.i1 = args.B_eff / TG_KC;
-    float racc[TG_BN];
+    float racc[TG_HN];
     long long *dbg = (args.dbg && blockIdx.x == 0) ? args.dbg + 8 * 40 : nullptr;
     tg_gemm_tile(t, smem, pp, racc, args.err, dbg);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp >= 2) {
-        // The GEMM leaves thread = row n with 64 k-values; parameters, moments and the forward copies are contiguous in
+        // The GEMM leaves thread = row n with 32 k-values; parameters, moments and the forward copies are contiguous in
         // k.  The tile goes through shared memory (the operand stages are free: every MMA has retired) so that pass 1
         // runs with lane = k (coalesced AdamW state, forward planes, backward FP32 copy) and pass 2 with lane = n
-        // (backward planes, forward FP32 copy).
+        // (backward planes, forward FP32 copy).  Warps w and w + 4 share the 32 rows of a quarter: 16 rows each in pass
+        // 1, 32 of the 64 k-columns each in pass 2.
         float *tile = reinterpret_cast<float *>(smem);
-        const int wq = warp & 3, row = wq * 32 + lane;
+        const int wq = warp & 3, row = wq * 32 + lane, hh = (warp - 2) >> 2;
 #pragma unroll
-        for (int j = 0; j < TG_BN; ++j) tile[row * TG_WT_LD + j] = L.gscale * racc[j];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int j = 0; j < TG_HN; ++j) tile[row * TG_WT_LD + TG_HN * hh + j] = L.gscale * racc[j];
+        tg_epi_sync();
         const AdamArgs &ad = args.adam;
         const int64_t pf = (int64_t)L.wf_rows * L.wf_ld;
         // four rows (eight coalesced 128-byte lines of each of p, m, v) in flight per batch
-        for (int r0 = 0; r0 < 32; r0 += 4) {
+        for (int r0 = 16 * hh; r0 < 16 * hh + 16; r0 += 4) {
             int idx[8];
             float g[8], pp_[8], mm_[8], vv_[8];
 #pragma unroll
@@ -751,12 +742,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_wgrad_kernel(const TgArgs ar
             }
         }
         if (ad.fuse) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            tg_epi_sync();
             const int n = wt.m0 + row;
             if (n < L.N) {
                 const int64_t pb = (int64_t)L.wb_rows * L.wb_ld;
 #pragma unroll 8
-                for (int j = 0; j < TG_BN; ++j) {
+                for (int j = TG_HN * hh; j < TG_HN * hh + TG_HN; ++j) {
                     const int k = wt.n0 + j;
                     if (k >= L.K) break;
                     const float p = tile[row * TG_WT_LD + j];
