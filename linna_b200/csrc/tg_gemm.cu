@@ -60,6 +60,7 @@ constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_BYTES + 1024;
 constexpr int TG_EPI_THREADS = 256;   // 8 epilogue warps: warps w and w + 4 share a tensor-memory lane quarter and split the 64 columns
 constexpr int TG_HN = TG_BN / 2;       // columns per epilogue thread
 constexpr int TG_THREADS = 64 + TG_EPI_THREADS;
+constexpr int TG_DEP_NT = 4;           // a fused res-block launch handles narrow steps of up to 4 column tiles
 
 enum TgEpi : int32_t { TG_ACT = 0, TG_HEAD = 1, TG_LOSSQ = 2, TG_BWD = 3 };
 
@@ -125,6 +126,18 @@ struct TgArgs {
     int32_t splitk;               // k-ranges per tile (CTAs per tile) of this launch: 1, 2 or 4
     long long *dbg;               // LINNA_TG_DEBUG: [launch slot][8] cycle stamps of CTA 0 (profiling aid), or nullptr
     int32_t dbg_slot;
+    // Fused res-block launch: the first `dep_ctas` CTAs run the block's NARROW step (`step_dep`: hidden layer, or its
+    // gradient), the others the two-phase step whose LAST phase contracts over that narrow output.  Both read the same
+    // predecessor, so the wide CTAs run their first phase (the skip GEMM, K = layer width) at once and only the producer of
+    // a CTA whose k-range reaches the second phase waits -- on per-tile flags that the narrow CTAs set to the launch's
+    // sequence number when their tile has landed in global memory.  The narrow step's launch, its ~10 us and the gap
+    // behind it disappear.
+    const TgStep *step_dep;
+    int32_t dep_ctas, dep_splitk;
+    int32_t dep_ws_base, dep_sem_base;   // the narrow step's split-K workspace (partial-tile units) and tickets
+    uint32_t *dep_cnt;            // [row tile][TG_DEP_NT] sequence number of the launch that last wrote the narrow tile
+    uint32_t dep_target;          // this launch's sequence number
+    int32_t dep_ntiles;           // column tiles of the narrow step (<= TG_DEP_NT)
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -269,7 +282,8 @@ struct TgPipe {
 };
 
 __device__ __forceinline__ void tg_gemm_tile(const TgTileDesc &t, uint8_t *smem, TgPipe &pp, float (&racc)[TG_HN], int *err,
-                                             long long *dbg = nullptr)
+                                             long long *dbg = nullptr, const uint32_t *dep_flag = nullptr, uint32_t dep_target = 0,
+                                             int dep_ntiles = 0)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (dbg && threadIdx.x == 64) dbg[0] = clock64();
@@ -303,9 +317,29 @@ __device__ __forceinline__ void tg_gemm_tile(const TgTileDesc &t, uint8_t *smem,
         // =============================== TMA producer ===============================
         int stage = 0;
         uint32_t ph = 0;
+        bool dep_ok = dep_flag == nullptr;
         for (int i = t.i0; i < t.i1; ++i) {
             {
                 const int p = i < nk0 ? 0 : 1, kc = i < nk0 ? i : i - nk0;
+                if (p == 1 && !dep_ok) {
+                    // fused res-block launch: the second phase reads the narrow step's output of this row tile, written
+                    // by other CTAs of this launch (TMA stores, completed before the counter was bumped)
+                    const long long t0 = clock64();
+                    for (int q = 0; q < dep_ntiles; ++q)
+                        for (;;) {
+                            uint32_t v;
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(dep_flag + q) : "memory");
+                            if (v == dep_target) break;
+                            __nanosleep(40);
+                            if (clock64() - t0 > 2000000000LL) {
+                                if (err) atomicExch(err, 25);
+                                __threadfence_system();
+                                __trap();
+                            }
+                        }
+                    asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> the TMA loads below
+                    dep_ok = true;
+                }
                 tg_mbar_wait(&pp.empty_bar[stage], ph ^ 1, err, 21);
                 if (tg_elect_one()) {
                     uint8_t *sa = smem + stage * TG_STAGE_BYTES, *sb = sa + 3 * TG_A_PLANE;
@@ -468,8 +502,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_layer_kernel(const TgArgs ar
     __shared__ TgPipe pp;
     __shared__ TgStep st;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tg_smem_raw) + 1023) & ~(uintptr_t)1023);
-    for (int i = threadIdx.x; i < (int)(sizeof(TgStep) / 4); i += TG_THREADS)
-        reinterpret_cast<uint32_t *>(&st)[i] = reinterpret_cast<const uint32_t *>(args.step)[i];
+    const bool is_dep = (int)blockIdx.x < args.dep_ctas;   // a narrow-step CTA of a fused res-block launch
+    const int bid = is_dep ? (int)blockIdx.x : (int)blockIdx.x - args.dep_ctas;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(is_dep ? args.step_dep : args.step);
+        for (int i = threadIdx.x; i < (int)(sizeof(TgStep) / 4); i += TG_THREADS) reinterpret_cast<uint32_t *>(&st)[i] = src[i];
+    }
     __syncthreads();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next layer may set itself up while this one runs
     TgTileDesc t;
@@ -478,17 +516,38 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_layer_kernel(const TgArgs ar
         t.mapA[p] = args.maps + st.mapA[p], t.mapB[p] = args.maps + st.mapB[p];
         t.rowsA[p] = st.rowsA[p], t.rowsB[p] = st.rowsB[p], t.K[p] = st.K[p];
     }
-    const int S = args.splitk;
-    const int tile = blockIdx.x / S, kr = blockIdx.x - tile * S;
+    const int S = is_dep ? args.dep_splitk : args.splitk;
+    const int tile = bid / S, kr = bid - tile * S;
+    const int ws_base = is_dep ? args.dep_ws_base : 0;   // in partial tiles
+    int32_t *sem = args.sem + (is_dep ? args.dep_sem_base : 0) + tile;
     const int nt = tile % st.n_tiles, mt = tile / st.n_tiles;
     t.m0 = mt * TG_BM, t.n0 = nt * TG_BN;
     {
         const int T = (st.K[0] + TG_KC - 1) / TG_KC + (st.nphase > 1 ? (st.K[1] + TG_KC - 1) / TG_KC : 0);
         t.i0 = (int)((int64_t)T * kr / S), t.i1 = (int)((int64_t)T * (kr + 1) / S);
     }
+    // Per-column constants of the epilogue (the layer's bias; the output transform and the data vector for the loss head)
+    // go to shared memory BEFORE the wait for the predecessor: read per column inside the epilogue loops they were a chain
+    // of L2 round trips (3-5 k cycles per tile).  Nothing in the launch chain of a step writes them: parameters change
+    // only in the weight-gradient / AdamW kernels, and the first kernel of every chain (tg_input_kernel) is an ordinary
+    // launch that starts after those have completed.
+    __shared__ float s_bias[TG_BN], s_cst[4][TG_BN];
+    if (threadIdx.x < TG_BN) {
+        const int col = t.n0 + (int)threadIdx.x;
+        s_bias[threadIdx.x] = (st.bias && col < st.N) ? __ldg(st.bias + col) : 0.f;
+    } else if (st.epi == TG_HEAD && threadIdx.x < 2 * TG_BN) {
+        const int j = (int)threadIdx.x - TG_BN, col = t.n0 + j;
+        const bool in = col < st.N;
+        s_cst[0][j] = in ? __ldg(args.c.y_std + col) : 1.f;
+        s_cst[1][j] = in ? __ldg(args.c.y_mean + col) : 0.f;
+        s_cst[2][j] = (in && args.c.sigma) ? __ldg(args.c.sigma + col) : 1.f;
+        s_cst[3][j] = in ? __ldg(args.c.data_hat + col) : 0.f;
+    }
     float racc[TG_HN];
-    long long *dbg = (args.dbg && blockIdx.x == 0) ? args.dbg + 8 * args.dbg_slot : nullptr;
-    tg_gemm_tile(t, smem, pp, racc, args.err, dbg);
+    long long *dbg = (args.dbg && bid == 0 && !is_dep) ? args.dbg + 8 * args.dbg_slot : nullptr;
+    const bool needs_dep = !is_dep && args.dep_ctas > 0 && st.nphase > 1;
+    tg_gemm_tile(t, smem, pp, racc, args.err, dbg, needs_dep ? args.dep_cnt + mt * TG_DEP_NT : nullptr, args.dep_target,
+                 args.dep_ntiles);   // (its first barrier publishes the constants)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int hh = (warp - 2) >> 2, j0 = TG_HN * hh;   // epilogue warps: this thread's half of the tile's columns
@@ -500,16 +559,16 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_layer_kernel(const TgArgs ar
         if (warp >= 2) {
             const int row = (warp & 3) * 32 + lane;
             // [tile][k-range][float4 column][row]: a warp instruction writes 32 consecutive rows = 512 contiguous bytes
-            float4 *wsp = reinterpret_cast<float4 *>(args.ws) + (size_t)(tile * S + kr) * (TG_BN / 4) * TG_BM + row;
+            float4 *wsp = reinterpret_cast<float4 *>(args.ws) + (size_t)(ws_base + tile * S + kr) * (TG_BN / 4) * TG_BM + row;
 #pragma unroll
             for (int j = 0; j < TG_HN; j += 4)
                 wsp[(size_t)((j0 + j) >> 2) * TG_BM] = make_float4(racc[j], racc[j + 1], racc[j + 2], racc[j + 3]);
             __threadfence();
             tg_epi_sync();
             if (threadIdx.x == 64) {
-                const int ticket = atomicAdd(args.sem + tile, 1);
+                const int ticket = atomicAdd(sem, 1);
                 s_last = ticket == S - 1 ? 1 : 0;
-                if (ticket == S - 1) args.sem[tile] = 0;   // ready for the next launch
+                if (ticket == S - 1) *sem = 0;   // ready for the next launch
                 __threadfence();
             }
             tg_epi_sync();
@@ -518,7 +577,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_layer_kernel(const TgArgs ar
 #pragma unroll
                 for (int j = 0; j < TG_HN; ++j) racc[j] = 0.f;
                 for (int r = 0; r < S; ++r) {
-                    const float4 *src = reinterpret_cast<const float4 *>(args.ws) + (size_t)(tile * S + r) * (TG_BN / 4) * TG_BM + row;
+                    const float4 *src = reinterpret_cast<const float4 *>(args.ws) + (size_t)(ws_base + tile * S + r) * (TG_BN / 4) * TG_BM + row;
 #pragma unroll
                     for (int j = 0; j < TG_HN; j += 4) {
                         const float4 v4 = __ldcg(src + (size_t)((j0 + j) >> 2) * TG_BM);
@@ -560,7 +619,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_layer_kernel(const TgArgs ar
             for (int jj = 0; jj < TG_HN; ++jj) {
                 const int j = j0 + jj, col = n0 + j;
                 float y = vrow[j];
-                if (bias && col < N) y += bscale * __ldg(bias + col);
+                if (bias && col < N) y += bscale * s_bias[j];
                 if (relu) y = fmaxf(y, 0.f);
                 y = ((mwh >> jj) & 1u) ? y : 0.f;
                 bits |= (y > 0.f ? 1u : 0u) << jj;
@@ -570,6 +629,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_layer_kernel(const TgArgs ar
             if (st.save_mask) *mword = bits;
             tg_stage_planes(stg, row, vrow, j0);
             tg_store_tile(stg, args.maps + st.mapOut, n0, t.m0, st.out_rows);
+            if (is_dep && threadIdx.x == 64) {   // the tile has landed (wait_group 0 above): tell the wide CTAs of this row tile
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(args.dep_cnt + mt * TG_DEP_NT + nt), "r"(args.dep_target) : "memory");
+            }
         } else if (epi == TG_HEAD) {
             // vrow = yhat - bias; residual in normalised space (Auxilleryfunc, linna/util.py:1070-1088)
             float *ytile = reinterpret_cast<float *>(smem + TG_STAGE_BYTES + 36 * 1024);
@@ -584,10 +648,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_layer_kernel(const TgArgs ar
                 const int j = j0 + jj, col = n0 + j;
                 float dv = 0.f;
                 if (valid && col < N) {
-                    const float yh = vrow[j] + (bias ? bscale * __ldg(bias + col) : 0.f);
-                    const float ys = __ldg(c.y_std + col), ym = __ldg(c.y_mean + col);
-                    const float sg = c.sigma ? __ldg(c.sigma + col) : 1.f;
-                    const float dh = __ldg(c.data_hat + col);
+                    const float yh = vrow[j] + (bias ? bscale * s_bias[j] : 0.f);
+                    const float ys = s_cst[0][j], ym = s_cst[1][j], sg = s_cst[2][j], dh = s_cst[3][j];
                     const float Y = yrow[j];
                     float tt = Y / sg;                                              // util.py:432
                     if (c.ypositive) tt = logf(tt);                                 // util.py:567-568
@@ -860,6 +922,15 @@ struct TgContext {
     cudaStream_t bucket_stream[3] = {nullptr, nullptr, nullptr};   // nullptr: the caller's stream
     cudaEvent_t bucket_ready[3] = {nullptr, nullptr, nullptr}, bucket_done[3] = {nullptr, nullptr, nullptr};
     bool buckets_unjoined = false;                  // the last grad-out step left the bucket streams for the caller to join
+    // the loss reduction of a training step (one CTA; only the host reads it) runs beside the backward chain
+    cudaStream_t loss_stream = nullptr;
+    cudaEvent_t loss_ready = nullptr, loss_done = nullptr;
+    // fused res-block launches (TgArgs::step_dep): fuse_with_next[si] = step si is the narrow step of a res-block and
+    // step si + 1 the two-phase step that consumes it; dep_cnt [n_steps][m_tiles_max] counters, dep_seq[si] launches so far
+    std::vector<uint8_t> fuse_with_next;
+    std::vector<uint32_t> dep_seq;
+    uint32_t *dep_cnt = nullptr;
+    int m_tiles_max = 0;
 };
 
 cudaError_t tg_repack(TgContext *t, const float *params, cudaStream_t stream);
@@ -869,7 +940,10 @@ void tg_destroy(TgContext *t)
     if (!t) return;
     cudaFree(t->act), cudaFree(t->wblob), cudaFree(t->masks), cudaFree(t->delta32), cudaFree(t->chi_part);
     cudaFree(t->maps_dev), cudaFree(t->steps_dev), cudaFree(t->wlayers_dev), cudaFree(t->wtiles_dev), cudaFree(t->err_dev);
-    cudaFree(t->ws), cudaFree(t->sem), cudaFree(t->dbg);
+    cudaFree(t->ws), cudaFree(t->sem), cudaFree(t->dbg), cudaFree(t->dep_cnt);
+    if (t->loss_stream) cudaStreamDestroy(t->loss_stream);
+    if (t->loss_ready) cudaEventDestroy(t->loss_ready);
+    if (t->loss_done) cudaEventDestroy(t->loss_done);
     for (int b = 0; b < 3; ++b) {
         if (t->bucket_stream[b]) cudaStreamDestroy(t->bucket_stream[b]);
         if (t->bucket_ready[b]) cudaEventDestroy(t->bucket_ready[b]);
@@ -1161,6 +1235,10 @@ TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> 
             cudaEventCreateWithFlags(&t->bucket_done[b], cudaEventDisableTiming) != cudaSuccess)
             return bail("bucket streams");
     }
+    if (cudaStreamCreateWithFlags(&t->loss_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t->loss_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t->loss_done, cudaEventDisableTiming) != cudaSuccess)
+        return bail("loss stream");
     t->n_wlayers = (int)wl.size(), t->n_wtiles = (int)tiles.size();
     for (const TgWLayer &L : wl) t->max_wn = std::max<int64_t>(t->max_wn, (int64_t)L.N * L.K);
 
@@ -1195,9 +1273,21 @@ TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> 
         cudaMemset(t->dbg, 0, 64 * 8 * sizeof(long long));
     }
     for (const TgStep &s : t->steps) t->max_tiles = std::max(t->max_tiles, (B_pad / TG_BM) * s.n_tiles);
-    if (cudaMalloc(&t->ws, (size_t)t->max_tiles * 4 * TG_BM * TG_BN * sizeof(float)) != cudaSuccess) return bail("cudaMalloc split-K workspace");
-    if (cudaMalloc(&t->sem, (size_t)t->max_tiles * sizeof(int32_t)) != cudaSuccess) return bail("cudaMalloc split-K tickets");
-    cudaMemset(t->sem, 0, (size_t)t->max_tiles * sizeof(int32_t));
+    // (twice: the narrow step of a fused res-block launch parks its partial tiles behind the wide step's)
+    if (cudaMalloc(&t->ws, (size_t)2 * t->max_tiles * 4 * TG_BM * TG_BN * sizeof(float)) != cudaSuccess) return bail("cudaMalloc split-K workspace");
+    if (cudaMalloc(&t->sem, (size_t)2 * t->max_tiles * sizeof(int32_t)) != cudaSuccess) return bail("cudaMalloc split-K tickets");
+    cudaMemset(t->sem, 0, (size_t)2 * t->max_tiles * sizeof(int32_t));
+    t->m_tiles_max = B_pad / TG_BM;
+    t->fuse_with_next.assign(t->steps.size(), 0), t->dep_seq.assign(t->steps.size(), 0);
+    for (size_t si = 0; si + 1 < t->steps.size(); ++si) {
+        const TgStep &a = t->steps[si], &b = t->steps[si + 1];
+        // the narrow step's output planes are the A operand of the next step's second phase
+        if (a.nphase == 1 && b.nphase == 2 && (a.epi == TG_ACT || a.epi == TG_BWD) && a.mapOut == b.mapA[1] && (int)si != t->i_lossq &&
+            (int)si + 1 != t->i_lossq && !getenv("LINNA_TG_NO_FUSE"))
+            t->fuse_with_next[si] = 1;
+    }
+    if (cudaMalloc(&t->dep_cnt, t->steps.size() * t->m_tiles_max * TG_DEP_NT * sizeof(uint32_t)) != cudaSuccess) return bail("cudaMalloc dep flags");
+    cudaMemset(t->dep_cnt, 0, t->steps.size() * t->m_tiles_max * TG_DEP_NT * sizeof(uint32_t));
     if (cudaFuncSetAttribute(tg_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(tg_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES) != cudaSuccess)
         return bail("cudaFuncSetAttribute(tg kernels)");
@@ -1261,23 +1351,48 @@ static cudaError_t tg_launch_pdl(Kern kern, int grid, cudaStream_t stream, const
 }
 
 // one layer step over `m_tiles` row tiles: up to 4 k-ranges per tile when the layer has few tiles and a long contraction
-static cudaError_t tg_launch_layer(TgContext *t, TgArgs &a, int si, int m_tiles, cudaStream_t stream)
+static int tg_splitk(const TgContext *t, const TgStep &s, int tiles)
 {
-    const TgStep &s = t->steps[si];
-    const int tiles = m_tiles * s.n_tiles;
     const int T = (s.K[0] + TG_KC - 1) / TG_KC + (s.nphase > 1 ? (s.K[1] + TG_KC - 1) / TG_KC : 0);
     int S = 1;
     while (S < 4 && tiles * (2 * S) <= t->num_sms && T >= 4 * S) S *= 2;
     if (getenv("LINNA_TG_NO_SPLITK")) S = 1;
-    a.step = t->steps_dev + si, a.splitk = S;
+    return S;
+}
+static cudaError_t tg_launch_layer(TgContext *t, TgArgs &a, int si, int m_tiles, cudaStream_t stream)
+{
+    const TgStep &s = t->steps[si];
+    const int tiles = m_tiles * s.n_tiles;
+    a.step = t->steps_dev + si, a.splitk = tg_splitk(t, s, tiles);
     a.dbg = t->dbg, a.dbg_slot = si;
-    return tg_launch_pdl(tg_layer_kernel, tiles * S, stream, a);
+    a.step_dep = nullptr, a.dep_ctas = 0;
+    return tg_launch_pdl(tg_layer_kernel, tiles * a.splitk, stream, a);
+}
+// Steps si (narrow) and si + 1 (two-phase) of a res-block in ONE launch when every CTA of both can be resident at once
+// (one CTA per SM: the wide CTAs spin on the narrow ones, which have the lower block indices and are dispatched first).
+// Returns false when the pair does not fit and has to be launched step by step.
+static bool tg_launch_fused(TgContext *t, TgArgs &a, int si, int m_tiles, cudaStream_t stream, cudaError_t *ce)
+{
+    const TgStep &n = t->steps[si], &w = t->steps[si + 1];
+    const int tiles_n = m_tiles * n.n_tiles, tiles_w = m_tiles * w.n_tiles;
+    const int Sn = tg_splitk(t, n, tiles_n), Sw = tg_splitk(t, w, tiles_w);
+    if (tiles_n * Sn + tiles_w * Sw > t->num_sms || tiles_n > t->max_tiles || n.n_tiles > TG_DEP_NT) return false;
+    a.step = t->steps_dev + si + 1, a.splitk = Sw;
+    a.dbg = t->dbg, a.dbg_slot = si + 1;
+    a.step_dep = t->steps_dev + si, a.dep_ctas = tiles_n * Sn, a.dep_splitk = Sn;
+    a.dep_ws_base = t->max_tiles * 4, a.dep_sem_base = t->max_tiles;
+    a.dep_cnt = t->dep_cnt + (size_t)si * t->m_tiles_max * TG_DEP_NT, a.dep_ntiles = n.n_tiles;
+    a.dep_target = ++t->dep_seq[si];                 // 1, 2, ...: the flags start at 0
+    *ce = tg_launch_pdl(tg_layer_kernel, tiles_n * Sn + tiles_w * Sw, stream, a);
+    a.step_dep = nullptr, a.dep_ctas = 0;
+    return true;
 }
 
 // forward + loss head + quadratic form over B <= max_batch rows; `want_grad` also leaves d loss / d yhat for the
 // backward pass.  Returns the number of kernels launched (negative: CUDA error).
+// `side`: run the loss reduction on the context's loss stream (joined by the caller) instead of in line.
 static int tg_forward_loss(const linna_model *m, TgContext *t, const float *X, const float *Y, const float *cmd,
-                           int64_t B, int delta_kind, bool want_grad, float *rows, float *mean, cudaStream_t stream)
+                           int64_t B, int delta_kind, bool want_grad, float *rows, float *mean, cudaStream_t stream, bool side = false)
 {
     TgArgs a = tg_args(m, t, B);
     a.target = Y, a.cmd = cmd, a.delta_kind = delta_kind, a.loss_inv_B = 1.0f / (float)B, a.want_grad = want_grad ? 1 : 0;
@@ -1290,10 +1405,20 @@ static int tg_forward_loss(const linna_model *m, TgContext *t, const float *X, c
     }
     // delta_kind 1 (target vs data) does not need the network at all, but the chi^2 calls are not hot: same path
     for (int si = 0; si <= t->i_lossq; ++si) {
-        if (tg_launch_layer(t, a, si, m_tiles, stream) != cudaSuccess) return -1;
+        cudaError_t ce = cudaSuccess;
+        if (t->fuse_with_next[si] && tg_launch_fused(t, a, si, m_tiles, stream, &ce)) ++si;
+        else ce = tg_launch_layer(t, a, si, m_tiles, stream);
+        if (ce != cudaSuccess) return -1;
         ++launches;
     }
-    tg_loss_kernel<<<1, 256, 0, stream>>>(t->chi_part, t->chi_ld, t->lossq_tiles, cmd, (int)B, rows, mean);
+    cudaStream_t ls = stream;
+    if (side) {
+        if (cudaEventRecord(t->loss_ready, stream) != cudaSuccess || cudaStreamWaitEvent(t->loss_stream, t->loss_ready, 0) != cudaSuccess)
+            return -1;
+        ls = t->loss_stream;
+    }
+    tg_loss_kernel<<<1, 256, 0, ls>>>(t->chi_part, t->chi_ld, t->lossq_tiles, cmd, (int)B, rows, mean);
+    if (side && cudaEventRecord(t->loss_done, ls) != cudaSuccess) return -1;
     ++launches;
     return cudaGetLastError() == cudaSuccess ? launches : -1;
 }
@@ -1303,7 +1428,7 @@ static int tg_forward_loss(const linna_model *m, TgContext *t, const float *X, c
 int tg_train_step(const linna_model *m, TgContext *t, const float *X, const float *Y, const float *cmd, int64_t B, const AdamArgs &ad,
                   float *loss_rows, float *loss_mean, cudaStream_t stream, bool leave_unjoined)
 {
-    int launches = tg_forward_loss(m, t, X, Y, cmd, B, 0, true, loss_rows, loss_mean, stream);
+    int launches = tg_forward_loss(m, t, X, Y, cmd, B, 0, true, loss_rows, loss_mean, stream, true);
     if (launches < 0) return -1;
     TgArgs a = tg_args(m, t, B);
     const int m_tiles = (int)((B + TG_BM - 1) / TG_BM);
@@ -1328,11 +1453,18 @@ int tg_train_step(const linna_model *m, TgContext *t, const float *X, const floa
     };
     if (!side_buckets_after(t->i_lossq)) return -1;
     for (int si = t->i_lossq + 1; si < t->n_steps; ++si) {
-        if (tg_launch_layer(t, a, si, m_tiles, stream) != cudaSuccess) return -1;
+        cudaError_t ce = cudaSuccess;
+        if (t->fuse_with_next[si] && tg_launch_fused(t, a, si, m_tiles, stream, &ce)) {
+            if (ce != cudaSuccess || !side_buckets_after(si)) return -1;
+            ++si;
+        } else
+            ce = tg_launch_layer(t, a, si, m_tiles, stream);
+        if (ce != cudaSuccess) return -1;
         ++launches;
         if (!side_buckets_after(si)) return -1;
     }
     if (!launch_bucket(t->n_buckets - 1, stream)) return -1;
+    if (cudaStreamWaitEvent(stream, t->loss_done, 0) != cudaSuccess) return -1;   // the loss of this step is part of the step
     t->buckets_unjoined = leave_unjoined && t->n_buckets > 1;
     if (!t->buckets_unjoined)
         for (int b = 0; b + 1 < t->n_buckets; ++b) {

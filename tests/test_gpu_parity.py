@@ -107,6 +107,35 @@ def test_host_buffer_entry_points_match_device():
     assert np.array_equal(e.predict(th), e.predict(_dev(th)).cpu().numpy())
 
 
+@pytest.mark.parametrize("n", [9000, 23681, 60000])
+def test_pipelined_host_buffers_match_device(n):
+    """linna_lnp_host / linna_lnp_grad_host on batches large enough to be cut into chunks (one chunk below 1.25 kernel
+    rounds, then 1 + 2 + ... rounds; pieces of 512 KB staged by the caller and the helper thread): pageable and pinned
+    arrays, every combination, must return exactly what the device-resident call returns -- a walker's value does not
+    depend on the chunk it travels in."""
+    g = load_golden("c3s")
+    p = problem_from_golden(g)
+    e = engine.engine_from_problem(p)
+    u = synthetic.walkers(n, p.n_in, scale=0.3, seed=n)
+    l_dev, g_dev = e.lnp_grad(_dev(u))
+    l_dev, g_dev = l_dev.cpu().numpy(), g_dev.cpu().numpy()
+    for rep in range(2):                      # the second call reuses the staging buffers and the helper thread
+        l_host, g_host = e.lnp_grad(u)
+        assert np.array_equal(l_dev, l_host) and np.array_equal(g_dev, g_host)
+        assert np.array_equal(e.lnp(u), l_dev)
+    pin = torch.from_numpy(u).pin_memory().numpy()
+    out_l = torch.empty(n, dtype=torch.float32).pin_memory().numpy()
+    out_g = torch.empty(n, p.n_in, dtype=torch.float32).pin_memory().numpy()
+    e.lnp_grad(pin, out=out_l, out_grad=out_g)                 # pinned in, pinned out: no staging at all
+    assert np.array_equal(out_l, l_dev) and np.array_equal(out_g, g_dev)
+    out_l[:] = 0
+    e.lnp(u, out=out_l)                                        # pageable in, pinned out
+    assert np.array_equal(out_l, l_dev)
+    assert np.array_equal(e.lnp(pin), l_dev)                   # pinned in, pageable out
+    # a smaller batch right after a larger one (staging buffers larger than the call)
+    assert np.array_equal(e.lnp(u[:4097]), l_dev[:4097])
+
+
 @pytest.mark.parametrize("path", ["auto", "ffma", "cluster"])
 def test_ragged_empty_and_nan(path):
     g = load_golden("tiny")
