@@ -304,14 +304,29 @@ __device__ __forceinline__ void tg_gemm_tile(const TgTileDesc &t, uint8_t *smem,
     tg_fence_before();
     __syncthreads();
     tg_fence_after();
+    const uint32_t tmem_base = pp.tmem_slot;
+    const int nk0 = (t.K[0] + TG_KC - 1) / TG_KC;
+    const int total = t.i1 - t.i0;
+    // K-major GEMMs (forward / backward-data): the B operand is a packed WEIGHT matrix, which nothing in the launch chain
+    // of a step writes (see the note on the epilogue constants in tg_layer_kernel), so the weight planes of the first
+    // stages are requested before the wait for the predecessor; the activation planes follow after it.
+    const int npre = t.mn_major ? 0 : (total < TG_STAGES ? total : TG_STAGES);
+    if (warp == 0 && tg_elect_one()) {
+        for (int s = 0; s < npre; ++s) {
+            const int i = t.i0 + s, p = i < nk0 ? 0 : 1, kc = i < nk0 ? i : i - nk0;
+            uint8_t *sb = smem + s * TG_STAGE_BYTES + 3 * TG_A_PLANE;
+            tg_mbar_expect_tx(&pp.full_bar[s], TG_STAGE_BYTES);
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl)
+                tg_tma_load_2d(sb + pl * TG_B_PLANE, t.mapB[p], &pp.full_bar[s], kc * TG_KC, pl * t.rowsB[p] + t.n0);
+        }
+    }
+    __syncwarp();
     // everything above overlapped the previous kernel's tail (programmatic dependent launch); from here on its
     // results are read
     if (dbg && threadIdx.x == 64) dbg[1] = clock64();
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (dbg && threadIdx.x == 64) dbg[2] = clock64();
-    const uint32_t tmem_base = pp.tmem_slot;
-    const int nk0 = (t.K[0] + TG_KC - 1) / TG_KC;
-    const int total = t.i1 - t.i0;
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
@@ -343,12 +358,13 @@ __device__ __forceinline__ void tg_gemm_tile(const TgTileDesc &t, uint8_t *smem,
                 tg_mbar_wait(&pp.empty_bar[stage], ph ^ 1, err, 21);
                 if (tg_elect_one()) {
                     uint8_t *sa = smem + stage * TG_STAGE_BYTES, *sb = sa + 3 * TG_A_PLANE;
-                    tg_mbar_expect_tx(&pp.full_bar[stage], TG_STAGE_BYTES);
+                    const bool pre = i - t.i0 < npre;   // this stage's barrier is armed and its weight planes are on their way
+                    if (!pre) tg_mbar_expect_tx(&pp.full_bar[stage], TG_STAGE_BYTES);
 #pragma unroll
                     for (int pl = 0; pl < 3; ++pl) {
                         if (!t.mn_major) {
                             tg_tma_load_2d(sa + pl * TG_A_PLANE, t.mapA[p], &pp.full_bar[stage], kc * TG_KC, pl * t.rowsA[p] + t.m0);
-                            tg_tma_load_2d(sb + pl * TG_B_PLANE, t.mapB[p], &pp.full_bar[stage], kc * TG_KC, pl * t.rowsB[p] + t.n0);
+                            if (!pre) tg_tma_load_2d(sb + pl * TG_B_PLANE, t.mapB[p], &pp.full_bar[stage], kc * TG_KC, pl * t.rowsB[p] + t.n0);
                         } else {
                             tg_tma_load_2d(sa + pl * TG_A_PLANE, t.mapA[p], &pp.full_bar[stage], t.m0, pl * t.rowsA[p] + kc * TG_KC);
                             tg_tma_load_2d(sa + pl * TG_A_PLANE + TG_A_PLANE / 2, t.mapA[p], &pp.full_bar[stage], t.m0 + 64,
@@ -461,7 +477,9 @@ __device__ __forceinline__ void tg_stage_planes(uint8_t *stg, int row, const flo
 // barrier of the epilogue warps (the two service warps never join it)
 __device__ __forceinline__ void tg_epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TG_EPI_THREADS) : "memory"); }
 // the epilogue threads have staged their half rows: one of them sends the three planes of the tile to global memory
-__device__ __forceinline__ void tg_store_tile(uint8_t *stg, const CUtensorMap *map, int col0, int row0, int plane_rows)
+// `landed`: wait until the tile is in global memory (a fused launch signals other CTAs afterwards); otherwise only until
+// the staging tile has been read -- the grid's completion makes the writes visible to the next launch.
+__device__ __forceinline__ void tg_store_tile(uint8_t *stg, const CUtensorMap *map, int col0, int row0, int plane_rows, bool landed = false)
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tg_epi_sync();
@@ -469,7 +487,8 @@ __device__ __forceinline__ void tg_store_tile(uint8_t *stg, const CUtensorMap *m
 #pragma unroll
         for (int pl = 0; pl < 3; ++pl) tg_tma_store_2d(stg + pl * TG_A_PLANE, map, col0, pl * plane_rows + row0);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (landed) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 }
 // [128 rows][64 floats] tile between global memory (row pitch `ld`) and shared memory (row pitch 65), coalesced: an
@@ -576,12 +595,19 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_layer_kernel(const TgArgs ar
             if (do_epilogue) {
 #pragma unroll
                 for (int j = 0; j < TG_HN; ++j) racc[j] = 0.f;
-                for (int r = 0; r < S; ++r) {
+                // two k-ranges' loads in flight at a time (S is 2 or 4), added in k-range order
+                for (int r = 0; r < S; r += 2) {
                     const float4 *src = reinterpret_cast<const float4 *>(args.ws) + (size_t)(ws_base + tile * S + r) * (TG_BN / 4) * TG_BM + row;
+                    float4 va[TG_HN / 4], vb[TG_HN / 4];
 #pragma unroll
                     for (int j = 0; j < TG_HN; j += 4) {
-                        const float4 v4 = __ldcg(src + (size_t)((j0 + j) >> 2) * TG_BM);
-                        racc[j] += v4.x, racc[j + 1] += v4.y, racc[j + 2] += v4.z, racc[j + 3] += v4.w;
+                        va[j >> 2] = __ldcg(src + (size_t)((j0 + j) >> 2) * TG_BM);
+                        vb[j >> 2] = __ldcg(src + (size_t)(TG_BN / 4) * TG_BM + (size_t)((j0 + j) >> 2) * TG_BM);
+                    }
+#pragma unroll
+                    for (int j = 0; j < TG_HN; j += 4) {
+                        racc[j] += va[j >> 2].x, racc[j + 1] += va[j >> 2].y, racc[j + 2] += va[j >> 2].z, racc[j + 3] += va[j >> 2].w;
+                        racc[j] += vb[j >> 2].x, racc[j + 1] += vb[j >> 2].y, racc[j + 2] += vb[j >> 2].z, racc[j + 3] += vb[j >> 2].w;
                     }
                 }
             }
@@ -628,7 +654,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_layer_kernel(const TgArgs ar
             }
             if (st.save_mask) *mword = bits;
             tg_stage_planes(stg, row, vrow, j0);
-            tg_store_tile(stg, args.maps + st.mapOut, n0, t.m0, st.out_rows);
+            tg_store_tile(stg, args.maps + st.mapOut, n0, t.m0, st.out_rows, is_dep);
             if (is_dep && threadIdx.x == 64) {   // the tile has landed (wait_group 0 above): tell the wide CTAs of this row tile
                 asm volatile("fence.proxy.async;" ::: "memory");
                 __threadfence();
