@@ -139,7 +139,12 @@ int linna_predict_vjp(linna_model_t *m, const float *theta, int64_t n, const flo
 /* Host-buffer forms of the three calls above: the arrays are HOST memory (any pageable or pinned
  * buffer); the library stages them through pinned memory, runs the kernel and copies the result
  * back before returning.  These are what a per-call numpy caller (emcee/zeus with vectorize=True)
- * binds, and what bench.py's `e2e` leg times. */
+ * binds, and what bench.py's `e2e` leg times.  Large lnP / lnP+gradient batches are cut into chunks
+ * whose copies overlap the kernels; pageable arrays are staged by the calling thread and ONE helper
+ * thread that the model starts at its first such call (it sleeps between calls and is joined by
+ * linna_model_destroy).  Like every entry point of a model, these calls must not run concurrently on
+ * the SAME model (its scratch arena and staging buffers are per-model state); different models are
+ * independent. */
 int linna_predict_host(linna_model_t *m, const float *theta, int64_t n, float *out, int32_t out_kind);
 int linna_lnp_host(linna_model_t *m, const float *u, int64_t n, float *lnp);
 int linna_lnp_grad_host(linna_model_t *m, const float *u, int64_t n, float *lnp, float *grad);

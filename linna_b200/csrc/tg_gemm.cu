@@ -788,6 +788,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_wgrad_kernel(const TgArgs ar
         const AdamArgs &ad = args.adam;
         const int64_t pf = (int64_t)L.wf_rows * L.wf_ld;
         // four rows (eight coalesced 128-byte lines of each of p, m, v) in flight per batch
+#pragma unroll 1
         for (int r0 = 16 * hh; r0 < 16 * hh + 16; r0 += 4) {
             int idx[8];
             float g[8], pp_[8], mm_[8], vv_[8];
