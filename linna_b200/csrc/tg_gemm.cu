@@ -854,15 +854,45 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_wgrad_kernel(const TgArgs ar
     if (dbg && threadIdx.x == 64) dbg[6] = clock64();
 }
 
-// params -> packed bf16x3 planes of every weight matrix (set-up, load_state_dict, after the stand-alone AdamW)
-__global__ void tg_repack_kernel(const float *__restrict__ params, __nv_bfloat16 *wblob, const TgWLayer *__restrict__ layers)
+// params -> packed bf16x3 planes of every weight matrix (set-up, load_state_dict, after the stand-alone AdamW of a
+// data-parallel step).  One CTA per 128 x 64 tile of the weight-gradient tile table: the forward copy [n][k] is written
+// with lane = k, the backward copy [k][n] with lane = n after a pass through shared memory -- written straight from a
+// flat loop over the parameters, the backward copy was 32 separate sectors per warp store (4 M two-byte stores at C3).
+__global__ void __launch_bounds__(256) tg_repack_kernel(const float *__restrict__ params, __nv_bfloat16 *wblob,
+                                                        const TgWLayer *__restrict__ layers, const TgWTile *__restrict__ tiles)
 {
-    const TgWLayer L = layers[blockIdx.y];
-    const int total = L.N * L.K;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const int n = e / L.K, k = e - n * L.K;
-        tg_pack_weight(wblob, L, n, k, params[L.w_flat + e]);
+    __shared__ float tile[TG_BM][TG_BN + 1];
+    const TgWTile wt = tiles[blockIdx.x];
+    const TgWLayer L = layers[wt.layer];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t pf = (int64_t)L.wf_rows * L.wf_ld, pb = (int64_t)L.wb_rows * L.wb_ld;
+    for (int r = warp; r < TG_BM; r += 8) {
+        const int n = wt.m0 + r;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = 32 * h + lane, k = wt.n0 + j;
+            float p = 0.f;
+            if (n < L.N && k < L.K) {
+                p = params[L.w_flat + n * L.K + k] * L.pack_scale;
+                __nv_bfloat16 b0, b1, b2;
+                tg_split3_1(p, b0, b1, b2);
+                const int64_t of = L.wf_off + (int64_t)n * L.wf_ld + k;
+                wblob[of] = b0, wblob[of + pf] = b1, wblob[of + 2 * pf] = b2;
+            }
+            tile[r][j] = p;
+        }
     }
+    __syncthreads();
+    const int r = threadIdx.x & (TG_BM - 1), n = wt.m0 + r;
+    if (n < L.N)
+        for (int j = 32 * (threadIdx.x >> 7); j < 32 * (threadIdx.x >> 7) + 32; ++j) {
+            const int k = wt.n0 + j;
+            if (k >= L.K) break;
+            __nv_bfloat16 b0, b1, b2;
+            tg_split3_1(tile[r][j], b0, b1, b2);
+            const int64_t ob = L.wb_off + (int64_t)k * L.wb_ld + n;
+            wblob[ob] = b0, wblob[ob + pb] = b1, wblob[ob + 2 * pb] = b2;
+        }
 }
 
 // physical parameters -> xhat = (theta' - mean)/std (util.py:483-497) as bf16x3 planes, bias column set to 1
@@ -1345,8 +1375,7 @@ TgContext *tg_build(const linna_model *m, const std::vector<std::array<int, 5>> 
 // packed planes <- flat parameter vector (device)
 cudaError_t tg_repack(TgContext *t, const float *params, cudaStream_t stream)
 {
-    const int bx = (int)std::min<int64_t>((t->max_wn + 255) / 256, 256);
-    tg_repack_kernel<<<dim3(bx, t->n_wlayers), 256, 0, stream>>>(params, t->wblob, t->wlayers_dev);
+    tg_repack_kernel<<<t->n_wtiles, 256, 0, stream>>>(params, t->wblob, t->wlayers_dev, t->wtiles_dev);
     return cudaGetLastError();
 }
 
