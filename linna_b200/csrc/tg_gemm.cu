@@ -742,17 +742,6 @@ __device__ __forceinline__ void tg_split3_1(float x, __nv_bfloat16 &h, __nv_bflo
     l = __float2bfloat16_rn(r1 - __bfloat162float(m));
 }
 
-// bf16x3 planes of one weight into the packed forward [n][k] and backward [k][n] copies (set-up / repack path)
-__device__ __forceinline__ void tg_pack_weight(__nv_bfloat16 *wblob, const TgWLayer &L, int n, int k, float p)
-{
-    __nv_bfloat16 h, m, l;
-    tg_split3_1(p * L.pack_scale, h, m, l);
-    const int64_t pf = (int64_t)L.wf_rows * L.wf_ld, of = L.wf_off + (int64_t)n * L.wf_ld + k;
-    wblob[of] = h, wblob[of + pf] = m, wblob[of + 2 * pf] = l;
-    const int64_t pb = (int64_t)L.wb_rows * L.wb_ld, ob = L.wb_off + (int64_t)k * L.wb_ld + n;
-    wblob[ob] = h, wblob[ob + pb] = m, wblob[ob + 2 * pb] = l;
-}
-
 constexpr int TG_WT_LD = TG_BN + 1;   // padded row pitch of the gradient tile in shared memory
 
 __global__ void __launch_bounds__(TG_THREADS, 1) tg_wgrad_kernel(const TgArgs args)

@@ -1,5 +1,5 @@
-"""Device time of the tensor-core lnP launch against the number of walkers (staircase in rounds; one or two walker
-pairs per CTA pair), and the pageable end-to-end time for LINNA_HOST_CHUNK_ROUNDS given in the environment."""
+"""Device time of the tensor-core lnP launch against the number of walkers (`device`: the staircase in rounds; one or
+two walker pairs per CTA pair), or the pageable end-to-end time of one 10^5-walker call (MODE=lnp|grad)."""
 import os
 import sys
 import time
@@ -40,5 +40,4 @@ else:
         call(u[s % 4])
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / 20
-    print("%s LINNA_HOST_CHUNK_ROUNDS=%s: pageable e2e %.3f ms per 1e5 walkers = %.1f M evals/s"
-          % (mode, os.environ.get("LINNA_HOST_CHUNK_ROUNDS"), dt * 1e3, n / dt / 1e6))
+    print("%s: pageable e2e %.3f ms per 1e5 walkers = %.1f M evals/s" % (mode, dt * 1e3, n / dt / 1e6))

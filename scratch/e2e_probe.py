@@ -43,8 +43,7 @@ for src, name in ((pin, "pinned"), (torch.from_numpy(u[0]), "pageable")):
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / 20
     print("H2D 12 MB from %s: %.3f ms = %.1f GB/s" % (name, dt * 1e3, 12e6 / dt / 1e9))
-for thr in sys.argv[1:] or ["1", "4", "8", "15"]:
-    os.environ["LINNA_STAGE_THREADS"] = thr
+for thr in sys.argv[1:] or ["-"]:   # (the staging pool and its LINNA_STAGE_THREADS switch are gone: one helper thread now)
     p, eng, data = bench.make_engine(D, "c3")
     for w in range(3):
         eng.lnp(u[w % 4])
@@ -54,6 +53,5 @@ for thr in sys.argv[1:] or ["1", "4", "8", "15"]:
         eng.lnp(u[s % 4])
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / 20
-    print("LINNA_STAGE_THREADS=%s (env LINNA_HOST_CHUNKS=%s): pageable e2e %.3f ms per 1e5 walkers = %.1f M evals/s"
-          % (thr, os.environ.get("LINNA_HOST_CHUNKS"), dt * 1e3, n / dt / 1e6))
+    print("pageable e2e %.3f ms per 1e5 walkers = %.1f M evals/s" % (dt * 1e3, n / dt / 1e6))
     eng.close()
