@@ -641,19 +641,32 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tg_layer_kernel(const TgArgs ar
             const float bscale = st.bias_scale;
             const bool relu = st.relu != 0, ones = st.write_ones != 0;
             uint32_t bits = 0u;
-#pragma unroll 4
-            for (int jj = 0; jj < TG_HN; ++jj) {
-                const int j = j0 + jj, col = n0 + j;
-                float y = vrow[j];
-                if (bias && col < N) y += bscale * s_bias[j];
-                if (relu) y = fmaxf(y, 0.f);
-                y = ((mwh >> jj) & 1u) ? y : 0.f;
-                bits |= (y > 0.f ? 1u : 0u) << jj;
-                if (!(valid && col < N)) y = (valid && col == N && ones) ? 1.f : 0.f;
-                vrow[j] = y;
+            // eight columns per trip, from the fp32 row straight into the three bf16 planes of the staging tile (128-byte
+            // swizzle: 16-byte chunk c of a row sits at chunk c ^ (row & 7)): one pass, no write-back of the row
+            const uint32_t stg_row = tg_smem_u32(stg) + (uint32_t)row * 128u, swz = (uint32_t)(row & 7);
+#pragma unroll 1
+            for (int g8 = 0; g8 < TG_HN; g8 += 8) {
+                float y8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int jj = g8 + e, j = j0 + jj, col = n0 + j;
+                    float y = vrow[j];
+                    if (bias && col < N) y += bscale * s_bias[j];
+                    if (relu) y = fmaxf(y, 0.f);
+                    y = ((mwh >> jj) & 1u) ? y : 0.f;
+                    bits |= (y > 0.f ? 1u : 0u) << jj;
+                    if (!(valid && col < N)) y = (valid && col == N && ones) ? 1.f : 0.f;
+                    y8[e] = y;
+                }
+                uint32_t h[4], m[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) tg_split3(y8[e], y8[e + 1], h[e >> 1], m[e >> 1], l[e >> 1]);
+                const uint32_t o = stg_row + ((((uint32_t)(j0 + g8) >> 3) ^ swz) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + TG_A_PLANE), "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + 2 * TG_A_PLANE), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
             }
             if (st.save_mask) *mword = bits;
-            tg_stage_planes(stg, row, vrow, j0);
             tg_store_tile(stg, args.maps + st.mapOut, n0, t.m0, st.out_rows, is_dep);
             if (is_dep && threadIdx.x == 64) {   // the tile has landed (wait_group 0 above): tell the wide CTAs of this row tile
                 asm volatile("fence.proxy.async;" ::: "memory");
