@@ -338,14 +338,17 @@ def measure_lnp(D, p, eng, n, mode, steps, warmup, want_e2e=True, sample_clocks=
     d2h = n * 4 * (1 + (p.n_in if mode == "grad" else 0))
 
     def timed(fn):
-        for w in range(2):
+        # host-side timing of a few-ms region is at the mercy of one scheduling hiccup: at least 50 calls, reported as
+        # the time of `steps` calls
+        reps = max(steps, 50)
+        for w in range(3):
             fn(w)
         D.barrier()
         t0 = time.perf_counter()
-        for s in range(steps):
+        for s in range(reps):
             fn(s)
         torch.cuda.synchronize()
-        return D.max(time.perf_counter() - t0)
+        return D.max(time.perf_counter() - t0) * steps / reps
 
     # (a) the reference-facing case: an emcee/zeus caller hands over PAGEABLE numpy arrays and receives fresh ones
     page = u_host[:4]
@@ -478,14 +481,19 @@ def measure_train(D, B_rank, steps, warmup, want_e2e=True):
         hx = [t_.cpu().pin_memory() for t_ in xb[:8]]
         hy = [t_.cpu().pin_memory() for t_ in yb[:8]]
         hc = [t_.cpu().pin_memory() for t_ in cb[:8]]
-        D.barrier()
-        t0 = time.perf_counter()
-        for s in range(steps):
+        def e2e_step(s):
             j = s % len(hx)
             l_ = tr.step(hx[j].cuda(non_blocking=True), hy[j].cuda(non_blocking=True), hc[j].cuda(non_blocking=True))
-            float(l_.item())
+            return float(l_.item())
+        reps = max(steps, 100)                     # (a 20-step region is 8 ms of host time: one hiccup moves it by 30 %)
+        for s in range(3):
+            e2e_step(s)
+        D.barrier()
+        t0 = time.perf_counter()
+        for s in range(reps):
+            e2e_step(s)
         torch.cuda.synchronize()
-        out["e2e_s"] = D.max(time.perf_counter() - t0)
+        out["e2e_s"] = D.max(time.perf_counter() - t0) * steps / reps
     tr.engine.close()
     return out
 
