@@ -1412,8 +1412,12 @@ static cudaError_t tg_launch_pdl(Kern kern, int grid, cudaStream_t stream, const
 static int tg_splitk(const TgContext *t, const TgStep &s, int tiles)
 {
     const int T = (s.K[0] + TG_KC - 1) / TG_KC + (s.nphase > 1 ? (s.K[1] + TG_KC - 1) / TG_KC : 0);
+    static const int smax = getenv("LINNA_TG_MAX_SPLITK") ? std::max(1, atoi(getenv("LINNA_TG_MAX_SPLITK"))) : 4;
+    // k-chunks per range: measured at C5 (scratch/splitk_sweep.sh) 0.261 ms per step with >= 4, 0.253 with >= 2, 0.257 with >= 1;
+    // no split-K at all 0.277 -- the k-loops are a small part of a launch
+    static const int tmin = getenv("LINNA_TG_SPLITK_MIN_CHUNKS") ? std::max(1, atoi(getenv("LINNA_TG_SPLITK_MIN_CHUNKS"))) : 2;
     int S = 1;
-    while (S < 4 && tiles * (2 * S) <= t->num_sms && T >= 4 * S) S *= 2;
+    while (S < smax && tiles * (2 * S) <= t->num_sms && T >= tmin * S) S *= 2;
     if (getenv("LINNA_TG_NO_SPLITK")) S = 1;
     return S;
 }
